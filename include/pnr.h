@@ -1,0 +1,136 @@
+/* pnr.h — C ABI of libpnr (PanopticNeRF render hot path, sm_100a).
+ *
+ * The reference exposes this path only as a Python plugin surface in lib/networks
+ * (make_network, Renderer.render, batchify_rays, raw2outputs, sample_pdf); it has
+ * no native/FFI boundary of its own, and its source is not in the mount (/root/reference holds the
+ * landing branch only: README.md:7, README.md:13), so no reference file:line can be cited per entry
+ * point.  Each entry point below names the SURVEY.md 8(a) row (a1..a10) it implements; the
+ * reference-side binding a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - every function returns 0 on success, <0 on error; pnr_last_error() gives a thread-local text.
+ *  - all array arguments are DEVICE pointers unless the name ends in _host.
+ *  - buffers are caller-owned; nothing is allocated on the stage entry points; all work is
+ *    enqueued asynchronously on `stream` (a cudaStream_t passed as void*).
+ *  - one context per device; a context is not thread-safe; outputs are deterministic
+ *    (no atomics), so any ray sharding reproduces the single-GPU result bit for bit.
+ */
+#ifndef PNR_H_
+#define PNR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PNR_VERSION 100
+
+enum { PNR_OK = 0, PNR_ERR_ARG = -1, PNR_ERR_CUDA = -2, PNR_ERR_STATE = -3, PNR_ERR_UNSUPPORTED = -4 };
+
+/* MLP arithmetic mode: element format of the tensor-core operands (accumulation is always fp32).
+ * The x3 modes split every operand x = hi + lo in that format and issue A_hi*B_hi + A_lo*B_hi + A_hi*B_lo. */
+enum { PNR_PREC_BF16X3 = 0, /* ~2^-17 per product, fp32 exponent range; ~1e-4 end to end (marginal)       */
+       PNR_PREC_BF16 = 1,   /* 1 pass, ~1e-2 end to end: fast mode, outside the tolerance                 */
+       PNR_PREC_FP16X3 = 2, /* ~2^-21 per product, needs |activation| < 65504; meets 1e-4 with margin     */
+       PNR_PREC_FP16 = 3    /* 1 pass, ~1e-3 end to end: fast mode, outside the tolerance                 */ };
+
+typedef struct pnr_ctx pnr_ctx;
+
+typedef struct pnr_config {
+  int32_t D;             /* trunk depth (8)                           a8 */
+  int32_t W;             /* trunk width (256); 64, 128 or 256         a8 */
+  int32_t xyz_res;       /* Lx, positional-encoding octaves for xyz   a7 */
+  int32_t view_res;      /* Ld, octaves for the view direction        a7 */
+  int32_t num_classes;   /* C semantic logits, 0 = no head            a8 */
+  int32_t num_instances; /* K instance logits, 0 = no head            a8 */
+  int32_t precision;     /* PNR_PREC_*                                   */
+  int32_t device;        /* CUDA ordinal                                 */
+} pnr_config;
+
+int pnr_version(void);
+const char* pnr_last_error(void);
+
+/* a1/a2: context = packed weights + kernel attributes for one Network on one device. */
+int pnr_create(const pnr_config* cfg, pnr_ctx** out);
+int pnr_destroy(pnr_ctx* ctx);
+
+/* a2: load a Network state_dict.  `tensors_host[i]` are HOST fp32 pointers in this fixed order:
+ *   pts_linears.{0..D-1}.weight/.bias (interleaved w,b), alpha_linear.w/.b, feature_linear.w/.b,
+ *   views_linears.0.w/.b, rgb_linear.w/.b, [semantic_linears.0.w/.b, semantic_linears.1.w/.b],
+ *   [instance_linears.0.w/.b, instance_linears.1.w/.b]
+ * `shapes[2*i], shapes[2*i+1]` = (out, in) for weights, (out, 1) for biases.  Weights are split
+ * into bf16 hi/lo, laid out as no-swizzle K-major UMMA stage images and uploaded. */
+int pnr_load_weights(pnr_ctx* ctx, const float* const* tensors_host, const int64_t* shapes, int32_t n);
+
+/* a5: ray / oriented-box slab test.  rays [R,6] (o||d); box_center, box_half [B,3]; box_rot [B,3,3]
+ * row-major, columns = box axes.  Out: hit_mask [R] u8, box_id [R,M] i32 (-1 pad), t_in/t_out [R,M]. */
+int pnr_intersect(const float* rays, int64_t R, const float* box_center, const float* box_half,
+                  const float* box_rot, int32_t B, int32_t M, uint8_t* hit_mask, int32_t* box_id,
+                  float* t_in, float* t_out, void* stream);
+
+/* a5 (AABB special case): per-ray near = max(tmin, near_min), far = tmax, or
+ * (near_min, far_default) when the scene box is missed.  aabb_host = {lo.xyz, hi.xyz}. */
+int pnr_scene_near_far(const float* rays, int64_t R, const float* aabb_host, float near_min,
+                       float far_default, float* near, float* far, void* stream);
+
+/* a5 helper (cfg.bound_by_primitives): clamp near/far to the hull of the hit intervals, in place. */
+int pnr_bound_by_primitives(const uint8_t* hit_mask, const int32_t* box_id, const float* t_in,
+                            const float* t_out, int64_t R, int32_t M, float* near, float* far,
+                            void* stream);
+
+/* a6: z[R,N] = near*(1-t)+far*t (t_vals [N]); if perturb>0, jittered with u [R,N].
+ * sample_box (nullable) [R,N] i32 = id of the first hit interval containing the sample, else -1. */
+int pnr_sample_stratified(const float* near, const float* far, const float* t_vals, const float* u,
+                          int64_t R, int32_t N, float perturb, const int32_t* box_id,
+                          const float* t_in, const float* t_out, int32_t M, float* z,
+                          int32_t* sample_box, void* stream);
+
+/* a6: re-tag an existing depth array (after the coarse+fine merge). */
+int pnr_tag_samples(const float* z, int64_t R, int32_t N, const int32_t* box_id, const float* t_in,
+                    const float* t_out, int32_t M, int32_t* sample_box, void* stream);
+
+/* a7: standalone positional encoding, out [n, 3+6L]. */
+int pnr_encode(const float* x, int64_t n, int32_t L, float* out, void* stream);
+
+/* a8: Network.forward.  Either (pts, viewdirs) [n,3] each, or (rays [R,6], z [R,N]) with pts and the
+ * normalised view direction formed in-kernel (pass pts = NULL).  raw [n or R*N, 4+C+K]. */
+int pnr_mlp_forward(pnr_ctx* ctx, const float* pts, const float* viewdirs, const float* rays,
+                    const float* z, int64_t R, int32_t N, float* raw, void* stream);
+
+/* a9: raw2outputs.  raw [R,N,4+C+K], z [R,N], rays [R,6].  Any output pointer may be NULL.
+ * sem_softmax: composite softmax(logits) instead of logits.  sample_box/box_sem/box_inst nullable. */
+typedef struct pnr_composite_out {
+  float* rgb_map;    /* [R,3] */
+  float* depth_map;  /* [R]   */
+  float* acc_map;    /* [R]   */
+  float* disp_map;   /* [R]   */
+  float* weights;    /* [R,N] */
+  float* semantic_map;        /* [R,C] */
+  float* instance_map;        /* [R,K] */
+  float* fixed_semantic_map;  /* [R,C] */
+  float* fixed_instance_map;  /* [R,K] */
+} pnr_composite_out;
+int pnr_composite(const float* raw, const float* z, const float* rays, int64_t R, int32_t N,
+                  int32_t C, int32_t K, int32_t white_bkgd, int32_t sem_softmax, int32_t mask_outside,
+                  const int32_t* sample_box, const int32_t* box_sem, const int32_t* box_inst,
+                  int32_t B, const pnr_composite_out* out, void* stream);
+
+/* a10: sample_pdf + merge.  z [R,N] coarse depths, weights [R,N] coarse weights; bins are the mid
+ * points, the pdf is weights[1:-1]+1e-5.  u [R,Ni] is required (deterministic sampler: the host's
+ * linspace(0,1,Ni) broadcast over rays, so the values are the caller's, bit for bit).
+ * Out (nullable each): z_fine [R,Ni], idx [R,Ni] i64 (searchsorted right), z_all [R,N+Ni] sorted. */
+int pnr_sample_pdf(const float* z, const float* weights, int64_t R, int32_t N, int32_t Ni,
+                   const float* u, float* z_fine, int64_t* idx, float* z_all, void* stream);
+
+/* Bytes of device scratch Renderer.render needs for R rays (z, raw, ids ...), for the caller to own. */
+size_t pnr_workspace_bytes(const pnr_ctx* ctx, int64_t R, int32_t N, int32_t Ni);
+
+/* Number of kernels this library has launched on this thread since the last reset (bench evidence). */
+int64_t pnr_launch_count(int32_t reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PNR_H_ */

@@ -205,7 +205,7 @@ def raw2outputs(raw, z_vals, rays_d, raw_noise_std: float = 0.0, white_bkgd: boo
     """SURVEY 8(a) a9.  raw [R,N,4+C+K], z_vals [R,N], rays_d [R,3]."""
     C, K = num_classes, num_instances
     dists = z_vals[:, 1:] - z_vals[:, :-1]
-    dists = torch.cat([dists, torch.full_like(dists[:, :1], 1e10)], -1)
+    dists = torch.cat([dists, torch.full_like(z_vals[:, :1], 1e10)], -1)   # (also right for N == 1)
     dists = dists * torch.norm(rays_d[:, None, :], dim=-1)
     rgb = torch.sigmoid(raw[..., :3])
     sig = raw[..., 3]

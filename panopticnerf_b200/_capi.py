@@ -1,0 +1,95 @@
+"""ctypes binding of the libpnr C ABI (include/pnr.h).  Thin by design: it only checks dtype /
+device / contiguity and forwards ``tensor.data_ptr()`` plus the current CUDA stream handle.
+
+There is no CPU or PyTorch fallback: if libpnr.so is missing or a call fails, this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+from typing import Optional
+
+import torch
+
+_LIB_PATH = Path(__file__).resolve().parent / "libpnr.so"
+_lib: Optional[C.CDLL] = None
+
+PREC = {"bf16x3": 0, "bf16": 1, "fp16x3": 2, "fp16": 3}
+
+
+class PnrError(RuntimeError):
+    pass
+
+
+class PnrConfig(C.Structure):
+    _fields_ = [("D", C.c_int32), ("W", C.c_int32), ("xyz_res", C.c_int32), ("view_res", C.c_int32),
+                ("num_classes", C.c_int32), ("num_instances", C.c_int32), ("precision", C.c_int32),
+                ("device", C.c_int32)]
+
+
+class PnrCompositeOut(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in
+                ("rgb_map", "depth_map", "acc_map", "disp_map", "weights", "semantic_map",
+                 "instance_map", "fixed_semantic_map", "fixed_instance_map")]
+
+
+# name -> (restype, argtypes); mirrors include/pnr.h one to one
+_vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+SIGNATURES = {
+    "pnr_version": (C.c_int, []),
+    "pnr_last_error": (C.c_char_p, []),
+    "pnr_create": (C.c_int, [C.POINTER(PnrConfig), C.POINTER(_vp)]),
+    "pnr_destroy": (C.c_int, [_vp]),
+    "pnr_load_weights": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_i64), _i32]),
+    "pnr_intersect": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "pnr_scene_near_far": (C.c_int, [_vp, _i64, C.POINTER(_f32), _f32, _f32, _vp, _vp, _vp]),
+    "pnr_bound_by_primitives": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "pnr_sample_stratified": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "pnr_tag_samples": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "pnr_encode": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
+    "pnr_mlp_forward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
+    "pnr_composite": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32,
+                                C.POINTER(PnrCompositeOut), _vp]),
+    "pnr_sample_pdf": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "pnr_workspace_bytes": (C.c_size_t, [_vp, _i64, _i32, _i32]),
+    "pnr_launch_count": (_i64, [_i32]),
+}
+
+
+def lib() -> C.CDLL:
+    """Load libpnr.so (once).  Fails loudly: the product has no path that works without it."""
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            raise PnrError(f"{_LIB_PATH} is missing - run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(nvcc, sm_100a).  panopticnerf_b200 has no CPU or PyTorch fallback.")
+        L = C.CDLL(str(_LIB_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)          # AttributeError here = header/library mismatch
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().pnr_last_error()
+        raise PnrError(f"{what or 'libpnr'} failed (rc={rc}): {msg.decode() if msg else '?'}")
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t: Optional[torch.Tensor], dtype: Optional[torch.dtype] = None, name: str = "tensor"):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise PnrError(f"{name}: expected a CUDA tensor, got {t.device} - panopticnerf_b200 is GPU-only "
+                       "(no CPU fallback)")
+    if dtype is not None and t.dtype != dtype:
+        raise PnrError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise PnrError(f"{name}: expected a contiguous tensor")
+    return t.data_ptr()

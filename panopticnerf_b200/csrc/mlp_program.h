@@ -1,0 +1,99 @@
+// mlp_program.h — the per-tile "program" the fused MLP kernel interprets (built once on the host when
+// weights are loaded, see pnr_api.cu) and the shared-memory / tensor-memory maps both sides agree on.
+#pragma once
+#include <stdint.h>
+
+namespace pnr {
+
+constexpr int kTileM = 128;               // samples per tile = TMEM lanes = UMMA M
+constexpr int kRing = 4;                  // weight stages in flight
+constexpr int kStageBytes = 32768;        // max stage: N=256 rows x 64 K x bf16
+constexpr int kEpiWarps = 8;              // TMEM->reg->TMEM activation warps (2 per lane quarter)
+constexpr int kProWarps = 4;              // positional-encoding producer warps (one thread per row)
+constexpr int kMlpThreads = (kEpiWarps + kProWarps + 2) * 32;   // + TMA warp + MMA warp = 448
+constexpr int kMaxStages = 192;
+constexpr int kMaxSteps = 24;
+constexpr int kMaxConsts = 4096;          // floats: biases + sigma / rgb weights
+
+// Tensor-memory column map (512 x 32-bit columns, 128 lanes).
+constexpr int kColAcc = 0;                // fp32 accumulators, up to 256 columns
+constexpr int kColAHi = 256;              // activations, bf16 hi halves, 2 per column (K <= 256)
+constexpr int kColALo = 384;              // activations, bf16 lo halves
+constexpr int kColHeadHi = 128;           // head hidden activations (K <= 128) live in the upper
+constexpr int kColHeadLo = 192;           //   half of the accumulator region while it is free
+
+// Shared-memory map (bytes from the 1024-aligned dynamic base).
+constexpr int kSmemRing = 0;
+constexpr int kSmemEmb = kRing * kStageBytes;          // xyz embedding, UMMA no-swizzle K-major: hi 16K, lo 16K
+constexpr int kEmbPartBytes = kTileM * 64 * 2;         // 16 KB
+constexpr int kSmemDir = kSmemEmb + 2 * kEmbPartBytes; // view-dir embedding, 2 buffers x (hi 8K, lo 8K)
+constexpr int kDirPartBytes = kTileM * 32 * 2;         // 8 KB
+constexpr int kSmemProg = kSmemDir + 4 * kDirPartBytes;
+
+enum : uint8_t { A_TMEM = 0, A_EMB = 1, A_DIR = 2 };
+enum : uint8_t {
+  F_FIRST = 1,         // first MMA of the step overwrites the accumulator
+  F_WAIT_A = 2,        // wait for the previous step's epilogue (activations staged, accumulator drained)
+  F_COMMIT_ACC = 4,    // last stage of the step: signal the epilogue when the MMAs retire
+  F_WAIT_EMB = 8, F_RELEASE_EMB = 16, F_WAIT_DIR = 32, F_RELEASE_DIR = 64
+};
+enum : uint8_t { EPI_RELU_TO_A = 0, EPI_LINEAR_TO_A = 1, EPI_VIEW_RGB = 2, EPI_LOGITS = 3 };
+
+struct StageDesc {     // one weight stage = one bulk copy + its MMAs
+  uint32_t gofs;       // byte offset into the packed weight stream
+  uint32_t bytes;
+  uint16_t n;          // UMMA N (rows of the weight tile)
+  uint16_t acc_col;
+  uint16_t a_off;      // A_TMEM: packed column of the first K16 step (hi);  A_EMB/A_DIR: unused
+  uint16_t a_lo_off;
+  uint8_t ksteps;      // K16 steps covered by this stage
+  uint8_t is_lo;       // weight part: 0 = bf16 hi, 1 = bf16 lo residual
+  uint8_t a_kind;
+  uint8_t flags;
+};
+
+struct EpiDesc {
+  uint8_t kind;
+  uint8_t sigma;       // also accumulate the sigma head (dot with consts[aux_off..]) on the activated values
+  uint16_t n;          // accumulator columns to process (multiple of 16)
+  uint16_t n_valid;    // EPI_LOGITS: real channel count
+  uint16_t acc_col;
+  uint16_t dst_col;    // packed destination column (hi) ; lo at dst_lo_col
+  uint16_t dst_lo_col;
+  uint16_t bias_off;   // float offset into consts
+  uint16_t aux_off;    // sigma weights (EPI_*_TO_A with sigma) or rgb weights [3][n] (EPI_VIEW_RGB)
+  uint16_t out_off;    // EPI_LOGITS: channel offset in the raw row
+  uint16_t pad;
+};
+
+struct MlpProgram {
+  int32_t n_stages, n_steps, n_consts;
+  int32_t sigma_bias_off, rgb_bias_off;   // float offsets into consts
+  int32_t Lx, Ld;
+  int32_t passes;                          // 1 or 3
+  StageDesc st[kMaxStages];
+  EpiDesc ep[kMaxSteps];
+};
+
+// Launch arguments of the fused kernel (device pointers).
+struct MlpParams {
+  const MlpProgram* prog;
+  const uint8_t* wpacked;
+  const float* consts;
+  const float* pts;       // [S,3] or null
+  const float* viewdirs;  // [S,3] or null
+  const float* rays;      // [R,6] (used when pts == null)
+  const float* z;         // [R,N]
+  int64_t S;              // samples
+  int32_t N;              // samples per ray (rays mode)
+  int32_t CH;             // raw row width 4 + C + K
+  float* raw;
+  int32_t num_tiles;
+};
+
+constexpr int kSmemConsts = kSmemProg + (int)sizeof(MlpProgram);
+constexpr int kSmemPart = kSmemConsts + kMaxConsts * 4;      // [2][128][4] floats
+constexpr int kSmemBars = kSmemPart + 2 * kTileM * 4 * 4;
+constexpr int kSmemTotal = kSmemBars + 256;
+
+}  // namespace pnr

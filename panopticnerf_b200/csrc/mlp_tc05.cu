@@ -1,0 +1,355 @@
+// mlp_tc05.cu — fused Network.forward (SURVEY.md 8(a) a7 + a8) on sm_100a tensor cores.
+//
+// One persistent CTA per SM walks 128-sample tiles.  Per tile the whole MLP runs on-chip:
+//   * 4 producer warps form pts = o + d*z, the positional encodings gamma(x), gamma(d), split them into
+//     bf16 hi/lo and write them into shared memory in the UMMA no-swizzle K-major operand layout;
+//   * 1 TMA warp streams the pre-packed weight stages (bf16 hi / lo images, 32 KB each) from L2 into
+//     a 4-deep shared-memory ring with cp.async.bulk + mbarrier complete_tx;
+//   * 1 MMA warp (one elected thread) issues tcgen05.mma kind::f16, M=128, N<=256, K=16:
+//     the A operand is the embedding in shared memory (SS form) or the previous layer's activations
+//     in TENSOR MEMORY (TS form); accumulators are fp32 in tensor memory;
+//   * 8 epilogue warps tcgen05.ld the accumulator, add bias, ReLU, split into bf16 hi/lo and
+//     tcgen05.st the result back to tensor memory as the next layer's A operand.  Activations never
+//     touch shared or global memory.  The sigma head (N=1) and rgb head (N=3) are CUDA-core dot
+//     products inside the epilogues; semantic / instance logits are written straight to `raw`.
+// Precision: operands are 16-bit (fp16 or bf16), accumulation fp32.  The "x3" modes compute every product
+// as A_hi*B_hi + A_lo*B_hi + A_hi*B_lo with x = hi + lo split in the operand format: ~2^-21 relative
+// per product for fp16x3 (default; what the 1e-4 parity tolerance needs with margin), ~2^-17 for
+// bf16x3 (fp32 exponent range).  The 1-pass modes keep the first term only (fast, out of tolerance).
+#include "common.cuh"
+#include "mlp_program.h"
+#include "tc05.cuh"
+
+namespace pnr {
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Write 8 consecutive K elements (one 16-byte core-matrix row) of this thread's row, split hi/lo.
+template <int PASSES, int FMT>
+__device__ __forceinline__ void store_core_row(uint8_t* hi_base, uint8_t* lo_base, int kcore, int row,
+                                               const float (&v)[8]) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) split_x2<FMT>(v[2 * j], v[2 * j + 1], h[j], l[j]);
+  const int off = (kcore * kTileM + row) * 16;
+  *reinterpret_cast<uint4*>(hi_base + off) = make_uint4(h[0], h[1], h[2], h[3]);
+  if (PASSES == 3) *reinterpret_cast<uint4*>(lo_base + off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// gamma(p) = [p, sin(2^0 p), cos(2^0 p), ...] padded with zeros to KPAD, streamed out 8 at a time.
+template <int PASSES, int FMT, int LMAX, int KPAD>
+__device__ __forceinline__ void encode_row(const float (&p)[3], int L, uint8_t* hi_base,
+                                           uint8_t* lo_base, int row) {
+  float v[KPAD];
+#pragma unroll
+  for (int i = 0; i < KPAD; ++i) v[i] = 0.f;
+  v[0] = p[0]; v[1] = p[1]; v[2] = p[2];
+  float f = 1.0f;
+#pragma unroll
+  for (int k = 0; k < LMAX; ++k) {
+    if (k < L) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float sn, cs;
+        sincosf(p[c] * f, &sn, &cs);
+        if (3 + 6 * k + c < KPAD) v[3 + 6 * k + c] = sn;
+        if (3 + 6 * k + 3 + c < KPAD) v[3 + 6 * k + 3 + c] = cs;
+      }
+    }
+    f *= 2.0f;
+  }
+#pragma unroll
+  for (int g = 0; g < KPAD / 8; ++g) {
+    float w8[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w8[j] = v[g * 8 + j];
+    store_core_row<PASSES, FMT>(hi_base, lo_base, g, row, w8);
+  }
+}
+
+template <int PASSES, int FMT>
+__global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  MlpProgram* prog = reinterpret_cast<MlpProgram*>(smem + kSmemProg);
+  float* consts = reinterpret_cast<float*>(smem + kSmemConsts);
+  float* part = reinterpret_cast<float*>(smem + kSmemPart);  // [2][128][4]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+
+  const uint32_t bar_full = smem_u32(&bars[0]);             // [kRing]
+  const uint32_t bar_empty = smem_u32(&bars[kRing]);        // [kRing]
+  const uint32_t bar_acc_full = smem_u32(&bars[2 * kRing]);
+  const uint32_t bar_a_ready = smem_u32(&bars[2 * kRing + 1]);
+  const uint32_t bar_emb_full = smem_u32(&bars[2 * kRing + 2]);
+  const uint32_t bar_emb_empty = smem_u32(&bars[2 * kRing + 3]);
+  const uint32_t bar_dir_full = smem_u32(&bars[2 * kRing + 4]);   // [2]
+  const uint32_t bar_dir_empty = smem_u32(&bars[2 * kRing + 6]);  // [2]
+
+  // ---- one-time setup: program + constants to shared memory, barriers, tensor memory
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(p.prog);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(prog);
+    for (int i = threadIdx.x; i < (int)(sizeof(MlpProgram) / 4); i += blockDim.x) dst[i] = src[i];
+    const int nc = p.prog->n_consts;
+    for (int i = threadIdx.x; i < nc; i += blockDim.x) consts[i] = p.consts[i];
+  }
+  if (warp == 0) {
+    tmem_alloc<512>(smem_u32(tmem_slot));
+    tmem_relinquish();
+  }
+  if (threadIdx.x == 32) {
+    for (int s = 0; s < kRing; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_acc_full, 1);
+    mbar_init(bar_a_ready, kEpiWarps * 32);
+    mbar_init(bar_emb_full, kProWarps * 32);
+    mbar_init(bar_emb_empty, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_dir_full + 8 * b, kProWarps * 32);
+      mbar_init(bar_dir_empty + 8 * b, 1);
+    }
+    fence_mbar_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int n_stages = prog->n_stages, n_steps = prog->n_steps;
+
+  if (warp < kEpiWarps) {
+    // =============================================================== epilogue warps
+    const int q = warp & 3, half = warp >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    uint32_t acc_phase = 0;
+    mbar_arrive(bar_a_ready);  // round 0: "accumulator free, nothing to stage" for the very first step
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int64_t s = (int64_t)tile * kTileM + row;
+      const bool valid = s < p.S;
+      for (int st = 0; st < n_steps; ++st) {
+        const EpiDesc ed = prog->ep[st];
+        mbar_wait(bar_acc_full, acc_phase);
+        acc_phase ^= 1;
+        tc_fence_after();
+        const int G = ed.n >> 4;
+        const int g0 = half == 0 ? 0 : (G + 1) / 2;
+        const int g1 = half == 0 ? (G + 1) / 2 : G;
+        const float* bias = consts + ed.bias_off;
+        if (ed.kind == EPI_RELU_TO_A || ed.kind == EPI_LINEAR_TO_A) {
+          const bool relu = ed.kind == EPI_RELU_TO_A;
+          const float* wsig = consts + ed.aux_off;
+          float sig = 0.f;
+          for (int g = g0; g < g1; ++g) {
+            uint32_t r[16];
+            tmem_ld16(tmem + lane_off + ed.acc_col + g * 16, r);
+            tc_wait_ld();
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float v0 = __uint_as_float(r[2 * j]) + bias[g * 16 + 2 * j];
+              float v1 = __uint_as_float(r[2 * j + 1]) + bias[g * 16 + 2 * j + 1];
+              if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+              if (ed.sigma) sig += v0 * wsig[g * 16 + 2 * j] + v1 * wsig[g * 16 + 2 * j + 1];
+              split_x2<FMT>(v0, v1, hi[j], lo[j]);
+            }
+            tmem_st8(tmem + lane_off + ed.dst_col + g * 8, hi);
+            if (PASSES == 3) tmem_st8(tmem + lane_off + ed.dst_lo_col + g * 8, lo);
+          }
+          if (ed.sigma) part[(half * kTileM + row) * 4 + 3] = sig;
+          tc_wait_st();
+        } else if (ed.kind == EPI_VIEW_RGB) {
+          const float* wr = consts + ed.aux_off;  // [3][n]
+          float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+          for (int g = g0; g < g1; ++g) {
+            uint32_t r[16];
+            tmem_ld16(tmem + lane_off + ed.acc_col + g * 16, r);
+            tc_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int c = g * 16 + j;
+              const float v = fmaxf(__uint_as_float(r[j]) + bias[c], 0.f);
+              c0 += v * wr[c];
+              c1 += v * wr[ed.n + c];
+              c2 += v * wr[2 * ed.n + c];
+            }
+          }
+          float* mine = part + (half * kTileM + row) * 4;
+          mine[0] = c0; mine[1] = c1; mine[2] = c2;
+          named_bar_sync(1, kEpiWarps * 32);
+          if (half == 0 && valid) {
+            const float* other = part + (kTileM + row) * 4;
+            const float* b3 = consts + prog->rgb_bias_off;
+            const float o0 = c0 + other[0] + b3[0];
+            const float o1 = c1 + other[1] + b3[1];
+            const float o2 = c2 + other[2] + b3[2];
+            const float o3 = mine[3] + other[3] + consts[prog->sigma_bias_off];
+            float* dst = p.raw + s * p.CH;
+            if (p.CH == 4) {
+              *reinterpret_cast<float4*>(dst) = make_float4(o0, o1, o2, o3);
+            } else {
+              dst[0] = o0; dst[1] = o1; dst[2] = o2; dst[3] = o3;
+            }
+          }
+        } else {  // EPI_LOGITS
+          for (int g = g0; g < g1; ++g) {
+            uint32_t r[16];
+            tmem_ld16(tmem + lane_off + ed.acc_col + g * 16, r);
+            tc_wait_ld();
+            if (valid) {
+              float* dst = p.raw + s * p.CH + ed.out_off;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int c = g * 16 + j;
+                if (c < ed.n_valid) dst[c] = __uint_as_float(r[j]) + bias[c];
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(bar_a_ready);
+      }
+    }
+  } else if (warp < kEpiWarps + kProWarps) {
+    // =============================================================== embedding producer warps
+    const int row = (warp - kEpiWarps) * 32 + lane;
+    uint8_t* emb_hi = smem + kSmemEmb;
+    uint8_t* emb_lo = emb_hi + kEmbPartBytes;
+    const int Lx = prog->Lx, Ld = prog->Ld;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      int64_t s = (int64_t)tile * kTileM + row;
+      if (s >= p.S) s = p.S - 1;  // clamp: tail rows compute on a valid sample, results are discarded
+      float x[3], d[3];
+      if (p.pts != nullptr) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { x[c] = p.pts[s * 3 + c]; d[c] = p.viewdirs[s * 3 + c]; }
+      } else {
+        const int64_t ray = s / p.N;
+        const float zi = p.z[s];
+        const float* rr = p.rays + ray * 6;
+        float dn2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float dc = rr[3 + c];
+          x[c] = __fadd_rn(rr[c], __fmul_rn(dc, zi));  // pts = o + d*z, separately rounded like the oracle
+          dn2 = (c == 0) ? __fmul_rn(dc, dc) : __fadd_rn(dn2, __fmul_rn(dc, dc));
+          d[c] = dc;
+        }
+        const float nrm = sqrtf(dn2);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) d[c] = __fdiv_rn(d[c], nrm);
+      }
+      mbar_wait(bar_emb_empty, (uint32_t)((it & 1) ^ 1));
+      encode_row<PASSES, FMT, 10, 64>(x, Lx, emb_hi, emb_lo, row);
+      fence_proxy_async_smem();
+      mbar_arrive(bar_emb_full);
+      const int b = it & 1;
+      uint8_t* dir_hi = smem + kSmemDir + b * 2 * kDirPartBytes;
+      mbar_wait(bar_dir_empty + 8 * b, (uint32_t)(((it >> 1) & 1) ^ 1));
+      encode_row<PASSES, FMT, 4, 32>(d, Ld, dir_hi, dir_hi + kDirPartBytes, row);
+      fence_proxy_async_smem();
+      mbar_arrive(bar_dir_full + 8 * b);
+    }
+  } else if (warp == kEpiWarps + kProWarps) {
+    // =============================================================== TMA producer (one lane)
+    if (lane == 0) {
+      uint32_t gs = 0;  // global stage counter
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int si = 0; si < n_stages; ++si, ++gs) {
+          const uint32_t slot = gs % kRing, ph = (gs / kRing) & 1;
+          const uint32_t gofs = prog->st[si].gofs, bytes = prog->st[si].bytes;
+          mbar_wait(bar_empty + 8 * slot, ph ^ 1);
+          mbar_arrive_expect_tx(bar_full + 8 * slot, bytes);
+          bulk_g2s(smem_u32(smem + kSmemRing + slot * kStageBytes), p.wpacked + gofs, bytes,
+                   bar_full + 8 * slot);
+        }
+      }
+    }
+  } else {
+    // =============================================================== MMA issuer (one lane)
+    if (lane == 0) {
+      uint32_t gs = 0, a_phase = 0;
+      int it = 0;
+      const uint32_t emb_hi = smem_u32(smem + kSmemEmb);
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int b = it & 1;
+        const uint32_t dir_hi = smem_u32(smem + kSmemDir + b * 2 * kDirPartBytes);
+        for (int si = 0; si < n_stages; ++si, ++gs) {
+          const StageDesc sd = prog->st[si];
+          if (sd.flags & F_WAIT_A) { mbar_wait(bar_a_ready, a_phase); a_phase ^= 1; }
+          if (sd.flags & F_WAIT_EMB) mbar_wait(bar_emb_full, (uint32_t)(it & 1));
+          if (sd.flags & F_WAIT_DIR) mbar_wait(bar_dir_full + 8 * b, (uint32_t)((it >> 1) & 1));
+          const uint32_t slot = gs % kRing, ph = (gs / kRing) & 1;
+          mbar_wait(bar_full + 8 * slot, ph);
+          tc_fence_after();
+          const uint32_t idesc = make_idesc_f32acc(kTileM, sd.n, FMT);
+          const uint32_t b_lbo = (uint32_t)sd.n * 16u;
+          const uint32_t sb = smem_u32(smem + kSmemRing + slot * kStageBytes);
+          const uint32_t d_tmem = tmem + sd.acc_col;
+          uint32_t accum = (sd.flags & F_FIRST) ? 0u : 1u;
+          for (int ks = 0; ks < sd.ksteps; ++ks) {
+            const uint64_t bdesc = make_smem_desc_noswz(sb + ks * 2 * b_lbo, b_lbo, 128);
+            if (sd.a_kind == A_TMEM) {
+              const uint32_t a_hi = tmem + sd.a_off + ks * 8;
+              if (!sd.is_lo) {
+                mma_ts(d_tmem, a_hi, bdesc, idesc, accum);
+                accum = 1;
+                if (PASSES == 3) mma_ts(d_tmem, tmem + sd.a_lo_off + ks * 8, bdesc, idesc, 1);
+              } else {
+                mma_ts(d_tmem, a_hi, bdesc, idesc, 1);
+              }
+            } else {
+              const uint32_t base = (sd.a_kind == A_EMB) ? emb_hi : dir_hi;
+              const uint32_t lo_delta = (sd.a_kind == A_EMB) ? kEmbPartBytes : kDirPartBytes;
+              const uint32_t a_addr = base + ks * 2 * (kTileM * 16);
+              const uint64_t adesc_hi = make_smem_desc_noswz(a_addr, kTileM * 16, 128);
+              if (!sd.is_lo) {
+                mma_ss(d_tmem, adesc_hi, bdesc, idesc, accum);
+                accum = 1;
+                if (PASSES == 3)
+                  mma_ss(d_tmem, make_smem_desc_noswz(a_addr + lo_delta, kTileM * 16, 128), bdesc, idesc, 1);
+              } else {
+                mma_ss(d_tmem, adesc_hi, bdesc, idesc, 1);
+              }
+            }
+          }
+          tc_commit(bar_empty + 8 * slot);
+          if (sd.flags & F_RELEASE_EMB) tc_commit(bar_emb_empty);
+          if (sd.flags & F_RELEASE_DIR) tc_commit(bar_dir_empty + 8 * b);
+          if (sd.flags & F_COMMIT_ACC) tc_commit(bar_acc_full);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+template <int PASSES, int FMT>
+static int launch_one(const MlpParams& p, int grid, cudaStream_t stream) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    PNR_CUDA(cudaFuncSetAttribute(mlp_fused_kernel<PASSES, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kSmemTotal));
+    attr_done = true;
+  }
+  mlp_fused_kernel<PASSES, FMT><<<grid, kMlpThreads, kSmemTotal, stream>>>(p);
+  PNR_LAUNCH_CHECK("mlp_fused_kernel");
+  return PNR_OK;
+}
+
+int launch_mlp(const MlpParams& p, int passes, int fmt, cudaStream_t stream) {
+  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  if (grid <= 0) return PNR_OK;
+  if (fmt == kFmtF16) return passes == 3 ? launch_one<3, kFmtF16>(p, grid, stream) : launch_one<1, kFmtF16>(p, grid, stream);
+  return passes == 3 ? launch_one<3, kFmtBF16>(p, grid, stream) : launch_one<1, kFmtBF16>(p, grid, stream);
+}
+
+}  // namespace pnr

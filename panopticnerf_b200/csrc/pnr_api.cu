@@ -1,0 +1,358 @@
+// pnr_api.cu — context management, weight packing / MLP program construction and the
+// pnr_mlp_forward entry point of the C ABI (include/pnr.h).
+#include <cstring>
+#include <cuda_fp16.h>
+#include <string>
+#include <vector>
+#include "common.cuh"
+#include "mlp_program.h"
+
+namespace pnr {
+
+// ---------------------------------------------------------------- error / accounting plumbing
+static thread_local char g_err[512] = "";
+static thread_local int64_t g_launches = 0;
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+void count_launch(int n) { g_launches += n; }
+
+int launch_mlp(const MlpParams& p, int passes, int fmt, cudaStream_t stream);  // mlp_tc05.cu
+
+}  // namespace pnr
+
+using namespace pnr;
+
+struct pnr_ctx {
+  pnr_config cfg;
+  int passes = 3;
+  int fmt = 0;   // 0 = fp16, 1 = bf16 (instruction-descriptor encoding)
+  bool loaded = false;
+  MlpProgram* d_prog = nullptr;
+  uint8_t* d_wpacked = nullptr;
+  float* d_consts = nullptr;
+  size_t wpacked_bytes = 0;
+};
+
+// ---------------------------------------------------------------- host-side 16-bit split (RNE, = cvt.rn.*.f32)
+static inline uint16_t f2h(float x) {
+  const __half h = __float2half_rn(x);
+  uint16_t u;
+  memcpy(&u, &h, 2);
+  return u;
+}
+static inline float h2f(uint16_t u) {
+  __half h;
+  memcpy(&h, &u, 2);
+  return __half2float(h);
+}
+static inline uint16_t f2bf(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  return (uint16_t)((u + 0x7FFFu + ((u >> 16) & 1u)) >> 16);
+}
+static inline float bf2f(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+namespace {
+
+struct Mat { const float* w; int out, in; };  // row-major [out, in]
+
+struct Seg {
+  uint8_t kind;        // A_TMEM / A_EMB / A_DIR
+  Mat m;
+  int col0, kvalid;    // columns of m feeding this segment
+  int kpad;            // K rounded up (multiple of 16)
+  int a_hi, a_lo;      // TMEM packed columns (A_TMEM)
+  bool release;        // A_EMB/A_DIR: last reader in the tile
+};
+
+struct Builder {
+  MlpProgram prog;
+  std::vector<uint16_t> wbuf;   // packed weight stream (bf16 elements)
+  std::vector<float> consts;
+  int passes, fmt;
+  std::string err;
+
+  Builder(int passes_, int fmt_) : passes(passes_), fmt(fmt_) { memset(&prog, 0, sizeof(prog)); }
+
+  int add_consts(const float* src, int n_valid, int n_pad) {
+    const int off = (int)consts.size();
+    for (int i = 0; i < n_pad; ++i) consts.push_back(i < n_valid ? src[i] : 0.f);
+    return off;
+  }
+
+  void pack_stage(const Mat& m, int n_pad, int col0, int kvalid, int k0, int kcores, int part) {
+    const size_t base = wbuf.size();
+    wbuf.resize(base + (size_t)n_pad * kcores * 8);
+    for (int kc = 0; kc < kcores; ++kc)
+      for (int n = 0; n < n_pad; ++n)
+        for (int e = 0; e < 8; ++e) {
+          const int k = k0 + kc * 8 + e;
+          const float w = (n < m.out && k < kvalid) ? m.w[(size_t)n * m.in + col0 + k] : 0.f;
+          uint16_t v;
+          if (fmt == 1) {
+            const uint16_t h = f2bf(w);
+            v = part == 0 ? h : f2bf(w - bf2f(h));
+          } else {
+            const uint16_t h = f2h(w);
+            v = part == 0 ? h : f2h(w - h2f(h));
+          }
+          wbuf[base + ((size_t)kc * n_pad + n) * 8 + e] = v;
+        }
+  }
+
+  // One GEMM step: acc[:, acc_col:acc_col+n_pad) = sum_seg A_seg * W_seg^T, then epilogue `ed`.
+  bool add_step(std::vector<Seg> segs, int n_pad, int acc_col, EpiDesc ed, bool first_of_tile) {
+    if (prog.n_steps >= kMaxSteps) { err = "too many steps"; return false; }
+    const int first_stage = prog.n_stages;
+    for (size_t si = 0; si < segs.size(); ++si) {
+      const Seg& sg = segs[si];
+      for (int k0 = 0; k0 < sg.kpad; k0 += 64) {
+        const int kcores = ((sg.kpad - k0) < 64 ? (sg.kpad - k0) : 64) / 8;
+        for (int part = 0; part < (passes == 3 ? 2 : 1); ++part) {
+          if (prog.n_stages >= kMaxStages) { err = "too many stages"; return false; }
+          StageDesc& sd = prog.st[prog.n_stages++];
+          sd.gofs = (uint32_t)(wbuf.size() * 2);
+          sd.bytes = (uint32_t)(n_pad * kcores * 16);
+          sd.n = (uint16_t)n_pad;
+          sd.acc_col = (uint16_t)acc_col;
+          sd.a_off = (uint16_t)(sg.a_hi + k0 / 2);
+          sd.a_lo_off = (uint16_t)(sg.a_lo + k0 / 2);
+          sd.ksteps = (uint8_t)(kcores / 2);
+          sd.is_lo = (uint8_t)part;
+          sd.a_kind = sg.kind;
+          sd.flags = 0;
+          const bool seg_first = (k0 == 0 && part == 0);
+          const bool seg_last = (k0 + 64 >= sg.kpad) && (part == (passes == 3 ? 1 : 0));
+          if (sg.kind == A_EMB && seg_first && first_of_tile) sd.flags |= F_WAIT_EMB;
+          if (sg.kind == A_EMB && seg_last && sg.release) sd.flags |= F_RELEASE_EMB;
+          if (sg.kind == A_DIR && seg_first) sd.flags |= F_WAIT_DIR;
+          if (sg.kind == A_DIR && seg_last && sg.release) sd.flags |= F_RELEASE_DIR;
+          pack_stage(sg.m, n_pad, sg.col0, sg.kvalid, k0, kcores, part);
+        }
+      }
+    }
+    prog.st[first_stage].flags |= F_FIRST | F_WAIT_A;
+    prog.st[prog.n_stages - 1].flags |= F_COMMIT_ACC;
+    ed.n = (uint16_t)n_pad;
+    ed.acc_col = (uint16_t)acc_col;
+    prog.ep[prog.n_steps++] = ed;
+    return true;
+  }
+};
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+}  // namespace
+
+extern "C" int pnr_version(void) { return PNR_VERSION; }
+extern "C" const char* pnr_last_error(void) { return g_err; }
+extern "C" int64_t pnr_launch_count(int32_t reset) {
+  const int64_t v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+extern "C" int pnr_create(const pnr_config* cfg, pnr_ctx** out) {
+  PNR_CHECK_ARG(cfg && out, "pnr_create: null pointer");
+  PNR_CHECK_ARG(cfg->D >= 3 && cfg->D <= 16, "pnr_create: D=%d outside [3,16]", cfg->D);
+  PNR_CHECK_ARG(cfg->W == 64 || cfg->W == 128 || cfg->W == 256, "pnr_create: W=%d not in {64,128,256}", cfg->W);
+  PNR_CHECK_ARG(cfg->xyz_res >= 0 && cfg->xyz_res <= 10, "pnr_create: xyz_res=%d outside [0,10]", cfg->xyz_res);
+  PNR_CHECK_ARG(cfg->view_res >= 0 && cfg->view_res <= 4, "pnr_create: view_res=%d outside [0,4]", cfg->view_res);
+  PNR_CHECK_ARG(cfg->num_classes >= 0 && cfg->num_classes <= 128, "pnr_create: num_classes=%d outside [0,128]", cfg->num_classes);
+  PNR_CHECK_ARG(cfg->num_instances >= 0 && cfg->num_instances <= 128, "pnr_create: num_instances=%d outside [0,128]", cfg->num_instances);
+  PNR_CHECK_ARG(cfg->precision >= 0 && cfg->precision <= 3, "pnr_create: bad precision %d", cfg->precision);
+  int ndev = 0;
+  PNR_CUDA(cudaGetDeviceCount(&ndev));
+  PNR_CHECK_ARG(cfg->device >= 0 && cfg->device < ndev, "pnr_create: device %d of %d", cfg->device, ndev);
+  cudaDeviceProp prop;
+  PNR_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10)
+    return set_error(PNR_ERR_UNSUPPORTED, "pnr_create: device %d is sm_%d%d; libpnr is sm_100a only (no fallback path)",
+                     cfg->device, prop.major, prop.minor);
+  PNR_CUDA(cudaSetDevice(cfg->device));
+  pnr_ctx* c = new pnr_ctx();
+  c->cfg = *cfg;
+  c->passes = (cfg->precision == PNR_PREC_BF16X3 || cfg->precision == PNR_PREC_FP16X3) ? 3 : 1;
+  c->fmt = (cfg->precision == PNR_PREC_BF16X3 || cfg->precision == PNR_PREC_BF16) ? 1 : 0;
+  *out = c;
+  return PNR_OK;
+}
+
+extern "C" int pnr_destroy(pnr_ctx* ctx) {
+  if (!ctx) return PNR_OK;
+  cudaFree(ctx->d_prog);
+  cudaFree(ctx->d_wpacked);
+  cudaFree(ctx->d_consts);
+  delete ctx;
+  return PNR_OK;
+}
+
+extern "C" int pnr_load_weights(pnr_ctx* ctx, const float* const* t, const int64_t* shapes, int32_t n) {
+  PNR_CHECK_ARG(ctx && t && shapes, "pnr_load_weights: null pointer");
+  const pnr_config& c = ctx->cfg;
+  const int D = c.D, W = c.W, W2 = W / 2, C = c.num_classes, K = c.num_instances;
+  const int Ex = 3 + 6 * c.xyz_res, Ed = 3 + 6 * c.view_res, skip = D / 2;
+  const int expected = 2 * D + 8 + (C > 0 ? 4 : 0) + (K > 0 ? 4 : 0);
+  PNR_CHECK_ARG(n == expected, "pnr_load_weights: got %d tensors, expected %d", n, expected);
+  int ti = 0;
+  auto take = [&](int out, int in, Mat* m, const float** bias) -> bool {
+    if (shapes[2 * ti] != out || shapes[2 * ti + 1] != in) return false;
+    if (shapes[2 * ti + 2] != out || shapes[2 * ti + 3] != 1) return false;
+    if (!t[ti] || !t[ti + 1]) return false;
+    *m = Mat{t[ti], out, in};
+    *bias = t[ti + 1];
+    ti += 2;
+    return true;
+  };
+#define PNR_TAKE(out, in, m, b)                                                                        \
+  if (!take(out, in, m, b))                                                                            \
+    return set_error(PNR_ERR_ARG, "pnr_load_weights: tensor %d: expected weight [%d,%d] + bias [%d,1]", \
+                     ti, out, in, out)
+
+  Builder bld(ctx->passes, ctx->fmt);
+  bld.prog.Lx = c.xyz_res;
+  bld.prog.Ld = c.view_res;
+  bld.prog.passes = ctx->passes;
+
+  std::vector<Mat> trunk(D);
+  std::vector<const float*> trunk_b(D);
+  for (int i = 0; i < D; ++i) {
+    const int in = i == 0 ? Ex : (i == skip + 1 ? W + Ex : W);
+    PNR_TAKE(W, in, &trunk[i], &trunk_b[i]);
+  }
+  Mat m_sig, m_feat, m_view, m_rgb, m_s1, m_s2, m_i1, m_i2;
+  const float *b_sig, *b_feat, *b_view, *b_rgb, *b_s1 = nullptr, *b_s2 = nullptr, *b_i1 = nullptr, *b_i2 = nullptr;
+  PNR_TAKE(1, W, &m_sig, &b_sig);
+  PNR_TAKE(W, W, &m_feat, &b_feat);
+  PNR_TAKE(W2, W + Ed, &m_view, &b_view);
+  PNR_TAKE(3, W2, &m_rgb, &b_rgb);
+  if (C > 0) { PNR_TAKE(W2, W, &m_s1, &b_s1); PNR_TAKE(C, W2, &m_s2, &b_s2); }
+  if (K > 0) { PNR_TAKE(W2, W, &m_i1, &b_i1); PNR_TAKE(K, W2, &m_i2, &b_i2); }
+#undef PNR_TAKE
+
+  const int sig_w_off = bld.add_consts(m_sig.w, W, W);
+  bld.prog.sigma_bias_off = bld.add_consts(b_sig, 1, 4);
+  std::vector<float> rgbw(3 * W2);
+  for (int ch = 0; ch < 3; ++ch)
+    for (int k = 0; k < W2; ++k) rgbw[ch * W2 + k] = m_rgb.w[ch * W2 + k];
+  const int rgb_w_off = bld.add_consts(rgbw.data(), 3 * W2, 3 * W2);
+  bld.prog.rgb_bias_off = bld.add_consts(b_rgb, 3, 4);
+
+  auto seg_tmem = [&](const Mat& m, int col0, int k, int a_hi, int a_lo) {
+    return Seg{A_TMEM, m, col0, k, round_up(k, 16), a_hi, a_lo, false};
+  };
+  bool ok = true;
+  // trunk
+  for (int i = 0; i < D && ok; ++i) {
+    EpiDesc ed{};
+    ed.kind = EPI_RELU_TO_A;
+    ed.sigma = (i == D - 1) ? 1 : 0;
+    ed.dst_col = kColAHi;
+    ed.dst_lo_col = kColALo;
+    ed.bias_off = (uint16_t)bld.add_consts(trunk_b[i], W, W);
+    ed.aux_off = (uint16_t)sig_w_off;
+    std::vector<Seg> segs;
+    if (i == 0) {
+      segs.push_back(Seg{A_EMB, trunk[i], 0, Ex, 64, 0, 0, false});
+    } else if (i == skip + 1) {
+      segs.push_back(Seg{A_EMB, trunk[i], 0, Ex, 64, 0, 0, true});
+      segs.push_back(seg_tmem(trunk[i], Ex, W, kColAHi, kColALo));
+    } else {
+      segs.push_back(seg_tmem(trunk[i], 0, W, kColAHi, kColALo));
+    }
+    ok = bld.add_step(segs, W, kColAcc, ed, i == 0);
+  }
+  // heads: hidden layer -> (upper half of the accumulator region) -> logits
+  auto add_head = [&](const Mat& m1, const float* b1, const Mat& m2, const float* b2, int nout, int out_off) {
+    EpiDesc e1{};
+    e1.kind = EPI_RELU_TO_A;
+    e1.dst_col = kColHeadHi;
+    e1.dst_lo_col = kColHeadLo;
+    e1.bias_off = (uint16_t)bld.add_consts(b1, W2, W2);
+    ok = ok && bld.add_step({seg_tmem(m1, 0, W, kColAHi, kColALo)}, W2, kColAcc, e1, false);
+    const int npad = round_up(nout, 16);
+    EpiDesc e2{};
+    e2.kind = EPI_LOGITS;
+    e2.n_valid = (uint16_t)nout;
+    e2.out_off = (uint16_t)out_off;
+    e2.bias_off = (uint16_t)bld.add_consts(b2, nout, npad);
+    ok = ok && bld.add_step({seg_tmem(m2, 0, W2, kColHeadHi, kColHeadLo)}, npad, kColAcc, e2, false);
+  };
+  if (ok && C > 0) add_head(m_s1, b_s1, m_s2, b_s2, C, 4);
+  if (ok && K > 0) add_head(m_i1, b_i1, m_i2, b_i2, K, 4 + C);
+  if (ok) {  // feature layer (no activation) -> A
+    EpiDesc ed{};
+    ed.kind = EPI_LINEAR_TO_A;
+    ed.dst_col = kColAHi;
+    ed.dst_lo_col = kColALo;
+    ed.bias_off = (uint16_t)bld.add_consts(b_feat, W, W);
+    ok = bld.add_step({seg_tmem(m_feat, 0, W, kColAHi, kColALo)}, W, kColAcc, ed, false);
+  }
+  if (ok) {  // view branch [feat, gamma(d)] -> relu -> rgb (CUDA cores) ; writes rgb + sigma
+    EpiDesc ed{};
+    ed.kind = EPI_VIEW_RGB;
+    ed.bias_off = (uint16_t)bld.add_consts(b_view, W2, W2);
+    ed.aux_off = (uint16_t)rgb_w_off;
+    std::vector<Seg> segs;
+    segs.push_back(seg_tmem(m_view, 0, W, kColAHi, kColALo));
+    segs.push_back(Seg{A_DIR, m_view, W, Ed, 32, 0, 0, true});
+    ok = bld.add_step(segs, W2, kColAcc, ed, false);
+  }
+  if (!ok) return set_error(PNR_ERR_UNSUPPORTED, "pnr_load_weights: program build failed: %s", bld.err.c_str());
+  if ((int)bld.consts.size() > kMaxConsts)
+    return set_error(PNR_ERR_UNSUPPORTED, "pnr_load_weights: %d constants > %d", (int)bld.consts.size(), kMaxConsts);
+  bld.prog.n_consts = (int)bld.consts.size();
+
+  PNR_CUDA(cudaSetDevice(c.device));
+  cudaFree(ctx->d_prog); cudaFree(ctx->d_wpacked); cudaFree(ctx->d_consts);
+  ctx->d_prog = nullptr; ctx->d_wpacked = nullptr; ctx->d_consts = nullptr;
+  ctx->wpacked_bytes = bld.wbuf.size() * 2;
+  PNR_CUDA(cudaMalloc(&ctx->d_prog, sizeof(MlpProgram)));
+  PNR_CUDA(cudaMalloc(&ctx->d_wpacked, ctx->wpacked_bytes));
+  PNR_CUDA(cudaMalloc(&ctx->d_consts, bld.consts.size() * 4));
+  PNR_CUDA(cudaMemcpy(ctx->d_prog, &bld.prog, sizeof(MlpProgram), cudaMemcpyHostToDevice));
+  PNR_CUDA(cudaMemcpy(ctx->d_wpacked, bld.wbuf.data(), ctx->wpacked_bytes, cudaMemcpyHostToDevice));
+  PNR_CUDA(cudaMemcpy(ctx->d_consts, bld.consts.data(), bld.consts.size() * 4, cudaMemcpyHostToDevice));
+  ctx->loaded = true;
+  return PNR_OK;
+}
+
+extern "C" int pnr_mlp_forward(pnr_ctx* ctx, const float* pts, const float* viewdirs, const float* rays,
+                               const float* z, int64_t R, int32_t N, float* raw, void* stream) {
+  if (R == 0) return PNR_OK;
+  PNR_CHECK_ARG(ctx && raw, "pnr_mlp_forward: null pointer");
+  if (!ctx->loaded) return set_error(PNR_ERR_STATE, "pnr_mlp_forward: pnr_load_weights has not been called");
+  PNR_CHECK_ARG(R >= 0 && N >= 1, "pnr_mlp_forward: bad sizes R=%lld N=%d", (long long)R, N);
+  PNR_CHECK_ARG((pts && viewdirs) || (!pts && rays && z), "pnr_mlp_forward: need (pts, viewdirs) or (rays, z)");
+  const int64_t S = R * (int64_t)N;
+  if (S == 0) return PNR_OK;
+  PNR_CHECK_ARG((S + kTileM - 1) / kTileM < (int64_t)1 << 31, "pnr_mlp_forward: too many samples");
+  MlpParams p;
+  p.prog = ctx->d_prog; p.wpacked = ctx->d_wpacked; p.consts = ctx->d_consts;
+  p.pts = pts; p.viewdirs = viewdirs; p.rays = rays; p.z = z;
+  p.S = S; p.N = N; p.CH = 4 + ctx->cfg.num_classes + ctx->cfg.num_instances; p.raw = raw;
+  p.num_tiles = (int32_t)((S + kTileM - 1) / kTileM);
+  return launch_mlp(p, ctx->passes, ctx->fmt, (cudaStream_t)stream);
+}
+
+extern "C" size_t pnr_workspace_bytes(const pnr_ctx* ctx, int64_t R, int32_t N, int32_t Ni) {
+  if (!ctx || R <= 0) return 0;
+  const size_t CH = 4 + ctx->cfg.num_classes + ctx->cfg.num_instances;
+  const size_t Nt = (size_t)N + (size_t)(Ni > 0 ? Ni : 0);
+  size_t b = 0;
+  b += (size_t)R * Nt * CH * 4;          // raw
+  b += (size_t)R * Nt * (4 + 4 + 4);     // z, weights, sample_box
+  b += (size_t)R * (8 + 1 + 8 * 12);     // near/far, hit mask, hit list (M <= 8)
+  return b;
+}

@@ -1,0 +1,277 @@
+// ray_kernels.cu — the bit-exact integer/compare stages of the render path:
+// ray / oriented-box slab intersection with M-nearest selection, scene near/far, stratified depths
+// with per-sample primitive ids, and the inverse-CDF fine sampler with merge-sort.
+// All are HBM-bound streaming kernels: one thread (or one warp) per ray, box table staged in shared
+// memory, coalesced row-major outputs.  Arithmetic order lives in ray_math.h.
+#include "common.cuh"
+#include "ray_math.h"
+
+namespace pnr {
+
+// ------------------------------------------------------------------------------------ a5 intersect
+constexpr int kBoxChunk = 512;  // boxes staged per shared-memory fill (15 floats each = 30 KB)
+
+__global__ void __launch_bounds__(256) intersect_kernel(const float* __restrict__ rays, int64_t R,
+                                                        const float* __restrict__ bc,
+                                                        const float* __restrict__ bh,
+                                                        const float* __restrict__ br, int B, int M,
+                                                        uint8_t* __restrict__ hit_mask,
+                                                        int32_t* __restrict__ box_id,
+                                                        float* __restrict__ t_in,
+                                                        float* __restrict__ t_out) {
+  __shared__ float sb[kBoxChunk * 15];
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 1;
+  if (r < R) {
+    const float2* p = reinterpret_cast<const float2*>(rays + r * 6);
+    const float2 a = p[0], b = p[1], c = p[2];
+    ox = a.x; oy = a.y; oz = b.x; dx = b.y; dy = c.x; dz = c.y;
+  }
+  PnrHitList L;
+  pnr_hits_init(&L);
+  for (int b0 = 0; b0 < B; b0 += kBoxChunk) {
+    const int nb = min(kBoxChunk, B - b0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb * 15; i += blockDim.x) {
+      const int b = i / 15, e = i % 15;
+      sb[i] = e < 3 ? bc[(b0 + b) * 3 + e] : (e < 6 ? bh[(b0 + b) * 3 + e - 3] : br[(b0 + b) * 9 + e - 6]);
+    }
+    __syncthreads();
+    if (r < R) {
+      for (int b = 0; b < nb; ++b) {
+        const float* q = sb + b * 15;
+        float tmin, tmax;
+        if (pnr_slab(ox, oy, oz, dx, dy, dz, q, q + 3, q + 6, &tmin, &tmax))
+          pnr_hits_insert(&L, M, tmin, tmax, b0 + b);
+      }
+    }
+  }
+  if (r < R) {
+    hit_mask[r] = L.n > 0 ? 1 : 0;
+#pragma unroll
+    for (int m = 0; m < PNR_MAX_HITS; ++m)
+      if (m < M) {
+        const bool v = m < L.n;
+        box_id[r * M + m] = v ? L.id[m] : -1;
+        t_in[r * M + m] = v ? pnr_max_nan(L.key[m], 0.f) : 0.f;
+        t_out[r * M + m] = v ? L.tout[m] : 0.f;
+      }
+  }
+}
+
+struct Aabb { float c[3], h[3]; };
+
+__global__ void __launch_bounds__(256) near_far_kernel(const float* __restrict__ rays, int64_t R,
+                                                       Aabb box, float near_min, float far_default,
+                                                       float* __restrict__ near,
+                                                       float* __restrict__ far) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const float2* p = reinterpret_cast<const float2*>(rays + r * 6);
+  const float2 a = p[0], b = p[1], c = p[2];
+  const float rot[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  float tmin, tmax;
+  const bool hit = pnr_slab(a.x, a.y, b.x, b.y, c.x, c.y, box.c, box.h, rot, &tmin, &tmax);
+  near[r] = hit ? pnr_max_nan(tmin, near_min) : near_min;
+  far[r] = hit ? tmax : far_default;
+}
+
+__global__ void __launch_bounds__(256) bound_kernel(const uint8_t* __restrict__ hit,
+                                                    const int32_t* __restrict__ box_id,
+                                                    const float* __restrict__ t_in,
+                                                    const float* __restrict__ t_out, int64_t R, int M,
+                                                    float* __restrict__ near, float* __restrict__ far) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R || !hit[r]) return;
+  float last = 0.f;  // max over t_out of valid slots (padding slots contribute 0, as in the oracle)
+  for (int m = 0; m < M; ++m) last = pnr_max_nan(last, box_id[r * M + m] >= 0 ? t_out[r * M + m] : 0.f);
+  near[r] = pnr_max_nan(near[r], t_in[r * M]);
+  far[r] = pnr_min_nan(far[r], last);
+}
+
+// ------------------------------------------------------------------------------------ a6 sampling
+__global__ void __launch_bounds__(256) stratified_kernel(
+    const float* __restrict__ near, const float* __restrict__ far, const float* __restrict__ t_vals,
+    const float* __restrict__ u, int64_t R, int N, float perturb, const int32_t* __restrict__ box_id,
+    const float* __restrict__ t_in, const float* __restrict__ t_out, int M, float* __restrict__ z,
+    int32_t* __restrict__ sample_box) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= R * N) return;
+  const int64_t r = idx / N;
+  const int i = (int)(idx - r * N);
+  const float nr = near[r], fr = far[r];
+  const float zi = (perturb > 0.f) ? pnr_strat_z_jitter(nr, fr, t_vals, i, N, u[idx])
+                                   : pnr_strat_z(nr, fr, t_vals[i]);
+  z[idx] = zi;
+  if (sample_box != nullptr)
+    sample_box[idx] = (box_id != nullptr) ? pnr_tag(zi, box_id + r * M, t_in + r * M, t_out + r * M, M) : -1;
+}
+
+// Re-tag an existing depth array (used after the fine-sample merge).
+__global__ void __launch_bounds__(256) tag_kernel(const float* __restrict__ z, int64_t R, int N,
+                                                  const int32_t* __restrict__ box_id,
+                                                  const float* __restrict__ t_in,
+                                                  const float* __restrict__ t_out, int M,
+                                                  int32_t* __restrict__ sample_box) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= R * N) return;
+  const int64_t r = idx / N;
+  sample_box[idx] = pnr_tag(z[idx], box_id + r * M, t_in + r * M, t_out + r * M, M);
+}
+
+// ------------------------------------------------------------------------------------ a10 sample_pdf
+// One warp per ray.  Lane 0 runs the two sequential double-accumulated running sums (their order is
+// part of the bit-exact contract); all lanes then search / interpolate, and the warp bitonic-sorts
+// the merged depths in shared memory.
+constexpr int kPdfWarps = 4;
+constexpr int kPdfMaxN = 256;     // coarse samples
+constexpr int kPdfMaxAll = 512;   // coarse + fine, padded to a power of two
+
+__global__ void __launch_bounds__(kPdfWarps * 32) sample_pdf_kernel(
+    const float* __restrict__ z, const float* __restrict__ weights, int64_t R, int N, int Ni,
+    const float* __restrict__ u, float* __restrict__ z_fine, int64_t* __restrict__ idx_out,
+    float* __restrict__ z_all) {
+  __shared__ float s_w[kPdfWarps][kPdfMaxN];
+  __shared__ float s_z[kPdfWarps][kPdfMaxN];
+  __shared__ float s_cdf[kPdfWarps][kPdfMaxN];
+  __shared__ float s_all[kPdfWarps][kPdfMaxAll];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * kPdfWarps + warp;
+  if (r >= R) return;
+  float* w = s_w[warp];
+  float* zz = s_z[warp];
+  float* cdf = s_cdf[warp];
+  float* all = s_all[warp];
+  for (int i = lane; i < N; i += 32) {
+    w[i] = weights[r * N + i];
+    zz[i] = z[r * N + i];
+  }
+  __syncwarp();
+  if (lane == 0) pnr_pdf_cdf(w, N, cdf);
+  __syncwarp();
+  const int Nb = N - 1;
+  int P = 1;
+  while (P < N + Ni) P <<= 1;
+  for (int j = lane; j < Ni; j += 32) {
+    const float uj = u[r * Ni + j];
+    int idx;
+    const float zf = pnr_pdf_sample(zz, cdf, Nb, uj, &idx);
+    if (z_fine != nullptr) z_fine[r * Ni + j] = zf;
+    if (idx_out != nullptr) idx_out[r * Ni + j] = idx;
+    all[N + j] = zf;
+  }
+  if (z_all == nullptr) return;
+  for (int i = lane; i < N; i += 32) all[i] = zz[i];
+  for (int i = N + Ni + lane; i < P; i += 32) all[i] = __int_as_float(0x7f800000);
+  __syncwarp();
+  for (int k = 2; k <= P; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < P; i += 32) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const bool asc = (i & k) == 0;
+          const float a = all[i], b = all[ixj];
+          if ((a > b) == asc) { all[i] = b; all[ixj] = a; }
+        }
+      }
+      __syncwarp();
+    }
+  for (int i = lane; i < N + Ni; i += 32) z_all[r * (N + Ni) + i] = all[i];
+}
+
+}  // namespace pnr
+
+using namespace pnr;
+
+static inline unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
+
+extern "C" int pnr_intersect(const float* rays, int64_t R, const float* box_center,
+                             const float* box_half, const float* box_rot, int32_t B, int32_t M,
+                             uint8_t* hit_mask, int32_t* box_id, float* t_in, float* t_out,
+                             void* stream) {
+  if (R == 0) return PNR_OK;  // empty input: nothing to do (pointers of empty tensors may be null)
+  PNR_CHECK_ARG(R >= 0 && B >= 0, "pnr_intersect: negative size");
+  PNR_CHECK_ARG(M >= 1 && M <= PNR_MAX_HITS, "pnr_intersect: M=%d outside [1,%d]", M, PNR_MAX_HITS);
+  PNR_CHECK_ARG(rays && hit_mask && box_id && t_in && t_out, "pnr_intersect: null pointer");
+  PNR_CHECK_ARG(B == 0 || (box_center && box_half && box_rot), "pnr_intersect: null box table");
+  if (R == 0) return PNR_OK;
+  intersect_kernel<<<blocks_for(R, 256), 256, 0, (cudaStream_t)stream>>>(
+      rays, R, box_center, box_half, box_rot, B, M, hit_mask, box_id, t_in, t_out);
+  PNR_LAUNCH_CHECK("intersect_kernel");
+  return PNR_OK;
+}
+
+extern "C" int pnr_scene_near_far(const float* rays, int64_t R, const float* aabb_host, float near_min,
+                                  float far_default, float* near, float* far, void* stream) {
+  if (R == 0) return PNR_OK;
+  PNR_CHECK_ARG(rays && aabb_host && near && far, "pnr_scene_near_far: null pointer");
+  if (R == 0) return PNR_OK;
+  Aabb box;
+  for (int j = 0; j < 3; ++j) {
+    // same fp32 expressions as the oracle: (lo+hi)*0.5, (hi-lo)*0.5
+    box.c[j] = (aabb_host[j] + aabb_host[3 + j]) * 0.5f;
+    box.h[j] = (aabb_host[3 + j] - aabb_host[j]) * 0.5f;
+  }
+  near_far_kernel<<<blocks_for(R, 256), 256, 0, (cudaStream_t)stream>>>(rays, R, box, near_min,
+                                                                         far_default, near, far);
+  PNR_LAUNCH_CHECK("near_far_kernel");
+  return PNR_OK;
+}
+
+extern "C" int pnr_bound_by_primitives(const uint8_t* hit_mask, const int32_t* box_id,
+                                       const float* t_in, const float* t_out, int64_t R, int32_t M,
+                                       float* near, float* far, void* stream) {
+  if (R == 0) return PNR_OK;
+  PNR_CHECK_ARG(hit_mask && box_id && t_in && t_out && near && far, "pnr_bound_by_primitives: null");
+  PNR_CHECK_ARG(M >= 1 && M <= PNR_MAX_HITS, "pnr_bound_by_primitives: bad M");
+  if (R == 0) return PNR_OK;
+  bound_kernel<<<blocks_for(R, 256), 256, 0, (cudaStream_t)stream>>>(hit_mask, box_id, t_in, t_out, R,
+                                                                      M, near, far);
+  PNR_LAUNCH_CHECK("bound_kernel");
+  return PNR_OK;
+}
+
+extern "C" int pnr_sample_stratified(const float* near, const float* far, const float* t_vals,
+                                     const float* u, int64_t R, int32_t N, float perturb,
+                                     const int32_t* box_id, const float* t_in, const float* t_out,
+                                     int32_t M, float* z, int32_t* sample_box, void* stream) {
+  if (R == 0) return PNR_OK;
+  PNR_CHECK_ARG(near && far && t_vals && z, "pnr_sample_stratified: null pointer");
+  PNR_CHECK_ARG(N >= 1, "pnr_sample_stratified: N < 1");
+  PNR_CHECK_ARG(!(perturb > 0.f) || u, "pnr_sample_stratified: perturb > 0 needs u");
+  PNR_CHECK_ARG(box_id == nullptr || (t_in && t_out && M >= 1 && M <= PNR_MAX_HITS),
+                "pnr_sample_stratified: bad interval table");
+  if (R == 0) return PNR_OK;
+  if (z == near) return set_error(PNR_ERR_ARG, "pnr_sample_stratified: in-place not allowed");
+  stratified_kernel<<<blocks_for(R * N, 256), 256, 0, (cudaStream_t)stream>>>(
+      near, far, t_vals, u, R, N, perturb, box_id, t_in, t_out, M, z, sample_box);
+  PNR_LAUNCH_CHECK("stratified_kernel");
+  return PNR_OK;
+}
+
+extern "C" int pnr_tag_samples(const float* z, int64_t R, int32_t N, const int32_t* box_id,
+                               const float* t_in, const float* t_out, int32_t M, int32_t* sample_box,
+                               void* stream) {
+  if (R == 0) return PNR_OK;
+  PNR_CHECK_ARG(z && box_id && t_in && t_out && sample_box, "pnr_tag_samples: null pointer");
+  PNR_CHECK_ARG(M >= 1 && M <= PNR_MAX_HITS, "pnr_tag_samples: bad M");
+  if (R == 0) return PNR_OK;
+  tag_kernel<<<blocks_for(R * N, 256), 256, 0, (cudaStream_t)stream>>>(z, R, N, box_id, t_in, t_out, M,
+                                                                        sample_box);
+  PNR_LAUNCH_CHECK("tag_kernel");
+  return PNR_OK;
+}
+
+extern "C" int pnr_sample_pdf(const float* z, const float* weights, int64_t R, int32_t N, int32_t Ni,
+                              const float* u, float* z_fine, int64_t* idx, float* z_all, void* stream) {
+  if (R == 0) return PNR_OK;
+  PNR_CHECK_ARG(z && weights && u, "pnr_sample_pdf: null pointer (u is required; for the deterministic\n"
+                "                 sampler pass torch.linspace(0,1,Ni) broadcast over rays)");
+  PNR_CHECK_ARG(N >= 3 && N <= kPdfMaxN, "pnr_sample_pdf: N=%d outside [3,%d]", N, kPdfMaxN);
+  PNR_CHECK_ARG(Ni >= 1 && N + Ni <= kPdfMaxAll, "pnr_sample_pdf: N+Ni=%d > %d", N + Ni, kPdfMaxAll);
+  if (R == 0) return PNR_OK;
+  sample_pdf_kernel<<<blocks_for(R, kPdfWarps), kPdfWarps * 32, 0, (cudaStream_t)stream>>>(
+      z, weights, R, N, Ni, u, z_fine, idx, z_all);
+  PNR_LAUNCH_CHECK("sample_pdf_kernel");
+  return PNR_OK;
+}

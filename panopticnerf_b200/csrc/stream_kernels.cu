@@ -1,0 +1,251 @@
+// stream_kernels.cu — the floating-point HBM-bound stages: standalone positional encoding
+//  and alpha compositing / raw2outputs (a9).
+//   encode    : 128 samples per CTA, each thread encodes one sample into a shared tile, the CTA then
+//               streams the contiguous [128, 3+6L] tile out with fully coalesced stores.
+//   composite : one warp per ray; lanes stride the sample axis; transmittance is an exclusive
+//               product scan done with warp shuffles; per-class logits are accumulated with lanes
+//               striding the (contiguous) channel axis so every raw row is read once, coalesced.
+#include "common.cuh"
+
+namespace pnr {
+
+// ------------------------------------------------------------------------------------ a7 encode
+constexpr int kEncTile = 128;
+
+__global__ void __launch_bounds__(kEncTile) encode_kernel(const float* __restrict__ x, int64_t n, int L,
+                                                          float* __restrict__ out) {
+  extern __shared__ float tile[];  // [kEncTile][E]
+  const int E = 3 + 6 * L;
+  const int64_t s0 = (int64_t)blockIdx.x * kEncTile;
+  const int64_t s = s0 + threadIdx.x;
+  if (s < n) {
+    float* row = tile + threadIdx.x * E;
+    float p[3] = {x[s * 3 + 0], x[s * 3 + 1], x[s * 3 + 2]};
+    row[0] = p[0]; row[1] = p[1]; row[2] = p[2];
+    float f = 1.0f;
+    for (int k = 0; k < L; ++k) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float sn, cs;
+        sincosf(p[c] * f, &sn, &cs);  // exact power-of-two scaling, accurate sin/cos
+        row[3 + 6 * k + c] = sn;
+        row[3 + 6 * k + 3 + c] = cs;
+      }
+      f *= 2.0f;
+    }
+  }
+  __syncthreads();
+  const int64_t cnt = (int64_t)min((int64_t)kEncTile, n - s0) * E;
+  float* dst = out + s0 * E;
+  for (int64_t i = threadIdx.x; i < cnt; i += kEncTile) dst[i] = tile[i];
+}
+
+// ------------------------------------------------------------------------------------ a9 composite
+constexpr int kCompMaxPerLane = 8;   // N <= 256
+constexpr int kCompMaxChan = 4;      // C, K <= 128 each
+constexpr int kCompWarps = 4;
+
+struct CompositeArgs {
+  const float* raw; const float* z; const float* rays;
+  int64_t R; int N, C, K, CH;
+  int white_bkgd, sem_softmax, mask_outside;
+  const int32_t* sample_box; const int32_t* box_sem; const int32_t* box_inst; int B;
+  pnr_composite_out o;
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, d));
+  return v;
+}
+
+__global__ void __launch_bounds__(kCompWarps * 32) composite_kernel(CompositeArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * kCompWarps + (threadIdx.x >> 5);
+  if (r >= a.R) return;
+  const int N = a.N, CH = a.CH;
+  const float* raw = a.raw + r * N * CH;
+  const float* z = a.z + r * N;
+  const float dx = a.rays[r * 6 + 3], dy = a.rays[r * 6 + 4], dz = a.rays[r * 6 + 5];
+  const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+
+  float w[kCompMaxPerLane];
+  float carry = 1.0f;  // product of (1 - alpha + 1e-10) over all earlier groups of 32 samples
+  float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_d = 0.f, acc_a = 0.f;
+#pragma unroll
+  for (int j = 0; j < kCompMaxPerLane; ++j) {
+    w[j] = 0.f;
+    const int i0 = j * 32;
+    if (i0 >= N) continue;
+    const int i = i0 + lane;
+    float alpha = 0.f, zi = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
+    if (i < N) {
+      zi = z[i];
+      const float dist = ((i + 1 < N) ? (z[i + 1] - zi) : 1e10f) * dnorm;
+      const float* q = raw + (int64_t)i * CH;
+      float sig = fmaxf(q[3], 0.f);
+      if (a.mask_outside && a.sample_box != nullptr && a.sample_box[r * N + i] < 0) sig = 0.f;
+      alpha = 1.0f - expf(-sig * dist);
+      cr = 1.0f / (1.0f + expf(-q[0]));
+      cg = 1.0f / (1.0f + expf(-q[1]));
+      cb = 1.0f / (1.0f + expf(-q[2]));
+    }
+    // exclusive product scan of t = 1 - alpha + 1e-10 across the warp
+    const float t = (i < N) ? (1.0f - alpha + 1e-10f) : 1.0f;
+    float incl = t;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const float o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl *= o;
+    }
+    float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = 1.0f;
+    const float T = carry * excl;
+    carry *= __shfl_sync(0xffffffffu, incl, 31);
+    const float wi = alpha * T;
+    w[j] = wi;
+    if (i < N) {
+      if (a.o.weights) a.o.weights[r * N + i] = wi;
+      acc_r += wi * cr; acc_g += wi * cg; acc_b += wi * cb; acc_d += wi * zi; acc_a += wi;
+    }
+  }
+  acc_r = warp_sum(acc_r); acc_g = warp_sum(acc_g); acc_b = warp_sum(acc_b);
+  acc_d = warp_sum(acc_d); acc_a = warp_sum(acc_a);
+  if (lane == 0) {
+    if (a.o.rgb_map) {
+      const float bg = a.white_bkgd ? (1.0f - acc_a) : 0.f;
+      a.o.rgb_map[r * 3 + 0] = acc_r + bg;
+      a.o.rgb_map[r * 3 + 1] = acc_g + bg;
+      a.o.rgb_map[r * 3 + 2] = acc_b + bg;
+    }
+    if (a.o.depth_map) a.o.depth_map[r] = acc_d;
+    if (a.o.acc_map) a.o.acc_map[r] = acc_a;
+    if (a.o.disp_map) {
+      const float q = acc_d / acc_a;  // NaN when acc == 0, as in the oracle
+      a.o.disp_map[r] = 1.0f / ((q != q) ? q : fmaxf(1e-10f, q));
+    }
+  }
+
+  const int C = a.C, K = a.K;
+  const bool want_sem = C > 0 && a.o.semantic_map, want_inst = K > 0 && a.o.instance_map;
+  const bool want_fsem = C > 0 && a.o.fixed_semantic_map && a.sample_box && a.box_sem;
+  const bool want_finst = K > 0 && a.o.fixed_instance_map && a.sample_box && a.box_inst;
+  if (!(want_sem || want_inst || want_fsem || want_finst)) return;
+
+  float sem[kCompMaxChan], ins[kCompMaxChan], fsem[kCompMaxChan], fins[kCompMaxChan];
+#pragma unroll
+  for (int q = 0; q < kCompMaxChan; ++q) sem[q] = ins[q] = fsem[q] = fins[q] = 0.f;
+  for (int i = 0; i < N; ++i) {
+    float wi = 0.f;
+#pragma unroll
+    for (int j = 0; j < kCompMaxPerLane; ++j)
+      if (j == (i >> 5)) wi = __shfl_sync(0xffffffffu, w[j], i & 31);
+    const float* q = raw + (int64_t)i * CH + 4;
+    if (want_sem) {
+      float v[kCompMaxChan];
+#pragma unroll
+      for (int s = 0; s < kCompMaxChan; ++s) {
+        const int c = lane + 32 * s;
+        v[s] = (c < C) ? q[c] : -INFINITY;
+      }
+      if (a.sem_softmax) {
+        float m = v[0];
+#pragma unroll
+        for (int s = 1; s < kCompMaxChan; ++s) m = fmaxf(m, v[s]);
+        m = warp_max(m);
+        float e = 0.f;
+#pragma unroll
+        for (int s = 0; s < kCompMaxChan; ++s) {
+          v[s] = (lane + 32 * s < C) ? expf(v[s] - m) : 0.f;
+          e += v[s];
+        }
+        e = warp_sum(e);
+#pragma unroll
+        for (int s = 0; s < kCompMaxChan; ++s) v[s] = v[s] / e;
+      }
+#pragma unroll
+      for (int s = 0; s < kCompMaxChan; ++s)
+        if (lane + 32 * s < C) sem[s] += wi * v[s];
+    }
+    if (want_inst) {
+#pragma unroll
+      for (int s = 0; s < kCompMaxChan; ++s) {
+        const int c = lane + 32 * s;
+        if (c < K) ins[s] += wi * q[C + c];
+      }
+    }
+    if (want_fsem || want_finst) {
+      const int32_t sb = a.sample_box[r * N + i];
+      if (sb >= 0 && sb < a.B) {
+        if (want_fsem) {
+          const int32_t id = a.box_sem[sb];
+#pragma unroll
+          for (int s = 0; s < kCompMaxChan; ++s)
+            if (lane + 32 * s == id) fsem[s] += wi;
+        }
+        if (want_finst) {
+          const int32_t id = a.box_inst[sb];
+#pragma unroll
+          for (int s = 0; s < kCompMaxChan; ++s)
+            if (lane + 32 * s == id) fins[s] += wi;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < kCompMaxChan; ++s) {
+    const int c = lane + 32 * s;
+    if (want_sem && c < C) a.o.semantic_map[r * C + c] = sem[s];
+    if (want_inst && c < K) a.o.instance_map[r * K + c] = ins[s];
+    if (want_fsem && c < C) a.o.fixed_semantic_map[r * C + c] = fsem[s];
+    if (want_finst && c < K) a.o.fixed_instance_map[r * K + c] = fins[s];
+  }
+}
+
+}  // namespace pnr
+
+using namespace pnr;
+
+extern "C" int pnr_encode(const float* x, int64_t n, int32_t L, float* out, void* stream) {
+  if (n == 0) return PNR_OK;
+  PNR_CHECK_ARG(x && out, "pnr_encode: null pointer");
+  PNR_CHECK_ARG(L >= 0 && L <= 16, "pnr_encode: L=%d outside [0,16]", L);
+  if (n == 0) return PNR_OK;
+  const size_t smem = (size_t)kEncTile * (3 + 6 * L) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    PNR_CUDA(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr_set = true;
+  }
+  encode_kernel<<<(unsigned)((n + kEncTile - 1) / kEncTile), kEncTile, smem, (cudaStream_t)stream>>>(
+      x, n, L, out);
+  PNR_LAUNCH_CHECK("encode_kernel");
+  return PNR_OK;
+}
+
+extern "C" int pnr_composite(const float* raw, const float* z, const float* rays, int64_t R, int32_t N,
+                             int32_t C, int32_t K, int32_t white_bkgd, int32_t sem_softmax,
+                             int32_t mask_outside, const int32_t* sample_box, const int32_t* box_sem,
+                             const int32_t* box_inst, int32_t B, const pnr_composite_out* out,
+                             void* stream) {
+  if (R == 0) return PNR_OK;
+  PNR_CHECK_ARG(raw && z && rays && out, "pnr_composite: null pointer");
+  PNR_CHECK_ARG(N >= 1 && N <= 32 * kCompMaxPerLane, "pnr_composite: N=%d outside [1,%d]", N,
+                32 * kCompMaxPerLane);
+  PNR_CHECK_ARG(C >= 0 && C <= 32 * kCompMaxChan && K >= 0 && K <= 32 * kCompMaxChan,
+                "pnr_composite: C=%d or K=%d outside [0,%d]", C, K, 32 * kCompMaxChan);
+  if (R == 0) return PNR_OK;
+  CompositeArgs a;
+  a.raw = raw; a.z = z; a.rays = rays; a.R = R; a.N = N; a.C = C; a.K = K; a.CH = 4 + C + K;
+  a.white_bkgd = white_bkgd; a.sem_softmax = sem_softmax; a.mask_outside = mask_outside;
+  a.sample_box = sample_box; a.box_sem = box_sem; a.box_inst = box_inst; a.B = B; a.o = *out;
+  composite_kernel<<<(unsigned)((R + kCompWarps - 1) / kCompWarps), kCompWarps * 32, 0,
+                     (cudaStream_t)stream>>>(a);
+  PNR_LAUNCH_CHECK("composite_kernel");
+  return PNR_OK;
+}

@@ -4,6 +4,7 @@
 // "matrix descriptor" and "instruction descriptor" tables.
 #pragma once
 #include <cstdint>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 namespace pnr {
@@ -117,11 +118,13 @@ __device__ __forceinline__ uint64_t make_smem_desc_noswz(uint32_t saddr, uint32_
   d |= static_cast<uint64_t>(1) << 46;  // descriptor version 1 (sm_100)
   return d;                             // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
 }
-// Instruction descriptor for kind::f16, A=B=bf16 (K-major both), D=f32, dense.
-__host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int M, int N) {
+// Operand element formats of kind::f16 (instruction-descriptor encoding).
+constexpr int kFmtF16 = 0, kFmtBF16 = 1;
+// Instruction descriptor for kind::f16, A and B of format `fmt` (K-major both), D=f32, dense.
+__host__ __device__ constexpr uint32_t make_idesc_f32acc(int M, int N, int fmt) {
   return (1u << 4)                     // c_format = F32
-         | (1u << 7)                   // a_format = BF16
-         | (1u << 10)                  // b_format = BF16
+         | (uint32_t(fmt) << 7)        // a_format
+         | (uint32_t(fmt) << 10)       // b_format
          | (uint32_t(N >> 3) << 17)    // n_dim
          | (uint32_t(M >> 4) << 24);   // m_dim
 }
@@ -149,8 +152,6 @@ __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_
 
 // ---------------------------------------------------------------- TMEM <-> registers
 // 32x32b: thread t of the warp touches TMEM lane (lane_base + t); register i <-> column (col + i).
-#define PNR_R8(r, o)  "%" #o ", %" #o "+1"  // (unused helper, kept out of asm strings)
-
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -189,19 +190,25 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       : "memory");
 }
 
-// ---------------------------------------------------------------- bf16 hi/lo split
-// x = hi + lo + O(2^-18 |x|); both round-to-nearest-even. Two floats are packed per 32-bit word
-// with the element of lower K index in the low half (what kind::f16 expects for K-major A).
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo_k, float hi_k) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_k), "f"(lo_k));  // d.hi = a, d.lo = b
-  return r;
-}
-__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-  hi = pack_bf16x2(x0, x1);
-  float h0 = __uint_as_float(hi << 16);
-  float h1 = __uint_as_float(hi & 0xFFFF0000u);
-  lo = pack_bf16x2(x0 - h0, x1 - h1);
+// ---------------------------------------------------------------- 16-bit hi/lo split
+// x = hi + lo + residual, both parts rounded to nearest even in the operand format:
+//   bf16 (8-bit significand):  residual <= 2^-18 |x|, fp32 exponent range (never overflows)
+//   fp16 (11-bit significand): residual <= 2^-22 |x|, requires |x| < 65504
+// Two values are packed per 32-bit word with the lower K index in the low half (K-major A operand).
+template <int FMT>
+__device__ __forceinline__ void split_x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  if (FMT == kFmtBF16) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));  // d.hi = a, d.lo = b
+    const float h0 = __uint_as_float(hi << 16);
+    const float h1 = __uint_as_float(hi & 0xFFFF0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - h1), "f"(x0 - h0));
+  } else {
+    const __half2 h = __floats2half2_rn(x0, x1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+  }
 }
 
 }  // namespace pnr

@@ -1,0 +1,135 @@
+"""Network — the PanopticNeRF MLP (reference: the Network class of the task's
+network module under lib/networks/, not in the mount).
+
+Parameter names follow nerf-pytorch, which the reference is recalled to inherit, so a reference
+``state_dict`` loads with ``load_state_dict`` unchanged:
+    pts_linears.{i}, alpha_linear, feature_linear, views_linears.0, rgb_linear,
+    semantic_linears.{0,1}, instance_linears.{0,1}
+
+``forward(pts, viewdirs)`` runs the fused sm_100a kernel (positional encoding + all layers + heads in one
+launch, activations resident in tensor memory) through the libpnr C ABI.  There is no PyTorch forward:
+CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from panopticnerf_b200 import _capi
+
+
+def embed_dim(L: int) -> int:
+    return 3 + 6 * L
+
+
+class Network(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.D, self.W = int(cfg.D), int(cfg.W)
+        self.Lx, self.Ld = int(cfg.xyz_res), int(cfg.view_res)
+        self.C = int(getattr(cfg, "num_classes", 0))
+        self.K = int(getattr(cfg, "num_instances", 0))
+        self.precision = str(getattr(cfg, "precision", "fp16x3"))
+        self.skip = self.D // 2
+        Ex, Ed, W = embed_dim(self.Lx), embed_dim(self.Ld), self.W
+        self.pts_linears = nn.ModuleList(
+            [nn.Linear(Ex, W)] + [nn.Linear(W + Ex if i == self.skip + 1 else W, W) for i in range(1, self.D)])
+        self.alpha_linear = nn.Linear(W, 1)
+        self.feature_linear = nn.Linear(W, W)
+        self.views_linears = nn.ModuleList([nn.Linear(W + Ed, W // 2)])
+        self.rgb_linear = nn.Linear(W // 2, 3)
+        if self.C > 0:
+            self.semantic_linears = nn.ModuleList([nn.Linear(W, W // 2), nn.Linear(W // 2, self.C)])
+        if self.K > 0:
+            self.instance_linears = nn.ModuleList([nn.Linear(W, W // 2), nn.Linear(W // 2, self.K)])
+        self._ctx: Optional[int] = None
+        self._ctx_key = None
+
+    # ------------------------------------------------------------------ libpnr context
+    @property
+    def out_channels(self) -> int:
+        return 4 + self.C + self.K
+
+    def _linears(self) -> List[nn.Linear]:
+        ls = list(self.pts_linears) + [self.alpha_linear, self.feature_linear, self.views_linears[0],
+                                       self.rgb_linear]
+        if self.C > 0:
+            ls += list(self.semantic_linears)
+        if self.K > 0:
+            ls += list(self.instance_linears)
+        return ls
+
+    def _weights_key(self, device):
+        return (str(device), self.precision) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def pack(self, device=None) -> int:
+        """(Re)build the libpnr context: weights are split into bf16 hi/lo UMMA stage images once, and
+        again only when a parameter changed ('weight packer')."""
+        device = torch.device(device if device is not None else next(self.parameters()).device)
+        if device.type != "cuda":
+            raise _capi.PnrError("Network.pack: parameters live on CPU - move the module to a CUDA device "
+                                 "(panopticnerf_b200 has no CPU path)")
+        key = self._weights_key(device)
+        if self._ctx is not None and key == self._ctx_key:
+            return self._ctx
+        L = _capi.lib()
+        self.release()
+        cfg = _capi.PnrConfig(self.D, self.W, self.Lx, self.Ld, self.C, self.K,
+                              _capi.PREC[self.precision], device.index if device.index is not None
+                              else torch.cuda.current_device())
+        handle = C.c_void_p()
+        _capi.check(L.pnr_create(C.byref(cfg), C.byref(handle)), "pnr_create")
+        host, shapes = [], []
+        for lin in self._linears():
+            w = lin.weight.detach().to("cpu", torch.float32).contiguous()
+            b = lin.bias.detach().to("cpu", torch.float32).contiguous()
+            host += [w, b]
+            shapes += [w.shape[0], w.shape[1], b.shape[0], 1]
+        ptrs = (C.c_void_p * len(host))(*[t.data_ptr() for t in host])
+        shp = (C.c_int64 * len(shapes))(*shapes)
+        rc = L.pnr_load_weights(handle, ptrs, shp, len(host))
+        if rc != 0:
+            msg = L.pnr_last_error()
+            L.pnr_destroy(handle)
+            raise _capi.PnrError(f"pnr_load_weights failed (rc={rc}): {msg.decode()}")
+        self._ctx, self._ctx_key = handle.value, key
+        return self._ctx
+
+    def release(self) -> None:
+        if self._ctx is not None:
+            _capi.lib().pnr_destroy(C.c_void_p(self._ctx))
+            self._ctx, self._ctx_key = None, None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, pts: torch.Tensor, viewdirs: torch.Tensor) -> torch.Tensor:
+        """raw[..., 4+C+K] = [rgb_raw(3), sigma_raw(1), semantic logits(C), instance logits(K)]."""
+        if pts.shape != viewdirs.shape or pts.shape[-1] != 3:
+            raise ValueError(f"Network.forward: pts {tuple(pts.shape)} / viewdirs {tuple(viewdirs.shape)}")
+        p = pts.reshape(-1, 3).to(torch.float32).contiguous()
+        v = viewdirs.reshape(-1, 3).to(torch.float32).contiguous()
+        ctx = self.pack(p.device if p.is_cuda else None)
+        raw = torch.empty(p.shape[0], self.out_channels, device=p.device, dtype=torch.float32)
+        _capi.check(_capi.lib().pnr_mlp_forward(ctx, _capi.ptr(p, torch.float32, "pts"),
+                                                _capi.ptr(v, torch.float32, "viewdirs"), None, None,
+                                                p.shape[0], 1, _capi.ptr(raw), _capi.stream_ptr()),
+                    "pnr_mlp_forward")
+        return raw.reshape(*pts.shape[:-1], self.out_channels)
+
+    def forward_rays(self, rays: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
+        """Fused form used by the Renderer: pts = o + d*z and viewdirs = d/|d| are formed in-kernel."""
+        R, N = z.shape
+        ctx = self.pack(rays.device if rays.is_cuda else None)
+        raw = torch.empty(R, N, self.out_channels, device=rays.device, dtype=torch.float32)
+        _capi.check(_capi.lib().pnr_mlp_forward(ctx, None, None, _capi.ptr(rays, torch.float32, "rays"),
+                                                _capi.ptr(z, torch.float32, "z"), R, N, _capi.ptr(raw),
+                                                _capi.stream_ptr()), "pnr_mlp_forward")
+        return raw

@@ -1,0 +1,263 @@
+"""Renderer / raw2outputs / sample_pdf — the volume-render loop of PanopticNeRF (SURVEY.md 8(a)
+a3, a4, a5, a6, a9, a10; reference: the Renderer module under lib/networks/renderer/ and its
+raw2outputs / sample_pdf helpers, not in the mount).
+
+Same names, argument meaning and returned keys as the oracle restatement (oracle/reference_renderer.py),
+but every stage is a libpnr CUDA kernel called through the C ABI; torch only owns the device buffers.
+CPU tensors raise: there is no CPU path in the product.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from panopticnerf_b200 import _capi
+
+_F32, _I32 = torch.float32, torch.int32
+
+
+def _f(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _capi.PnrError(f"{name}: expected a CUDA tensor, got {t.device} (panopticnerf_b200 is GPU-only)")
+    return t.to(_F32).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# stage wrappers (one libpnr call each)
+# ------------------------------------------------------------------------------------------------
+def intersect(rays, box_center, box_half, box_rot, max_hits: int):
+    """a5 -> hit_mask [R] bool, box_id [R,M] i32, t_in, t_out [R,M]."""
+    rays = _f(rays, "rays")
+    R, B, M = rays.shape[0], box_center.shape[0], int(max_hits)
+    dev = rays.device
+    hit = torch.empty(R, dtype=torch.uint8, device=dev)
+    box_id = torch.empty(R, M, dtype=_I32, device=dev)
+    t_in = torch.empty(R, M, dtype=_F32, device=dev)
+    t_out = torch.empty(R, M, dtype=_F32, device=dev)
+    bc, bh, br = _f(box_center, "box_center"), _f(box_half, "box_half"), _f(box_rot, "box_rot")
+    _capi.check(_capi.lib().pnr_intersect(_capi.ptr(rays), R, _capi.ptr(bc), _capi.ptr(bh), _capi.ptr(br), B, M,
+                                          _capi.ptr(hit), _capi.ptr(box_id), _capi.ptr(t_in), _capi.ptr(t_out),
+                                          _capi.stream_ptr()), "pnr_intersect")
+    return hit.bool(), box_id, t_in, t_out
+
+
+def scene_near_far(rays, aabb, near_min: float, far_default: float):
+    rays = _f(rays, "rays")
+    R = rays.shape[0]
+    near = torch.empty(R, dtype=_F32, device=rays.device)
+    far = torch.empty(R, dtype=_F32, device=rays.device)
+    a = (C.c_float * 6)(*[float(x) for x in aabb.detach().to("cpu", _F32).reshape(-1).tolist()])
+    _capi.check(_capi.lib().pnr_scene_near_far(_capi.ptr(rays), R, a, float(near_min), float(far_default),
+                                               _capi.ptr(near), _capi.ptr(far), _capi.stream_ptr()),
+                "pnr_scene_near_far")
+    return near, far
+
+
+def bound_by_primitives(hit, box_id, t_in, t_out, near, far):
+    hit8 = hit.to(torch.uint8).contiguous()
+    near, far = near.clone(), far.clone()
+    _capi.check(_capi.lib().pnr_bound_by_primitives(_capi.ptr(hit8), _capi.ptr(box_id, _I32), _capi.ptr(t_in),
+                                                    _capi.ptr(t_out), near.shape[0], box_id.shape[1],
+                                                    _capi.ptr(near), _capi.ptr(far), _capi.stream_ptr()),
+                "pnr_bound_by_primitives")
+    return near, far
+
+
+def stratified_z(near, far, t_vals, perturb: float = 0.0, u: Optional[torch.Tensor] = None,
+                 box_id=None, t_in=None, t_out=None, want_tags: bool = False):
+    """a6 -> z [R,N] (and sample_box [R,N] i32 when want_tags)."""
+    near, far, t_vals = _f(near, "near"), _f(far, "far"), _f(t_vals, "t_vals")
+    R, N = near.shape[0], t_vals.shape[0]
+    if perturb > 0.0 and u is None:
+        u = torch.rand(R, N, device=near.device, dtype=_F32)
+    u = _f(u, "u") if (u is not None and perturb > 0.0) else None
+    z = torch.empty(R, N, dtype=_F32, device=near.device)
+    sb = torch.empty(R, N, dtype=_I32, device=near.device) if want_tags else None
+    M = box_id.shape[1] if box_id is not None else 0
+    _capi.check(_capi.lib().pnr_sample_stratified(
+        _capi.ptr(near), _capi.ptr(far), _capi.ptr(t_vals), _capi.ptr(u), R, N, float(perturb),
+        _capi.ptr(box_id, _I32) if box_id is not None else None, _capi.ptr(t_in), _capi.ptr(t_out), M,
+        _capi.ptr(z), _capi.ptr(sb), _capi.stream_ptr()), "pnr_sample_stratified")
+    return (z, sb) if want_tags else z
+
+
+def tag_samples(z, box_id, t_in, t_out):
+    z = _f(z, "z")
+    sb = torch.empty(z.shape, dtype=_I32, device=z.device)
+    _capi.check(_capi.lib().pnr_tag_samples(_capi.ptr(z), z.shape[0], z.shape[1], _capi.ptr(box_id, _I32),
+                                            _capi.ptr(t_in), _capi.ptr(t_out), box_id.shape[1], _capi.ptr(sb),
+                                            _capi.stream_ptr()), "pnr_tag_samples")
+    return sb
+
+
+def embed(x: torch.Tensor, L: int) -> torch.Tensor:
+    """a7 standalone positional encoding (the Renderer uses the copy fused into the MLP kernel)."""
+    xf = _f(x.reshape(-1, 3), "x")
+    out = torch.empty(xf.shape[0], 3 + 6 * L, dtype=_F32, device=xf.device)
+    _capi.check(_capi.lib().pnr_encode(_capi.ptr(xf), xf.shape[0], int(L), _capi.ptr(out), _capi.stream_ptr()),
+                "pnr_encode")
+    return out.reshape(*x.shape[:-1], 3 + 6 * L)
+
+
+def raw2outputs(raw, z_vals, rays_d, raw_noise_std: float = 0.0, white_bkgd: bool = False,
+                num_classes: int = 0, num_instances: int = 0, sem_activation: str = "none",
+                sample_box: Optional[torch.Tensor] = None, box_sem: Optional[torch.Tensor] = None,
+                box_inst: Optional[torch.Tensor] = None, mask_outside: bool = False,
+                noise: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    """a9.  raw [R,N,4+C+K], z_vals [R,N], rays_d [R,3] (or rays [R,6])."""
+    raw, z_vals = _f(raw, "raw"), _f(z_vals, "z_vals")
+    R, N = z_vals.shape
+    Cn, Kn = int(num_classes), int(num_instances)
+    if raw.shape[-1] != 4 + Cn + Kn:
+        raise ValueError(f"raw2outputs: raw has {raw.shape[-1]} channels, expected {4 + Cn + Kn}")
+    if raw_noise_std > 0.0:
+        nz = noise if noise is not None else torch.randn(R, N, device=raw.device)
+        raw = raw.clone()
+        raw[..., 3] += nz.to(raw.device, _F32) * raw_noise_std
+    if rays_d.shape[-1] == 3:
+        rays = torch.cat([torch.zeros_like(rays_d), rays_d], -1)
+    else:
+        rays = rays_d
+    rays = _f(rays, "rays")
+    dev = raw.device
+    out = {"rgb_map": torch.empty(R, 3, dtype=_F32, device=dev), "depth_map": torch.empty(R, dtype=_F32, device=dev),
+           "acc_map": torch.empty(R, dtype=_F32, device=dev), "disp_map": torch.empty(R, dtype=_F32, device=dev),
+           "weights": torch.empty(R, N, dtype=_F32, device=dev)}
+    if Cn > 0:
+        out["semantic_map"] = torch.empty(R, Cn, dtype=_F32, device=dev)
+    if Kn > 0:
+        out["instance_map"] = torch.empty(R, Kn, dtype=_F32, device=dev)
+    B = 0
+    if sample_box is not None and box_sem is not None and Cn > 0:
+        out["fixed_semantic_map"] = torch.empty(R, Cn, dtype=_F32, device=dev)
+        B = box_sem.shape[0]
+    if sample_box is not None and box_inst is not None and Kn > 0:
+        out["fixed_instance_map"] = torch.empty(R, Kn, dtype=_F32, device=dev)
+        B = box_inst.shape[0]
+    co = _capi.PnrCompositeOut(**{k: _capi.ptr(out[k]) if k in out else None
+                                  for k, _ in _capi.PnrCompositeOut._fields_})
+    sb = sample_box.to(_I32).contiguous() if sample_box is not None else None
+    bs = box_sem.to(_I32).contiguous() if box_sem is not None else None
+    bi = box_inst.to(_I32).contiguous() if box_inst is not None else None
+    _capi.check(_capi.lib().pnr_composite(
+        _capi.ptr(raw), _capi.ptr(z_vals), _capi.ptr(rays), R, N, Cn, Kn, int(bool(white_bkgd)),
+        int(sem_activation == "softmax"), int(bool(mask_outside)), _capi.ptr(sb), _capi.ptr(bs), _capi.ptr(bi),
+        B, C.byref(co), _capi.stream_ptr()), "pnr_composite")
+    return out
+
+
+def sample_pdf(z, weights, N_importance: int, det: bool = True, u: Optional[torch.Tensor] = None,
+               want_idx: bool = False):
+    """a10 on coarse depths z [R,N] and coarse weights [R,N] (bins = mid points, pdf = weights[1:-1]).
+    Returns (z_fine [R,Ni], z_all [R,N+Ni] sorted[, idx [R,Ni] i64])."""
+    z, weights = _f(z, "z"), _f(weights, "weights")
+    R, N = z.shape
+    Ni = int(N_importance)
+    if u is None:
+        if det:
+            u = torch.linspace(0.0, 1.0, Ni).to(z.device)[None].expand(R, Ni)   # host linspace = oracle's
+        else:
+            u = torch.rand(R, Ni, device=z.device)
+    u = _f(u, "u")
+    z_f = torch.empty(R, Ni, dtype=_F32, device=z.device)
+    z_all = torch.empty(R, N + Ni, dtype=_F32, device=z.device)
+    idx = torch.empty(R, Ni, dtype=torch.int64, device=z.device) if want_idx else None
+    _capi.check(_capi.lib().pnr_sample_pdf(_capi.ptr(z), _capi.ptr(weights), R, N, Ni, _capi.ptr(u),
+                                           _capi.ptr(z_f), _capi.ptr(idx), _capi.ptr(z_all), _capi.stream_ptr()),
+                "pnr_sample_pdf")
+    return (z_f, z_all, idx) if want_idx else (z_f, z_all)
+
+
+# ------------------------------------------------------------------------------------------------
+# Renderer
+# ------------------------------------------------------------------------------------------------
+class Renderer:
+    """Renderer(cfg, net).render(batch) -> dict of per-ray maps (a3).  batch keys: rays [R,6] (o||d),
+    optional near/far [R], scene_aabb [2,3], box_center/box_half [B,3], box_rot [B,3,3], box_sem/box_inst [B],
+    u [R,N] / u_fine [R,Ni] (externally supplied jitter), perturb."""
+
+    def __init__(self, cfg, net, net_fine=None):
+        self.cfg, self.net = cfg, net
+        self.net_fine = net_fine if net_fine is not None else net
+        self._t_vals = {}
+
+    def _tv(self, N: int, device) -> torch.Tensor:
+        key = (N, str(device))
+        if key not in self._t_vals:
+            self._t_vals[key] = torch.linspace(0.0, 1.0, N).to(device)   # CPU linspace, as the oracle's
+        return self._t_vals[key]
+
+    # -- a4: results are invariant to `chunk`; None renders every ray in one pass of persistent kernels
+    def batchify_rays(self, rays, near, far, batch, chunk: Optional[int] = None):
+        R = rays.shape[0]
+        chunk = int(chunk) if chunk else R
+        if chunk >= R:
+            return self.render_rays(rays, near, far, batch, slice(0, R))
+        outs = []
+        for i in range(0, R, chunk):
+            sl = slice(i, min(i + chunk, R))
+            outs.append(self.render_rays(rays[sl].contiguous(), near[sl].contiguous(), far[sl].contiguous(),
+                                         batch, sl))
+        return {k: torch.cat([o[k] for o in outs], 0) for k in outs[0]}
+
+    def render_rays(self, rays, near, far, batch, sl):
+        cfg = self.cfg
+        N, Ni = int(cfg.N_samples), int(getattr(cfg, "N_importance", 0))
+        Cn, Kn = int(getattr(cfg, "num_classes", 0)), int(getattr(cfg, "num_instances", 0))
+        M = int(getattr(cfg, "max_hits", 4))
+        perturb = float(batch.get("perturb", getattr(cfg, "perturb", 0.0)))
+        out = {}
+        has_boxes = "box_center" in batch and batch["box_center"].shape[0] > 0
+        box_id = t_in = t_out = None
+        if has_boxes:
+            hit, box_id, t_in, t_out = intersect(rays, batch["box_center"], batch["box_half"],
+                                                 batch["box_rot"], M)
+            out.update(hit_mask=hit, box_id=box_id, t_in=t_in, t_out=t_out)
+            if bool(getattr(cfg, "bound_by_primitives", False)):
+                near, far = bound_by_primitives(hit, box_id, t_in, t_out, near, far)
+        u = batch["u"][sl] if "u" in batch else None
+        res = stratified_z(near, far, self._tv(N, rays.device), perturb, u, box_id, t_in, t_out,
+                           want_tags=has_boxes)
+        z, sb = res if has_boxes else (res, None)
+        kw = dict(white_bkgd=bool(getattr(cfg, "white_bkgd", False)), num_classes=Cn, num_instances=Kn,
+                  sem_activation=str(getattr(cfg, "sem_activation", "none")),
+                  mask_outside=bool(getattr(cfg, "mask_outside", False)))
+        if has_boxes:
+            kw.update(box_sem=batch.get("box_sem"), box_inst=batch.get("box_inst"))
+        raw = self.net.forward_rays(rays, z)
+        res = raw2outputs(raw, z, rays, sample_box=sb, **kw)
+        if Ni > 0:
+            for k, v in res.items():
+                out[k + "_0"] = v
+            out["z_vals_0"] = z
+            u_f = batch["u_fine"][sl] if "u_fine" in batch else None
+            _, z = sample_pdf(z, res["weights"], Ni, det=(perturb == 0.0), u=u_f)
+            sb = tag_samples(z, box_id, t_in, t_out) if has_boxes else None
+            raw = self.net_fine.forward_rays(rays, z)
+            res = raw2outputs(raw, z, rays, sample_box=sb, **kw)
+        out.update(res)
+        out["z_vals"] = z
+        if sb is not None:
+            out["sample_box"] = sb
+        if bool(getattr(cfg, "return_raw", False)):
+            out["raw"] = raw
+        return out
+
+    # -- a3
+    @torch.no_grad()
+    def render(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        cfg = self.cfg
+        rays = _f(batch["rays"], "batch['rays']")
+        if "near" in batch and "far" in batch:
+            near, far = _f(batch["near"], "near"), _f(batch["far"], "far")
+        elif "scene_aabb" in batch:
+            near, far = scene_near_far(rays, batch["scene_aabb"], float(cfg.near), float(cfg.far))
+        else:
+            near = torch.full((rays.shape[0],), float(cfg.near), dtype=_F32, device=rays.device)
+            far = torch.full((rays.shape[0],), float(cfg.far), dtype=_F32, device=rays.device)
+        chunk = getattr(cfg, "gpu_chunk", None)
+        out = self.batchify_rays(rays, near, far, batch, chunk)
+        out["near"], out["far"] = near, far
+        return out

@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(192, 1) probe_kernel(ProbeParams p) {
     }
   } else if (warp == 1) {
     if (lane == 0) {  // ---- MMA issuer
-      const uint32_t idesc = make_idesc_bf16_f32(kM, N);
+      const uint32_t idesc = make_idesc_f32acc(kM, N, kFmtBF16);
       const uint32_t b_lbo = N * 16, b_sbo = 128;
       const uint32_t a_lbo = kM * 16, a_sbo = 128;
       mbar_wait(bar_a_ready, 0);
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(192, 1) probe_kernel(ProbeParams p) {
     for (int k0 = 0; k0 < K; k0 += 16) {
       uint32_t hi[8], lo[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) split_bf16x2(arow[k0 + 2 * j], arow[k0 + 2 * j + 1], hi[j], lo[j]);
+      for (int j = 0; j < 8; ++j) split_x2<kFmtBF16>(arow[k0 + 2 * j], arow[k0 + 2 * j + 1], hi[j], lo[j]);
       if (!p.mode_ss) {
         tmem_st8(t_ahi + lane_off + k0 / 2, hi);
         tmem_st8(t_alo + lane_off + k0 / 2, lo);
