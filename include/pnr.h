@@ -99,6 +99,12 @@ int pnr_encode(const float* x, int64_t n, int32_t L, float* out, void* stream);
 int pnr_mlp_forward(pnr_ctx* ctx, const float* pts, const float* viewdirs, const float* rays,
                     const float* z, int64_t R, int32_t N, float* raw, void* stream);
 
+/* Development aid: as pnr_mlp_forward(rays, z) but block 0 also records a clock64 timeline of its third
+ * tile into timeline[8192] (i64, device): [3*stage+{0,1,2}] MMA issuer (arrive / ready / issued),
+ * [4096 + 3*(2*step+half)+{0,1,2}] epilogue (wait / accumulator ready / done), [6144 + stage] TMA issue. */
+int pnr_mlp_forward_timeline(pnr_ctx* ctx, const float* rays, const float* z, int64_t R, int32_t N,
+                             float* raw, int64_t* timeline, void* stream);
+
 /* a9: raw2outputs.  raw [R,N,4+C+K], z [R,N], rays [R,6].  Any output pointer may be NULL.
  * sem_softmax: composite softmax(logits) instead of logits.  sample_box/box_sem/box_inst nullable. */
 typedef struct pnr_composite_out {

@@ -48,6 +48,7 @@ SIGNATURES = {
     "pnr_tag_samples": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp]),
     "pnr_encode": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
     "pnr_mlp_forward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
+    "pnr_mlp_forward_timeline": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "pnr_composite": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32,
                                 C.POINTER(PnrCompositeOut), _vp]),
     "pnr_sample_pdf": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),

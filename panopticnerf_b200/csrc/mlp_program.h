@@ -1,24 +1,30 @@
 // mlp_program.h — the per-tile "program" the fused MLP kernel interprets (built once on the host when
 // weights are loaded, see pnr_api.cu) and the shared-memory / tensor-memory maps both sides agree on.
+//
+// A tile (128 samples) runs a fixed sequence of STEPS (one GEMM + epilogue each: trunk layers, heads,
+// feature layer, view branch).  Every step is issued as two N-HALVES (h0, h1) with separate accumulator
+// column ranges, so that the epilogue of h0 (E0) overlaps the MMAs of h1, and the epilogue of h1 (E1)
+// overlaps the first K-chunks of the next step's h0 (which only need what E0 wrote).  Each half is a
+// list of weight STAGES (<= 16 KB: up to 128 rows x 64 K of one 16-bit part), streamed by TMA.
 #pragma once
 #include <stdint.h>
 
 namespace pnr {
 
 constexpr int kTileM = 128;               // samples per tile = TMEM lanes = UMMA M
-constexpr int kRing = 4;                  // weight stages in flight
-constexpr int kStageBytes = 32768;        // max stage: N=256 rows x 64 K x bf16
+constexpr int kRing = 8;                  // weight stages in flight
+constexpr int kStageBytes = 16384;        // max stage: N=128 rows x 64 K x 2 bytes
 constexpr int kEpiWarps = 8;              // TMEM->reg->TMEM activation warps (2 per lane quarter)
 constexpr int kProWarps = 4;              // positional-encoding producer warps (one thread per row)
 constexpr int kMlpThreads = (kEpiWarps + kProWarps + 2) * 32;   // + TMA warp + MMA warp = 448
-constexpr int kMaxStages = 192;
+constexpr int kMaxStages = 384;
 constexpr int kMaxSteps = 24;
 constexpr int kMaxConsts = 4096;          // floats: biases + sigma / rgb weights
 
 // Tensor-memory column map (512 x 32-bit columns, 128 lanes).
 constexpr int kColAcc = 0;                // fp32 accumulators, up to 256 columns
-constexpr int kColAHi = 256;              // activations, bf16 hi halves, 2 per column (K <= 256)
-constexpr int kColALo = 384;              // activations, bf16 lo halves
+constexpr int kColAHi = 256;              // activations, 16-bit hi parts, 2 per column (K <= 256)
+constexpr int kColALo = 384;              // activations, 16-bit lo parts
 constexpr int kColHeadHi = 128;           // head hidden activations (K <= 128) live in the upper
 constexpr int kColHeadLo = 192;           //   half of the accumulator region while it is free
 
@@ -31,39 +37,43 @@ constexpr int kDirPartBytes = kTileM * 32 * 2;         // 8 KB
 constexpr int kSmemProg = kSmemDir + 4 * kDirPartBytes;
 
 enum : uint8_t { A_TMEM = 0, A_EMB = 1, A_DIR = 2 };
-enum : uint8_t {
-  F_FIRST = 1,         // first MMA of the step overwrites the accumulator
-  F_WAIT_A = 2,        // wait for the previous step's epilogue (activations staged, accumulator drained)
-  F_COMMIT_ACC = 4,    // last stage of the step: signal the epilogue when the MMAs retire
-  F_WAIT_EMB = 8, F_RELEASE_EMB = 16, F_WAIT_DIR = 32, F_RELEASE_DIR = 64
+enum : uint16_t {
+  F_FIRST = 1,          // first MMA of this half overwrites the accumulator
+  F_WAIT_E0 = 2,        // first stage of a step: wait for E0 of the previous step
+  F_WAIT_E1 = 4,        // first stage that touches anything E1 of the previous step reads or writes
+  F_COMMIT_ACC0 = 8,    // last stage of h0: signal E0 when the MMAs so far retire
+  F_COMMIT_ACC1 = 16,   // last stage of the step: signal E1
+  F_COMMIT_WAR = 32,    // last stage reading the activation columns E0 of THIS step overwrites
+  F_WAIT_EMB = 64, F_RELEASE_EMB = 128, F_WAIT_DIR = 256, F_RELEASE_DIR = 512
 };
 enum : uint8_t { EPI_RELU_TO_A = 0, EPI_LINEAR_TO_A = 1, EPI_VIEW_RGB = 2, EPI_LOGITS = 3 };
 
 struct StageDesc {     // one weight stage = one bulk copy + its MMAs
   uint32_t gofs;       // byte offset into the packed weight stream
   uint32_t bytes;
-  uint16_t n;          // UMMA N (rows of the weight tile)
-  uint16_t acc_col;
-  uint16_t a_off;      // A_TMEM: packed column of the first K16 step (hi);  A_EMB/A_DIR: unused
-  uint16_t a_lo_off;
+  uint16_t n;          // UMMA N (rows of the weight tile = width of this half)
+  uint16_t acc_col;    // accumulator column of this half
+  uint16_t a_off;      // A_TMEM: packed column of the first K16 step (hi part)
+  uint16_t a_lo_off;   //         and of the lo part
+  uint16_t flags;
   uint8_t ksteps;      // K16 steps covered by this stage
-  uint8_t is_lo;       // weight part: 0 = bf16 hi, 1 = bf16 lo residual
+  uint8_t is_lo;       // weight part: 0 = hi, 1 = lo residual
   uint8_t a_kind;
-  uint8_t flags;
+  uint8_t pad[3];
 };
 
 struct EpiDesc {
   uint8_t kind;
   uint8_t sigma;       // also accumulate the sigma head (dot with consts[aux_off..]) on the activated values
-  uint16_t n;          // accumulator columns to process (multiple of 16)
+  uint16_t n;          // accumulator columns of the step (multiple of 16)
+  uint16_t n0;         // columns handled by E0 (h0); E1 handles [n0, n)
   uint16_t n_valid;    // EPI_LOGITS: real channel count
   uint16_t acc_col;
   uint16_t dst_col;    // packed destination column (hi) ; lo at dst_lo_col
   uint16_t dst_lo_col;
-  uint16_t bias_off;   // float offset into consts
+  uint16_t bias_off;   // float offset into consts (16-byte aligned)
   uint16_t aux_off;    // sigma weights (EPI_*_TO_A with sigma) or rgb weights [3][n] (EPI_VIEW_RGB)
   uint16_t out_off;    // EPI_LOGITS: channel offset in the raw row
-  uint16_t pad;
 };
 
 struct MlpProgram {
@@ -89,11 +99,13 @@ struct MlpParams {
   int32_t CH;             // raw row width 4 + C + K
   float* raw;
   int32_t num_tiles;
+  long long* dbg;         // optional clock64 timeline of block 0 (development aid), else null
 };
 
-constexpr int kSmemConsts = kSmemProg + (int)sizeof(MlpProgram);
+constexpr int kSmemConsts = (kSmemProg + (int)sizeof(MlpProgram) + 15) / 16 * 16;
 constexpr int kSmemPart = kSmemConsts + kMaxConsts * 4;      // [2][128][4] floats
 constexpr int kSmemBars = kSmemPart + 2 * kTileM * 4 * 4;
 constexpr int kSmemTotal = kSmemBars + 256;
+static_assert(kSmemTotal <= 232448, "shared-memory map exceeds the 227 KB per-CTA limit");
 
 }  // namespace pnr

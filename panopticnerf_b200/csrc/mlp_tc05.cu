@@ -2,20 +2,28 @@
 //
 // One persistent CTA per SM walks 128-sample tiles.  Per tile the whole MLP runs on-chip:
 //   * 4 producer warps form pts = o + d*z, the positional encodings gamma(x), gamma(d), split them into
-//     bf16 hi/lo and write them into shared memory in the UMMA no-swizzle K-major operand layout;
-//   * 1 TMA warp streams the pre-packed weight stages (bf16 hi / lo images, 32 KB each) from L2 into
-//     a 4-deep shared-memory ring with cp.async.bulk + mbarrier complete_tx;
-//   * 1 MMA warp (one elected thread) issues tcgen05.mma kind::f16, M=128, N<=256, K=16:
+//     16-bit hi/lo parts and write them into shared memory in the UMMA no-swizzle K-major operand layout;
+//   * 1 TMA warp streams the pre-packed weight stages (hi / lo images, <= 16 KB each) from L2 into an
+//     8-deep shared-memory ring with cp.async.bulk + mbarrier complete_tx;
+//   * 1 MMA warp (one elected thread) issues tcgen05.mma kind::f16, M=128, N<=128, K=16:
 //     the A operand is the embedding in shared memory (SS form) or the previous layer's activations
 //     in TENSOR MEMORY (TS form); accumulators are fp32 in tensor memory;
-//   * 8 epilogue warps tcgen05.ld the accumulator, add bias, ReLU, split into bf16 hi/lo and
-//     tcgen05.st the result back to tensor memory as the next layer's A operand.  Activations never
-//     touch shared or global memory.  The sigma head (N=1) and rgb head (N=3) are CUDA-core dot
-//     products inside the epilogues; semantic / instance logits are written straight to `raw`.
+//   * 8 epilogue warps tcgen05.ld the accumulator, add bias, ReLU, split into hi/lo and tcgen05.st the
+//     result back to tensor memory as the next layer's A operand.  Activations never touch shared or
+//     global memory.  The sigma head (N=1) and rgb head (N=3) are CUDA-core dot products inside the
+//     epilogues; semantic / instance logits are written straight to `raw`.
+//
+// Overlap: every step (layer) is issued as two N-halves h0, h1 with separate accumulator columns.
+// E0 (epilogue of h0) runs while the tensor pipe works on h1; E1 runs while the next step's h0 consumes
+// the K-chunks E0 already produced.  Hazards are tracked with five mbarriers that each complete once
+// per step: acc_full[0/1] (MMA -> epilogue), war_ok (MMA -> E0: the activation columns E0 overwrites
+// have been read), e_done[0/1] (epilogue -> MMA).
+//
 // Precision: operands are 16-bit (fp16 or bf16), accumulation fp32.  The "x3" modes compute every product
 // as A_hi*B_hi + A_lo*B_hi + A_hi*B_lo with x = hi + lo split in the operand format: ~2^-21 relative
 // per product for fp16x3 (default; what the 1e-4 parity tolerance needs with margin), ~2^-17 for
 // bf16x3 (fp32 exponent range).  The 1-pass modes keep the first term only (fast, out of tolerance).
+#include <cstddef>
 #include "common.cuh"
 #include "mlp_program.h"
 #include "tc05.cuh"
@@ -69,6 +77,64 @@ __device__ __forceinline__ void encode_row(const float (&p)[3], int L, uint8_t* 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Epilogue building blocks.  One thread owns one accumulator row (TMEM lane); groups are 16 columns.
+// ------------------------------------------------------------------------------------------------
+struct EpiCtx {
+  uint32_t tmem_lane;      // tmem base | lane offset of this thread's quarter
+  uint32_t bar_war;
+  uint32_t parity;
+};
+
+// activation -> next layer's A operand: v = act(acc + bias); [sigma += v . wsig]; split; tcgen05.st
+template <int PASSES, int FMT>
+__device__ __forceinline__ void epi_group_to_a(const uint32_t (&r)[16], int g, const EpiDesc& ed, float clamp_lo,
+                                               const float* bias, const float* wsig, float& sig,
+                                               const EpiCtx& cx, bool& war_pending) {
+  uint32_t hi[8], lo[8];
+  const float4* b4 = reinterpret_cast<const float4*>(bias + g * 16);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 b = b4[q];
+    const float v0 = fmaxf(__uint_as_float(r[4 * q + 0]) + b.x, clamp_lo);
+    const float v1 = fmaxf(__uint_as_float(r[4 * q + 1]) + b.y, clamp_lo);
+    const float v2 = fmaxf(__uint_as_float(r[4 * q + 2]) + b.z, clamp_lo);
+    const float v3 = fmaxf(__uint_as_float(r[4 * q + 3]) + b.w, clamp_lo);
+    if (ed.sigma) {
+      const float4 w = reinterpret_cast<const float4*>(wsig + g * 16)[q];
+      sig += v0 * w.x + v1 * w.y + v2 * w.z + v3 * w.w;
+    }
+    split_x2<FMT>(v0, v1, hi[2 * q], lo[2 * q]);
+    split_x2<FMT>(v2, v3, hi[2 * q + 1], lo[2 * q + 1]);
+  }
+  if (war_pending) {  // the columns we are about to overwrite must have been consumed by this step's MMAs
+    mbar_wait(cx.bar_war, cx.parity);
+    tc_fence_after();
+    war_pending = false;
+  }
+  tmem_st8(cx.tmem_lane + ed.dst_col + g * 8, hi);
+  if (PASSES == 3) tmem_st8(cx.tmem_lane + ed.dst_lo_col + g * 8, lo);
+}
+
+__device__ __forceinline__ void epi_group_rgb(const uint32_t (&r)[16], int g, const EpiDesc& ed, const float* bias,
+                                              const float* wr, float& c0, float& c1, float& c2) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int c = g * 16 + j;
+    const float v = fmaxf(__uint_as_float(r[j]) + bias[c], 0.f);
+    c0 += v * wr[c];
+    c1 += v * wr[ed.n + c];
+    c2 += v * wr[2 * ed.n + c];
+  }
+}
+
+__device__ __forceinline__ void epi_group_logits(const uint32_t (&r)[16], int g, const EpiDesc& ed,
+                                                 const float* bias, float* dst) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    if (g * 16 + j < ed.n_valid) dst[g * 16 + j] = __uint_as_float(r[j]) + bias[g * 16 + j];
+}
+
 template <int PASSES, int FMT>
 __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -78,22 +144,27 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpPara
   float* consts = reinterpret_cast<float*>(smem + kSmemConsts);
   float* part = reinterpret_cast<float*>(smem + kSmemPart);  // [2][128][4]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBars);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
 
-  const uint32_t bar_full = smem_u32(&bars[0]);             // [kRing]
-  const uint32_t bar_empty = smem_u32(&bars[kRing]);        // [kRing]
-  const uint32_t bar_acc_full = smem_u32(&bars[2 * kRing]);
-  const uint32_t bar_a_ready = smem_u32(&bars[2 * kRing + 1]);
-  const uint32_t bar_emb_full = smem_u32(&bars[2 * kRing + 2]);
-  const uint32_t bar_emb_empty = smem_u32(&bars[2 * kRing + 3]);
-  const uint32_t bar_dir_full = smem_u32(&bars[2 * kRing + 4]);   // [2]
-  const uint32_t bar_dir_empty = smem_u32(&bars[2 * kRing + 6]);  // [2]
+  const uint32_t bar_full = smem_u32(&bars[0]);                 // [kRing]
+  const uint32_t bar_empty = smem_u32(&bars[kRing]);            // [kRing]
+  const uint32_t bar_acc_full = smem_u32(&bars[2 * kRing]);     // [2]
+  const uint32_t bar_e_done = smem_u32(&bars[2 * kRing + 2]);   // [2]
+  const uint32_t bar_war = smem_u32(&bars[2 * kRing + 4]);
+  const uint32_t bar_emb_full = smem_u32(&bars[2 * kRing + 5]);
+  const uint32_t bar_emb_empty = smem_u32(&bars[2 * kRing + 6]);
+  const uint32_t bar_dir_full = smem_u32(&bars[2 * kRing + 7]);   // [2]
+  const uint32_t bar_dir_empty = smem_u32(&bars[2 * kRing + 9]);  // [2]
 
   // ---- one-time setup: program + constants to shared memory, barriers, tensor memory
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(p.prog);
     uint32_t* dst = reinterpret_cast<uint32_t*>(prog);
-    for (int i = threadIdx.x; i < (int)(sizeof(MlpProgram) / 4); i += blockDim.x) dst[i] = src[i];
+    const int nst = p.prog->n_stages;
+    const int head_words = (int)((offsetof(MlpProgram, st) + sizeof(StageDesc) * nst + 3) / 4);
+    for (int i = threadIdx.x; i < head_words; i += blockDim.x) dst[i] = src[i];
+    const int ep0 = (int)(offsetof(MlpProgram, ep) / 4), ep1 = (int)(sizeof(MlpProgram) / 4);
+    for (int i = ep0 + threadIdx.x; i < ep1; i += blockDim.x) dst[i] = src[i];
     const int nc = p.prog->n_consts;
     for (int i = threadIdx.x; i < nc; i += blockDim.x) consts[i] = p.consts[i];
   }
@@ -106,14 +177,15 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpPara
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
-    mbar_init(bar_acc_full, 1);
-    mbar_init(bar_a_ready, kEpiWarps * 32);
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(bar_acc_full + 8 * h, 1);
+      mbar_init(bar_e_done + 8 * h, kEpiWarps * 32);
+      mbar_init(bar_dir_full + 8 * h, kProWarps * 32);
+      mbar_init(bar_dir_empty + 8 * h, 1);
+    }
+    mbar_init(bar_war, 1);
     mbar_init(bar_emb_full, kProWarps * 32);
     mbar_init(bar_emb_empty, 1);
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(bar_dir_full + 8 * b, kProWarps * 32);
-      mbar_init(bar_dir_empty + 8 * b, 1);
-    }
     fence_mbar_init();
   }
   tc_fence_before();
@@ -124,95 +196,100 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpPara
 
   if (warp < kEpiWarps) {
     // =============================================================== epilogue warps
-    const int q = warp & 3, half = warp >> 2;
+    const int q = warp & 3, ch = warp >> 2;     // TMEM lane quarter ; which half of a column range
     const int row = q * 32 + lane;
-    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    uint32_t acc_phase = 0;
-    mbar_arrive(bar_a_ready);  // round 0: "accumulator free, nothing to stage" for the very first step
+    EpiCtx cx;
+    cx.tmem_lane = tmem + ((uint32_t)(q * 32) << 16);
+    cx.bar_war = bar_war;
+    uint32_t gstep = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int64_t s = (int64_t)tile * kTileM + row;
       const bool valid = s < p.S;
-      for (int st = 0; st < n_steps; ++st) {
+      float sig = 0.f;
+      for (int st = 0; st < n_steps; ++st, ++gstep) {
         const EpiDesc ed = prog->ep[st];
-        mbar_wait(bar_acc_full, acc_phase);
-        acc_phase ^= 1;
-        tc_fence_after();
-        const int G = ed.n >> 4;
-        const int g0 = half == 0 ? 0 : (G + 1) / 2;
-        const int g1 = half == 0 ? (G + 1) / 2 : G;
+        const uint32_t parity = gstep & 1u;
+        cx.parity = parity;
         const float* bias = consts + ed.bias_off;
-        if (ed.kind == EPI_RELU_TO_A || ed.kind == EPI_LINEAR_TO_A) {
-          const bool relu = ed.kind == EPI_RELU_TO_A;
-          const float* wsig = consts + ed.aux_off;
-          float sig = 0.f;
-          for (int g = g0; g < g1; ++g) {
-            uint32_t r[16];
-            tmem_ld16(tmem + lane_off + ed.acc_col + g * 16, r);
+        const float* aux = consts + ed.aux_off;
+        const bool to_a = ed.kind == EPI_RELU_TO_A || ed.kind == EPI_LINEAR_TO_A;
+        const float clamp_lo = ed.kind == EPI_RELU_TO_A ? 0.f : -INFINITY;
+        float* out_row = p.raw + (valid ? s : 0) * p.CH + ed.out_off;
+        bool war_pending = to_a;
+        float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          const bool rec = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && tile == 2 * (int)gridDim.x;
+          if (rec) p.dbg[4096 + (st * 2 + h) * 3 + 0] = clock64();
+          mbar_wait(bar_acc_full + 8 * h, parity);
+          tc_fence_after();
+          if (rec) p.dbg[4096 + (st * 2 + h) * 3 + 1] = clock64();
+          const int gb_all = h == 0 ? 0 : (ed.n0 >> 4);
+          const int ge_all = h == 0 ? (ed.n0 >> 4) : (ed.n >> 4);
+          const int G = ge_all - gb_all;
+          const int gb = gb_all + (ch == 0 ? 0 : (G + 1) / 2);
+          const int ge = gb_all + (ch == 0 ? (G + 1) / 2 : G);
+          const uint32_t acc = cx.tmem_lane + ed.acc_col;
+          // software pipeline: the load of group g+1 is in flight while group g is processed
+          uint32_t ra[16], rb[16];
+          if (gb < ge) tmem_ld16(acc + gb * 16, ra);
+#pragma unroll 1
+          for (int g = gb; g < ge; g += 2) {
             tc_wait_ld();
-            uint32_t hi[8], lo[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float v0 = __uint_as_float(r[2 * j]) + bias[g * 16 + 2 * j];
-              float v1 = __uint_as_float(r[2 * j + 1]) + bias[g * 16 + 2 * j + 1];
-              if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-              if (ed.sigma) sig += v0 * wsig[g * 16 + 2 * j] + v1 * wsig[g * 16 + 2 * j + 1];
-              split_x2<FMT>(v0, v1, hi[j], lo[j]);
+            if (g + 1 < ge) tmem_ld16(acc + (g + 1) * 16, rb);
+            if (to_a) {
+              epi_group_to_a<PASSES, FMT>(ra, g, ed, clamp_lo, bias, aux, sig, cx, war_pending);
+            } else if (ed.kind == EPI_VIEW_RGB) {
+              epi_group_rgb(ra, g, ed, bias, aux, c0, c1, c2);
+            } else if (valid) {
+              epi_group_logits(ra, g, ed, bias, out_row);
             }
-            tmem_st8(tmem + lane_off + ed.dst_col + g * 8, hi);
-            if (PASSES == 3) tmem_st8(tmem + lane_off + ed.dst_lo_col + g * 8, lo);
-          }
-          if (ed.sigma) part[(half * kTileM + row) * 4 + 3] = sig;
-          tc_wait_st();
-        } else if (ed.kind == EPI_VIEW_RGB) {
-          const float* wr = consts + ed.aux_off;  // [3][n]
-          float c0 = 0.f, c1 = 0.f, c2 = 0.f;
-          for (int g = g0; g < g1; ++g) {
-            uint32_t r[16];
-            tmem_ld16(tmem + lane_off + ed.acc_col + g * 16, r);
-            tc_wait_ld();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int c = g * 16 + j;
-              const float v = fmaxf(__uint_as_float(r[j]) + bias[c], 0.f);
-              c0 += v * wr[c];
-              c1 += v * wr[ed.n + c];
-              c2 += v * wr[2 * ed.n + c];
-            }
-          }
-          float* mine = part + (half * kTileM + row) * 4;
-          mine[0] = c0; mine[1] = c1; mine[2] = c2;
-          named_bar_sync(1, kEpiWarps * 32);
-          if (half == 0 && valid) {
-            const float* other = part + (kTileM + row) * 4;
-            const float* b3 = consts + prog->rgb_bias_off;
-            const float o0 = c0 + other[0] + b3[0];
-            const float o1 = c1 + other[1] + b3[1];
-            const float o2 = c2 + other[2] + b3[2];
-            const float o3 = mine[3] + other[3] + consts[prog->sigma_bias_off];
-            float* dst = p.raw + s * p.CH;
-            if (p.CH == 4) {
-              *reinterpret_cast<float4*>(dst) = make_float4(o0, o1, o2, o3);
-            } else {
-              dst[0] = o0; dst[1] = o1; dst[2] = o2; dst[3] = o3;
-            }
-          }
-        } else {  // EPI_LOGITS
-          for (int g = g0; g < g1; ++g) {
-            uint32_t r[16];
-            tmem_ld16(tmem + lane_off + ed.acc_col + g * 16, r);
-            tc_wait_ld();
-            if (valid) {
-              float* dst = p.raw + s * p.CH + ed.out_off;
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const int c = g * 16 + j;
-                if (c < ed.n_valid) dst[c] = __uint_as_float(r[j]) + bias[c];
+            if (g + 1 < ge) {
+              tc_wait_ld();
+              if (g + 2 < ge) tmem_ld16(acc + (g + 2) * 16, ra);
+              if (to_a) {
+                epi_group_to_a<PASSES, FMT>(rb, g + 1, ed, clamp_lo, bias, aux, sig, cx, war_pending);
+              } else if (ed.kind == EPI_VIEW_RGB) {
+                epi_group_rgb(rb, g + 1, ed, bias, aux, c0, c1, c2);
+              } else if (valid) {
+                epi_group_logits(rb, g + 1, ed, bias, out_row);
               }
             }
           }
+          if (h == 0 && war_pending) {  // no columns of h0 for this thread: still consume the barrier phase
+            mbar_wait(bar_war, parity);
+            war_pending = false;
+          }
+          if (h == 1) {
+            if (ed.sigma) {
+              part[(ch * kTileM + row) * 4 + 3] = sig;
+              sig = 0.f;
+            }
+            if (ed.kind == EPI_VIEW_RGB) {
+              float* mine = part + (ch * kTileM + row) * 4;
+              mine[0] = c0; mine[1] = c1; mine[2] = c2;
+              named_bar_sync(1, kEpiWarps * 32);
+              if (ch == 0 && valid) {
+                const float* other = part + (kTileM + row) * 4;
+                const float* b3 = consts + prog->rgb_bias_off;
+                const float o0 = c0 + other[0] + b3[0];
+                const float o1 = c1 + other[1] + b3[1];
+                const float o2 = c2 + other[2] + b3[2];
+                const float o3 = mine[3] + other[3] + consts[prog->sigma_bias_off];
+                float* dst = p.raw + s * p.CH;
+                if (p.CH == 4) {
+                  *reinterpret_cast<float4*>(dst) = make_float4(o0, o1, o2, o3);
+                } else {
+                  dst[0] = o0; dst[1] = o1; dst[2] = o2; dst[3] = o3;
+                }
+              }
+            }
+          }
+          if (to_a) tc_wait_st();
+          tc_fence_before();
+          mbar_arrive(bar_e_done + 8 * h);
+          if (rec) p.dbg[4096 + (st * 2 + h) * 3 + 2] = clock64();
         }
-        tc_fence_before();
-        mbar_arrive(bar_a_ready);
       }
     }
   } else if (warp < kEpiWarps + kProWarps) {
@@ -265,6 +342,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpPara
           const uint32_t slot = gs % kRing, ph = (gs / kRing) & 1;
           const uint32_t gofs = prog->st[si].gofs, bytes = prog->st[si].bytes;
           mbar_wait(bar_empty + 8 * slot, ph ^ 1);
+          if (p.dbg != nullptr && blockIdx.x == 0 && tile == 2 * (int)gridDim.x) p.dbg[6144 + si] = clock64();
           mbar_arrive_expect_tx(bar_full + 8 * slot, bytes);
           bulk_g2s(smem_u32(smem + kSmemRing + slot * kStageBytes), p.wpacked + gofs, bytes,
                    bar_full + 8 * slot);
@@ -272,58 +350,83 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpPara
       }
     }
   } else {
-    // =============================================================== MMA issuer (one lane)
-    if (lane == 0) {
-      uint32_t gs = 0, a_phase = 0;
-      int it = 0;
-      const uint32_t emb_hi = smem_u32(smem + kSmemEmb);
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        const int b = it & 1;
-        const uint32_t dir_hi = smem_u32(smem + kSmemDir + b * 2 * kDirPartBytes);
-        for (int si = 0; si < n_stages; ++si, ++gs) {
-          const StageDesc sd = prog->st[si];
-          if (sd.flags & F_WAIT_A) { mbar_wait(bar_a_ready, a_phase); a_phase ^= 1; }
-          if (sd.flags & F_WAIT_EMB) mbar_wait(bar_emb_full, (uint32_t)(it & 1));
-          if (sd.flags & F_WAIT_DIR) mbar_wait(bar_dir_full + 8 * b, (uint32_t)((it >> 1) & 1));
-          const uint32_t slot = gs % kRing, ph = (gs / kRing) & 1;
-          mbar_wait(bar_full + 8 * slot, ph);
-          tc_fence_after();
-          const uint32_t idesc = make_idesc_f32acc(kTileM, sd.n, FMT);
-          const uint32_t b_lbo = (uint32_t)sd.n * 16u;
-          const uint32_t sb = smem_u32(smem + kSmemRing + slot * kStageBytes);
-          const uint32_t d_tmem = tmem + sd.acc_col;
-          uint32_t accum = (sd.flags & F_FIRST) ? 0u : 1u;
-          for (int ks = 0; ks < sd.ksteps; ++ks) {
-            const uint64_t bdesc = make_smem_desc_noswz(sb + ks * 2 * b_lbo, b_lbo, 128);
-            if (sd.a_kind == A_TMEM) {
-              const uint32_t a_hi = tmem + sd.a_off + ks * 8;
-              if (!sd.is_lo) {
-                mma_ts(d_tmem, a_hi, bdesc, idesc, accum);
-                accum = 1;
-                if (PASSES == 3) mma_ts(d_tmem, tmem + sd.a_lo_off + ks * 8, bdesc, idesc, 1);
+    // =============================================================== MMA issuer warp
+    // All 32 lanes walk the stage list (warp-uniform control flow keeps descriptors in uniform registers and
+    // lets the compiler emit bare UTCHMMA instead of a per-lane serialisation loop); one elected lane issues.
+    uint32_t gs = 0;
+    int64_t gstep = -1;  // global step counter; the epilogue barriers complete once per step
+    int it = 0;
+    const uint32_t emb_hi = smem_u32(smem + kSmemEmb);
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int b = it & 1;
+      const uint32_t dir_hi = smem_u32(smem + kSmemDir + b * 2 * kDirPartBytes);
+      for (int si = 0; si < n_stages; ++si, ++gs) {
+        const StageDesc sd = prog->st[si];
+        const bool rec = p.dbg != nullptr && blockIdx.x == 0 && it == 2 && lane == 0;
+        if (rec) p.dbg[si * 5 + 0] = clock64();
+        if (sd.flags & F_WAIT_E0) {
+          ++gstep;
+          if (gstep > 0) mbar_wait(bar_e_done, (uint32_t)((gstep - 1) & 1));
+        }
+        if ((sd.flags & F_WAIT_E1) && gstep > 0) mbar_wait(bar_e_done + 8, (uint32_t)((gstep - 1) & 1));
+        if (sd.flags & F_WAIT_EMB) mbar_wait(bar_emb_full, (uint32_t)(it & 1));
+        if (sd.flags & F_WAIT_DIR) mbar_wait(bar_dir_full + 8 * b, (uint32_t)((it >> 1) & 1));
+        const uint32_t slot = gs % kRing, ph = (gs / kRing) & 1;
+        mbar_wait(bar_full + 8 * slot, ph);
+        tc_fence_after();
+        if (rec) p.dbg[si * 5 + 1] = clock64();
+        const uint32_t idesc = make_idesc_f32acc(kTileM, sd.n, FMT);
+        const uint32_t b_lbo = (uint32_t)sd.n * 16u;
+        const uint32_t sb = smem_u32(smem + kSmemRing + slot * kStageBytes);
+        const uint32_t d_tmem = tmem + sd.acc_col;
+        const uint32_t acc0 = (sd.flags & F_FIRST) ? 0u : 1u;
+        // descriptors of K16 step 0; step ks adds ks * (2 * lbo >> 4) to the 14-bit address field
+        const uint64_t bdesc0 = make_smem_desc_noswz(sb, b_lbo, 128);
+        const uint32_t b_inc = (2u * b_lbo) >> 4;
+        const uint32_t a_base = (sd.a_kind == A_EMB) ? emb_hi : dir_hi;
+        const uint32_t a_lo_delta = (sd.a_kind == A_EMB) ? (uint32_t)kEmbPartBytes : (uint32_t)kDirPartBytes;
+        const uint64_t adesc0 = make_smem_desc_noswz(a_base, kTileM * 16, 128);
+        const uint64_t adesc0_lo = make_smem_desc_noswz(a_base + a_lo_delta, kTileM * 16, 128);
+        constexpr uint32_t a_inc = (2u * kTileM * 16u) >> 4;
+        if (elect_one()) {
+          const bool rec2 = p.dbg != nullptr && blockIdx.x == 0 && it == 2;
+          if (rec2) p.dbg[2048 + si * 6 + 0] = clock64();
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            if (rec2) p.dbg[2048 + si * 6 + 1 + ks] = clock64();
+            if (ks < sd.ksteps) {
+              const uint64_t bdesc = bdesc0 + (uint64_t)(ks * b_inc);
+              const uint32_t accum = (ks == 0) ? acc0 : 1u;
+              if (sd.a_kind == A_TMEM) {
+                const uint32_t a_hi = tmem + sd.a_off + ks * 8;
+                if (!sd.is_lo) {
+                  mma_ts(d_tmem, a_hi, bdesc, idesc, accum);
+                  if (PASSES == 3) mma_ts(d_tmem, tmem + sd.a_lo_off + ks * 8, bdesc, idesc, 1);
+                } else {
+                  mma_ts(d_tmem, a_hi, bdesc, idesc, 1);
+                }
               } else {
-                mma_ts(d_tmem, a_hi, bdesc, idesc, 1);
-              }
-            } else {
-              const uint32_t base = (sd.a_kind == A_EMB) ? emb_hi : dir_hi;
-              const uint32_t lo_delta = (sd.a_kind == A_EMB) ? kEmbPartBytes : kDirPartBytes;
-              const uint32_t a_addr = base + ks * 2 * (kTileM * 16);
-              const uint64_t adesc_hi = make_smem_desc_noswz(a_addr, kTileM * 16, 128);
-              if (!sd.is_lo) {
-                mma_ss(d_tmem, adesc_hi, bdesc, idesc, accum);
-                accum = 1;
-                if (PASSES == 3)
-                  mma_ss(d_tmem, make_smem_desc_noswz(a_addr + lo_delta, kTileM * 16, 128), bdesc, idesc, 1);
-              } else {
-                mma_ss(d_tmem, adesc_hi, bdesc, idesc, 1);
+                const uint64_t adesc_hi = adesc0 + (uint64_t)(ks * a_inc);
+                if (!sd.is_lo) {
+                  mma_ss(d_tmem, adesc_hi, bdesc, idesc, accum);
+                  if (PASSES == 3) mma_ss(d_tmem, adesc0_lo + (uint64_t)(ks * a_inc), bdesc, idesc, 1);
+                } else {
+                  mma_ss(d_tmem, adesc_hi, bdesc, idesc, 1);
+                }
               }
             }
           }
+          if (p.dbg != nullptr && blockIdx.x == 0 && it == 2) p.dbg[si * 5 + 2] = clock64();
           tc_commit(bar_empty + 8 * slot);
           if (sd.flags & F_RELEASE_EMB) tc_commit(bar_emb_empty);
           if (sd.flags & F_RELEASE_DIR) tc_commit(bar_dir_empty + 8 * b);
-          if (sd.flags & F_COMMIT_ACC) tc_commit(bar_acc_full);
+          if (sd.flags & F_COMMIT_WAR) tc_commit(bar_war);
+          if (sd.flags & F_COMMIT_ACC0) tc_commit(bar_acc_full);
+          if (sd.flags & F_COMMIT_ACC1) tc_commit(bar_acc_full + 8);
+          if (p.dbg != nullptr && blockIdx.x == 0 && it == 2) p.dbg[si * 5 + 3] = clock64();
         }
+        __syncwarp();
+        if (rec) p.dbg[si * 5 + 4] = clock64();
       }
     }
   }

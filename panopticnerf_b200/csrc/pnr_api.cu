@@ -91,12 +91,16 @@ struct Builder {
     return off;
   }
 
-  void pack_stage(const Mat& m, int n_pad, int col0, int kvalid, int k0, int kcores, int part) {
+  // Stage image of rows [row0, row0 + n_rows) x K [k0, k0 + 8*kcores): no-swizzle K-major core matrices,
+  // byte offset of element (n, k) = ((k/8) * n_rows + n) * 16 + (k%8) * 2  (LBO = n_rows*16, SBO = 128).
+  void pack_stage(const Mat& m, int row0, int n_rows, int col0, int kvalid, int k0, int kcores, int part) {
     const size_t base = wbuf.size();
+    const int n_pad = n_rows;
     wbuf.resize(base + (size_t)n_pad * kcores * 8);
     for (int kc = 0; kc < kcores; ++kc)
-      for (int n = 0; n < n_pad; ++n)
+      for (int nn = 0; nn < n_pad; ++nn)
         for (int e = 0; e < 8; ++e) {
+          const int n = row0 + nn;
           const int k = k0 + kc * 8 + e;
           const float w = (n < m.out && k < kvalid) ? m.w[(size_t)n * m.in + col0 + k] : 0.f;
           uint16_t v;
@@ -107,47 +111,122 @@ struct Builder {
             const uint16_t h = f2h(w);
             v = part == 0 ? h : f2h(w - h2f(h));
           }
-          wbuf[base + ((size_t)kc * n_pad + n) * 8 + e] = v;
+          wbuf[base + ((size_t)kc * n_pad + nn) * 8 + e] = v;
         }
   }
 
+  struct StepInfo { int first_stage, n_stages, n0_stage; };  // n0_stage = first stage of h1 (or end)
+  std::vector<StepInfo> steps;
+
   // One GEMM step: acc[:, acc_col:acc_col+n_pad) = sum_seg A_seg * W_seg^T, then epilogue `ed`.
+  // Issued as two N-halves (rows [0,n0) then [n0,n_pad)) when n_pad >= 64, each its own stage list.
   bool add_step(std::vector<Seg> segs, int n_pad, int acc_col, EpiDesc ed, bool first_of_tile) {
     if (prog.n_steps >= kMaxSteps) { err = "too many steps"; return false; }
-    const int first_stage = prog.n_stages;
-    for (size_t si = 0; si < segs.size(); ++si) {
-      const Seg& sg = segs[si];
-      for (int k0 = 0; k0 < sg.kpad; k0 += 64) {
-        const int kcores = ((sg.kpad - k0) < 64 ? (sg.kpad - k0) : 64) / 8;
-        for (int part = 0; part < (passes == 3 ? 2 : 1); ++part) {
-          if (prog.n_stages >= kMaxStages) { err = "too many stages"; return false; }
-          StageDesc& sd = prog.st[prog.n_stages++];
-          sd.gofs = (uint32_t)(wbuf.size() * 2);
-          sd.bytes = (uint32_t)(n_pad * kcores * 16);
-          sd.n = (uint16_t)n_pad;
-          sd.acc_col = (uint16_t)acc_col;
-          sd.a_off = (uint16_t)(sg.a_hi + k0 / 2);
-          sd.a_lo_off = (uint16_t)(sg.a_lo + k0 / 2);
-          sd.ksteps = (uint8_t)(kcores / 2);
-          sd.is_lo = (uint8_t)part;
-          sd.a_kind = sg.kind;
-          sd.flags = 0;
-          const bool seg_first = (k0 == 0 && part == 0);
-          const bool seg_last = (k0 + 64 >= sg.kpad) && (part == (passes == 3 ? 1 : 0));
-          if (sg.kind == A_EMB && seg_first && first_of_tile) sd.flags |= F_WAIT_EMB;
-          if (sg.kind == A_EMB && seg_last && sg.release) sd.flags |= F_RELEASE_EMB;
-          if (sg.kind == A_DIR && seg_first) sd.flags |= F_WAIT_DIR;
-          if (sg.kind == A_DIR && seg_last && sg.release) sd.flags |= F_RELEASE_DIR;
-          pack_stage(sg.m, n_pad, sg.col0, sg.kvalid, k0, kcores, part);
+    const int n0 = n_pad >= 64 ? n_pad / 2 : n_pad;
+    const int halves = n0 < n_pad ? 2 : 1;
+    StepInfo info{prog.n_stages, 0, 0};
+    bool emb_waited = false;
+    for (int h = 0; h < halves; ++h) {
+      const int r0 = h == 0 ? 0 : n0, r1 = h == 0 ? n0 : n_pad;
+      const int half_first = prog.n_stages;
+      if (h == 1) info.n0_stage = prog.n_stages;
+      for (size_t si = 0; si < segs.size(); ++si) {
+        const Seg& sg = segs[si];
+        for (int k0 = 0; k0 < sg.kpad; k0 += 64) {
+          const int kcores = ((sg.kpad - k0) < 64 ? (sg.kpad - k0) : 64) / 8;
+          for (int part = 0; part < (passes == 3 ? 2 : 1); ++part) {
+            if (prog.n_stages >= kMaxStages) { err = "too many stages"; return false; }
+            StageDesc& sd = prog.st[prog.n_stages++];
+            memset(&sd, 0, sizeof(sd));
+            sd.gofs = (uint32_t)(wbuf.size() * 2);
+            sd.bytes = (uint32_t)((r1 - r0) * kcores * 16);
+            sd.n = (uint16_t)(r1 - r0);
+            sd.acc_col = (uint16_t)(acc_col + r0);
+            sd.a_off = (uint16_t)(sg.a_hi + k0 / 2);
+            sd.a_lo_off = (uint16_t)(sg.a_lo + k0 / 2);
+            sd.ksteps = (uint8_t)(kcores / 2);
+            sd.is_lo = (uint8_t)part;
+            sd.a_kind = sg.kind;
+            const bool seg_first = (k0 == 0 && part == 0);
+            const bool seg_last = (k0 + 64 >= sg.kpad) && (part == (passes == 3 ? 1 : 0));
+            const bool last_half = h == halves - 1;
+            if (sg.kind == A_EMB && seg_first && first_of_tile && !emb_waited) { sd.flags |= F_WAIT_EMB; emb_waited = true; }
+            if (sg.kind == A_EMB && seg_last && sg.release && last_half) sd.flags |= F_RELEASE_EMB;
+            if (sg.kind == A_DIR && seg_first && h == 0) sd.flags |= F_WAIT_DIR;
+            if (sg.kind == A_DIR && seg_last && sg.release && last_half) sd.flags |= F_RELEASE_DIR;
+            pack_stage(sg.m, r0, r1 - r0, sg.col0, sg.kvalid, k0, kcores, part);
+          }
         }
       }
+      prog.st[half_first].flags |= F_FIRST;
+      prog.st[prog.n_stages - 1].flags |= (h == 0 ? F_COMMIT_ACC0 : F_COMMIT_ACC1);
     }
-    prog.st[first_stage].flags |= F_FIRST | F_WAIT_A;
-    prog.st[prog.n_stages - 1].flags |= F_COMMIT_ACC;
+    if (halves == 1) {
+      prog.st[prog.n_stages - 1].flags |= F_COMMIT_ACC1;
+      info.n0_stage = prog.n_stages;
+    }
+    prog.st[info.first_stage].flags |= F_WAIT_E0;
+    info.n_stages = prog.n_stages - info.first_stage;
+    steps.push_back(info);
     ed.n = (uint16_t)n_pad;
+    ed.n0 = (uint16_t)n0;
     ed.acc_col = (uint16_t)acc_col;
     prog.ep[prog.n_steps++] = ed;
     return true;
+  }
+
+  static bool overlap(int a0, int a1, int b0, int b1) { return a0 < a1 && b0 < b1 && a0 < b1 && b0 < a1; }
+
+  // Tensor-memory footprints (column intervals) used to place the cross-step hazard flags.
+  struct Foot { int acc0, acc1, hi0, hi1, lo0, lo1; };
+  Foot e1_foot(int s) const {   // what E1 of step s reads (acc) and writes (activation columns)
+    const EpiDesc& e = prog.ep[s];
+    Foot f{e.acc_col + e.n0, e.acc_col + e.n, 0, 0, 0, 0};
+    if ((e.kind == EPI_RELU_TO_A || e.kind == EPI_LINEAR_TO_A) && e.n0 < e.n) {
+      f.hi0 = e.dst_col + e.n0 / 2; f.hi1 = e.dst_col + e.n / 2;
+      if (passes == 3) { f.lo0 = e.dst_lo_col + e.n0 / 2; f.lo1 = e.dst_lo_col + e.n / 2; }
+    }
+    return f;
+  }
+  bool stage_touches(const StageDesc& sd, const Foot& f) const {
+    const int a0 = sd.acc_col, a1 = sd.acc_col + sd.n;   // accumulator columns this stage writes
+    if (overlap(a0, a1, f.acc0, f.acc1) || overlap(a0, a1, f.hi0, f.hi1) || overlap(a0, a1, f.lo0, f.lo1)) return true;
+    if (sd.a_kind == A_TMEM) {
+      const int h0 = sd.a_off, h1 = sd.a_off + sd.ksteps * 8;
+      if (overlap(h0, h1, f.hi0, f.hi1) || overlap(h0, h1, f.acc0, f.acc1)) return true;
+      if (passes == 3) {
+        const int l0 = sd.a_lo_off, l1 = sd.a_lo_off + sd.ksteps * 8;
+        if (overlap(l0, l1, f.lo0, f.lo1) || overlap(l0, l1, f.acc0, f.acc1)) return true;
+      }
+    }
+    return false;
+  }
+
+  // Place F_WAIT_E1 (against the previous step, cyclically: the first step of a tile follows the last
+  // step of the previous tile) and F_COMMIT_WAR (against this step's own E0 destination).
+  void finalize() {
+    const int S = prog.n_steps;
+    for (int s = 0; s < S; ++s) {
+      const StepInfo& in = steps[s];
+      const Foot prev = e1_foot((s + S - 1) % S);
+      int at = -1;
+      for (int i = in.first_stage; i < in.first_stage + in.n_stages && at < 0; ++i)
+        if (stage_touches(prog.st[i], prev)) at = i;
+      const bool split = in.n0_stage < in.first_stage + in.n_stages;
+      if (at < 0) at = split ? in.n0_stage : in.first_stage;
+      else if (split && at > in.n0_stage) at = in.n0_stage;   // never later than the first stage of h1
+      prog.st[at].flags |= F_WAIT_E1;
+      // E0 of this step overwrites dst columns [dst, dst + n0/2) (hi and lo): last stage reading them
+      const EpiDesc& e = prog.ep[s];
+      int war = in.first_stage;
+      if (e.kind == EPI_RELU_TO_A || e.kind == EPI_LINEAR_TO_A) {
+        Foot f{0, 0, e.dst_col, e.dst_col + e.n0 / 2, 0, 0};
+        if (passes == 3) { f.lo0 = e.dst_lo_col; f.lo1 = e.dst_lo_col + e.n0 / 2; }
+        for (int i = in.first_stage; i < in.first_stage + in.n_stages; ++i)
+          if (stage_touches(prog.st[i], f)) war = i;
+      }
+      prog.st[war].flags |= F_COMMIT_WAR;
+    }
   }
 };
 
@@ -313,6 +392,7 @@ extern "C" int pnr_load_weights(pnr_ctx* ctx, const float* const* t, const int64
   if ((int)bld.consts.size() > kMaxConsts)
     return set_error(PNR_ERR_UNSUPPORTED, "pnr_load_weights: %d constants > %d", (int)bld.consts.size(), kMaxConsts);
   bld.prog.n_consts = (int)bld.consts.size();
+  bld.finalize();
 
   PNR_CUDA(cudaSetDevice(c.device));
   cudaFree(ctx->d_prog); cudaFree(ctx->d_wpacked); cudaFree(ctx->d_consts);
@@ -328,8 +408,21 @@ extern "C" int pnr_load_weights(pnr_ctx* ctx, const float* const* t, const int64
   return PNR_OK;
 }
 
+static int mlp_forward_impl(pnr_ctx* ctx, const float* pts, const float* viewdirs, const float* rays,
+                            const float* z, int64_t R, int32_t N, float* raw, void* stream, long long* dbg);
+
 extern "C" int pnr_mlp_forward(pnr_ctx* ctx, const float* pts, const float* viewdirs, const float* rays,
                                const float* z, int64_t R, int32_t N, float* raw, void* stream) {
+  return mlp_forward_impl(ctx, pts, viewdirs, rays, z, R, N, raw, stream, nullptr);
+}
+
+extern "C" int pnr_mlp_forward_timeline(pnr_ctx* ctx, const float* rays, const float* z, int64_t R, int32_t N,
+                                        float* raw, int64_t* timeline, void* stream) {
+  return mlp_forward_impl(ctx, nullptr, nullptr, rays, z, R, N, raw, stream, (long long*)timeline);
+}
+
+static int mlp_forward_impl(pnr_ctx* ctx, const float* pts, const float* viewdirs, const float* rays,
+                            const float* z, int64_t R, int32_t N, float* raw, void* stream, long long* dbg) {
   if (R == 0) return PNR_OK;
   PNR_CHECK_ARG(ctx && raw, "pnr_mlp_forward: null pointer");
   if (!ctx->loaded) return set_error(PNR_ERR_STATE, "pnr_mlp_forward: pnr_load_weights has not been called");
@@ -343,6 +436,7 @@ extern "C" int pnr_mlp_forward(pnr_ctx* ctx, const float* pts, const float* view
   p.pts = pts; p.viewdirs = viewdirs; p.rays = rays; p.z = z;
   p.S = S; p.N = N; p.CH = 4 + ctx->cfg.num_classes + ctx->cfg.num_instances; p.raw = raw;
   p.num_tiles = (int32_t)((S + kTileM - 1) / kTileM);
+  p.dbg = dbg;
   return launch_mlp(p, ctx->passes, ctx->fmt, (cudaStream_t)stream);
 }
 
