@@ -5,15 +5,17 @@
 // feature layer, view branch).  Every step is issued as two N-HALVES (h0, h1) with separate accumulator
 // column ranges, so that the epilogue of h0 (E0) overlaps the MMAs of h1, and the epilogue of h1 (E1)
 // overlaps the first K-chunks of the next step's h0 (which only need what E0 wrote).  Each half is a
-// list of weight STAGES (<= 16 KB: up to 128 rows x 64 K of one 16-bit part), streamed by TMA.
+// list of weight STAGES (<= 32 KB: up to 128 rows x 64 K, hi image then lo image), streamed by TMA.
+// The program lives in __constant__ memory so the single MMA-issuing thread reads it through the uniform
+// datapath (no register->uniform moves on the issue path).
 #pragma once
 #include <stdint.h>
 
 namespace pnr {
 
 constexpr int kTileM = 128;               // samples per tile = TMEM lanes = UMMA M
-constexpr int kRing = 8;                  // weight stages in flight
-constexpr int kStageBytes = 16384;        // max stage: N=128 rows x 64 K x 2 bytes
+constexpr int kRing = 4;                  // weight stages in flight
+constexpr int kStageBytes = 32768;        // max stage: N=128 rows x 64 K x 2 bytes x (hi + lo images)
 constexpr int kEpiWarps = 8;              // TMEM->reg->TMEM activation warps (2 per lane quarter)
 constexpr int kProWarps = 4;              // positional-encoding producer warps (one thread per row)
 constexpr int kMlpThreads = (kEpiWarps + kProWarps + 2) * 32;   // + TMA warp + MMA warp = 448
@@ -56,10 +58,9 @@ struct StageDesc {     // one weight stage = one bulk copy + its MMAs
   uint16_t a_off;      // A_TMEM: packed column of the first K16 step (hi part)
   uint16_t a_lo_off;   //         and of the lo part
   uint16_t flags;
+  uint16_t lo_off16;   // offset of the lo image inside the stage, in 16-byte units (x3 modes)
   uint8_t ksteps;      // K16 steps covered by this stage
-  uint8_t is_lo;       // weight part: 0 = hi, 1 = lo residual
   uint8_t a_kind;
-  uint8_t pad[3];
 };
 
 struct EpiDesc {
@@ -102,7 +103,7 @@ struct MlpParams {
   long long* dbg;         // optional clock64 timeline of block 0 (development aid), else null
 };
 
-constexpr int kSmemConsts = (kSmemProg + (int)sizeof(MlpProgram) + 15) / 16 * 16;
+constexpr int kSmemConsts = kSmemProg;   // (the program itself is in __constant__ memory)
 constexpr int kSmemPart = kSmemConsts + kMaxConsts * 4;      // [2][128][4] floats
 constexpr int kSmemBars = kSmemPart + 2 * kTileM * 4 * 4;
 constexpr int kSmemTotal = kSmemBars + 256;

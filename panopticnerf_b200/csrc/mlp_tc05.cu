@@ -30,6 +30,8 @@
 
 namespace pnr {
 
+__constant__ MlpProgram c_prog;   // the program of the context being launched (uploaded when it changes)
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -140,7 +142,6 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpPara
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  MlpProgram* prog = reinterpret_cast<MlpProgram*>(smem + kSmemProg);
   float* consts = reinterpret_cast<float*>(smem + kSmemConsts);
   float* part = reinterpret_cast<float*>(smem + kSmemPart);  // [2][128][4]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBars);
@@ -156,18 +157,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpPara
   const uint32_t bar_dir_full = smem_u32(&bars[2 * kRing + 7]);   // [2]
   const uint32_t bar_dir_empty = smem_u32(&bars[2 * kRing + 9]);  // [2]
 
-  // ---- one-time setup: program + constants to shared memory, barriers, tensor memory
-  {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(p.prog);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(prog);
-    const int nst = p.prog->n_stages;
-    const int head_words = (int)((offsetof(MlpProgram, st) + sizeof(StageDesc) * nst + 3) / 4);
-    for (int i = threadIdx.x; i < head_words; i += blockDim.x) dst[i] = src[i];
-    const int ep0 = (int)(offsetof(MlpProgram, ep) / 4), ep1 = (int)(sizeof(MlpProgram) / 4);
-    for (int i = ep0 + threadIdx.x; i < ep1; i += blockDim.x) dst[i] = src[i];
-    const int nc = p.prog->n_consts;
-    for (int i = threadIdx.x; i < nc; i += blockDim.x) consts[i] = p.consts[i];
-  }
+  // ---- one-time setup: constants to shared memory, barriers, tensor memory
+  for (int i = threadIdx.x; i < c_prog.n_consts; i += blockDim.x) consts[i] = p.consts[i];
   if (warp == 0) {
     tmem_alloc<512>(smem_u32(tmem_slot));
     tmem_relinquish();
@@ -192,7 +183,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpPara
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const int n_stages = prog->n_stages, n_steps = prog->n_steps;
+  const int n_stages = c_prog.n_stages, n_steps = c_prog.n_steps;
 
   if (warp < kEpiWarps) {
     // =============================================================== epilogue warps
@@ -207,7 +198,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpPara
       const bool valid = s < p.S;
       float sig = 0.f;
       for (int st = 0; st < n_steps; ++st, ++gstep) {
-        const EpiDesc ed = prog->ep[st];
+        const EpiDesc ed = c_prog.ep[st];
         const uint32_t parity = gstep & 1u;
         cx.parity = parity;
         const float* bias = consts + ed.bias_off;
@@ -219,11 +210,15 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpPara
         float c0 = 0.f, c1 = 0.f, c2 = 0.f;
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
+#ifdef PNR_TIMELINE
           const bool rec = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && tile == 2 * (int)gridDim.x;
           if (rec) p.dbg[4096 + (st * 2 + h) * 3 + 0] = clock64();
+#endif
           mbar_wait(bar_acc_full + 8 * h, parity);
           tc_fence_after();
+#ifdef PNR_TIMELINE
           if (rec) p.dbg[4096 + (st * 2 + h) * 3 + 1] = clock64();
+#endif
           const int gb_all = h == 0 ? 0 : (ed.n0 >> 4);
           const int ge_all = h == 0 ? (ed.n0 >> 4) : (ed.n >> 4);
           const int G = ge_all - gb_all;
@@ -271,11 +266,11 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpPara
               named_bar_sync(1, kEpiWarps * 32);
               if (ch == 0 && valid) {
                 const float* other = part + (kTileM + row) * 4;
-                const float* b3 = consts + prog->rgb_bias_off;
+                const float* b3 = consts + c_prog.rgb_bias_off;
                 const float o0 = c0 + other[0] + b3[0];
                 const float o1 = c1 + other[1] + b3[1];
                 const float o2 = c2 + other[2] + b3[2];
-                const float o3 = mine[3] + other[3] + consts[prog->sigma_bias_off];
+                const float o3 = mine[3] + other[3] + consts[c_prog.sigma_bias_off];
                 float* dst = p.raw + s * p.CH;
                 if (p.CH == 4) {
                   *reinterpret_cast<float4*>(dst) = make_float4(o0, o1, o2, o3);
@@ -288,7 +283,9 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpPara
           if (to_a) tc_wait_st();
           tc_fence_before();
           mbar_arrive(bar_e_done + 8 * h);
+#ifdef PNR_TIMELINE
           if (rec) p.dbg[4096 + (st * 2 + h) * 3 + 2] = clock64();
+#endif
         }
       }
     }
@@ -297,7 +294,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpPara
     const int row = (warp - kEpiWarps) * 32 + lane;
     uint8_t* emb_hi = smem + kSmemEmb;
     uint8_t* emb_lo = emb_hi + kEmbPartBytes;
-    const int Lx = prog->Lx, Ld = prog->Ld;
+    const int Lx = c_prog.Lx, Ld = c_prog.Ld;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       int64_t s = (int64_t)tile * kTileM + row;
@@ -334,15 +331,17 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpPara
       mbar_arrive(bar_dir_full + 8 * b);
     }
   } else if (warp == kEpiWarps + kProWarps) {
-    // =============================================================== TMA producer (one lane)
-    if (lane == 0) {
+    // =============================================================== TMA producer (one elected thread)
+    if (elect_one()) {
       uint32_t gs = 0;  // global stage counter
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         for (int si = 0; si < n_stages; ++si, ++gs) {
           const uint32_t slot = gs % kRing, ph = (gs / kRing) & 1;
-          const uint32_t gofs = prog->st[si].gofs, bytes = prog->st[si].bytes;
+          const uint32_t gofs = c_prog.st[si].gofs, bytes = c_prog.st[si].bytes;
           mbar_wait(bar_empty + 8 * slot, ph ^ 1);
+#ifdef PNR_TIMELINE
           if (p.dbg != nullptr && blockIdx.x == 0 && tile == 2 * (int)gridDim.x) p.dbg[6144 + si] = clock64();
+#endif
           mbar_arrive_expect_tx(bar_full + 8 * slot, bytes);
           bulk_g2s(smem_u32(smem + kSmemRing + slot * kStageBytes), p.wpacked + gofs, bytes,
                    bar_full + 8 * slot);
@@ -350,83 +349,95 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpPara
       }
     }
   } else {
-    // =============================================================== MMA issuer warp
-    // All 32 lanes walk the stage list (warp-uniform control flow keeps descriptors in uniform registers and
-    // lets the compiler emit bare UTCHMMA instead of a per-lane serialisation loop); one elected lane issues.
-    uint32_t gs = 0;
-    int64_t gstep = -1;  // global step counter; the epilogue barriers complete once per step
-    int it = 0;
-    const uint32_t emb_hi = smem_u32(smem + kSmemEmb);
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const int b = it & 1;
-      const uint32_t dir_hi = smem_u32(smem + kSmemDir + b * 2 * kDirPartBytes);
-      for (int si = 0; si < n_stages; ++si, ++gs) {
-        const StageDesc sd = prog->st[si];
-        const bool rec = p.dbg != nullptr && blockIdx.x == 0 && it == 2 && lane == 0;
-        if (rec) p.dbg[si * 5 + 0] = clock64();
-        if (sd.flags & F_WAIT_E0) {
-          ++gstep;
-          if (gstep > 0) mbar_wait(bar_e_done, (uint32_t)((gstep - 1) & 1));
-        }
-        if ((sd.flags & F_WAIT_E1) && gstep > 0) mbar_wait(bar_e_done + 8, (uint32_t)((gstep - 1) & 1));
-        if (sd.flags & F_WAIT_EMB) mbar_wait(bar_emb_full, (uint32_t)(it & 1));
-        if (sd.flags & F_WAIT_DIR) mbar_wait(bar_dir_full + 8 * b, (uint32_t)((it >> 1) & 1));
-        const uint32_t slot = gs % kRing, ph = (gs / kRing) & 1;
-        mbar_wait(bar_full + 8 * slot, ph);
-        tc_fence_after();
-        if (rec) p.dbg[si * 5 + 1] = clock64();
-        const uint32_t idesc = make_idesc_f32acc(kTileM, sd.n, FMT);
-        const uint32_t b_lbo = (uint32_t)sd.n * 16u;
-        const uint32_t sb = smem_u32(smem + kSmemRing + slot * kStageBytes);
-        const uint32_t d_tmem = tmem + sd.acc_col;
-        const uint32_t acc0 = (sd.flags & F_FIRST) ? 0u : 1u;
-        // descriptors of K16 step 0; step ks adds ks * (2 * lbo >> 4) to the 14-bit address field
-        const uint64_t bdesc0 = make_smem_desc_noswz(sb, b_lbo, 128);
-        const uint32_t b_inc = (2u * b_lbo) >> 4;
-        const uint32_t a_base = (sd.a_kind == A_EMB) ? emb_hi : dir_hi;
-        const uint32_t a_lo_delta = (sd.a_kind == A_EMB) ? (uint32_t)kEmbPartBytes : (uint32_t)kDirPartBytes;
-        const uint64_t adesc0 = make_smem_desc_noswz(a_base, kTileM * 16, 128);
-        const uint64_t adesc0_lo = make_smem_desc_noswz(a_base + a_lo_delta, kTileM * 16, 128);
-        constexpr uint32_t a_inc = (2u * kTileM * 16u) >> 4;
-        if (elect_one()) {
-          const bool rec2 = p.dbg != nullptr && blockIdx.x == 0 && it == 2;
-          if (rec2) p.dbg[2048 + si * 6 + 0] = clock64();
+    // =============================================================== MMA issuer
+    // One elected thread walks the stage list.  Everything it needs comes from __constant__ memory or is
+    // derived from uniform values, so descriptors are built on the uniform datapath.
+    if (elect_one()) {
+      uint32_t gs = 0;
+      int64_t gstep = -1;  // global step counter; the epilogue barriers complete once per step
+      int it = 0;
+      const uint32_t emb_hi = smem_u32(smem + kSmemEmb);
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int b = it & 1;
+        const uint32_t dir_hi = smem_u32(smem + kSmemDir + b * 2 * kDirPartBytes);
+#pragma unroll 1
+        for (int si = 0; si < n_stages; ++si, ++gs) {
+          const uint32_t flags = c_prog.st[si].flags;
+          const uint32_t n = c_prog.st[si].n;
+          const uint32_t ksteps = c_prog.st[si].ksteps;
+          const uint32_t a_kind = c_prog.st[si].a_kind;
+#ifdef PNR_TIMELINE
+          const bool rec = p.dbg != nullptr && blockIdx.x == 0 && it == 2;
+          if (rec) p.dbg[si * 5 + 0] = clock64();
+#endif
+          if (flags & (F_WAIT_E0 | F_WAIT_E1)) {
+            if (flags & F_WAIT_E0) {
+              ++gstep;
+              if (gstep > 0) mbar_wait(bar_e_done, (uint32_t)((gstep - 1) & 1));
+            }
+            if ((flags & F_WAIT_E1) && gstep > 0) mbar_wait(bar_e_done + 8, (uint32_t)((gstep - 1) & 1));
+            tc_fence_after();   // order our MMAs after the epilogue's tcgen05.ld / tcgen05.st
+          }
+          if (flags & F_WAIT_EMB) mbar_wait(bar_emb_full, (uint32_t)(it & 1));
+          if (flags & F_WAIT_DIR) mbar_wait(bar_dir_full + 8 * b, (uint32_t)((it >> 1) & 1));
+          const uint32_t slot = gs % kRing, ph = (gs / kRing) & 1;
+          mbar_wait(bar_full + 8 * slot, ph);
+#ifdef PNR_TIMELINE
+          if (rec) p.dbg[si * 5 + 1] = clock64();
+#endif
+          const uint32_t idesc = make_idesc_f32acc(kTileM, n, FMT);
+          const uint32_t b_lbo = n * 16u;
+          const uint32_t sb = smem_u32(smem + kSmemRing + slot * kStageBytes);
+          const uint32_t d_tmem = tmem + c_prog.st[si].acc_col;
+          const uint32_t acc0 = (flags & F_FIRST) ? 0u : 1u;
+          // descriptors of K16 step 0; step ks adds ks * (2 * lbo >> 4) to the 14-bit address field
+          const uint64_t bdesc0 = make_smem_desc_noswz(sb, b_lbo, 128);
+          const uint64_t bdesc0_lo = bdesc0 + (uint64_t)c_prog.st[si].lo_off16;
+          const uint32_t b_inc = (2u * b_lbo) >> 4;
+          if (a_kind == A_TMEM) {
+            const uint32_t a_hi = tmem + c_prog.st[si].a_off, a_lo = tmem + c_prog.st[si].a_lo_off;
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            if (rec2) p.dbg[2048 + si * 6 + 1 + ks] = clock64();
-            if (ks < sd.ksteps) {
-              const uint64_t bdesc = bdesc0 + (uint64_t)(ks * b_inc);
-              const uint32_t accum = (ks == 0) ? acc0 : 1u;
-              if (sd.a_kind == A_TMEM) {
-                const uint32_t a_hi = tmem + sd.a_off + ks * 8;
-                if (!sd.is_lo) {
-                  mma_ts(d_tmem, a_hi, bdesc, idesc, accum);
-                  if (PASSES == 3) mma_ts(d_tmem, tmem + sd.a_lo_off + ks * 8, bdesc, idesc, 1);
-                } else {
-                  mma_ts(d_tmem, a_hi, bdesc, idesc, 1);
+            for (uint32_t ks = 0; ks < 4; ++ks) {
+              if (ks < ksteps) {
+                mma_ts(d_tmem, a_hi + ks * 8, bdesc0 + (uint64_t)(ks * b_inc), idesc, ks == 0 ? acc0 : 1u);
+                if (PASSES == 3) {
+                  mma_ts(d_tmem, a_lo + ks * 8, bdesc0 + (uint64_t)(ks * b_inc), idesc, 1u);
+                  mma_ts(d_tmem, a_hi + ks * 8, bdesc0_lo + (uint64_t)(ks * b_inc), idesc, 1u);
                 }
-              } else {
-                const uint64_t adesc_hi = adesc0 + (uint64_t)(ks * a_inc);
-                if (!sd.is_lo) {
-                  mma_ss(d_tmem, adesc_hi, bdesc, idesc, accum);
-                  if (PASSES == 3) mma_ss(d_tmem, adesc0_lo + (uint64_t)(ks * a_inc), bdesc, idesc, 1);
-                } else {
-                  mma_ss(d_tmem, adesc_hi, bdesc, idesc, 1);
+              }
+            }
+          } else {
+            const uint32_t a_base = (a_kind == A_EMB) ? emb_hi : dir_hi;
+            const uint32_t a_lo_delta = (a_kind == A_EMB) ? (uint32_t)kEmbPartBytes : (uint32_t)kDirPartBytes;
+            const uint64_t adesc0 = make_smem_desc_noswz(a_base, kTileM * 16, 128);
+            const uint64_t adesc0_lo = make_smem_desc_noswz(a_base + a_lo_delta, kTileM * 16, 128);
+            constexpr uint32_t a_inc = (2u * kTileM * 16u) >> 4;
+#pragma unroll
+            for (uint32_t ks = 0; ks < 4; ++ks) {
+              if (ks < ksteps) {
+                mma_ss(d_tmem, adesc0 + (uint64_t)(ks * a_inc), bdesc0 + (uint64_t)(ks * b_inc), idesc, ks == 0 ? acc0 : 1u);
+                if (PASSES == 3) {
+                  mma_ss(d_tmem, adesc0_lo + (uint64_t)(ks * a_inc), bdesc0 + (uint64_t)(ks * b_inc), idesc, 1u);
+                  mma_ss(d_tmem, adesc0 + (uint64_t)(ks * a_inc), bdesc0_lo + (uint64_t)(ks * b_inc), idesc, 1u);
                 }
               }
             }
           }
-          if (p.dbg != nullptr && blockIdx.x == 0 && it == 2) p.dbg[si * 5 + 2] = clock64();
+#ifdef PNR_TIMELINE
+          if (rec) p.dbg[si * 5 + 2] = clock64();
+#endif
           tc_commit(bar_empty + 8 * slot);
-          if (sd.flags & F_RELEASE_EMB) tc_commit(bar_emb_empty);
-          if (sd.flags & F_RELEASE_DIR) tc_commit(bar_dir_empty + 8 * b);
-          if (sd.flags & F_COMMIT_WAR) tc_commit(bar_war);
-          if (sd.flags & F_COMMIT_ACC0) tc_commit(bar_acc_full);
-          if (sd.flags & F_COMMIT_ACC1) tc_commit(bar_acc_full + 8);
-          if (p.dbg != nullptr && blockIdx.x == 0 && it == 2) p.dbg[si * 5 + 3] = clock64();
+          if (flags & (F_RELEASE_EMB | F_RELEASE_DIR | F_COMMIT_WAR | F_COMMIT_ACC0 | F_COMMIT_ACC1)) {
+            if (flags & F_RELEASE_EMB) tc_commit(bar_emb_empty);
+            if (flags & F_RELEASE_DIR) tc_commit(bar_dir_empty + 8 * b);
+            if (flags & F_COMMIT_WAR) tc_commit(bar_war);
+            if (flags & F_COMMIT_ACC0) tc_commit(bar_acc_full);
+            if (flags & F_COMMIT_ACC1) tc_commit(bar_acc_full + 8);
+          }
+#ifdef PNR_TIMELINE
+          if (rec) { p.dbg[si * 5 + 3] = clock64(); p.dbg[si * 5 + 4] = p.dbg[si * 5 + 3]; }
+#endif
         }
-        __syncwarp();
-        if (rec) p.dbg[si * 5 + 4] = clock64();
       }
     }
   }
@@ -448,9 +459,19 @@ static int launch_one(const MlpParams& p, int grid, cudaStream_t stream) {
   return PNR_OK;
 }
 
-int launch_mlp(const MlpParams& p, int passes, int fmt, cudaStream_t stream) {
+// `host_prog` / `prog_id`: the context's program; it is copied to __constant__ memory (stream-ordered) only
+// when it differs from the one last uploaded on this device.
+int launch_mlp(const MlpParams& p, const MlpProgram* host_prog, uint64_t prog_id, int passes, int fmt,
+               cudaStream_t stream) {
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   if (grid <= 0) return PNR_OK;
+  static uint64_t loaded_id[64] = {0};
+  int dev = 0;
+  PNR_CUDA(cudaGetDevice(&dev));
+  if (loaded_id[dev & 63] != prog_id) {
+    PNR_CUDA(cudaMemcpyToSymbolAsync(c_prog, host_prog, sizeof(MlpProgram), 0, cudaMemcpyHostToDevice, stream));
+    loaded_id[dev & 63] = prog_id;
+  }
   if (fmt == kFmtF16) return passes == 3 ? launch_one<3, kFmtF16>(p, grid, stream) : launch_one<1, kFmtF16>(p, grid, stream);
   return passes == 3 ? launch_one<3, kFmtBF16>(p, grid, stream) : launch_one<1, kFmtBF16>(p, grid, stream);
 }

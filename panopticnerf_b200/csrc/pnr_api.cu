@@ -22,7 +22,8 @@ int set_error(int code, const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches += n; }
 
-int launch_mlp(const MlpParams& p, int passes, int fmt, cudaStream_t stream);  // mlp_tc05.cu
+int launch_mlp(const MlpParams& p, const MlpProgram* host_prog, uint64_t prog_id, int passes, int fmt,
+               cudaStream_t stream);  // mlp_tc05.cu
 
 }  // namespace pnr
 
@@ -33,7 +34,8 @@ struct pnr_ctx {
   int passes = 3;
   int fmt = 0;   // 0 = fp16, 1 = bf16 (instruction-descriptor encoding)
   bool loaded = false;
-  MlpProgram* d_prog = nullptr;
+  MlpProgram h_prog;            // uploaded to __constant__ memory at launch when it is not the resident one
+  uint64_t prog_id = 0;
   uint8_t* d_wpacked = nullptr;
   float* d_consts = nullptr;
   size_t wpacked_bytes = 0;
@@ -134,27 +136,28 @@ struct Builder {
         const Seg& sg = segs[si];
         for (int k0 = 0; k0 < sg.kpad; k0 += 64) {
           const int kcores = ((sg.kpad - k0) < 64 ? (sg.kpad - k0) : 64) / 8;
-          for (int part = 0; part < (passes == 3 ? 2 : 1); ++part) {
+          {
             if (prog.n_stages >= kMaxStages) { err = "too many stages"; return false; }
+            const int parts = passes == 3 ? 2 : 1;
             StageDesc& sd = prog.st[prog.n_stages++];
             memset(&sd, 0, sizeof(sd));
             sd.gofs = (uint32_t)(wbuf.size() * 2);
-            sd.bytes = (uint32_t)((r1 - r0) * kcores * 16);
+            sd.bytes = (uint32_t)((r1 - r0) * kcores * 16 * parts);
             sd.n = (uint16_t)(r1 - r0);
             sd.acc_col = (uint16_t)(acc_col + r0);
             sd.a_off = (uint16_t)(sg.a_hi + k0 / 2);
             sd.a_lo_off = (uint16_t)(sg.a_lo + k0 / 2);
+            sd.lo_off16 = (uint16_t)((r1 - r0) * kcores);
             sd.ksteps = (uint8_t)(kcores / 2);
-            sd.is_lo = (uint8_t)part;
             sd.a_kind = sg.kind;
-            const bool seg_first = (k0 == 0 && part == 0);
-            const bool seg_last = (k0 + 64 >= sg.kpad) && (part == (passes == 3 ? 1 : 0));
+            const bool seg_first = (k0 == 0);
+            const bool seg_last = (k0 + 64 >= sg.kpad);
             const bool last_half = h == halves - 1;
             if (sg.kind == A_EMB && seg_first && first_of_tile && !emb_waited) { sd.flags |= F_WAIT_EMB; emb_waited = true; }
             if (sg.kind == A_EMB && seg_last && sg.release && last_half) sd.flags |= F_RELEASE_EMB;
             if (sg.kind == A_DIR && seg_first && h == 0) sd.flags |= F_WAIT_DIR;
             if (sg.kind == A_DIR && seg_last && sg.release && last_half) sd.flags |= F_RELEASE_DIR;
-            pack_stage(sg.m, r0, r1 - r0, sg.col0, sg.kvalid, k0, kcores, part);
+            for (int part = 0; part < parts; ++part) pack_stage(sg.m, r0, r1 - r0, sg.col0, sg.kvalid, k0, kcores, part);
           }
         }
       }
@@ -270,7 +273,6 @@ extern "C" int pnr_create(const pnr_config* cfg, pnr_ctx** out) {
 
 extern "C" int pnr_destroy(pnr_ctx* ctx) {
   if (!ctx) return PNR_OK;
-  cudaFree(ctx->d_prog);
   cudaFree(ctx->d_wpacked);
   cudaFree(ctx->d_consts);
   delete ctx;
@@ -395,13 +397,14 @@ extern "C" int pnr_load_weights(pnr_ctx* ctx, const float* const* t, const int64
   bld.finalize();
 
   PNR_CUDA(cudaSetDevice(c.device));
-  cudaFree(ctx->d_prog); cudaFree(ctx->d_wpacked); cudaFree(ctx->d_consts);
-  ctx->d_prog = nullptr; ctx->d_wpacked = nullptr; ctx->d_consts = nullptr;
+  cudaFree(ctx->d_wpacked); cudaFree(ctx->d_consts);
+  ctx->d_wpacked = nullptr; ctx->d_consts = nullptr;
   ctx->wpacked_bytes = bld.wbuf.size() * 2;
-  PNR_CUDA(cudaMalloc(&ctx->d_prog, sizeof(MlpProgram)));
   PNR_CUDA(cudaMalloc(&ctx->d_wpacked, ctx->wpacked_bytes));
   PNR_CUDA(cudaMalloc(&ctx->d_consts, bld.consts.size() * 4));
-  PNR_CUDA(cudaMemcpy(ctx->d_prog, &bld.prog, sizeof(MlpProgram), cudaMemcpyHostToDevice));
+  static uint64_t next_id = 0;
+  ctx->h_prog = bld.prog;
+  ctx->prog_id = ++next_id;
   PNR_CUDA(cudaMemcpy(ctx->d_wpacked, bld.wbuf.data(), ctx->wpacked_bytes, cudaMemcpyHostToDevice));
   PNR_CUDA(cudaMemcpy(ctx->d_consts, bld.consts.data(), bld.consts.size() * 4, cudaMemcpyHostToDevice));
   ctx->loaded = true;
@@ -432,12 +435,12 @@ static int mlp_forward_impl(pnr_ctx* ctx, const float* pts, const float* viewdir
   if (S == 0) return PNR_OK;
   PNR_CHECK_ARG((S + kTileM - 1) / kTileM < (int64_t)1 << 31, "pnr_mlp_forward: too many samples");
   MlpParams p;
-  p.prog = ctx->d_prog; p.wpacked = ctx->d_wpacked; p.consts = ctx->d_consts;
+  p.prog = nullptr; p.wpacked = ctx->d_wpacked; p.consts = ctx->d_consts;
   p.pts = pts; p.viewdirs = viewdirs; p.rays = rays; p.z = z;
   p.S = S; p.N = N; p.CH = 4 + ctx->cfg.num_classes + ctx->cfg.num_instances; p.raw = raw;
   p.num_tiles = (int32_t)((S + kTileM - 1) / kTileM);
   p.dbg = dbg;
-  return launch_mlp(p, ctx->passes, ctx->fmt, (cudaStream_t)stream);
+  return launch_mlp(p, &ctx->h_prog, ctx->prog_id, ctx->passes, ctx->fmt, (cudaStream_t)stream);
 }
 
 extern "C" size_t pnr_workspace_bytes(const pnr_ctx* ctx, int64_t R, int32_t N, int32_t Ni) {
