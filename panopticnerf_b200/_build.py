@@ -16,7 +16,7 @@ CSRC = PKG / "csrc"
 LIB = PKG / "libpnr.so"
 SOURCES = ["pnr_api.cu", "ray_kernels.cu", "stream_kernels.cu", "mlp_tc05.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC"]
+              "-Xcompiler", "-fPIC"] + os.environ.get("PNR_NVCC_FLAGS", "").split()   # e.g. -DPNR_TIMELINE
 
 
 def _nvcc() -> str:

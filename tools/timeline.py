@@ -30,10 +30,6 @@ print(f"precision {prec}: {len(mma)} stages; tile span {mma[-1][4] - t0} cycles"
 print("stage: arrive  ready  issued   (waits=ready-arrive, issue=issued-ready) | tma_issue")
 for i, (a, r, m, c, d) in enumerate(mma):
     print(f"{i:4d} {a - t0:8d}  wait {r - a:5d} mma {m - r:5d} commit {c - m:5d} sync {d - c:5d} | next-gap {(mma[i + 1][0] - d) if i + 1 < len(mma) else 0:5d} | tma {t[6144 + i] - t0:8d}")
-print("per-MMA issue clocks inside the elected branch: enter, before ks0..ks3 (deltas)")
-for i in range(min(len(mma), 40)):
-    q = t[2048 + i * 6:2048 + i * 6 + 5]
-    print(f"{i:4d} enter->ks0 {q[1]-q[0]:5d} ks0->ks1 {q[2]-q[1]:5d} ks1->ks2 {q[3]-q[2]:5d} ks2->ks3 {q[4]-q[3]:5d}  (ready->enter {q[0]-mma[i][1]:5d}; ks3->after_mma {mma[i][2]-q[4]:5d})")
 print("step half: wait_start acc_ready done  (wait, work)")
 for k in range(48):
     w, a, d = t[4096 + k * 3:4096 + k * 3 + 3]
