@@ -231,6 +231,9 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpPara
 #pragma unroll 1
           for (int g = gb; g < ge; g += 2) {
             tc_wait_ld();
+#ifdef PNR_TIMELINE
+            if (rec && h == 1 && g == gb) p.dbg[7168 + st * 4 + 0] = clock64();
+#endif
             if (g + 1 < ge) tmem_ld16(acc + (g + 1) * 16, rb);
             if (to_a) {
               epi_group_to_a<PASSES, FMT>(ra, g, ed, clamp_lo, bias, aux, sig, cx, war_pending);
@@ -239,8 +242,14 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpPara
             } else if (valid) {
               epi_group_logits(ra, g, ed, bias, out_row);
             }
+#ifdef PNR_TIMELINE
+            if (rec && h == 1 && g == gb) p.dbg[7168 + st * 4 + 1] = clock64();
+#endif
             if (g + 1 < ge) {
               tc_wait_ld();
+#ifdef PNR_TIMELINE
+              if (rec && h == 1 && g == gb) p.dbg[7168 + st * 4 + 2] = clock64();
+#endif
               if (g + 2 < ge) tmem_ld16(acc + (g + 2) * 16, ra);
               if (to_a) {
                 epi_group_to_a<PASSES, FMT>(rb, g + 1, ed, clamp_lo, bias, aux, sig, cx, war_pending);
@@ -397,7 +406,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpPara
           if (a_kind == A_TMEM) {
             const uint32_t a_hi = tmem + c_prog.st[si].a_off, a_lo = tmem + c_prog.st[si].a_lo_off;
 #pragma unroll
-            for (uint32_t ks = 0; ks < 4; ++ks) {
+            for (uint32_t ks = 0; ks < (PASSES == 3 ? 4u : 8u); ++ks) {
               if (ks < ksteps) {
                 mma_ts(d_tmem, a_hi + ks * 8, bdesc0 + (uint64_t)(ks * b_inc), idesc, ks == 0 ? acc0 : 1u);
                 if (PASSES == 3) {
@@ -413,7 +422,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpPara
             const uint64_t adesc0_lo = make_smem_desc_noswz(a_base + a_lo_delta, kTileM * 16, 128);
             constexpr uint32_t a_inc = (2u * kTileM * 16u) >> 4;
 #pragma unroll
-            for (uint32_t ks = 0; ks < 4; ++ks) {
+            for (uint32_t ks = 0; ks < (PASSES == 3 ? 4u : 8u); ++ks) {
               if (ks < ksteps) {
                 mma_ss(d_tmem, adesc0 + (uint64_t)(ks * a_inc), bdesc0 + (uint64_t)(ks * b_inc), idesc, ks == 0 ? acc0 : 1u);
                 if (PASSES == 3) {

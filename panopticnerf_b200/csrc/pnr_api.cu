@@ -134,8 +134,10 @@ struct Builder {
       if (h == 1) info.n0_stage = prog.n_stages;
       for (size_t si = 0; si < segs.size(); ++si) {
         const Seg& sg = segs[si];
-        for (int k0 = 0; k0 < sg.kpad; k0 += 64) {
-          const int kcores = ((sg.kpad - k0) < 64 ? (sg.kpad - k0) : 64) / 8;
+        // K per stage: 64 with hi+lo images (x3), 128 with the hi image only (1-pass): <= 32 KB either way
+        const int chunk = passes == 3 ? 64 : 128;
+        for (int k0 = 0; k0 < sg.kpad; k0 += chunk) {
+          const int kcores = ((sg.kpad - k0) < chunk ? (sg.kpad - k0) : chunk) / 8;
           {
             if (prog.n_stages >= kMaxStages) { err = "too many stages"; return false; }
             const int parts = passes == 3 ? 2 : 1;
@@ -151,7 +153,7 @@ struct Builder {
             sd.ksteps = (uint8_t)(kcores / 2);
             sd.a_kind = sg.kind;
             const bool seg_first = (k0 == 0);
-            const bool seg_last = (k0 + 64 >= sg.kpad);
+            const bool seg_last = (k0 + chunk >= sg.kpad);
             const bool last_half = h == halves - 1;
             if (sg.kind == A_EMB && seg_first && first_of_tile && !emb_waited) { sd.flags |= F_WAIT_EMB; emb_waited = true; }
             if (sg.kind == A_EMB && seg_last && sg.release && last_half) sd.flags |= F_RELEASE_EMB;
