@@ -196,7 +196,7 @@ def main():
     def step():
         out = ren.render(batch)
         if dist is not None:
-            gathered[0] = parallel.all_gather_maps(out, R)             # every rank ends with all tiles
+            gathered[0] = parallel.all_gather_maps(out, R * world)     # every rank ends with all tiles
         return out
 
     L = _capi.lib()
@@ -272,7 +272,7 @@ def main():
         e2e_batch["rays"] = dev_rays
         o = ren.render(e2e_batch)
         if dist is not None:
-            parallel.all_gather_maps(o, R)
+            parallel.all_gather_maps(o, R * world)
         packed = torch.cat([o["rgb_map"], o["depth_map"][:, None], o["acc_map"][:, None]], 1)
         host_out.copy_(packed, non_blocking=True)
         torch.cuda.current_stream().synchronize()

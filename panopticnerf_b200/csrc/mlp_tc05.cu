@@ -110,7 +110,7 @@ __device__ __forceinline__ void epi_group_to_a(const uint32_t (&r)[16], int g, c
     split_x2<FMT>(v2, v3, hi[2 * q + 1], lo[2 * q + 1]);
   }
   if (war_pending) {  // the columns we are about to overwrite must have been consumed by this step's MMAs
-    mbar_wait(cx.bar_war, cx.parity);
+    mbar_wait_backoff(cx.bar_war, cx.parity);
     tc_fence_after();
     war_pending = false;
   }
@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpPara
   float* part = reinterpret_cast<float*>(smem + kSmemPart);  // [2][128][4]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
+  const uint32_t ready_word = smem_u32(bars + 31);   // number of weight stages whose inputs are all ready
 
   const uint32_t bar_full = smem_u32(&bars[0]);                 // [kRing]
   const uint32_t bar_empty = smem_u32(&bars[kRing]);            // [kRing]
@@ -175,6 +176,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpPara
       mbar_init(bar_dir_empty + 8 * h, 1);
     }
     mbar_init(bar_war, 1);
+    *reinterpret_cast<volatile uint32_t*>(bars + 31) = 0u;
     mbar_init(bar_emb_full, kProWarps * 32);
     mbar_init(bar_emb_empty, 1);
     fence_mbar_init();
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpPara
           const bool rec = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && tile == 2 * (int)gridDim.x;
           if (rec) p.dbg[4096 + (st * 2 + h) * 3 + 0] = clock64();
 #endif
-          mbar_wait(bar_acc_full + 8 * h, parity);
+          mbar_wait_backoff(bar_acc_full + 8 * h, parity);
           tc_fence_after();
 #ifdef PNR_TIMELINE
           if (rec) p.dbg[4096 + (st * 2 + h) * 3 + 1] = clock64();
@@ -261,7 +263,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpPara
             }
           }
           if (h == 0 && war_pending) {  // no columns of h0 for this thread: still consume the barrier phase
-            mbar_wait(bar_war, parity);
+            mbar_wait_backoff(bar_war, parity);
             war_pending = false;
           }
           if (h == 1) {
@@ -328,13 +330,13 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpPara
 #pragma unroll
         for (int c = 0; c < 3; ++c) d[c] = __fdiv_rn(d[c], nrm);
       }
-      mbar_wait(bar_emb_empty, (uint32_t)((it & 1) ^ 1));
+      mbar_wait_backoff(bar_emb_empty, (uint32_t)((it & 1) ^ 1));
       encode_row<PASSES, FMT, 10, 64>(x, Lx, emb_hi, emb_lo, row);
       fence_proxy_async_smem();
       mbar_arrive(bar_emb_full);
       const int b = it & 1;
       uint8_t* dir_hi = smem + kSmemDir + b * 2 * kDirPartBytes;
-      mbar_wait(bar_dir_empty + 8 * b, (uint32_t)(((it >> 1) & 1) ^ 1));
+      mbar_wait_backoff(bar_dir_empty + 8 * b, (uint32_t)(((it >> 1) & 1) ^ 1));
       encode_row<PASSES, FMT, 4, 32>(d, Ld, dir_hi, dir_hi + kDirPartBytes, row);
       fence_proxy_async_smem();
       mbar_arrive(bar_dir_full + 8 * b);
@@ -347,7 +349,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpPara
         for (int si = 0; si < n_stages; ++si, ++gs) {
           const uint32_t slot = gs % kRing, ph = (gs / kRing) & 1;
           const uint32_t gofs = c_prog.st[si].gofs, bytes = c_prog.st[si].bytes;
-          mbar_wait(bar_empty + 8 * slot, ph ^ 1);
+          mbar_wait_backoff(bar_empty + 8 * slot, ph ^ 1);
 #ifdef PNR_TIMELINE
           if (p.dbg != nullptr && blockIdx.x == 0 && tile == 2 * (int)gridDim.x) p.dbg[6144 + si] = clock64();
 #endif
@@ -357,13 +359,40 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpPara
         }
       }
     }
+  } else if (warp == kEpiWarps + kProWarps + 2) {
+    // =============================================================== scout (one elected thread)
+    // Does every wait the MMA issue depends on (epilogue hand-offs, embeddings, weight stage landed), in
+    // stage order, and publishes "stages ready" through a shared-memory counter.  The issuer never touches an
+    // mbarrier wait (each costs ~100 cycles even when already complete), it only polls that word.
+    if (elect_one()) {
+      uint32_t gs = 0;
+      int64_t gstep = -1;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int b = it & 1;
+#pragma unroll 1
+        for (int si = 0; si < n_stages; ++si, ++gs) {
+          const uint32_t flags = c_prog.st[si].flags;
+          if (flags & F_WAIT_E0) {
+            ++gstep;
+            if (gstep > 0) mbar_wait(bar_e_done, (uint32_t)((gstep - 1) & 1));
+          }
+          if ((flags & F_WAIT_E1) && gstep > 0) mbar_wait(bar_e_done + 8, (uint32_t)((gstep - 1) & 1));
+          if (flags & F_WAIT_EMB) mbar_wait(bar_emb_full, (uint32_t)(it & 1));
+          if (flags & F_WAIT_DIR) mbar_wait(bar_dir_full + 8 * b, (uint32_t)((it >> 1) & 1));
+          const uint32_t slot = gs % kRing, ph = (gs / kRing) & 1;
+          mbar_wait(bar_full + 8 * slot, ph);
+          tc_fence_before();
+          st_release_smem(ready_word, gs + 1);
+        }
+      }
+    }
   } else {
     // =============================================================== MMA issuer
     // One elected thread walks the stage list.  Everything it needs comes from __constant__ memory or is
     // derived from uniform values, so descriptors are built on the uniform datapath.
     if (elect_one()) {
       uint32_t gs = 0;
-      int64_t gstep = -1;  // global step counter; the epilogue barriers complete once per step
       int it = 0;
       const uint32_t emb_hi = smem_u32(smem + kSmemEmb);
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -379,18 +408,17 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpPara
           const bool rec = p.dbg != nullptr && blockIdx.x == 0 && it == 2;
           if (rec) p.dbg[si * 5 + 0] = clock64();
 #endif
-          if (flags & (F_WAIT_E0 | F_WAIT_E1)) {
-            if (flags & F_WAIT_E0) {
-              ++gstep;
-              if (gstep > 0) mbar_wait(bar_e_done, (uint32_t)((gstep - 1) & 1));
+          const uint32_t slot = gs % kRing;
+          if (ld_acquire_smem(ready_word) <= gs) {
+            long long t0 = clock64();
+            while (ld_acquire_smem(ready_word) <= gs) {
+              if ((clock64() - t0) > PNR_WATCHDOG_CYCLES) {
+                printf("pnr: issuer watchdog: block %d stage %u\n", (int)blockIdx.x, gs);
+                __trap();
+              }
             }
-            if ((flags & F_WAIT_E1) && gstep > 0) mbar_wait(bar_e_done + 8, (uint32_t)((gstep - 1) & 1));
-            tc_fence_after();   // order our MMAs after the epilogue's tcgen05.ld / tcgen05.st
           }
-          if (flags & F_WAIT_EMB) mbar_wait(bar_emb_full, (uint32_t)(it & 1));
-          if (flags & F_WAIT_DIR) mbar_wait(bar_dir_full + 8 * b, (uint32_t)((it >> 1) & 1));
-          const uint32_t slot = gs % kRing, ph = (gs / kRing) & 1;
-          mbar_wait(bar_full + 8 * slot, ph);
+          tc_fence_after();   // order our MMAs after the epilogue's tcgen05.ld / tcgen05.st (seen by the scout)
 #ifdef PNR_TIMELINE
           if (rec) p.dbg[si * 5 + 1] = clock64();
 #endif
