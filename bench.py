@@ -59,24 +59,55 @@ def flops_per_sample(cfg) -> int:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md).  Uses NVML in-process
+    (nvidia_ml_py) - spawning nvidia-smi every 100 ms perturbs the GPU - with nvidia-smi as the fallback.
+    Created (NVML initialised) before the warm-up so no first-call cost lands in the timed steps."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, index: int):
-        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+        self.index, self.sm, self.mx, self.reasons = index, [], [], set()
+        self._stop, self._t, self.nv, self.h = threading.Event(), None, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = pynvml
+            self._sample()
+        except Exception:
+            self.nv = None
+
+    def _sample(self):
+        nv = self.nv
+        if nv is not None:
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+            self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)))
+            fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            mask = int(fn(self.h))
+            self.reasons |= {k for k, b in self.BITS.items() if mask & b}
+        else:
+            o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+            r = [x.strip() for x in o.strip().split(",")]
+            if len(r) >= 7:
+                self.sm.append(float(r[0])); self.mx.append(float(r[1]))
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                self.reasons |= {n for n, v in zip(names, r[3:7]) if v.lower().startswith("active")}
 
     def start(self):
+        self.sm, self.mx, self.reasons = [], [], set()
+
         def run():
             while not self._stop.is_set():
                 try:
-                    o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                        "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                    self.rows.append([x.strip() for x in o.strip().split(",")])
+                    self._sample()
                 except Exception:
                     pass
-                self._stop.wait(0.1)
+                self._stop.wait(0.1 if self.nv is not None else 0.5)
         self._t = threading.Thread(target=run, daemon=True)
         self._t.start()
 
@@ -84,12 +115,9 @@ class ClockSampler:
         self._stop.set()
         if self._t:
             self._t.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None,
+                "sm_max_mhz": max(self.mx) if self.mx else None, "reasons": sorted(self.reasons),
+                "samples": len(self.sm), "source": "nvml" if self.nv is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -200,10 +228,10 @@ def main():
         return out
 
     L = _capi.lib()
+    sampler = ClockSampler(local_rank)
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
     sampler.start()
     L.pnr_launch_count(1)
     evs = []
@@ -338,7 +366,8 @@ def main():
                                    "64 boxes, one frame per GPU" + (" + NCCL all-gather of rendered tiles" if world > 1 else ""),
                        "rays_per_gpu_per_step": R, "samples_per_ray": N, "precision": args.precision,
                        "parallelism": f"ray-sharded x{world}", "l2": "flushed between steps (256 MiB memset, outside the events)",
-                       "wall_s_timed_region": t_wall},
+                       "wall_s_timed_region": t_wall,
+                       "step_ms": [round(x, 2) for x in step_ms]},
             "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_baseline, "gpu_launches": launches,
             "clocks": clocks, "fast_mode": fast,
         }
