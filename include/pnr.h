@@ -91,6 +91,14 @@ int pnr_sample_stratified(const float* near, const float* far, const float* t_va
 int pnr_tag_samples(const float* z, int64_t R, int32_t N, const int32_t* box_id, const float* t_in,
                     const float* t_out, int32_t M, int32_t* sample_box, void* stream);
 
+/* 8(f) rank 3 (the step before the path): camera rays for image rows [row0, row0+rows) of an H x W image,
+ * rays [rows*W, 6] = origin || unnormalised direction, row-major over (v, u).
+ * camera 0 = pinhole: d_cam = ((u-cx)/fx, (v-cy)/fy, 1); camera 1 = equirectangular:
+ * lon = (u/W-0.5)*2pi, lat = (0.5-v/H)*pi, d_cam = (cos lat sin lon, -sin lat, cos lat cos lon).
+ * intr_host = {fx, fy, cx, cy}; c2w_host = row-major 3x4 [R|t]: d = R d_cam, o = t. */
+int pnr_generate_rays(int32_t H, int32_t W, int32_t row0, int32_t rows, int32_t camera, const float* intr_host,
+                      const float* c2w_host, float* rays, void* stream);
+
 /* a7: standalone positional encoding, out [n, 3+6L]. */
 int pnr_encode(const float* x, int64_t n, int32_t L, float* out, void* stream);
 

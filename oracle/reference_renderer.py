@@ -382,6 +382,27 @@ def make_renderer(cfg, net, net_fine=None) -> Renderer:
     return Renderer(cfg, net, net_fine)
 
 
+def generate_rays(H: int, W: int, intr, c2w: torch.Tensor, camera: str = "pinhole", row0: int = 0,
+                  rows: Optional[int] = None) -> torch.Tensor:
+    """SURVEY 8(f) rank 3 (the step before the path; reference: ray generation in the KITTI-360 dataset
+    loader, not in the mount).  rays [rows*W, 6] = origin || unnormalised direction for a pinhole or an
+    equirectangular camera with camera-to-world [R|t] (3x4).  Elementwise fp32, fixed association order."""
+    rows = H - row0 if rows is None else rows
+    fx, fy, cx, cy = [float(x) for x in intr]
+    v, u = torch.meshgrid(torch.arange(row0, row0 + rows, dtype=torch.float32),
+                          torch.arange(W, dtype=torch.float32), indexing="ij")
+    if camera == "pinhole":
+        x, y, z = (u - cx) / fx, (v - cy) / fy, torch.ones_like(u)
+    else:
+        lon = (u / float(W) - 0.5) * 6.2831853071795864769
+        lat = (0.5 - v / float(H)) * 3.14159265358979323846
+        x, y, z = torch.cos(lat) * torch.sin(lon), -torch.sin(lat), torch.cos(lat) * torch.cos(lon)
+    c = c2w.to(torch.float32)
+    d = [(c[i, 0] * x + c[i, 1] * y) + c[i, 2] * z for i in range(3)]
+    o = [torch.full_like(x, float(c[i, 3])) for i in range(3)]
+    return torch.stack(o + d, -1).reshape(-1, 6).contiguous()
+
+
 def mlp_flops_per_sample(cfg) -> int:
     """Algorithmic FLOPs (2 x MAC, true layer shapes) per SURVEY 8(d) / BASELINE.md section 3."""
     D, W = int(cfg.D), int(cfg.W)

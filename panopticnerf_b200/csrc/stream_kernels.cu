@@ -40,6 +40,35 @@ __global__ void __launch_bounds__(kEncTile) encode_kernel(const float* __restric
   for (int64_t i = threadIdx.x; i < cnt; i += kEncTile) dst[i] = tile[i];
 }
 
+// ------------------------------------------------------------------------------------ ray generation
+struct CamArgs { float fx, fy, cx, cy; float c2w[12]; int H, W, row0, rows, camera; };
+
+__global__ void __launch_bounds__(256) rays_kernel(CamArgs a, float* __restrict__ rays) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)a.rows * a.W) return;
+  const int v = a.row0 + (int)(i / a.W), u = (int)(i % a.W);
+  float x, y, z;
+  if (a.camera == 0) {  // pinhole; every op separately rounded so the result equals the oracle's bit for bit
+    x = __fdiv_rn(__fsub_rn((float)u, a.cx), a.fx);
+    y = __fdiv_rn(__fsub_rn((float)v, a.cy), a.fy);
+    z = 1.0f;
+  } else {
+    const float lon = __fmul_rn(__fsub_rn(__fdiv_rn((float)u, (float)a.W), 0.5f), 6.2831853071795864769f);
+    const float lat = __fmul_rn(__fsub_rn(0.5f, __fdiv_rn((float)v, (float)a.H)), 3.14159265358979323846f);
+    float sl, cl, so, co;
+    sincosf(lat, &sl, &cl);
+    sincosf(lon, &so, &co);
+    x = cl * so; y = -sl; z = cl * co;
+  }
+  float2* o = reinterpret_cast<float2*>(rays + i * 6);
+  const float d0 = __fadd_rn(__fadd_rn(__fmul_rn(a.c2w[0], x), __fmul_rn(a.c2w[1], y)), __fmul_rn(a.c2w[2], z));
+  const float d1 = __fadd_rn(__fadd_rn(__fmul_rn(a.c2w[4], x), __fmul_rn(a.c2w[5], y)), __fmul_rn(a.c2w[6], z));
+  const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(a.c2w[8], x), __fmul_rn(a.c2w[9], y)), __fmul_rn(a.c2w[10], z));
+  o[0] = make_float2(a.c2w[3], a.c2w[7]);
+  o[1] = make_float2(a.c2w[11], d0);
+  o[2] = make_float2(d1, d2);
+}
+
 // ------------------------------------------------------------------------------------ a9 composite
 constexpr int kCompMaxPerLane = 8;   // N <= 256
 constexpr int kCompMaxChan = 4;      // C, K <= 128 each
@@ -210,6 +239,22 @@ __global__ void __launch_bounds__(kCompWarps * 32) composite_kernel(CompositeArg
 }  // namespace pnr
 
 using namespace pnr;
+
+extern "C" int pnr_generate_rays(int32_t H, int32_t W, int32_t row0, int32_t rows, int32_t camera,
+                                 const float* intr_host, const float* c2w_host, float* rays, void* stream) {
+  if (rows == 0 || W == 0) return PNR_OK;
+  PNR_CHECK_ARG(intr_host && c2w_host && rays, "pnr_generate_rays: null pointer");
+  PNR_CHECK_ARG(H > 0 && W > 0 && rows > 0 && row0 >= 0 && row0 + rows <= H, "pnr_generate_rays: bad image window");
+  PNR_CHECK_ARG(camera == 0 || camera == 1, "pnr_generate_rays: camera %d (0 pinhole, 1 equirect)", camera);
+  CamArgs a;
+  a.fx = intr_host[0]; a.fy = intr_host[1]; a.cx = intr_host[2]; a.cy = intr_host[3];
+  for (int i = 0; i < 12; ++i) a.c2w[i] = c2w_host[i];
+  a.H = H; a.W = W; a.row0 = row0; a.rows = rows; a.camera = camera;
+  const int64_t n = (int64_t)rows * W;
+  rays_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, rays);
+  PNR_LAUNCH_CHECK("rays_kernel");
+  return PNR_OK;
+}
 
 extern "C" int pnr_encode(const float* x, int64_t n, int32_t L, float* out, void* stream) {
   if (n == 0) return PNR_OK;

@@ -92,6 +92,19 @@ def tag_samples(z, box_id, t_in, t_out):
     return sb
 
 
+def generate_rays(H: int, W: int, intr, c2w: torch.Tensor, camera: str = "pinhole", row0: int = 0,
+                  rows: Optional[int] = None, device="cuda") -> torch.Tensor:
+    """Camera rays on the device: only 16 floats cross the host/device boundary."""
+    rows = H - row0 if rows is None else rows
+    rays = torch.empty(rows * W, 6, dtype=_F32, device=device)
+    k = (C.c_float * 4)(*[float(x) for x in intr])
+    m = (C.c_float * 12)(*[float(x) for x in c2w.detach().to("cpu", _F32).reshape(-1)[:12].tolist()])
+    with torch.cuda.device(rays.device):
+        _capi.check(_capi.lib().pnr_generate_rays(int(H), int(W), int(row0), int(rows), 0 if camera == "pinhole" else 1,
+                                                  k, m, _capi.ptr(rays), _capi.stream_ptr()), "pnr_generate_rays")
+    return rays
+
+
 def embed(x: torch.Tensor, L: int) -> torch.Tensor:
     """a7 standalone positional encoding (the Renderer uses the copy fused into the MLP kernel)."""
     xf = _f(x.reshape(-1, 3), "x")
@@ -189,6 +202,17 @@ class Renderer:
             self._t_vals[key] = torch.linspace(0.0, 1.0, N).to(device)   # CPU linspace, as the oracle's
         return self._t_vals[key]
 
+    def _auto_chunk(self, rays) -> int:
+        """Largest ray chunk whose intermediates (raw is the big one: N x (4+C+K) floats per ray, coarse + fine)
+        fit in half of the free device memory; usually the whole frame (results do not depend on it)."""
+        cfg = self.cfg
+        N, Ni = int(cfg.N_samples), int(getattr(cfg, "N_importance", 0))
+        ch = 4 + int(getattr(cfg, "num_classes", 0)) + int(getattr(cfg, "num_instances", 0))
+        per_ray = 4 * ((N + (N + Ni if Ni else 0)) * (ch + 4) + 64)
+        free, _ = torch.cuda.mem_get_info(rays.device)
+        chunk = max(1024, int(0.5 * free // per_ray) // 1024 * 1024)
+        return min(rays.shape[0], chunk)
+
     # -- a4: results are invariant to `chunk`; None renders every ray in one pass of persistent kernels
     def batchify_rays(self, rays, near, far, batch, chunk: Optional[int] = None):
         R = rays.shape[0]
@@ -249,6 +273,12 @@ class Renderer:
     @torch.no_grad()
     def render(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         cfg = self.cfg
+        if "rays" not in batch and "c2w" in batch:     # camera given instead of rays: generate them on the device
+            dev = next(self.net.parameters()).device
+            batch = dict(batch)
+            batch["rays"] = generate_rays(int(cfg.H), int(cfg.W_img), batch.get("intrinsics", (cfg.fx, cfg.fy, cfg.cx, cfg.cy)),
+                                          batch["c2w"], getattr(cfg, "camera", "pinhole"),
+                                          int(batch.get("row0", 0)), batch.get("rows"), dev)
         rays = _f(batch["rays"], "batch['rays']")
         if "near" in batch and "far" in batch:
             near, far = _f(batch["near"], "near"), _f(batch["far"], "far")
@@ -257,7 +287,7 @@ class Renderer:
         else:
             near = torch.full((rays.shape[0],), float(cfg.near), dtype=_F32, device=rays.device)
             far = torch.full((rays.shape[0],), float(cfg.far), dtype=_F32, device=rays.device)
-        chunk = getattr(cfg, "gpu_chunk", None)
+        chunk = getattr(cfg, "gpu_chunk", None) or self._auto_chunk(rays)
         out = self.batchify_rays(rays, near, far, batch, chunk)
         out["near"], out["far"] = near, far
         return out
