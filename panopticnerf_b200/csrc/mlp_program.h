@@ -19,6 +19,7 @@ constexpr int kStageBytes = 32768;        // max stage: N=128 rows x 64 K x 2 by
 constexpr int kEpiWarps = 8;              // TMEM->reg->TMEM activation warps (2 per lane quarter)
 constexpr int kProWarps = 4;              // positional-encoding producer warps (one thread per row)
 constexpr int kMlpThreads = (kEpiWarps + kProWarps + 3) * 32;   // + TMA warp + MMA issuer warp + scout warp = 480
+constexpr int kClusterSize = 2;           // CTAs sharing one weight stream by TMA multicast
 constexpr int kMaxStages = 384;
 constexpr int kMaxSteps = 24;
 constexpr int kMaxConsts = 4096;          // floats: biases + sigma / rgb weights

@@ -137,10 +137,18 @@ __device__ __forceinline__ void epi_group_logits(const uint32_t (&r)[16], int g,
     if (g * 16 + j < ed.n_valid) dst[g * 16 + j] = __uint_as_float(r[j]) + bias[g * 16 + j];
 }
 
+// CTAs run as clusters of two that stream the SAME weight stages in lock step: each CTA fetches half of every
+// stage from L2 and multicasts it into both shared memories, halving L2 -> SM weight traffic (the weight
+// stream, 29 B/clk/SM at full rate, was L2-latency bound with every SM fetching every byte).
 template <int PASSES, int FMT>
-__global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpParams p) {
+__global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kMlpThreads, 1)
+mlp_fused_kernel(const MlpParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  // every CTA runs the same number of tile iterations (tiles past the end are dummies whose stores are
+  // masked) so that both CTAs of a cluster consume the shared weight stream the same number of times
+  const int tile_end = (int)(((p.num_tiles + (int)gridDim.x - 1) / (int)gridDim.x) * (int)gridDim.x);
 
   float* consts = reinterpret_cast<float*>(smem + kSmemConsts);
   float* part = reinterpret_cast<float*>(smem + kSmemPart);  // [2][128][4]
@@ -167,7 +175,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpPara
   if (threadIdx.x == 32) {
     for (int s = 0; s < kRing; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, kClusterSize);   // released by the MMA commits of every CTA in the cluster
     }
     for (int h = 0; h < 2; ++h) {
       mbar_init(bar_acc_full + 8 * h, 1);
@@ -183,6 +191,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpPara
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync();   // the peer's barriers must be initialised before anything is multicast into them
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int n_stages = c_prog.n_stages, n_steps = c_prog.n_steps;
@@ -195,7 +204,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpPara
     cx.tmem_lane = tmem + ((uint32_t)(q * 32) << 16);
     cx.bar_war = bar_war;
     uint32_t gstep = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
       const int64_t s = (int64_t)tile * kTileM + row;
       const bool valid = s < p.S;
       float sig = 0.f;
@@ -307,7 +316,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpPara
     uint8_t* emb_lo = emb_hi + kEmbPartBytes;
     const int Lx = c_prog.Lx, Ld = c_prog.Ld;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
       int64_t s = (int64_t)tile * kTileM + row;
       if (s >= p.S) s = p.S - 1;  // clamp: tail rows compute on a valid sample, results are discarded
       float x[3], d[3];
@@ -345,7 +354,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpPara
     // =============================================================== TMA producer (one elected thread)
     if (elect_one()) {
       uint32_t gs = 0;  // global stage counter
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
         for (int si = 0; si < n_stages; ++si, ++gs) {
           const uint32_t slot = gs % kRing, ph = (gs / kRing) & 1;
           const uint32_t gofs = c_prog.st[si].gofs, bytes = c_prog.st[si].bytes;
@@ -353,9 +362,13 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpPara
 #ifdef PNR_TIMELINE
           if (p.dbg != nullptr && blockIdx.x == 0 && tile == 2 * (int)gridDim.x) p.dbg[6144 + si] = clock64();
 #endif
+          // our barrier expects the whole stage; we fetch our 1/kClusterSize of it and multicast that part into
+          // every CTA of the cluster (same shared-memory offset, same barrier offset in each of them)
           mbar_arrive_expect_tx(bar_full + 8 * slot, bytes);
-          bulk_g2s(smem_u32(smem + kSmemRing + slot * kStageBytes), p.wpacked + gofs, bytes,
-                   bar_full + 8 * slot);
+          const uint32_t part_bytes = bytes / kClusterSize;
+          bulk_g2s_multicast(smem_u32(smem + kSmemRing + slot * kStageBytes) + cta_rank * part_bytes,
+                             p.wpacked + gofs + cta_rank * part_bytes, part_bytes, bar_full + 8 * slot,
+                             (uint16_t)((1u << kClusterSize) - 1u));
         }
       }
     }
@@ -368,7 +381,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpPara
       uint32_t gs = 0;
       int64_t gstep = -1;
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
         const int b = it & 1;
 #pragma unroll 1
         for (int si = 0; si < n_stages; ++si, ++gs) {
@@ -395,7 +408,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpPara
       uint32_t gs = 0;
       int it = 0;
       const uint32_t emb_hi = smem_u32(smem + kSmemEmb);
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
         const int b = it & 1;
         const uint32_t dir_hi = smem_u32(smem + kSmemDir + b * 2 * kDirPartBytes);
 #pragma unroll 1
@@ -463,7 +476,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpPara
 #ifdef PNR_TIMELINE
           if (rec) p.dbg[si * 5 + 2] = clock64();
 #endif
-          tc_commit(bar_empty + 8 * slot);
+          tc_commit_multicast(bar_empty + 8 * slot, (uint16_t)((1u << kClusterSize) - 1u));   // slot free in all CTAs
           if (flags & (F_RELEASE_EMB | F_RELEASE_DIR | F_COMMIT_WAR | F_COMMIT_ACC0 | F_COMMIT_ACC1)) {
             if (flags & F_RELEASE_EMB) tc_commit(bar_emb_empty);
             if (flags & F_RELEASE_DIR) tc_commit(bar_dir_empty + 8 * b);
@@ -480,6 +493,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_kernel(const MlpPara
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync();   // no CTA may exit while its peer can still multicast into it or arrive on its barriers
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
@@ -500,8 +514,10 @@ static int launch_one(const MlpParams& p, int grid, cudaStream_t stream) {
 // when it differs from the one last uploaded on this device.
 int launch_mlp(const MlpParams& p, const MlpProgram* host_prog, uint64_t prog_id, int passes, int fmt,
                cudaStream_t stream) {
-  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   if (grid <= 0) return PNR_OK;
+  grid = (grid + kClusterSize - 1) / kClusterSize * kClusterSize;   // whole clusters (spare CTAs run dummy tiles)
+  if (grid > num_sms()) grid = num_sms() / kClusterSize * kClusterSize;
   static uint64_t loaded_id[64] = {0};
   int dev = 0;
   PNR_CUDA(cudaGetDevice(&dev));

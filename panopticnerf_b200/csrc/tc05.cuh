@@ -104,6 +104,26 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src_gmem
       "l"(src_gmem), "r"(bytes), "r"(bar)
       : "memory");
 }
+// Same copy, multicast: the bytes land at the same shared-memory offset, and complete_tx is signalled on the
+// mbarrier at the same offset, in every CTA of the cluster whose bit is set in cta_mask.
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst_smem, const void* src_gmem, uint32_t bytes,
+                                                   uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+          dst_smem),
+      "l"(src_gmem), "r"(bytes), "r"(bar), "h"(cta_mask)
+      : "memory");
+}
+
+// ---------------------------------------------------------------- thread-block clusters
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
 // ---------------------------------------------------------------- TMEM management
 template <int NCOLS>
@@ -138,6 +158,13 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                    bar)
                : "memory");
+}
+// Same, arriving on the mbarrier at this offset in every CTA of the cluster selected by cta_mask.
+__device__ __forceinline__ void tc_commit_multicast(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(cta_mask)
+      : "memory");
 }
 
 // ---------------------------------------------------------------- descriptors
