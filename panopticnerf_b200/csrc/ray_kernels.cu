@@ -90,21 +90,43 @@ __global__ void __launch_bounds__(256) bound_kernel(const uint8_t* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------ a6 sampling
+// One warp per ray: the ray's near/far and its <= 8 hit intervals are loaded once (lane m holds interval m,
+// broadcast by shuffle), lanes stride the sample axis so z / sample_box stores are fully coalesced.
 __global__ void __launch_bounds__(256) stratified_kernel(
     const float* __restrict__ near, const float* __restrict__ far, const float* __restrict__ t_vals,
     const float* __restrict__ u, int64_t R, int N, float perturb, const int32_t* __restrict__ box_id,
     const float* __restrict__ t_in, const float* __restrict__ t_out, int M, float* __restrict__ z,
     int32_t* __restrict__ sample_box) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= R * N) return;
-  const int64_t r = idx / N;
-  const int i = (int)(idx - r * N);
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= R) return;
   const float nr = near[r], fr = far[r];
-  const float zi = (perturb > 0.f) ? pnr_strat_z_jitter(nr, fr, t_vals, i, N, u[idx])
-                                   : pnr_strat_z(nr, fr, t_vals[i]);
-  z[idx] = zi;
-  if (sample_box != nullptr)
-    sample_box[idx] = (box_id != nullptr) ? pnr_tag(zi, box_id + r * M, t_in + r * M, t_out + r * M, M) : -1;
+  int32_t my_id = -1;
+  float my_in = 0.f, my_out = 0.f;
+  if (box_id != nullptr && lane < M) {
+    my_id = box_id[r * M + lane];
+    my_in = t_in[r * M + lane];
+    my_out = t_out[r * M + lane];
+  }
+  for (int i0 = 0; i0 < N; i0 += 32) {   // warp-uniform trip count: the shuffles below need all lanes
+    const int i = i0 + lane;
+    const bool live = i < N;
+    float zi = 0.f;
+    if (live) {
+      const int64_t idx = r * N + i;
+      zi = (perturb > 0.f) ? pnr_strat_z_jitter(nr, fr, t_vals, i, N, u[idx]) : pnr_strat_z(nr, fr, t_vals[i]);
+      z[idx] = zi;
+    }
+    if (sample_box != nullptr) {
+      int32_t tag = -1;
+      for (int m = M - 1; m >= 0; --m) {   // first (nearest) containing interval wins
+        const int32_t id = __shfl_sync(0xffffffffu, my_id, m);
+        const float a = __shfl_sync(0xffffffffu, my_in, m), b = __shfl_sync(0xffffffffu, my_out, m);
+        if (id >= 0 && zi >= a && zi <= b) tag = id;
+      }
+      if (live) sample_box[r * N + i] = (box_id != nullptr) ? tag : -1;
+    }
+  }
 }
 
 // Re-tag an existing depth array (used after the fine-sample merge).
@@ -243,7 +265,7 @@ extern "C" int pnr_sample_stratified(const float* near, const float* far, const 
                 "pnr_sample_stratified: bad interval table");
   if (R == 0) return PNR_OK;
   if (z == near) return set_error(PNR_ERR_ARG, "pnr_sample_stratified: in-place not allowed");
-  stratified_kernel<<<blocks_for(R * N, 256), 256, 0, (cudaStream_t)stream>>>(
+  stratified_kernel<<<blocks_for(R, 8), 256, 0, (cudaStream_t)stream>>>(
       near, far, t_vals, u, R, N, perturb, box_id, t_in, t_out, M, z, sample_box);
   PNR_LAUNCH_CHECK("stratified_kernel");
   return PNR_OK;
