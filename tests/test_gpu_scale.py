@@ -94,3 +94,16 @@ def test_cfg5_equirect_shard_192_samples():
     out = PN.make_renderer(cfg, net).render(dict(scene, c2w=pose, row0=448, rows=128))
     assert out["rgb_map"].shape[0] == 128 * 2048
     _properties(out, 192)
+
+
+def test_empty_ray_shard_renders():
+    """a rank whose shard is empty (R < world) must still produce well-shaped (0-row) outputs."""
+    cfg = PN.make_cfg("cfg3", N_importance=16)
+    net = S.init_network_weights(PN.make_network(cfg)).to(DEV)
+    batch = {k: v.to(DEV) for k, v in S.make_batch(cfg, rows=1).items()}
+    batch["rays"] = batch["rays"][:0]
+    out = PN.make_renderer(cfg, net).render(batch)
+    assert out["rgb_map"].shape == (0, 3) and out["semantic_map"].shape == (0, 45) and out["weights"].shape == (0, 80)
+    one = dict(batch, rays=S.make_rays(cfg, rows=1)[:1].to(DEV))          # and a single ray
+    out = PN.make_renderer(cfg, net).render(one)
+    assert out["rgb_map"].shape == (1, 3) and torch.isfinite(out["rgb_map"]).all()
