@@ -88,12 +88,11 @@ struct EpiCtx {
   uint32_t parity;
 };
 
-// activation -> next layer's A operand: v = act(acc + bias); [sigma += v . wsig]; split; tcgen05.st
+// activation -> next layer's A operand: v = act(acc + bias); [sigma += v . wsig]; split into hi / lo parts
 template <int PASSES, int FMT>
-__device__ __forceinline__ void epi_group_to_a(const uint32_t (&r)[16], int g, const EpiDesc& ed, float clamp_lo,
-                                               const float* bias, const float* wsig, float& sig,
-                                               const EpiCtx& cx, bool& war_pending) {
-  uint32_t hi[8], lo[8];
+__device__ __forceinline__ void epi_group_act(const uint32_t (&r)[16], int g, const EpiDesc& ed, float clamp_lo,
+                                              const float* bias, const float* wsig, float& sig,
+                                              uint32_t (&hi)[8], uint32_t (&lo)[8]) {
   const float4* b4 = reinterpret_cast<const float4*>(bias + g * 16);
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -109,11 +108,11 @@ __device__ __forceinline__ void epi_group_to_a(const uint32_t (&r)[16], int g, c
     split_x2<FMT>(v0, v1, hi[2 * q], lo[2 * q]);
     split_x2<FMT>(v2, v3, hi[2 * q + 1], lo[2 * q + 1]);
   }
-  if (war_pending) {  // the columns we are about to overwrite must have been consumed by this step's MMAs
-    mbar_wait_backoff(cx.bar_war, cx.parity);
-    tc_fence_after();
-    war_pending = false;
-  }
+}
+
+template <int PASSES>
+__device__ __forceinline__ void epi_group_store(int g, const EpiDesc& ed, const EpiCtx& cx,
+                                                const uint32_t (&hi)[8], const uint32_t (&lo)[8]) {
   tmem_st8(cx.tmem_lane + ed.dst_col + g * 8, hi);
   if (PASSES == 3) tmem_st8(cx.tmem_lane + ed.dst_lo_col + g * 8, lo);
 }
@@ -239,35 +238,56 @@ mlp_fused_kernel(const MlpParams p) {
           // software pipeline: the load of group g+1 is in flight while group g is processed
           uint32_t ra[16], rb[16];
           if (gb < ge) tmem_ld16(acc + gb * 16, ra);
+          if (to_a) {
+            // Two groups are converted before anything is stored: E0 reaches the write-after-read barrier
+            // (this step's MMAs still read the columns it overwrites) with two groups of work already done.
 #pragma unroll 1
-          for (int g = gb; g < ge; g += 2) {
-            tc_wait_ld();
-#ifdef PNR_TIMELINE
-            if (rec && h == 1 && g == gb) p.dbg[7168 + st * 4 + 0] = clock64();
-#endif
-            if (g + 1 < ge) tmem_ld16(acc + (g + 1) * 16, rb);
-            if (to_a) {
-              epi_group_to_a<PASSES, FMT>(ra, g, ed, clamp_lo, bias, aux, sig, cx, war_pending);
-            } else if (ed.kind == EPI_VIEW_RGB) {
-              epi_group_rgb(ra, g, ed, bias, aux, c0, c1, c2);
-            } else if (valid) {
-              epi_group_logits(ra, g, ed, bias, out_row);
-            }
-#ifdef PNR_TIMELINE
-            if (rec && h == 1 && g == gb) p.dbg[7168 + st * 4 + 1] = clock64();
-#endif
-            if (g + 1 < ge) {
+            for (int g = gb; g < ge; g += 2) {
+              uint32_t ha[8], la[8], hb[8], lb[8];
+              const bool two = g + 1 < ge;
               tc_wait_ld();
 #ifdef PNR_TIMELINE
-              if (rec && h == 1 && g == gb) p.dbg[7168 + st * 4 + 2] = clock64();
+              if (rec && h == 1 && g == gb) p.dbg[7168 + st * 4 + 0] = clock64();
 #endif
-              if (g + 2 < ge) tmem_ld16(acc + (g + 2) * 16, ra);
-              if (to_a) {
-                epi_group_to_a<PASSES, FMT>(rb, g + 1, ed, clamp_lo, bias, aux, sig, cx, war_pending);
-              } else if (ed.kind == EPI_VIEW_RGB) {
-                epi_group_rgb(rb, g + 1, ed, bias, aux, c0, c1, c2);
+              if (two) tmem_ld16(acc + (g + 1) * 16, rb);
+              epi_group_act<PASSES, FMT>(ra, g, ed, clamp_lo, bias, aux, sig, ha, la);
+#ifdef PNR_TIMELINE
+              if (rec && h == 1 && g == gb) p.dbg[7168 + st * 4 + 1] = clock64();
+#endif
+              if (two) {
+                tc_wait_ld();
+#ifdef PNR_TIMELINE
+                if (rec && h == 1 && g == gb) p.dbg[7168 + st * 4 + 2] = clock64();
+#endif
+                if (g + 2 < ge) tmem_ld16(acc + (g + 2) * 16, ra);
+                epi_group_act<PASSES, FMT>(rb, g + 1, ed, clamp_lo, bias, aux, sig, hb, lb);
+              }
+              if (war_pending) {  // the columns we are about to overwrite must have been consumed by the MMAs
+                mbar_wait_backoff(bar_war, parity);
+                tc_fence_after();
+                war_pending = false;
+              }
+              epi_group_store<PASSES>(g, ed, cx, ha, la);
+              if (two) epi_group_store<PASSES>(g + 1, ed, cx, hb, lb);
+            }
+          } else {
+#pragma unroll 1
+            for (int g = gb; g < ge; g += 2) {
+              tc_wait_ld();
+              if (g + 1 < ge) tmem_ld16(acc + (g + 1) * 16, rb);
+              if (ed.kind == EPI_VIEW_RGB) {
+                epi_group_rgb(ra, g, ed, bias, aux, c0, c1, c2);
               } else if (valid) {
-                epi_group_logits(rb, g + 1, ed, bias, out_row);
+                epi_group_logits(ra, g, ed, bias, out_row);
+              }
+              if (g + 1 < ge) {
+                tc_wait_ld();
+                if (g + 2 < ge) tmem_ld16(acc + (g + 2) * 16, ra);
+                if (ed.kind == EPI_VIEW_RGB) {
+                  epi_group_rgb(rb, g + 1, ed, bias, aux, c0, c1, c2);
+                } else if (valid) {
+                  epi_group_logits(rb, g + 1, ed, bias, out_row);
+                }
               }
             }
           }
@@ -405,29 +425,37 @@ mlp_fused_kernel(const MlpParams p) {
     // One elected thread walks the stage list.  Everything it needs comes from __constant__ memory or is
     // derived from uniform values, so descriptors are built on the uniform datapath.
     if (elect_one()) {
-      uint32_t gs = 0;
+      uint32_t gs = 0, ready = 0;
       int it = 0;
       const uint32_t emb_hi = smem_u32(smem + kSmemEmb);
       for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
         const int b = it & 1;
         const uint32_t dir_hi = smem_u32(smem + kSmemDir + b * 2 * kDirPartBytes);
+        // The descriptor of stage si+1 is fetched while stage si is being issued (constant-bank latency is
+        // otherwise exposed once per stage on this single in-order thread).
+        StageDesc sd = c_prog.st[0];
 #pragma unroll 1
         for (int si = 0; si < n_stages; ++si, ++gs) {
-          const uint32_t flags = c_prog.st[si].flags;
-          const uint32_t n = c_prog.st[si].n;
-          const uint32_t ksteps = c_prog.st[si].ksteps;
-          const uint32_t a_kind = c_prog.st[si].a_kind;
+          const uint32_t flags = sd.flags;
+          const uint32_t n = sd.n;
+          const uint32_t ksteps = sd.ksteps;
+          const uint32_t a_kind = sd.a_kind;
+          const uint32_t acc_col = sd.acc_col, lo_off16 = sd.lo_off16, a_off = sd.a_off, a_lo_off = sd.a_lo_off;
+          sd = c_prog.st[si + 1 < n_stages ? si + 1 : 0];
 #ifdef PNR_TIMELINE
           const bool rec = p.dbg != nullptr && blockIdx.x == 0 && it == 2;
           if (rec) p.dbg[si * 5 + 0] = clock64();
 #endif
           const uint32_t slot = gs % kRing;
-          if (ld_acquire_smem(ready_word) <= gs) {
-            long long t0 = clock64();
-            while (ld_acquire_smem(ready_word) <= gs) {
-              if ((clock64() - t0) > PNR_WATCHDOG_CYCLES) {
-                printf("pnr: issuer watchdog: block %d stage %u\n", (int)blockIdx.x, gs);
-                __trap();
+          if (ready <= gs) {   // the scout may be several stages ahead: poll only when our copy is stale
+            ready = ld_acquire_smem(ready_word);
+            if (ready <= gs) {
+              long long t0 = clock64();
+              while ((ready = ld_acquire_smem(ready_word)) <= gs) {
+                if ((clock64() - t0) > PNR_WATCHDOG_CYCLES) {
+                  printf("pnr: issuer watchdog: block %d stage %u\n", (int)blockIdx.x, gs);
+                  __trap();
+                }
               }
             }
           }
@@ -438,14 +466,14 @@ mlp_fused_kernel(const MlpParams p) {
           const uint32_t idesc = make_idesc_f32acc(kTileM, n, FMT);
           const uint32_t b_lbo = n * 16u;
           const uint32_t sb = smem_u32(smem + kSmemRing + slot * kStageBytes);
-          const uint32_t d_tmem = tmem + c_prog.st[si].acc_col;
+          const uint32_t d_tmem = tmem + acc_col;
           const uint32_t acc0 = (flags & F_FIRST) ? 0u : 1u;
           // descriptors of K16 step 0; step ks adds ks * (2 * lbo >> 4) to the 14-bit address field
           const uint64_t bdesc0 = make_smem_desc_noswz(sb, b_lbo, 128);
-          const uint64_t bdesc0_lo = bdesc0 + (uint64_t)c_prog.st[si].lo_off16;
+          const uint64_t bdesc0_lo = bdesc0 + (uint64_t)lo_off16;
           const uint32_t b_inc = (2u * b_lbo) >> 4;
           if (a_kind == A_TMEM) {
-            const uint32_t a_hi = tmem + c_prog.st[si].a_off, a_lo = tmem + c_prog.st[si].a_lo_off;
+            const uint32_t a_hi = tmem + a_off, a_lo = tmem + a_lo_off;
 #pragma unroll
             for (uint32_t ks = 0; ks < (PASSES == 3 ? 4u : 8u); ++ks) {
               if (ks < ksteps) {
