@@ -286,8 +286,11 @@ def main():
                 "peak_source": f"bf16_tflops_sustained, {pk['_src']}", "kernel_ms": mlp_t,
                 "kernel_share_of_step": mlp_t / (total_ms / args.steps),
                 "alg_flop_per_launch": alg_flop, "passes": 3 if args.precision.endswith("x3") else 1,
-                "note": "algorithmic FLOPs (true layer shapes, 1 pass); the x3 modes issue 3 tensor-core passes "
-                        "per product, so tensor-pipe busy is ~3x this fraction"}
+                "executed_flop_per_launch_one_pass": (flops_per_sample(cfg) - 2 * cfg.W * cfg.W) * R * N,
+                "note": "achieved = the reference network's algorithmic FLOPs (true layer shapes, 1 pass) / time; "
+                        "the kernel executes 2*W*W fewer per sample (feature_linear is folded into the view "
+                        "layer at weight load, exact algebra) and the x3 modes issue 3 tensor-core passes per "
+                        "product, so tensor-pipe busy is ~2.7x this fraction"}
 
     # ---------------- e2e: public API from pinned host rays, H2D + D2H inside the timed region
     host_rays = cpu_batch["rays"].pin_memory()

@@ -374,22 +374,33 @@ extern "C" int pnr_load_weights(pnr_ctx* ctx, const float* const* t, const int64
   };
   if (ok && C > 0) add_head(m_s1, b_s1, m_s2, b_s2, C, 4);
   if (ok && K > 0) add_head(m_i1, b_i1, m_i2, b_i2, K, 4 + C);
-  if (ok) {  // feature layer (no activation) -> A
-    EpiDesc ed{};
-    ed.kind = EPI_LINEAR_TO_A;
-    ed.dst_col = kColAHi;
-    ed.dst_lo_col = kColALo;
-    ed.bias_off = (uint16_t)bld.add_consts(b_feat, W, W);
-    ok = bld.add_step({seg_tmem(m_feat, 0, W, kColAHi, kColALo)}, W, kColAcc, ed, false);
+  // feature_linear has no activation, so it is folded into the view layer when the weights are loaded
+  // (exact algebra, done in double):  W_view [feat ; gamma(d)] + b_view  with  feat = W_feat h + b_feat
+  //   = (W_view[:, :W] W_feat) h + W_view[:, W:] gamma(d) + (W_view[:, :W] b_feat + b_view).
+  // One 256x256 GEMM per sample (11 % of the MLP) and its epilogue disappear; the view step reads the trunk
+  // output h directly.
+  std::vector<float> fold((size_t)W2 * (W + Ed)), fold_b(W2);
+  for (int n_ = 0; n_ < W2; ++n_) {
+    const float* vrow = m_view.w + (size_t)n_ * (W + Ed);
+    for (int k = 0; k < W; ++k) {
+      double acc = 0.0;
+      for (int j = 0; j < W; ++j) acc += (double)vrow[j] * (double)m_feat.w[(size_t)j * W + k];
+      fold[(size_t)n_ * (W + Ed) + k] = (float)acc;
+    }
+    for (int e = 0; e < Ed; ++e) fold[(size_t)n_ * (W + Ed) + W + e] = vrow[W + e];
+    double accb = (double)b_view[n_];
+    for (int j = 0; j < W; ++j) accb += (double)vrow[j] * (double)b_feat[j];
+    fold_b[n_] = (float)accb;
   }
-  if (ok) {  // view branch [feat, gamma(d)] -> relu -> rgb (CUDA cores) ; writes rgb + sigma
+  const Mat m_fold{fold.data(), W2, W + Ed};
+  if (ok) {  // view branch [h, gamma(d)] -> relu -> rgb (CUDA cores) ; writes rgb + sigma
     EpiDesc ed{};
     ed.kind = EPI_VIEW_RGB;
-    ed.bias_off = (uint16_t)bld.add_consts(b_view, W2, W2);
+    ed.bias_off = (uint16_t)bld.add_consts(fold_b.data(), W2, W2);
     ed.aux_off = (uint16_t)rgb_w_off;
     std::vector<Seg> segs;
-    segs.push_back(seg_tmem(m_view, 0, W, kColAHi, kColALo));
-    segs.push_back(Seg{A_DIR, m_view, W, Ed, 32, 0, 0, true});
+    segs.push_back(seg_tmem(m_fold, 0, W, kColAHi, kColALo));
+    segs.push_back(Seg{A_DIR, m_fold, W, Ed, 32, 0, 0, true});
     ok = bld.add_step(segs, W2, kColAcc, ed, false);
   }
   if (!ok) return set_error(PNR_ERR_UNSUPPORTED, "pnr_load_weights: program build failed: %s", bld.err.c_str());
