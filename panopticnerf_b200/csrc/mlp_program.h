@@ -64,6 +64,16 @@ struct StageDesc {     // one weight stage = one bulk copy + its MMAs
   uint8_t a_kind;
 };
 
+struct IssueDesc {     // the same stage, pre-digested for the MMA-issuing warp: every word is used as it is
+  uint32_t idesc;      // tcgen05 instruction descriptor (M=128, N=n, operand format)
+  uint32_t b_lo_base;  // low word of the weight-tile descriptor without its address: (n*16 >> 4) << 16
+  uint32_t b_inc;      // address-field step per K16: 2 * n*16 >> 4
+  uint32_t lo_off16;
+  uint32_t acc_col;
+  uint32_t a_off, a_lo_off;
+  uint32_t flags_k;    // flags | ksteps << 16 | a_kind << 24
+};
+
 struct EpiDesc {
   uint8_t kind;
   uint8_t sigma;       // also accumulate the sigma head (dot with consts[aux_off..]) on the activated values
@@ -84,6 +94,7 @@ struct MlpProgram {
   int32_t Lx, Ld;
   int32_t passes;                          // 1 or 3
   StageDesc st[kMaxStages];
+  IssueDesc is[kMaxStages];
   EpiDesc ep[kMaxSteps];
 };
 

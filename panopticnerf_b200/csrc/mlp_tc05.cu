@@ -422,66 +422,72 @@ mlp_fused_kernel(const MlpParams p) {
     }
   } else {
     // =============================================================== MMA issuer
-    // One elected thread walks the stage list.  Everything it needs comes from __constant__ memory or is
-    // derived from uniform values, so descriptors are built on the uniform datapath.
-    if (elect_one()) {
-      uint32_t gs = 0, ready = 0;
-      int it = 0;
-      const uint32_t emb_hi = smem_u32(smem + kSmemEmb);
-      for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
-        const int b = it & 1;
-        const uint32_t dir_hi = smem_u32(smem + kSmemDir + b * 2 * kDirPartBytes);
-        // The descriptor of stage si+1 is fetched while stage si is being issued (constant-bank latency is
-        // otherwise exposed once per stage on this single in-order thread).
-        StageDesc sd = c_prog.st[0];
+    // The whole warp walks the stage list in lock step, so the loop state (stage words from __constant__
+    // memory, ring slot, descriptors) stays on the uniform datapath; only the tcgen05 instructions sit in an
+    // elect.sync branch.  The issue table (IssueDesc) holds every per-stage word ready to use: measured on
+    // a stand-alone replica (tools/probe_issue3.cu) this loop needs ~570 cycles per 12-MMA stage next to
+    // ALU-saturating warps, the field-by-field version it replaces ~1000 (the tensor work is 768).
+    uint32_t gs = 0, ready = 0, slot = 0;
+    int it = 0;
+    // (address field only: in a cluster the shared-window address of CTA rank > 0 carries the rank above it)
+    const uint32_t ring16 = (smem_u32(smem + kSmemRing) >> 4) & 0x3FFFu;
+    const uint32_t emb_hi = smem_u32(smem + kSmemEmb);
+    constexpr uint32_t kFullK = PASSES == 3 ? 4u : 8u;   // K16 steps of a full stage
+    for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
+      const int b = it & 1;
+      const uint32_t dir_hi = smem_u32(smem + kSmemDir + b * 2 * kDirPartBytes);
 #pragma unroll 1
-        for (int si = 0; si < n_stages; ++si, ++gs) {
-          const uint32_t flags = sd.flags;
-          const uint32_t n = sd.n;
-          const uint32_t ksteps = sd.ksteps;
-          const uint32_t a_kind = sd.a_kind;
-          const uint32_t acc_col = sd.acc_col, lo_off16 = sd.lo_off16, a_off = sd.a_off, a_lo_off = sd.a_lo_off;
-          sd = c_prog.st[si + 1 < n_stages ? si + 1 : 0];
+      for (int si = 0; si < n_stages; ++si, ++gs) {
+        const uint32_t idesc = c_prog.is[si].idesc, b_lo_base = c_prog.is[si].b_lo_base;
+        const uint32_t b_inc = c_prog.is[si].b_inc, lo_off16 = c_prog.is[si].lo_off16;
+        const uint32_t acc_col = c_prog.is[si].acc_col, a_off = c_prog.is[si].a_off;
+        const uint32_t a_lo_off = c_prog.is[si].a_lo_off, fk = c_prog.is[si].flags_k;
+        const uint32_t flags = fk & 0xFFFFu, ksteps = (fk >> 16) & 0xFFu, a_kind = fk >> 24;
 #ifdef PNR_TIMELINE
-          const bool rec = p.dbg != nullptr && blockIdx.x == 0 && it == 2;
-          if (rec) p.dbg[si * 5 + 0] = clock64();
+        const bool rec = p.dbg != nullptr && blockIdx.x == 0 && it == 2 && lane == 0;
+        if (rec) p.dbg[si * 5 + 0] = clock64();
 #endif
-          const uint32_t slot = gs % kRing;
-          if (ready <= gs) {   // the scout may be several stages ahead: poll only when our copy is stale
-            ready = ld_acquire_smem(ready_word);
-            if (ready <= gs) {
-              long long t0 = clock64();
-              while ((ready = ld_acquire_smem(ready_word)) <= gs) {
-                if ((clock64() - t0) > PNR_WATCHDOG_CYCLES) {
-                  printf("pnr: issuer watchdog: block %d stage %u\n", (int)blockIdx.x, gs);
-                  __trap();
-                }
+        if (ready <= gs) {   // the scout may be several stages ahead: poll only when our copy is stale
+          ready = ld_acquire_smem(ready_word);
+          if (ready <= gs) {
+            long long t0 = clock64();
+            while ((ready = ld_acquire_smem(ready_word)) <= gs) {
+              if ((clock64() - t0) > PNR_WATCHDOG_CYCLES) {
+                if (lane == 0) printf("pnr: issuer watchdog: block %d stage %u\n", (int)blockIdx.x, gs);
+                __trap();
               }
             }
           }
-          tc_fence_after();   // order our MMAs after the epilogue's tcgen05.ld / tcgen05.st (seen by the scout)
+        }
 #ifdef PNR_TIMELINE
-          if (rec) p.dbg[si * 5 + 1] = clock64();
+        if (rec) p.dbg[si * 5 + 1] = clock64();
 #endif
-          const uint32_t idesc = make_idesc_f32acc(kTileM, n, FMT);
-          const uint32_t b_lbo = n * 16u;
-          const uint32_t sb = smem_u32(smem + kSmemRing + slot * kStageBytes);
-          const uint32_t d_tmem = tmem + acc_col;
-          const uint32_t acc0 = (flags & F_FIRST) ? 0u : 1u;
-          // descriptors of K16 step 0; step ks adds ks * (2 * lbo >> 4) to the 14-bit address field
-          const uint64_t bdesc0 = make_smem_desc_noswz(sb, b_lbo, 128);
-          const uint64_t bdesc0_lo = bdesc0 + (uint64_t)lo_off16;
-          const uint32_t b_inc = (2u * b_lbo) >> 4;
-          if (a_kind == A_TMEM) {
-            const uint32_t a_hi = tmem + a_off, a_lo = tmem + a_lo_off;
+        // low words of the weight-tile descriptors (K16 step 0; step ks adds ks * b_inc to the address field);
+        // the high word is the same for every operand: SBO = 128 B, descriptor version 1
+        const uint32_t b_hi0 = b_lo_base | (ring16 + slot * (uint32_t)(kStageBytes >> 4));
+        const uint32_t b_lo0 = b_hi0 + lo_off16;
+        const uint32_t d_tmem = tmem + acc_col;
+        const uint32_t acc0 = (flags & F_FIRST) ? 0u : 1u;
+        const uint32_t a_hi = tmem + a_off, a_lo = tmem + a_lo_off;
+        const bool fast = a_kind == A_TMEM && ksteps == kFullK;
+        if (elect_one()) {
+          tc_fence_after();   // order our MMAs after the epilogue's tcgen05.ld / tcgen05.st (seen by the scout)
+          if (fast) {
 #pragma unroll
-            for (uint32_t ks = 0; ks < (PASSES == 3 ? 4u : 8u); ++ks) {
-              if (ks < ksteps) {
-                mma_ts(d_tmem, a_hi + ks * 8, bdesc0 + (uint64_t)(ks * b_inc), idesc, ks == 0 ? acc0 : 1u);
-                if (PASSES == 3) {
-                  mma_ts(d_tmem, a_lo + ks * 8, bdesc0 + (uint64_t)(ks * b_inc), idesc, 1u);
-                  mma_ts(d_tmem, a_hi + ks * 8, bdesc0_lo + (uint64_t)(ks * b_inc), idesc, 1u);
-                }
+            for (uint32_t ks = 0; ks < kFullK; ++ks) {
+              mma_ts_lo(d_tmem, a_hi + ks * 8, b_hi0 + ks * b_inc, idesc, ks == 0 ? acc0 : 1u);
+              if (PASSES == 3) {
+                mma_ts_lo(d_tmem, a_lo + ks * 8, b_hi0 + ks * b_inc, idesc, 1u);
+                mma_ts_lo(d_tmem, a_hi + ks * 8, b_lo0 + ks * b_inc, idesc, 1u);
+              }
+            }
+          } else if (a_kind == A_TMEM) {
+#pragma unroll 1
+            for (uint32_t ks = 0; ks < ksteps; ++ks) {
+              mma_ts_lo(d_tmem, a_hi + ks * 8, b_hi0 + ks * b_inc, idesc, ks == 0 ? acc0 : 1u);
+              if (PASSES == 3) {
+                mma_ts_lo(d_tmem, a_lo + ks * 8, b_hi0 + ks * b_inc, idesc, 1u);
+                mma_ts_lo(d_tmem, a_hi + ks * 8, b_lo0 + ks * b_inc, idesc, 1u);
               }
             }
           } else {
@@ -490,14 +496,14 @@ mlp_fused_kernel(const MlpParams p) {
             const uint64_t adesc0 = make_smem_desc_noswz(a_base, kTileM * 16, 128);
             const uint64_t adesc0_lo = make_smem_desc_noswz(a_base + a_lo_delta, kTileM * 16, 128);
             constexpr uint32_t a_inc = (2u * kTileM * 16u) >> 4;
-#pragma unroll
-            for (uint32_t ks = 0; ks < (PASSES == 3 ? 4u : 8u); ++ks) {
-              if (ks < ksteps) {
-                mma_ss(d_tmem, adesc0 + (uint64_t)(ks * a_inc), bdesc0 + (uint64_t)(ks * b_inc), idesc, ks == 0 ? acc0 : 1u);
-                if (PASSES == 3) {
-                  mma_ss(d_tmem, adesc0_lo + (uint64_t)(ks * a_inc), bdesc0 + (uint64_t)(ks * b_inc), idesc, 1u);
-                  mma_ss(d_tmem, adesc0 + (uint64_t)(ks * a_inc), bdesc0_lo + (uint64_t)(ks * b_inc), idesc, 1u);
-                }
+            const uint64_t bdesc0 = ((uint64_t)kDescHiWord << 32) | b_hi0;
+            const uint64_t bdesc0_lo = ((uint64_t)kDescHiWord << 32) | b_lo0;
+#pragma unroll 1
+            for (uint32_t ks = 0; ks < ksteps; ++ks) {
+              mma_ss(d_tmem, adesc0 + (uint64_t)(ks * a_inc), bdesc0 + (uint64_t)(ks * b_inc), idesc, ks == 0 ? acc0 : 1u);
+              if (PASSES == 3) {
+                mma_ss(d_tmem, adesc0_lo + (uint64_t)(ks * a_inc), bdesc0 + (uint64_t)(ks * b_inc), idesc, 1u);
+                mma_ss(d_tmem, adesc0 + (uint64_t)(ks * a_inc), bdesc0_lo + (uint64_t)(ks * b_inc), idesc, 1u);
               }
             }
           }
@@ -516,6 +522,8 @@ mlp_fused_kernel(const MlpParams p) {
           if (rec) { p.dbg[si * 5 + 3] = clock64(); p.dbg[si * 5 + 4] = p.dbg[si * 5 + 3]; }
 #endif
         }
+        __syncwarp();
+        slot = (slot + 1 == (uint32_t)kRing) ? 0u : slot + 1;
       }
     }
   }

@@ -6,6 +6,7 @@
 #include <vector>
 #include "common.cuh"
 #include "mlp_program.h"
+#include "tc05.cuh"
 
 namespace pnr {
 
@@ -231,6 +232,18 @@ struct Builder {
           if (stage_touches(prog.st[i], f)) war = i;
       }
       prog.st[war].flags |= F_COMMIT_WAR;
+    }
+    for (int i = 0; i < prog.n_stages; ++i) {   // issue table (flags are final now)
+      const StageDesc& sd = prog.st[i];
+      IssueDesc& d = prog.is[i];
+      d.idesc = make_idesc_f32acc(kTileM, sd.n, fmt);   // fmt: 0 = fp16, 1 = bf16 (kFmtF16 / kFmtBF16)
+      d.b_lo_base = (uint32_t)(((sd.n * 16u) >> 4) & 0x3FFFu) << 16;
+      d.b_inc = (2u * sd.n * 16u) >> 4;
+      d.lo_off16 = sd.lo_off16;
+      d.acc_col = sd.acc_col;
+      d.a_off = sd.a_off;
+      d.a_lo_off = sd.a_lo_off;
+      d.flags_k = (uint32_t)sd.flags | ((uint32_t)sd.ksteps << 16) | ((uint32_t)sd.a_kind << 24);
     }
   }
 };

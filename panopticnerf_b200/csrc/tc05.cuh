@@ -203,6 +203,19 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same with the weight-tile descriptor given as its low word only (address | LBO << 16); the high word is the
+// constant kDescHiWord (SBO = 128 B, version 1), so advancing K is one 32-bit add.
+constexpr uint32_t kDescHiWord = 0x4008u;
+__device__ __forceinline__ void mma_ts_lo(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_desc_lo,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\t"
+      "mov.b64 bd, {%2, 0x4008};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_desc_lo), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
                                        uint32_t idesc, uint32_t accumulate) {
   asm volatile(
