@@ -18,7 +18,7 @@ constexpr int kRing = 4;                  // weight stages in flight
 constexpr int kStageBytes = 32768;        // max stage: N=128 rows x 64 K x 2 bytes x (hi + lo images)
 constexpr int kEpiWarps = 8;              // TMEM->reg->TMEM activation warps (2 per lane quarter)
 constexpr int kProWarps = 4;              // positional-encoding producer warps (one thread per row)
-constexpr int kMlpThreads = (kEpiWarps + kProWarps + 3) * 32;   // + TMA warp + MMA issuer warp + scout warp = 480
+constexpr int kMlpThreads = (kEpiWarps + kProWarps + 4) * 32;   // + TMA warp, MMA issuer, scout, second MMA issuer = 512
 constexpr int kClusterSize = 2;           // CTAs sharing one weight stream by TMA multicast
 constexpr int kMaxStages = 384;
 constexpr int kMaxSteps = 24;

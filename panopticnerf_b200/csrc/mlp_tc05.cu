@@ -184,6 +184,7 @@ mlp_fused_kernel(const MlpParams p) {
     }
     mbar_init(bar_war, 1);
     *reinterpret_cast<volatile uint32_t*>(bars + 31) = 0u;
+    *reinterpret_cast<volatile uint32_t*>(bars + 29) = 0u;
     mbar_init(bar_emb_full, kProWarps * 32);
     mbar_init(bar_emb_empty, 1);
     fence_mbar_init();
@@ -427,7 +428,16 @@ mlp_fused_kernel(const MlpParams p) {
     // elect.sync branch.  The issue table (IssueDesc) holds every per-stage word ready to use: measured on
     // a stand-alone replica (tools/probe_issue3.cu) this loop needs ~570 cycles per 12-MMA stage next to
     // ALU-saturating warps, the field-by-field version it replaces ~1000 (the tensor work is 768).
-    uint32_t gs = 0, ready = 0, slot = 0;
+    //
+    // Two such warps (on different SM sub-partitions) take alternate stages.  The tensor pipe's queue is only a
+    // few MMAs deep, so the ~400-600 cycles one warp spends between two bursts (commits, next stage's words,
+    // loop) drain it; with two warps that work overlaps the other warp's burst.  The owner of stage g bursts
+    // only after the owner of g-1 has issued (shared counter `issued`): MMAs of one accumulator keep their
+    // order, and because the pipe retires a CTA's MMAs in issue order, the commit that follows a half's last
+    // stage also covers the stages the other warp issued for it.
+    const uint32_t me = (warp == kEpiWarps + kProWarps + 1) ? 0u : 1u;
+    volatile uint32_t* issued_w = reinterpret_cast<volatile uint32_t*>(bars + 29);
+    uint32_t gs = 0, ready = 0, slot = 0, issued = 0;
     int it = 0;
     // (address field only: in a cluster the shared-window address of CTA rank > 0 carries the rank above it)
     const uint32_t ring16 = (smem_u32(smem + kSmemRing) >> 4) & 0x3FFFu;
@@ -437,7 +447,8 @@ mlp_fused_kernel(const MlpParams p) {
       const int b = it & 1;
       const uint32_t dir_hi = smem_u32(smem + kSmemDir + b * 2 * kDirPartBytes);
 #pragma unroll 1
-      for (int si = 0; si < n_stages; ++si, ++gs) {
+      for (int si = 0; si < n_stages; ++si, ++gs, slot = (slot + 1 == (uint32_t)kRing) ? 0u : slot + 1) {
+        if ((gs & 1u) != me) continue;
         const uint32_t idesc = c_prog.is[si].idesc, b_lo_base = c_prog.is[si].b_lo_base;
         const uint32_t b_inc = c_prog.is[si].b_inc, lo_off16 = c_prog.is[si].lo_off16;
         const uint32_t acc_col = c_prog.is[si].acc_col, a_off = c_prog.is[si].a_off;
@@ -470,6 +481,15 @@ mlp_fused_kernel(const MlpParams p) {
         const uint32_t acc0 = (flags & F_FIRST) ? 0u : 1u;
         const uint32_t a_hi = tmem + a_off, a_lo = tmem + a_lo_off;
         const bool fast = a_kind == A_TMEM && ksteps == kFullK;
+        if (issued < gs) {   // the other warp must have issued stage gs-1
+          long long t0 = clock64();
+          while ((issued = *issued_w) < gs) {
+            if ((clock64() - t0) > PNR_WATCHDOG_CYCLES) {
+              if (lane == 0) printf("pnr: issuer hand-off watchdog: block %d stage %u\n", (int)blockIdx.x, gs);
+              __trap();
+            }
+          }
+        }
         if (elect_one()) {
           tc_fence_after();   // order our MMAs after the epilogue's tcgen05.ld / tcgen05.st (seen by the scout)
           if (fast) {
@@ -507,6 +527,7 @@ mlp_fused_kernel(const MlpParams p) {
               }
             }
           }
+          *issued_w = gs + 1;
 #ifdef PNR_TIMELINE
           if (rec) p.dbg[si * 5 + 2] = clock64();
 #endif
@@ -523,7 +544,7 @@ mlp_fused_kernel(const MlpParams p) {
 #endif
         }
         __syncwarp();
-        slot = (slot + 1 == (uint32_t)kRing) ? 0u : slot + 1;
+        issued = gs + 1;
       }
     }
   }
