@@ -26,6 +26,11 @@ import threading
 import time
 from pathlib import Path
 
+# stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION prints it to stdout) must not
+# precede it.  INFO / TRACE set by the caller are respected.
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 import torch
 
 ROOT = Path(__file__).resolve().parent
