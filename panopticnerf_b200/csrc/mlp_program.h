@@ -16,7 +16,7 @@ namespace pnr {
 constexpr int kTileM = 128;               // samples per tile = TMEM lanes = UMMA M
 constexpr int kRing = 4;                  // weight stages in flight
 constexpr int kStageBytes = 32768;        // max stage: N=128 rows x 64 K x 2 bytes x (hi + lo images)
-constexpr int kEpiWarps = 8;              // TMEM->reg->TMEM activation warps (2 per lane quarter)
+constexpr int kEpiWarps = 8;              // TMEM->reg->TMEM activation warps (2 per lane quarter; 12 and 16 measured slower)
 constexpr int kProWarps = 4;              // positional-encoding producer warps (one thread per row)
 constexpr int kMlpThreads = (kEpiWarps + kProWarps + 4) * 32;   // + TMA warp, MMA issuer, scout, second MMA issuer = 512
 constexpr int kClusterSize = 2;           // CTAs sharing one weight stream by TMA multicast
@@ -116,8 +116,8 @@ struct MlpParams {
 };
 
 constexpr int kSmemConsts = kSmemProg;   // (the program itself is in __constant__ memory)
-constexpr int kSmemPart = kSmemConsts + kMaxConsts * 4;      // [2][128][4] floats
-constexpr int kSmemBars = kSmemPart + 2 * kTileM * 4 * 4;
+constexpr int kSmemPart = kSmemConsts + kMaxConsts * 4;      // [kEpiWarps/4][128][4] floats
+constexpr int kSmemBars = kSmemPart + (kEpiWarps / 4) * kTileM * 4 * 4;
 constexpr int kSmemTotal = kSmemBars + 256;
 static_assert(kSmemTotal <= 232448, "shared-memory map exceeds the 227 KB per-CTA limit");
 

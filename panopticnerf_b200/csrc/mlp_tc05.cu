@@ -233,8 +233,9 @@ mlp_fused_kernel(const MlpParams p) {
           const int gb_all = h == 0 ? 0 : (ed.n0 >> 4);
           const int ge_all = h == 0 ? (ed.n0 >> 4) : (ed.n >> 4);
           const int G = ge_all - gb_all;
-          const int gb = gb_all + (ch == 0 ? 0 : (G + 1) / 2);
-          const int ge = gb_all + (ch == 0 ? (G + 1) / 2 : G);
+          constexpr int kCh = kEpiWarps / 4;                     // warps sharing one lane quarter
+          const int gb = gb_all + (ch * G + kCh - 1) / kCh;      // ceil(ch*G/kCh): near-equal contiguous shares
+          const int ge = gb_all + ((ch + 1) * G + kCh - 1) / kCh;
           const uint32_t acc = cx.tmem_lane + ed.acc_col;
           // software pipeline: the load of group g+1 is in flight while group g is processed
           uint32_t ra[16], rb[16];
@@ -306,12 +307,14 @@ mlp_fused_kernel(const MlpParams p) {
               mine[0] = c0; mine[1] = c1; mine[2] = c2;
               named_bar_sync(1, kEpiWarps * 32);
               if (ch == 0 && valid) {
-                const float* other = part + (kTileM + row) * 4;
                 const float* b3 = consts + c_prog.rgb_bias_off;
-                const float o0 = c0 + other[0] + b3[0];
-                const float o1 = c1 + other[1] + b3[1];
-                const float o2 = c2 + other[2] + b3[2];
-                const float o3 = mine[3] + other[3] + consts[c_prog.sigma_bias_off];
+                float o0 = c0, o1 = c1, o2 = c2, o3 = mine[3];
+#pragma unroll
+                for (int oc = 1; oc < kEpiWarps / 4; ++oc) {   // fixed order: deterministic sums
+                  const float* other = part + (oc * kTileM + row) * 4;
+                  o0 += other[0]; o1 += other[1]; o2 += other[2]; o3 += other[3];
+                }
+                o0 += b3[0]; o1 += b3[1]; o2 += b3[2]; o3 += consts[c_prog.sigma_bias_off];
                 float* dst = p.raw + s * p.CH;
                 if (p.CH == 4) {
                   *reinterpret_cast<float4*>(dst) = make_float4(o0, o1, o2, o3);
