@@ -131,6 +131,24 @@ int pnr_composite(const float* raw, const float* z, const float* rays, int64_t R
                   const int32_t* sample_box, const int32_t* box_sem, const int32_t* box_inst,
                   int32_t B, const pnr_composite_out* out, void* stream);
 
+/* a9 backward (first stage of the backward chain): d(loss)/d(raw) [R,N,4+C+K] from the
+ * gradients of the composited maps (any pointer may be NULL = zero gradient; disp_map is not differentiated).
+ * Same arguments as pnr_composite.  sem_softmax != 0 returns PNR_ERR_UNSUPPORTED. */
+typedef struct pnr_composite_grads {
+  const float* rgb_map;    /* [R,3] */
+  const float* depth_map;  /* [R]   */
+  const float* acc_map;    /* [R]   */
+  const float* weights;    /* [R,N] */
+  const float* semantic_map;        /* [R,C] */
+  const float* instance_map;        /* [R,K] */
+  const float* fixed_semantic_map;  /* [R,C] */
+  const float* fixed_instance_map;  /* [R,K] */
+} pnr_composite_grads;
+int pnr_composite_backward(const float* raw, const float* z, const float* rays, int64_t R, int32_t N,
+                           int32_t C, int32_t K, int32_t white_bkgd, int32_t sem_softmax, int32_t mask_outside,
+                           const int32_t* sample_box, const int32_t* box_sem, const int32_t* box_inst,
+                           int32_t B, const pnr_composite_grads* g, float* d_raw, void* stream);
+
 /* a10: sample_pdf + merge.  z [R,N] coarse depths, weights [R,N] coarse weights; bins are the mid
  * points, the pdf is weights[1:-1]+1e-5.  u [R,Ni] is required (deterministic sampler: the host's
  * linspace(0,1,Ni) broadcast over rays, so the values are the caller's, bit for bit).

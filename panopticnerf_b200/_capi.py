@@ -33,6 +33,12 @@ class PnrCompositeOut(C.Structure):
                  "instance_map", "fixed_semantic_map", "fixed_instance_map")]
 
 
+class PnrCompositeGrads(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in
+                ("rgb_map", "depth_map", "acc_map", "weights", "semantic_map",
+                 "instance_map", "fixed_semantic_map", "fixed_instance_map")]
+
+
 # name -> (restype, argtypes); mirrors include/pnr.h one to one
 _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 SIGNATURES = {
@@ -52,6 +58,8 @@ SIGNATURES = {
     "pnr_mlp_forward_timeline": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "pnr_composite": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32,
                                 C.POINTER(PnrCompositeOut), _vp]),
+    "pnr_composite_backward": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp,
+                                         _i32, C.POINTER(PnrCompositeGrads), _vp, _vp]),
     "pnr_sample_pdf": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "pnr_workspace_bytes": (C.c_size_t, [_vp, _i64, _i32, _i32]),
     "pnr_launch_count": (_i64, [_i32]),

@@ -236,9 +236,178 @@ __global__ void __launch_bounds__(kCompWarps * 32) composite_kernel(CompositeArg
   }
 }
 
+// ------------------------------------------------------------------------------------ a9 backward
+// d(loss)/d(raw) given d(loss)/d(maps) (the first stage of the backward chain).
+// With t_i = 1 - alpha_i + 1e-10, T_i = prod_{j<i} t_j, w_i = alpha_i T_i and
+//   G_i = dL/dw_i = g_rgb . c_i + g_depth z_i + g_acc + g_sem . s_i + g_inst . u_i + g_w[i] + fixed-map terms:
+//   dL/dalpha_i = G_i T_i - (sum_{j>i} G_j w_j) / t_i,   dalpha/dsigma = delta_i exp(-sigma_i delta_i),
+//   dL/dc_i = w_i g_rgb (through the sigmoid), dL/ds_i = w_i g_sem, dL/du_i = w_i g_inst.
+// Same work distribution as the forward kernel: one warp per ray, lanes stride samples for the scans and
+// channels for the logits; T is recomputed with the forward's scan so that w matches it bit for bit.
+struct CompositeBwdArgs {
+  const float* raw; const float* z; const float* rays;
+  int64_t R; int N, C, K, CH;
+  int white_bkgd, mask_outside;
+  const int32_t* sample_box; const int32_t* box_sem; const int32_t* box_inst; int B;
+  pnr_composite_grads g;
+  float* d_raw;
+};
+
+__global__ void __launch_bounds__(kCompWarps * 32) composite_backward_kernel(CompositeBwdArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * kCompWarps + (threadIdx.x >> 5);
+  if (r >= a.R) return;
+  const int N = a.N, CH = a.CH, C = a.C, K = a.K;
+  const float* raw = a.raw + r * N * CH;
+  float* d_raw = a.d_raw + r * N * CH;
+  const float* z = a.z + r * N;
+  const float dx = a.rays[r * 6 + 3], dy = a.rays[r * 6 + 4], dz = a.rays[r * 6 + 5];
+  const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+  float g_r = 0.f, g_g = 0.f, g_b = 0.f;
+  if (a.g.rgb_map) { g_r = a.g.rgb_map[r * 3 + 0]; g_g = a.g.rgb_map[r * 3 + 1]; g_b = a.g.rgb_map[r * 3 + 2]; }
+  const float g_depth = a.g.depth_map ? a.g.depth_map[r] : 0.f;
+  float g_acc = a.g.acc_map ? a.g.acc_map[r] : 0.f;
+  if (a.white_bkgd) g_acc -= g_r + g_g + g_b;   // rgb_map += 1 - acc_map
+  const bool fsem = C > 0 && a.g.fixed_semantic_map && a.sample_box && a.box_sem;
+  const bool finst = K > 0 && a.g.fixed_instance_map && a.sample_box && a.box_inst;
+
+  float w[kCompMaxPerLane], T[kCompMaxPerLane], G[kCompMaxPerLane], dsig[kCompMaxPerLane], tv[kCompMaxPerLane];
+  float carry = 1.0f;
+#pragma unroll
+  for (int j = 0; j < kCompMaxPerLane; ++j) {
+    w[j] = T[j] = G[j] = dsig[j] = 0.f;
+    tv[j] = 1.0f;
+    const int i0 = j * 32;
+    if (i0 >= N) continue;
+    const int i = i0 + lane;
+    float alpha = 0.f, Gi = 0.f, ds = 0.f;
+    float cr = 0.f, cg = 0.f, cb = 0.f;
+    if (i < N) {
+      const float zi = z[i];
+      const float dist = ((i + 1 < N) ? (z[i + 1] - zi) : 1e10f) * dnorm;
+      const float* q = raw + (int64_t)i * CH;
+      float sig = fmaxf(q[3], 0.f);
+      bool live = q[3] > 0.f;
+      int32_t sb = -1;
+      if (a.sample_box != nullptr) sb = a.sample_box[r * N + i];
+      if (a.mask_outside && a.sample_box != nullptr && sb < 0) { sig = 0.f; live = false; }
+      const float e = expf(-sig * dist);
+      alpha = 1.0f - e;
+      ds = live ? dist * e : 0.f;                       // dalpha / draw_sigma
+      cr = 1.0f / (1.0f + expf(-q[0]));
+      cg = 1.0f / (1.0f + expf(-q[1]));
+      cb = 1.0f / (1.0f + expf(-q[2]));
+      Gi = g_r * cr + g_g * cg + g_b * cb + g_depth * zi + g_acc;
+      if (a.g.weights) Gi += a.g.weights[r * N + i];
+      if (sb >= 0 && sb < a.B) {
+        if (fsem) { const int32_t id = a.box_sem[sb]; if (id >= 0 && id < C) Gi += a.g.fixed_semantic_map[r * C + id]; }
+        if (finst) { const int32_t id = a.box_inst[sb]; if (id >= 0 && id < K) Gi += a.g.fixed_instance_map[r * K + id]; }
+      }
+    }
+    const float t = (i < N) ? (1.0f - alpha + 1e-10f) : 1.0f;
+    tv[j] = t;
+    float incl = t;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const float o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl *= o;
+    }
+    float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = 1.0f;
+    T[j] = carry * excl;
+    carry *= __shfl_sync(0xffffffffu, incl, 31);
+    w[j] = alpha * T[j];
+    G[j] = Gi;
+    dsig[j] = ds;
+    if (i < N) {   // colour gradients need nothing else
+      const float wi = w[j];
+      float* dq = d_raw + (int64_t)i * CH;
+      dq[0] = wi * g_r * cr * (1.0f - cr);
+      dq[1] = wi * g_g * cg * (1.0f - cg);
+      dq[2] = wi * g_b * cb * (1.0f - cb);
+    }
+  }
+
+  // logits: G_i += g_sem . s_i + g_inst . u_i ; d_raw[i, 4 + c] = w_i g[c]   (lanes stride channels)
+  const bool have_sem = C > 0 && a.g.semantic_map, have_inst = K > 0 && a.g.instance_map;
+  if (C + K > 0) {
+    float gs[kCompMaxChan], gi[kCompMaxChan];
+#pragma unroll
+    for (int s = 0; s < kCompMaxChan; ++s) {
+      const int c = lane + 32 * s;
+      gs[s] = (have_sem && c < C) ? a.g.semantic_map[r * C + c] : 0.f;
+      gi[s] = (have_inst && c < K) ? a.g.instance_map[r * K + c] : 0.f;
+    }
+    for (int i = 0; i < N; ++i) {
+      float wi = 0.f;
+#pragma unroll
+      for (int j = 0; j < kCompMaxPerLane; ++j)
+        if (j == (i >> 5)) wi = __shfl_sync(0xffffffffu, w[j], i & 31);
+      const float* q = raw + (int64_t)i * CH + 4;
+      float* dq = d_raw + (int64_t)i * CH + 4;
+      float dot = 0.f;
+#pragma unroll
+      for (int s = 0; s < kCompMaxChan; ++s) {
+        const int c = lane + 32 * s;
+        if (c < C) { dot += gs[s] * q[c]; dq[c] = wi * gs[s]; }
+        if (c < K) { dot += gi[s] * q[C + c]; dq[C + c] = wi * gi[s]; }
+      }
+      dot = warp_sum(dot);
+#pragma unroll
+      for (int j = 0; j < kCompMaxPerLane; ++j)
+        if (j == (i >> 5) && lane == (i & 31)) G[j] += dot;
+    }
+  }
+
+  // suffix sums of G_j w_j, last group of 32 first
+  float tail = 0.f;   // sum over all later groups
+#pragma unroll
+  for (int j = kCompMaxPerLane - 1; j >= 0; --j) {
+    const int i0 = j * 32;
+    if (i0 >= N) continue;
+    const int i = i0 + lane;
+    const float v = (i < N) ? G[j] * w[j] : 0.f;
+    float incl = v;   // inclusive suffix sum within the group
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const float o = __shfl_down_sync(0xffffffffu, incl, d);
+      if (lane + d < 32) incl += o;
+    }
+    const float S = tail + (incl - v);   // strictly later samples
+    tail += __shfl_sync(0xffffffffu, incl, 0);
+    if (i < N) {
+      const float t = tv[j];
+      d_raw[(int64_t)i * CH + 3] = (G[j] * T[j] - S / t) * dsig[j];
+    }
+  }
+}
+
 }  // namespace pnr
 
 using namespace pnr;
+
+extern "C" int pnr_composite_backward(const float* raw, const float* z, const float* rays, int64_t R, int32_t N,
+                                      int32_t C, int32_t K, int32_t white_bkgd, int32_t sem_softmax,
+                                      int32_t mask_outside, const int32_t* sample_box, const int32_t* box_sem,
+                                      const int32_t* box_inst, int32_t B, const pnr_composite_grads* g,
+                                      float* d_raw, void* stream) {
+  if (R == 0) return PNR_OK;
+  PNR_CHECK_ARG(raw && z && rays && g && d_raw, "pnr_composite_backward: null pointer");
+  PNR_CHECK_ARG(N >= 1 && N <= 32 * kCompMaxPerLane, "pnr_composite_backward: N=%d outside [1,%d]", N,
+                32 * kCompMaxPerLane);
+  PNR_CHECK_ARG(C >= 0 && C <= 32 * kCompMaxChan && K >= 0 && K <= 32 * kCompMaxChan,
+                "pnr_composite_backward: C=%d or K=%d outside [0,%d]", C, K, 32 * kCompMaxChan);
+  if (sem_softmax)
+    return set_error(PNR_ERR_UNSUPPORTED, "pnr_composite_backward: sem_activation=softmax is not implemented");
+  CompositeBwdArgs a;
+  a.raw = raw; a.z = z; a.rays = rays; a.R = R; a.N = N; a.C = C; a.K = K; a.CH = 4 + C + K;
+  a.white_bkgd = white_bkgd; a.mask_outside = mask_outside;
+  a.sample_box = sample_box; a.box_sem = box_sem; a.box_inst = box_inst; a.B = B; a.g = *g; a.d_raw = d_raw;
+  composite_backward_kernel<<<(unsigned)((R + kCompWarps - 1) / kCompWarps), kCompWarps * 32, 0,
+                              (cudaStream_t)stream>>>(a);
+  PNR_LAUNCH_CHECK("composite_backward_kernel");
+  return PNR_OK;
+}
 
 extern "C" int pnr_generate_rays(int32_t H, int32_t W, int32_t row0, int32_t rows, int32_t camera,
                                  const float* intr_host, const float* c2w_host, float* rays, void* stream) {

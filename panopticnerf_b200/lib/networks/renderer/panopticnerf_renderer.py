@@ -161,6 +161,100 @@ def raw2outputs(raw, z_vals, rays_d, raw_noise_std: float = 0.0, white_bkgd: boo
     return out
 
 
+def raw2outputs_backward(raw, z_vals, rays_d, grads: Dict[str, torch.Tensor], white_bkgd: bool = False,
+                         num_classes: int = 0, num_instances: int = 0, sem_activation: str = "none",
+                         sample_box: Optional[torch.Tensor] = None, box_sem: Optional[torch.Tensor] = None,
+                         box_inst: Optional[torch.Tensor] = None, mask_outside: bool = False) -> torch.Tensor:
+    """Gradient of a scalar loss with respect to `raw` [R,N,4+C+K], given its gradients with respect to the maps
+    `raw2outputs` returns (`grads`: any subset of rgb_map, depth_map, acc_map, weights, semantic_map,
+    instance_map, fixed_semantic_map, fixed_instance_map; `disp_map` is not differentiated).  First stage of
+    the backward chain of the render path; checked against autograd through the oracle."""
+    raw, z_vals = _f(raw, "raw"), _f(z_vals, "z_vals")
+    R, N = z_vals.shape
+    Cn, Kn = int(num_classes), int(num_instances)
+    if raw.shape[-1] != 4 + Cn + Kn:
+        raise ValueError(f"raw2outputs_backward: raw has {raw.shape[-1]} channels, expected {4 + Cn + Kn}")
+    if "disp_map" in grads:
+        raise ValueError("raw2outputs_backward: disp_map is not differentiated")
+    rays = torch.cat([torch.zeros_like(rays_d), rays_d], -1) if rays_d.shape[-1] == 3 else rays_d
+    rays = _f(rays, "rays")
+    shapes = {"rgb_map": (R, 3), "depth_map": (R,), "acc_map": (R,), "weights": (R, N), "semantic_map": (R, Cn),
+              "instance_map": (R, Kn), "fixed_semantic_map": (R, Cn), "fixed_instance_map": (R, Kn)}
+    held = {}
+    for k, g in grads.items():
+        if k not in shapes:
+            raise ValueError(f"raw2outputs_backward: unknown map {k!r}")
+        if g is None:
+            continue
+        g = _f(g, k)
+        if tuple(g.shape) != shapes[k]:
+            raise ValueError(f"raw2outputs_backward: grad of {k} has shape {tuple(g.shape)}, expected {shapes[k]}")
+        held[k] = g
+    cg = _capi.PnrCompositeGrads(**{k: _capi.ptr(held[k]) if k in held else None
+                                    for k, _ in _capi.PnrCompositeGrads._fields_})
+    B = 0
+    if sample_box is not None and box_sem is not None:
+        B = box_sem.shape[0]
+    if sample_box is not None and box_inst is not None:
+        B = box_inst.shape[0]
+    sb = sample_box.to(_I32).contiguous() if sample_box is not None else None
+    bs = box_sem.to(_I32).contiguous() if box_sem is not None else None
+    bi = box_inst.to(_I32).contiguous() if box_inst is not None else None
+    d_raw = torch.empty_like(raw)
+    _capi.check(_capi.lib().pnr_composite_backward(
+        _capi.ptr(raw), _capi.ptr(z_vals), _capi.ptr(rays), R, N, Cn, Kn, int(bool(white_bkgd)),
+        int(sem_activation == "softmax"), int(bool(mask_outside)), _capi.ptr(sb), _capi.ptr(bs), _capi.ptr(bi),
+        B, C.byref(cg), _capi.ptr(d_raw), _capi.stream_ptr()), "pnr_composite_backward")
+    return d_raw
+
+
+class _Raw2OutputsFn(torch.autograd.Function):
+    """`raw2outputs` as an autograd node: losses written in torch on the composited maps back-propagate to `raw`
+    through `pnr_composite_backward`.  The maps are returned in a fixed key order."""
+    KEYS = ("rgb_map", "depth_map", "acc_map", "weights", "semantic_map", "instance_map",
+            "fixed_semantic_map", "fixed_instance_map")
+
+    @staticmethod
+    def forward(ctx, raw, z_vals, rays_d, kw):
+        out = raw2outputs(raw.detach(), z_vals, rays_d, **kw)
+        ctx.save_for_backward(raw.detach(), z_vals, rays_d)
+        ctx.kw = kw
+        ctx.present = [k for k in _Raw2OutputsFn.KEYS if k in out]
+        ctx.mark_non_differentiable(out["disp_map"])
+        return tuple(out[k] for k in ctx.present) + (out["disp_map"],)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        raw, z_vals, rays_d = ctx.saved_tensors
+        grads = {k: g for k, g in zip(ctx.present, gs[:-1]) if g is not None}
+        return raw2outputs_backward(raw, z_vals, rays_d, grads, **ctx.kw), None, None, None
+
+
+def raw2outputs_autograd(raw, z_vals, rays_d, white_bkgd: bool = False, num_classes: int = 0,
+                         num_instances: int = 0, sem_activation: str = "none",
+                         sample_box: Optional[torch.Tensor] = None, box_sem: Optional[torch.Tensor] = None,
+                         box_inst: Optional[torch.Tensor] = None, mask_outside: bool = False) -> Dict[str, torch.Tensor]:
+    """`raw2outputs` whose outputs carry gradients back to `raw` (z_vals and rays are treated as constants, as in
+    the reference's training step where the sampler is not differentiated)."""
+    kw = dict(white_bkgd=white_bkgd, num_classes=num_classes, num_instances=num_instances,
+              sem_activation=sem_activation, sample_box=sample_box, box_sem=box_sem, box_inst=box_inst,
+              mask_outside=mask_outside)
+    res = _Raw2OutputsFn.apply(raw, z_vals, rays_d, kw)
+    Cn, Kn = int(num_classes), int(num_instances)
+    present = ["rgb_map", "depth_map", "acc_map", "weights"]
+    if Cn > 0:
+        present.append("semantic_map")
+    if Kn > 0:
+        present.append("instance_map")
+    if sample_box is not None and box_sem is not None and Cn > 0:
+        present.append("fixed_semantic_map")
+    if sample_box is not None and box_inst is not None and Kn > 0:
+        present.append("fixed_instance_map")
+    out = dict(zip(present, res[:-1]))
+    out["disp_map"] = res[-1]
+    return out
+
+
 def sample_pdf(z, weights, N_importance: int, det: bool = True, u: Optional[torch.Tensor] = None,
                want_idx: bool = False):
     """a10 on coarse depths z [R,N] and coarse weights [R,N] (bins = mid points, pdf = weights[1:-1]).

@@ -1,0 +1,125 @@
+"""GPU parity of the compositing backward pass (first stage of the backward chain):
+`pnr_composite_backward` through the C ABI vs torch.autograd through the oracle's raw2outputs on identical
+inputs and identical upstream gradients.  Tolerance: 1e-4 relative, floor = RMS of the oracle's gradient
+tensor per channel group (gradients span many orders of magnitude along a ray).
+Parity is "vs in-repo oracle" - the reference source is not in the mount (parity unpinned)."""
+import pytest
+import torch
+
+from oracle import reference_renderer as O
+from panopticnerf_b200.lib.networks.renderer import panopticnerf_renderer as P
+from util import assert_close, rms
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _case(R, N, C, K, seed, boxes=False, far=60.0):
+    g = torch.Generator().manual_seed(seed)
+    raw = torch.randn(R, N, 4 + C + K, generator=g)
+    raw[..., 3] = raw[..., 3] * 0.6 - 0.1           # a mix of empty (sigma_raw <= 0) and occupied samples
+    z = torch.sort(torch.rand(R, N, generator=g) * (far - 2.0) + 2.0, -1).values
+    d = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1) * (0.5 + torch.rand(R, 1, generator=g))
+    kw = {}
+    if boxes:
+        B = 9
+        kw["sample_box"] = torch.randint(-1, B, (R, N), generator=g, dtype=torch.int32)
+        kw["box_sem"] = torch.randint(0, max(C, 1), (B,), generator=g, dtype=torch.int32)
+        kw["box_inst"] = torch.randint(0, max(K, 1), (B,), generator=g, dtype=torch.int32)
+    return raw, z, d, kw
+
+
+def _oracle_grad(raw, z, d, kw, ups, **opts):
+    raw = raw.clone().requires_grad_(True)
+    out = O.raw2outputs(raw, z, d, num_classes=opts.get("C", 0), num_instances=opts.get("K", 0),
+                        white_bkgd=opts.get("white_bkgd", False), mask_outside=opts.get("mask_outside", False), **kw)
+    loss = sum((out[k] * u).sum() for k, u in ups.items())
+    (g,) = torch.autograd.grad(loss, raw)
+    return g
+
+
+def _ups(out_keys, R, N, C, K, seed):
+    g = torch.Generator().manual_seed(seed + 100)
+    shapes = {"rgb_map": (R, 3), "depth_map": (R,), "acc_map": (R,), "weights": (R, N), "semantic_map": (R, C),
+              "instance_map": (R, K), "fixed_semantic_map": (R, C), "fixed_instance_map": (R, K)}
+    return {k: torch.randn(*shapes[k], generator=g) for k in out_keys}
+
+
+def _check(g_gpu, g_ref, C, K, what):
+    g_gpu = g_gpu.cpu()
+    assert torch.isfinite(g_ref).all()
+    groups = [("rgb", slice(0, 3)), ("sigma", slice(3, 4))]
+    if C:
+        groups.append(("sem", slice(4, 4 + C)))
+    if K:
+        groups.append(("inst", slice(4 + C, 4 + C + K)))
+    for name, sl in groups:
+        ref = g_ref[..., sl]
+        assert_close(g_gpu[..., sl], ref, max(rms(ref), 1e-12), f"{what}: d_raw[{name}]")
+
+
+@pytest.mark.parametrize("R,N,C,K", [(300, 64, 0, 0), (257, 33, 7, 5), (64, 192, 45, 50), (5, 1, 3, 0), (40, 256, 0, 4)])
+def test_composite_backward_matches_autograd(R, N, C, K):
+    raw, z, d, kw = _case(R, N, C, K, seed=R + N)
+    keys = ["rgb_map", "depth_map", "acc_map", "weights"] + (["semantic_map"] if C else []) + (["instance_map"] if K else [])
+    ups = _ups(keys, R, N, C, K, seed=N)
+    ref = _oracle_grad(raw, z, d, kw, ups, C=C, K=K)
+    got = P.raw2outputs_backward(raw.to(DEV), z.to(DEV), d.to(DEV), {k: v.to(DEV) for k, v in ups.items()},
+                                 num_classes=C, num_instances=K)
+    _check(got, ref, C, K, f"R={R} N={N} C={C} K={K}")
+
+
+def test_composite_backward_options_and_fixed_maps():
+    """white background, density masked outside the primitives, gradients of the fixed (bounding-box) maps."""
+    R, N, C, K = 200, 64, 6, 4
+    raw, z, d, kw = _case(R, N, C, K, seed=11, boxes=True)
+    keys = ["rgb_map", "acc_map", "semantic_map", "fixed_semantic_map", "fixed_instance_map"]
+    ups = _ups(keys, R, N, C, K, seed=5)
+    ref = _oracle_grad(raw, z, d, kw, ups, C=C, K=K, white_bkgd=True, mask_outside=True)
+    got = P.raw2outputs_backward(raw.to(DEV), z.to(DEV), d.to(DEV), {k: v.to(DEV) for k, v in ups.items()},
+                                 white_bkgd=True, mask_outside=True, num_classes=C, num_instances=K,
+                                 **{k: v.to(DEV) for k, v in kw.items()})
+    _check(got, ref, C, K, "options")
+    outside = kw["sample_box"] < 0
+    assert outside.any() and bool((got.cpu()[..., 3][outside] == 0).all())
+
+
+def test_composite_backward_subset_of_maps_and_empty():
+    R, N = 100, 64
+    raw, z, d, kw = _case(R, N, 0, 0, seed=3)
+    ups = _ups(["depth_map"], R, N, 0, 0, seed=1)
+    ref = _oracle_grad(raw, z, d, kw, ups)
+    got = P.raw2outputs_backward(raw.to(DEV), z.to(DEV), d.to(DEV), {"depth_map": ups["depth_map"].to(DEV)})
+    _check(got, ref, 0, 0, "depth only")
+    assert bool((got.cpu()[..., :3] == 0).all())          # no colour gradient was supplied
+    e = P.raw2outputs_backward(raw[:0].to(DEV), z[:0].to(DEV), d[:0].to(DEV), {})
+    assert e.shape == (0, N, 4)
+
+
+def test_losses_backpropagate_through_the_autograd_node():
+    """A torch-side photometric + cross-entropy + depth loss on the composited maps reaches `raw`."""
+    R, N, C = 150, 64, 8
+    raw, z, d, kw = _case(R, N, C, 0, seed=21)
+    g = torch.Generator().manual_seed(2)
+    rgb_gt, label, depth_gt = torch.rand(R, 3, generator=g), torch.randint(0, C, (R,), generator=g), torch.rand(R, generator=g) * 50
+
+    def loss_fn(out):
+        return (((out["rgb_map"] - rgb_gt.to(out["rgb_map"].device)) ** 2).mean()
+                + 0.1 * torch.nn.functional.cross_entropy(out["semantic_map"], label.to(out["rgb_map"].device))
+                + 0.01 * (out["depth_map"] - depth_gt.to(out["rgb_map"].device)).abs().mean())
+
+    raw_c = raw.clone().requires_grad_(True)
+    loss_fn(O.raw2outputs(raw_c, z, d, num_classes=C)).backward()
+    raw_g = raw.to(DEV).requires_grad_(True)
+    out = P.raw2outputs_autograd(raw_g, z.to(DEV), d.to(DEV), num_classes=C)
+    loss_fn(out).backward()
+    _check(raw_g.grad, raw_c.grad, C, 0, "loss")
+    assert not out["disp_map"].requires_grad
+
+
+def test_composite_backward_rejects_what_it_does_not_implement():
+    raw, z, d, _ = _case(4, 8, 3, 0, seed=0)
+    with pytest.raises(Exception, match="softmax"):
+        P.raw2outputs_backward(raw.to(DEV), z.to(DEV), d.to(DEV), {}, num_classes=3, sem_activation="softmax")
+    with pytest.raises(ValueError, match="disp_map"):
+        P.raw2outputs_backward(raw.to(DEV), z.to(DEV), d.to(DEV), {"disp_map": torch.zeros(4, device=DEV)}, num_classes=3)

@@ -71,12 +71,15 @@ def main():
         if prec == "fp16x3":
             raw = net.forward_rays(rays, z)
             hit = P.intersect(rays, batch["box_center"], batch["box_half"], batch["box_rot"], 4)
+            grads = {"rgb_map": torch.randn(R, 3, device=DEV), "depth_map": torch.randn(R, device=DEV)}
             for name, fn, byt in [
                 ("near_far", lambda: P.scene_near_far(rays, batch["scene_aabb"], cfg.near, cfg.far), R * 32),
                 ("intersect", lambda: P.intersect(rays, batch["box_center"], batch["box_half"], batch["box_rot"], 4), R * (24 + 1 + 48)),
                 ("stratified+tag", lambda: P.stratified_z(near, far, t_vals, 0.0, None, hit[1], hit[2], hit[3], want_tags=True), R * (8 + 48 + 8 * N)),
                 ("composite", lambda: P.raw2outputs(raw, z, rays, num_classes=cfg.num_classes, num_instances=cfg.num_instances),
                  R * N * (4 * raw.shape[-1] + 8) + R * 20),
+                ("composite_bwd", lambda: P.raw2outputs_backward(raw, z, rays, grads, num_classes=cfg.num_classes, num_instances=cfg.num_instances),
+                 R * N * (8 * raw.shape[-1] + 8) + R * 20),
                 ("render_total", lambda: PN.make_renderer(cfg, net).render(batch), 0),
             ]:
                 med, best = timeit(fn, flush=flush)
