@@ -26,10 +26,15 @@ import threading
 import time
 from pathlib import Path
 
-# stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION prints it to stdout) must not
-# precede it.  INFO / TRACE set by the caller are respected.
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries exactly one JSON line.  Libraries write to it too (NCCL prints its version banner there at
+# NCCL_DEBUG=VERSION/WARN), so file descriptor 1 is pointed at stderr for the whole run and the JSON line is
+# written to a saved copy of the real stdout.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 import torch
 
@@ -173,7 +178,7 @@ def run_reference(args, cfg, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -379,7 +384,7 @@ def main():
             "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_baseline, "gpu_launches": launches,
             "clocks": clocks, "fast_mode": fast,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
