@@ -239,6 +239,55 @@ def raw2outputs(raw, z_vals, rays_d, raw_noise_std: float = 0.0, white_bkgd: boo
     return out
 
 
+def raw2outputs_backward(raw, z_vals, rays_d, grads: Dict[str, torch.Tensor], white_bkgd: bool = False,
+                         num_classes: int = 0, num_instances: int = 0,
+                         sample_box: Optional[torch.Tensor] = None, box_sem: Optional[torch.Tensor] = None,
+                         box_inst: Optional[torch.Tensor] = None, mask_outside: bool = False) -> torch.Tensor:
+    """Closed form of d(loss)/d(raw) for `raw2outputs` (sem_activation "none", no noise), the algorithm
+    `pnr_composite_backward` implements.  With t_i = 1 - alpha_i + 1e-10, T_i = prod_{j<i} t_j, w_i = alpha_i T_i,
+    G_i = dL/dw_i:   dL/dalpha_i = G_i T_i - (sum_{j>i} G_j w_j) / t_i.
+    tests/test_cpu_backward.py pins it against autograd through `raw2outputs`."""
+    C, K = num_classes, num_instances
+    R, N = z_vals.shape
+    zero = torch.zeros(())
+    g = lambda k, shape: grads[k] if k in grads and grads[k] is not None else torch.zeros(shape)
+    dists = torch.cat([z_vals[:, 1:] - z_vals[:, :-1], torch.full_like(z_vals[:, :1], 1e10)], -1)
+    dists = dists * torch.norm(rays_d[:, None, :], dim=-1)
+    live = raw[..., 3] > 0
+    if mask_outside and sample_box is not None:
+        live = live & (sample_box >= 0)
+    sig = torch.where(live, raw[..., 3], torch.zeros_like(raw[..., 3]))
+    e = torch.exp(-sig * dists)
+    alpha = 1.0 - e
+    t = 1.0 - alpha + 1e-10
+    T = torch.cumprod(torch.cat([torch.ones_like(t[:, :1]), t], -1), -1)[:, :-1]
+    w = alpha * T
+    c = torch.sigmoid(raw[..., :3])
+    g_rgb = g("rgb_map", (R, 3))
+    g_acc = g("acc_map", (R,)) - (g_rgb.sum(-1) if white_bkgd else zero)
+    G = (c * g_rgb[:, None]).sum(-1) + g("depth_map", (R,))[:, None] * z_vals + g_acc[:, None] + g("weights", (R, N))
+    d_raw = torch.zeros_like(raw)
+    d_raw[..., :3] = w[..., None] * g_rgb[:, None] * c * (1.0 - c)
+    if C > 0:
+        gs = g("semantic_map", (R, C))
+        G = G + (raw[..., 4:4 + C] * gs[:, None]).sum(-1)
+        d_raw[..., 4:4 + C] = w[..., None] * gs[:, None]
+    if K > 0:
+        gi = g("instance_map", (R, K))
+        G = G + (raw[..., 4 + C:4 + C + K] * gi[:, None]).sum(-1)
+        d_raw[..., 4 + C:4 + C + K] = w[..., None] * gi[:, None]
+    for key, table, n in (("fixed_semantic_map", box_sem, C), ("fixed_instance_map", box_inst, K)):
+        if sample_box is not None and table is not None and n > 0 and grads.get(key) is not None:
+            ids = torch.where(sample_box >= 0, table.to(torch.int64)[sample_box.clamp(min=0).to(torch.int64)],
+                              torch.full_like(sample_box, -1, dtype=torch.int64))
+            ok = (ids >= 0) & (ids < n)
+            G = G + torch.where(ok, torch.gather(grads[key], 1, ids.clamp(0, n - 1)), torch.zeros_like(G))
+    Gw = G * w
+    S = torch.flip(torch.cumsum(torch.flip(Gw, [-1]), -1), [-1]) - Gw        # strictly later samples
+    d_raw[..., 3] = (G * T - S / t) * torch.where(live, dists * e, torch.zeros_like(e))
+    return d_raw
+
+
 def _composite_onehot(weights, sample_box, table, n):
     """sum_i w_i * onehot(table[sample_box_i]) ; samples with box -1 or an id outside [0,n) add nothing."""
     ids = torch.where(sample_box >= 0, table.to(torch.int64)[sample_box.clamp(min=0).to(torch.int64)],
