@@ -156,6 +156,16 @@ int pnr_composite_backward(const float* raw, const float* z, const float* rays, 
 int pnr_sample_pdf(const float* z, const float* weights, int64_t R, int32_t N, int32_t Ni,
                    const float* u, float* z_fine, int64_t* idx, float* z_all, void* stream);
 
+/* Host-only twin of pnr_load_weights (no CUDA call, no context): builds the per-tile program of the fused MLP
+ * kernel, the packed 16-bit weight stream and the constant table for `cfg` and returns them in caller buffers
+ * (each may be NULL to query sizes only).  `program` receives the MlpProgram struct of csrc/mlp_program.h.
+ * For the CPU test tier: tests/test_cpu_program.py replays the program on the host and compares it with
+ * the oracle's Network.forward. */
+int pnr_program_host(const pnr_config* cfg, const float* const* tensors_host, const int64_t* shapes, int32_t n,
+                     void* program, size_t program_cap, size_t* program_bytes,
+                     void* wpacked, size_t wpacked_cap, size_t* wpacked_bytes,
+                     float* consts, size_t consts_cap, size_t* n_consts);
+
 /* Bytes of device scratch Renderer.render needs for R rays (z, raw, ids ...), for the caller to own. */
 size_t pnr_workspace_bytes(const pnr_ctx* ctx, int64_t R, int32_t N, int32_t Ni);
 

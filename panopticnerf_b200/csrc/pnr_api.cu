@@ -260,8 +260,14 @@ extern "C" int64_t pnr_launch_count(int32_t reset) {
   return v;
 }
 
-extern "C" int pnr_create(const pnr_config* cfg, pnr_ctx** out) {
-  PNR_CHECK_ARG(cfg && out, "pnr_create: null pointer");
+static int precision_passes(int precision) {
+  return (precision == PNR_PREC_BF16X3 || precision == PNR_PREC_FP16X3) ? 3 : 1;
+}
+static int precision_fmt(int precision) {   // instruction-descriptor operand format: 0 = fp16, 1 = bf16
+  return (precision == PNR_PREC_BF16X3 || precision == PNR_PREC_BF16) ? 1 : 0;
+}
+
+static int check_config(const pnr_config* cfg) {
   PNR_CHECK_ARG(cfg->D >= 3 && cfg->D <= 16, "pnr_create: D=%d outside [3,16]", cfg->D);
   PNR_CHECK_ARG(cfg->W == 64 || cfg->W == 128 || cfg->W == 256, "pnr_create: W=%d not in {64,128,256}", cfg->W);
   PNR_CHECK_ARG(cfg->xyz_res >= 0 && cfg->xyz_res <= 10, "pnr_create: xyz_res=%d outside [0,10]", cfg->xyz_res);
@@ -269,6 +275,12 @@ extern "C" int pnr_create(const pnr_config* cfg, pnr_ctx** out) {
   PNR_CHECK_ARG(cfg->num_classes >= 0 && cfg->num_classes <= 128, "pnr_create: num_classes=%d outside [0,128]", cfg->num_classes);
   PNR_CHECK_ARG(cfg->num_instances >= 0 && cfg->num_instances <= 128, "pnr_create: num_instances=%d outside [0,128]", cfg->num_instances);
   PNR_CHECK_ARG(cfg->precision >= 0 && cfg->precision <= 3, "pnr_create: bad precision %d", cfg->precision);
+  return PNR_OK;
+}
+
+extern "C" int pnr_create(const pnr_config* cfg, pnr_ctx** out) {
+  PNR_CHECK_ARG(cfg && out, "pnr_create: null pointer");
+  if (const int rc = check_config(cfg)) return rc;
   int ndev = 0;
   PNR_CUDA(cudaGetDeviceCount(&ndev));
   PNR_CHECK_ARG(cfg->device >= 0 && cfg->device < ndev, "pnr_create: device %d of %d", cfg->device, ndev);
@@ -280,8 +292,8 @@ extern "C" int pnr_create(const pnr_config* cfg, pnr_ctx** out) {
   PNR_CUDA(cudaSetDevice(cfg->device));
   pnr_ctx* c = new pnr_ctx();
   c->cfg = *cfg;
-  c->passes = (cfg->precision == PNR_PREC_BF16X3 || cfg->precision == PNR_PREC_FP16X3) ? 3 : 1;
-  c->fmt = (cfg->precision == PNR_PREC_BF16X3 || cfg->precision == PNR_PREC_BF16) ? 1 : 0;
+  c->passes = precision_passes(cfg->precision);
+  c->fmt = precision_fmt(cfg->precision);
   *out = c;
   return PNR_OK;
 }
@@ -294,9 +306,10 @@ extern "C" int pnr_destroy(pnr_ctx* ctx) {
   return PNR_OK;
 }
 
-extern "C" int pnr_load_weights(pnr_ctx* ctx, const float* const* t, const int64_t* shapes, int32_t n) {
-  PNR_CHECK_ARG(ctx && t && shapes, "pnr_load_weights: null pointer");
-  const pnr_config& c = ctx->cfg;
+// Host only (no CUDA call): checks the tensor list against cfg, builds the per-tile program, the packed
+// weight stream and the constant table.  Shared by pnr_load_weights and pnr_program_host.
+static int build_program(const pnr_config& c, const float* const* t, const int64_t* shapes, int32_t n,
+                         Builder& bld) {
   const int D = c.D, W = c.W, W2 = W / 2, C = c.num_classes, K = c.num_instances;
   const int Ex = 3 + 6 * c.xyz_res, Ed = 3 + 6 * c.view_res, skip = D / 2;
   const int expected = 2 * D + 8 + (C > 0 ? 4 : 0) + (K > 0 ? 4 : 0);
@@ -316,10 +329,9 @@ extern "C" int pnr_load_weights(pnr_ctx* ctx, const float* const* t, const int64
     return set_error(PNR_ERR_ARG, "pnr_load_weights: tensor %d: expected weight [%d,%d] + bias [%d,1]", \
                      ti, out, in, out)
 
-  Builder bld(ctx->passes, ctx->fmt);
   bld.prog.Lx = c.xyz_res;
   bld.prog.Ld = c.view_res;
-  bld.prog.passes = ctx->passes;
+  bld.prog.passes = bld.passes;
 
   std::vector<Mat> trunk(D);
   std::vector<const float*> trunk_b(D);
@@ -421,6 +433,15 @@ extern "C" int pnr_load_weights(pnr_ctx* ctx, const float* const* t, const int64
     return set_error(PNR_ERR_UNSUPPORTED, "pnr_load_weights: %d constants > %d", (int)bld.consts.size(), kMaxConsts);
   bld.prog.n_consts = (int)bld.consts.size();
   bld.finalize();
+  return PNR_OK;
+}
+
+extern "C" int pnr_load_weights(pnr_ctx* ctx, const float* const* t, const int64_t* shapes, int32_t n) {
+  PNR_CHECK_ARG(ctx && t && shapes, "pnr_load_weights: null pointer");
+  const pnr_config& c = ctx->cfg;
+  Builder bld(ctx->passes, ctx->fmt);
+  const int rc = build_program(c, t, shapes, n, bld);
+  if (rc != PNR_OK) return rc;
 
   PNR_CUDA(cudaSetDevice(c.device));
   cudaFree(ctx->d_wpacked); cudaFree(ctx->d_consts);
@@ -434,6 +455,33 @@ extern "C" int pnr_load_weights(pnr_ctx* ctx, const float* const* t, const int64
   PNR_CUDA(cudaMemcpy(ctx->d_wpacked, bld.wbuf.data(), ctx->wpacked_bytes, cudaMemcpyHostToDevice));
   PNR_CUDA(cudaMemcpy(ctx->d_consts, bld.consts.data(), bld.consts.size() * 4, cudaMemcpyHostToDevice));
   ctx->loaded = true;
+  return PNR_OK;
+}
+
+extern "C" int pnr_program_host(const pnr_config* cfg, const float* const* t, const int64_t* shapes, int32_t n,
+                                void* program, size_t program_cap, size_t* program_bytes, void* wpacked,
+                                size_t wpacked_cap, size_t* wpacked_bytes, float* consts, size_t consts_cap,
+                                size_t* n_consts) {
+  PNR_CHECK_ARG(cfg && t && shapes && program_bytes && wpacked_bytes && n_consts, "pnr_program_host: null pointer");
+  if (const int rc = check_config(cfg)) return rc;
+  Builder bld(precision_passes(cfg->precision), precision_fmt(cfg->precision));
+  const int rc = build_program(*cfg, t, shapes, n, bld);
+  if (rc != PNR_OK) return rc;
+  *program_bytes = sizeof(MlpProgram);
+  *wpacked_bytes = bld.wbuf.size() * 2;
+  *n_consts = bld.consts.size();
+  if (program) {
+    PNR_CHECK_ARG(program_cap >= sizeof(MlpProgram), "pnr_program_host: program buffer too small");
+    memcpy(program, &bld.prog, sizeof(MlpProgram));
+  }
+  if (wpacked) {
+    PNR_CHECK_ARG(wpacked_cap >= *wpacked_bytes, "pnr_program_host: weight buffer too small");
+    memcpy(wpacked, bld.wbuf.data(), *wpacked_bytes);
+  }
+  if (consts) {
+    PNR_CHECK_ARG(consts_cap >= *n_consts, "pnr_program_host: constant buffer too small");
+    memcpy(consts, bld.consts.data(), *n_consts * 4);
+  }
   return PNR_OK;
 }
 

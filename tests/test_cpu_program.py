@@ -1,0 +1,203 @@
+"""CPU tier: the host side of the fused MLP kernel.  `pnr_program_host` (the host-only twin of pnr_load_weights)
+builds the per-tile program, the packed 16-bit weight stream and the constant table; this test REPLAYS that
+program on the CPU - stage by stage, from the packed bytes, following the same StageDesc / EpiDesc semantics
+the kernel interprets - and compares the result with the oracle's Network.forward.  It pins the weight packing
+(tile order, hi/lo split, K padding), the feature_linear fold, the skip connection, the head wiring, the bias /
+sigma / rgb constant offsets and the hazard-flag invariants without a GPU."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_renderer as O
+from panopticnerf_b200 import _capi, make_cfg, make_network, synthetic as S
+from util import assert_close, rms
+
+K_MAX_STAGES, K_MAX_STEPS = 384, 24
+A_TMEM, A_EMB, A_DIR = 0, 1, 2
+F_FIRST, F_WAIT_E0, F_WAIT_E1, F_COMMIT_ACC0, F_COMMIT_ACC1, F_COMMIT_WAR = 1, 2, 4, 8, 16, 32
+EPI_RELU_TO_A, EPI_LINEAR_TO_A, EPI_VIEW_RGB, EPI_LOGITS = 0, 1, 2, 3
+COL_A_HI, COL_HEAD_HI = 256, 128
+
+
+class StageDesc(C.Structure):
+    _fields_ = [("gofs", C.c_uint32), ("bytes", C.c_uint32), ("n", C.c_uint16), ("acc_col", C.c_uint16),
+                ("a_off", C.c_uint16), ("a_lo_off", C.c_uint16), ("flags", C.c_uint16), ("lo_off16", C.c_uint16),
+                ("ksteps", C.c_uint8), ("a_kind", C.c_uint8)]
+
+
+class IssueDesc(C.Structure):
+    _fields_ = [(k, C.c_uint32) for k in ("idesc", "b_lo_base", "b_inc", "lo_off16", "acc_col", "a_off", "a_lo_off", "flags_k")]
+
+
+class EpiDesc(C.Structure):
+    _fields_ = [("kind", C.c_uint8), ("sigma", C.c_uint8)] + [(k, C.c_uint16) for k in
+                ("n", "n0", "n_valid", "acc_col", "dst_col", "dst_lo_col", "bias_off", "aux_off", "out_off")]
+
+
+class MlpProgram(C.Structure):
+    _fields_ = [("n_stages", C.c_int32), ("n_steps", C.c_int32), ("n_consts", C.c_int32),
+                ("sigma_bias_off", C.c_int32), ("rgb_bias_off", C.c_int32), ("Lx", C.c_int32), ("Ld", C.c_int32),
+                ("passes", C.c_int32), ("st", StageDesc * K_MAX_STAGES), ("is_", IssueDesc * K_MAX_STAGES),
+                ("ep", EpiDesc * K_MAX_STEPS)]
+
+
+def build(cfg, net):
+    host, shapes = [], []
+    for lin in net._linears():
+        w, b = lin.weight.detach().float().contiguous(), lin.bias.detach().float().contiguous()
+        host += [w, b]
+        shapes += [w.shape[0], w.shape[1], b.shape[0], 1]
+    L = _capi.lib()
+    pc = _capi.PnrConfig(cfg.D, cfg.W, cfg.xyz_res, cfg.view_res, cfg.num_classes, cfg.num_instances,
+                         _capi.PREC[cfg.precision], 0)
+    ptrs = (C.c_void_p * len(host))(*[t.data_ptr() for t in host])
+    shp = (C.c_int64 * len(shapes))(*shapes)
+    pb, wb, nc = C.c_size_t(), C.c_size_t(), C.c_size_t()
+    _capi.check(L.pnr_program_host(C.byref(pc), ptrs, shp, len(host), None, 0, C.byref(pb), None, 0, C.byref(wb),
+                                   None, 0, C.byref(nc)), "pnr_program_host (sizes)")
+    assert pb.value == C.sizeof(MlpProgram), "MlpProgram layout in this test is out of date"
+    prog = MlpProgram()
+    w16 = np.zeros(wb.value // 2, dtype=np.uint16)
+    consts = np.zeros(nc.value, dtype=np.float32)
+    _capi.check(L.pnr_program_host(C.byref(pc), ptrs, shp, len(host), C.byref(prog), pb.value, C.byref(pb),
+                                   w16.ctypes.data, wb.value, C.byref(wb), consts.ctypes.data, nc.value, C.byref(nc)),
+                "pnr_program_host")
+    return prog, w16, consts
+
+
+def to_f32(u16: np.ndarray, bf16: bool) -> np.ndarray:
+    if bf16:
+        return (u16.astype(np.uint32) << 16).view(np.float32)
+    return u16.view(np.float16).astype(np.float32)
+
+
+def replay(prog, w16, consts, cfg, pts, viewdirs):
+    """What the kernel computes for these samples, in float64, from the packed program."""
+    S_ = pts.shape[0]
+    bf16 = cfg.precision.startswith("bf16")
+    emb = np.zeros((S_, 64)); emb[:, :3 + 6 * cfg.xyz_res] = O.embed(pts, cfg.xyz_res).double().numpy()
+    dirs = np.zeros((S_, 32)); dirs[:, :3 + 6 * cfg.view_res] = O.embed(viewdirs, cfg.view_res).double().numpy()
+    act = {COL_A_HI: np.zeros((S_, 256)), COL_HEAD_HI: np.zeros((S_, 128))}
+    acc = np.zeros((S_, 256))
+    CH = 4 + cfg.num_classes + cfg.num_instances
+    out = np.zeros((S_, CH))
+    sig = np.zeros(S_)
+    step = -1
+    stages_of = []
+    for i in range(prog.n_stages):
+        sd = prog.st[i]
+        if sd.flags & F_WAIT_E0:
+            step += 1
+            stages_of.append([])
+        stages_of[step].append(i)
+    assert len(stages_of) == prog.n_steps
+    for s, idxs in enumerate(stages_of):
+        ed = prog.ep[s]
+        for i in idxs:
+            sd = prog.st[i]
+            n, kc = sd.n, sd.ksteps * 2
+            base = sd.gofs // 2
+            hi = to_f32(w16[base:base + n * kc * 8], bf16).reshape(kc, n, 8)
+            W = hi.astype(np.float64)
+            if prog.passes == 3:
+                lo0 = base + sd.lo_off16 * 8
+                assert sd.bytes == 2 * n * kc * 16
+                W = W + to_f32(w16[lo0:lo0 + n * kc * 8], bf16).reshape(kc, n, 8)
+            else:
+                assert sd.bytes == n * kc * 16
+            W = W.transpose(1, 0, 2).reshape(n, kc * 8)            # [row, k]
+            if sd.a_kind == A_TMEM:
+                region = COL_A_HI if sd.a_off >= COL_A_HI else COL_HEAD_HI
+                k0 = (sd.a_off - region) * 2
+                assert sd.a_lo_off - sd.a_off in (128, 64)          # lo parts sit one region further
+                A = act[region][:, k0:k0 + kc * 8]
+            elif sd.a_kind == A_EMB:
+                A = emb[:, sd.a_off * 2:sd.a_off * 2 + kc * 8]
+            else:
+                A = dirs[:, sd.a_off * 2:sd.a_off * 2 + kc * 8]
+            assert A.shape[1] == kc * 8
+            if sd.flags & F_FIRST:
+                acc[:, sd.acc_col:sd.acc_col + n] = 0.0
+            acc[:, sd.acc_col:sd.acc_col + n] += A @ W.T
+            # issue table = the same stage, pre-digested
+            d = prog.is_[i]
+            assert d.acc_col == sd.acc_col and d.a_off == sd.a_off and d.lo_off16 == sd.lo_off16
+            assert d.flags_k == (sd.flags | (sd.ksteps << 16) | (sd.a_kind << 24))
+            assert d.b_lo_base == (n << 16) and d.b_inc == 2 * n
+            assert (d.idesc >> 17) & 0x3F == n >> 3 and (d.idesc >> 24) & 0x1F == 8 and (d.idesc >> 7) & 7 == int(bf16)
+        n = ed.n
+        v = acc[:, ed.acc_col:ed.acc_col + n] + consts[ed.bias_off:ed.bias_off + n][None]
+        if ed.kind in (EPI_RELU_TO_A, EPI_LINEAR_TO_A):
+            if ed.kind == EPI_RELU_TO_A:
+                v = np.maximum(v, 0.0)
+            if ed.sigma:
+                sig = v @ consts[ed.aux_off:ed.aux_off + n].astype(np.float64)
+            act[ed.dst_col][:, :n] = v
+        elif ed.kind == EPI_VIEW_RGB:
+            v = np.maximum(v, 0.0)
+            wr = consts[ed.aux_off:ed.aux_off + 3 * n].astype(np.float64).reshape(3, n)
+            out[:, :3] = v @ wr.T + consts[prog.rgb_bias_off:prog.rgb_bias_off + 3][None]
+            out[:, 3] = sig + consts[prog.sigma_bias_off]
+        else:
+            out[:, ed.out_off:ed.out_off + ed.n_valid] = v[:, :ed.n_valid]
+    return out, stages_of
+
+
+def check_invariants(prog, stages_of):
+    """Every step signals each accumulator half once, waits for the previous step's epilogues once, and releases
+    the activation columns its first epilogue overwrites once."""
+    for idxs in stages_of:
+        fl = [prog.st[i].flags for i in idxs]
+        assert sum(bool(f & F_WAIT_E0) for f in fl) == 1 and fl[0] & F_WAIT_E0
+        assert sum(bool(f & F_WAIT_E1) for f in fl) == 1
+        assert sum(bool(f & F_COMMIT_ACC1) for f in fl) == 1 and fl[-1] & F_COMMIT_ACC1
+        assert sum(bool(f & F_COMMIT_ACC0) for f in fl) <= 1
+        assert sum(bool(f & F_COMMIT_WAR) for f in fl) == 1
+        for i in idxs:
+            sd = prog.st[i]
+            assert sd.bytes <= 32768 and sd.n % 16 == 0 and 16 <= sd.n <= 128 and 1 <= sd.ksteps <= 8
+
+
+@pytest.mark.parametrize("preset,over", [
+    ("cfg1", {}), ("cfg2", {}), ("cfg3", {}), ("cfg2", dict(precision="bf16x3")), ("cfg2", dict(precision="fp16")),
+    ("cfg2", dict(D=5, W=128, num_classes=7, num_instances=3)), ("cfg1", dict(xyz_res=4, view_res=2))])
+def test_program_replay_matches_oracle_network(preset, over):
+    cfg = make_cfg(preset, **over)
+    net = S.init_network_weights(make_network(cfg), seed=3)
+    prog, w16, consts = build(cfg, net)
+    assert prog.passes == (3 if cfg.precision.endswith("x3") else 1)
+    g = torch.Generator().manual_seed(5)
+    pts = (torch.rand(257, 3, generator=g) * 2 - 1) * 4
+    vd = torch.nn.functional.normalize(torch.randn(257, 3, generator=g), dim=-1)
+    got, stages_of = replay(prog, w16, consts, cfg, pts, vd)
+    check_invariants(prog, stages_of)
+    onet = O.Network(cfg)
+    onet.load_state_dict(net.state_dict())
+    with torch.no_grad():
+        ref = onet(pts, vd).double()
+    got = torch.from_numpy(got)
+    # the replay keeps activations exact, so only the 16-bit split of the WEIGHTS separates it from fp32:
+    # 2^-22 (fp16 hi+lo), 2^-17 (bf16 hi+lo), 2^-11 (one fp16 part) per weight
+    tol = {"fp16x3": 2e-5, "bf16x3": 1e-4, "fp16": 4e-3, "bf16": 3e-2}[cfg.precision]
+    C_, K_ = cfg.num_classes, cfg.num_instances
+    for name, sl in (("rgb", slice(0, 3)), ("sigma", slice(3, 4)), ("sem", slice(4, 4 + C_)), ("inst", slice(4 + C_, 4 + C_ + K_))):
+        if ref[:, sl].numel():
+            assert_close(got[:, sl], ref[:, sl], rms(ref[:, sl]), f"{preset} {over} {name}", rel=tol)
+
+
+def test_program_host_rejects_bad_input():
+    cfg = make_cfg("cfg1")
+    net = S.init_network_weights(make_network(cfg), seed=0)
+    L = _capi.lib()
+    pc = _capi.PnrConfig(cfg.D, cfg.W, cfg.xyz_res, cfg.view_res, 0, 0, _capi.PREC["fp16x3"], 0)
+    w = net._linears()[0].weight.detach().float().contiguous()
+    ptrs = (C.c_void_p * 2)(w.data_ptr(), w.data_ptr())
+    shp = (C.c_int64 * 4)(w.shape[0], w.shape[1], w.shape[0], 1)
+    pb, wb, nc = C.c_size_t(), C.c_size_t(), C.c_size_t()
+    rc = L.pnr_program_host(C.byref(pc), ptrs, shp, 2, None, 0, C.byref(pb), None, 0, C.byref(wb), None, 0, C.byref(nc))
+    assert rc != 0 and b"tensors" in L.pnr_last_error()
+    bad = _capi.PnrConfig(cfg.D, 100, cfg.xyz_res, cfg.view_res, 0, 0, _capi.PREC["fp16x3"], 0)
+    rc = L.pnr_program_host(C.byref(bad), ptrs, shp, 2, None, 0, C.byref(pb), None, 0, C.byref(wb), None, 0, C.byref(nc))
+    assert rc != 0 and b"W=100" in L.pnr_last_error()
