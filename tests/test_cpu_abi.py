@@ -30,6 +30,19 @@ def test_build_and_symbols():
     assert _capi.lib().pnr_version() == 100
 
 
+def test_ctypes_argument_counts_match_header():
+    """Every prototype in include/pnr.h has as many parameters as its ctypes signature (a mismatch would corrupt
+    the call stack silently)."""
+    from panopticnerf_b200 import _capi
+    txt = re.sub(r"/\*.*?\*/", "", (ROOT / "include" / "pnr.h").read_text(), flags=re.S)
+    protos = dict(re.findall(r"\b(pnr_[a-z_0-9]+)\s*\(([^;{]*?)\)\s*;", txt, flags=re.S))
+    assert set(protos) == set(_capi.SIGNATURES)
+    for name, args in protos.items():
+        args = " ".join(args.split())
+        n = 0 if args in ("", "void") else args.count(",") + 1
+        assert n == len(_capi.SIGNATURES[name][1]), f"{name}: header has {n} parameters, ctypes {len(_capi.SIGNATURES[name][1])}"
+
+
 def test_sass_is_blackwell_native():
     """cuobjdump evidence (B200_PROFILING.md): tcgen05.mma -> UTC*MMA, tcgen05.ld/st -> LDTM/STTM,
     bulk TMA -> UBLKCP; and only sm_100a code is embedded."""
