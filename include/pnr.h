@@ -161,8 +161,9 @@ int pnr_sample_pdf(const float* z, const float* weights, int64_t R, int32_t N, i
  * (each may be NULL to query sizes only).  `program` receives the MlpProgram struct of csrc/mlp_program.h.
  * For the CPU test tier: tests/test_cpu_program.py replays the program on the host and compares it with
  * the oracle's Network.forward. */
+#define PNR_PROGRAM_PAIR 1 /* flags: CTA-pair weight layout (two n/2-row images per stage; host side only so far) */
 int pnr_program_host(const pnr_config* cfg, const float* const* tensors_host, const int64_t* shapes, int32_t n,
-                     void* program, size_t program_cap, size_t* program_bytes,
+                     int32_t flags, void* program, size_t program_cap, size_t* program_bytes,
                      void* wpacked, size_t wpacked_cap, size_t* wpacked_bytes,
                      float* consts, size_t consts_cap, size_t* n_consts);
 

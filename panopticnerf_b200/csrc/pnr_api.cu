@@ -84,6 +84,10 @@ struct Builder {
   std::vector<uint16_t> wbuf;   // packed weight stream (bf16 elements)
   std::vector<float> consts;
   int passes, fmt;
+  // CTA-pair layout (round 2, tcgen05.mma.cta_group::2): every stage is stored as two images, rows [0, n/2)
+  // for CTA 0 and [n/2, n) for CTA 1, each in the core-matrix layout of an n/2-row tile.  Host side only so
+  // far (pnr_program_host + tests/test_cpu_program.py); the kernel that consumes it is not written yet.
+  bool pair = false;
   std::string err;
 
   Builder(int passes_, int fmt_) : passes(passes_), fmt(fmt_) { memset(&prog, 0, sizeof(prog)); }
@@ -150,7 +154,7 @@ struct Builder {
             sd.acc_col = (uint16_t)(acc_col + r0);
             sd.a_off = (uint16_t)(sg.a_hi + k0 / 2);
             sd.a_lo_off = (uint16_t)(sg.a_lo + k0 / 2);
-            sd.lo_off16 = (uint16_t)((r1 - r0) * kcores);
+            sd.lo_off16 = (uint16_t)((pair ? (r1 - r0) / 2 : (r1 - r0)) * kcores);
             sd.ksteps = (uint8_t)(kcores / 2);
             sd.a_kind = sg.kind;
             const bool seg_first = (k0 == 0);
@@ -160,7 +164,14 @@ struct Builder {
             if (sg.kind == A_EMB && seg_last && sg.release && last_half) sd.flags |= F_RELEASE_EMB;
             if (sg.kind == A_DIR && seg_first && h == 0) sd.flags |= F_WAIT_DIR;
             if (sg.kind == A_DIR && seg_last && sg.release && last_half) sd.flags |= F_RELEASE_DIR;
-            for (int part = 0; part < parts; ++part) pack_stage(sg.m, r0, r1 - r0, sg.col0, sg.kvalid, k0, kcores, part);
+            if (!pair) {
+              for (int part = 0; part < parts; ++part) pack_stage(sg.m, r0, r1 - r0, sg.col0, sg.kvalid, k0, kcores, part);
+            } else {
+              const int nh = (r1 - r0) / 2;
+              for (int cta = 0; cta < 2; ++cta)
+                for (int part = 0; part < parts; ++part)
+                  pack_stage(sg.m, r0 + cta * nh, nh, sg.col0, sg.kvalid, k0, kcores, part);
+            }
           }
         }
       }
@@ -236,9 +247,10 @@ struct Builder {
     for (int i = 0; i < prog.n_stages; ++i) {   // issue table (flags are final now)
       const StageDesc& sd = prog.st[i];
       IssueDesc& d = prog.is[i];
-      d.idesc = make_idesc_f32acc(kTileM, sd.n, fmt);   // fmt: 0 = fp16, 1 = bf16 (kFmtF16 / kFmtBF16)
-      d.b_lo_base = (uint32_t)(((sd.n * 16u) >> 4) & 0x3FFFu) << 16;
-      d.b_inc = (2u * sd.n * 16u) >> 4;
+      const uint32_t rows = pair ? sd.n / 2u : sd.n;     // rows of the weight tile one CTA holds
+      d.idesc = make_idesc_f32acc(pair ? 2 * kTileM : kTileM, sd.n, fmt);   // fmt: 0 = fp16, 1 = bf16
+      d.b_lo_base = (uint32_t)(((rows * 16u) >> 4) & 0x3FFFu) << 16;
+      d.b_inc = (2u * rows * 16u) >> 4;
       d.lo_off16 = sd.lo_off16;
       d.acc_col = sd.acc_col;
       d.a_off = sd.a_off;
@@ -459,12 +471,14 @@ extern "C" int pnr_load_weights(pnr_ctx* ctx, const float* const* t, const int64
 }
 
 extern "C" int pnr_program_host(const pnr_config* cfg, const float* const* t, const int64_t* shapes, int32_t n,
-                                void* program, size_t program_cap, size_t* program_bytes, void* wpacked,
+                                int32_t flags, void* program, size_t program_cap, size_t* program_bytes, void* wpacked,
                                 size_t wpacked_cap, size_t* wpacked_bytes, float* consts, size_t consts_cap,
                                 size_t* n_consts) {
   PNR_CHECK_ARG(cfg && t && shapes && program_bytes && wpacked_bytes && n_consts, "pnr_program_host: null pointer");
   if (const int rc = check_config(cfg)) return rc;
+  PNR_CHECK_ARG((flags & ~1) == 0, "pnr_program_host: unknown flags 0x%x", flags);
   Builder bld(precision_passes(cfg->precision), precision_fmt(cfg->precision));
+  bld.pair = (flags & 1) != 0;
   const int rc = build_program(*cfg, t, shapes, n, bld);
   if (rc != PNR_OK) return rc;
   *program_bytes = sizeof(MlpProgram);

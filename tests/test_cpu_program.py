@@ -43,7 +43,7 @@ class MlpProgram(C.Structure):
                 ("ep", EpiDesc * K_MAX_STEPS)]
 
 
-def build(cfg, net):
+def build(cfg, net, pair: bool = False):
     host, shapes = [], []
     for lin in net._linears():
         w, b = lin.weight.detach().float().contiguous(), lin.bias.detach().float().contiguous()
@@ -55,13 +55,13 @@ def build(cfg, net):
     ptrs = (C.c_void_p * len(host))(*[t.data_ptr() for t in host])
     shp = (C.c_int64 * len(shapes))(*shapes)
     pb, wb, nc = C.c_size_t(), C.c_size_t(), C.c_size_t()
-    _capi.check(L.pnr_program_host(C.byref(pc), ptrs, shp, len(host), None, 0, C.byref(pb), None, 0, C.byref(wb),
-                                   None, 0, C.byref(nc)), "pnr_program_host (sizes)")
+    _capi.check(L.pnr_program_host(C.byref(pc), ptrs, shp, len(host), int(pair), None, 0, C.byref(pb), None, 0,
+                                   C.byref(wb), None, 0, C.byref(nc)), "pnr_program_host (sizes)")
     assert pb.value == C.sizeof(MlpProgram), "MlpProgram layout in this test is out of date"
     prog = MlpProgram()
     w16 = np.zeros(wb.value // 2, dtype=np.uint16)
     consts = np.zeros(nc.value, dtype=np.float32)
-    _capi.check(L.pnr_program_host(C.byref(pc), ptrs, shp, len(host), C.byref(prog), pb.value, C.byref(pb),
+    _capi.check(L.pnr_program_host(C.byref(pc), ptrs, shp, len(host), int(pair), C.byref(prog), pb.value, C.byref(pb),
                                    w16.ctypes.data, wb.value, C.byref(wb), consts.ctypes.data, nc.value, C.byref(nc)),
                 "pnr_program_host")
     return prog, w16, consts
@@ -82,7 +82,7 @@ def split16(x: np.ndarray, bf16: bool):
     return hi.double().numpy(), lo.double().numpy()
 
 
-def replay(prog, w16, consts, cfg, pts, viewdirs, operand_precision: bool = False):
+def replay(prog, w16, consts, cfg, pts, viewdirs, operand_precision: bool = False, pair: bool = False):
     """What the kernel computes for these samples, from the packed program.  Default: exact activations, float64
     (tests the program).  operand_precision=True also rounds the A operands like the tensor cores see them:
     fp32 activations split into 16-bit hi (+ lo in the x3 modes), products hi*Whi (+ lo*Whi + hi*Wlo)."""
@@ -110,17 +110,22 @@ def replay(prog, w16, consts, cfg, pts, viewdirs, operand_precision: bool = Fals
             sd = prog.st[i]
             n, kc = sd.n, sd.ksteps * 2
             base = sd.gofs // 2
-            hi = to_f32(w16[base:base + n * kc * 8], bf16).reshape(kc, n, 8)
-            W = hi.astype(np.float64)
-            Wlo = np.zeros_like(W)
-            if prog.passes == 3:
-                lo0 = base + sd.lo_off16 * 8
-                assert sd.bytes == 2 * n * kc * 16
-                Wlo = to_f32(w16[lo0:lo0 + n * kc * 8], bf16).reshape(kc, n, 8).astype(np.float64)
-            else:
-                assert sd.bytes == n * kc * 16
-            W = W.transpose(1, 0, 2).reshape(n, kc * 8)            # [row, k]
-            Wlo = Wlo.transpose(1, 0, 2).reshape(n, kc * 8)
+            parts = 2 if prog.passes == 3 else 1
+            assert sd.bytes == parts * n * kc * 16
+            images = 2 if pair else 1                               # one image per CTA of the pair
+            nh = n // images
+            assert sd.lo_off16 == nh * kc
+            Ws, Wlos = [], []
+            for c in range(images):
+                b0 = base + c * parts * nh * kc * 8
+                hi = to_f32(w16[b0:b0 + nh * kc * 8], bf16).reshape(kc, nh, 8).astype(np.float64)
+                lo = np.zeros_like(hi)
+                if parts == 2:
+                    lo0 = b0 + sd.lo_off16 * 8
+                    lo = to_f32(w16[lo0:lo0 + nh * kc * 8], bf16).reshape(kc, nh, 8).astype(np.float64)
+                Ws.append(hi.transpose(1, 0, 2).reshape(nh, kc * 8))   # [row, k]
+                Wlos.append(lo.transpose(1, 0, 2).reshape(nh, kc * 8))
+            W, Wlo = np.concatenate(Ws, 0), np.concatenate(Wlos, 0)
             if sd.a_kind == A_TMEM:
                 region = COL_A_HI if sd.a_off >= COL_A_HI else COL_HEAD_HI
                 k0 = (sd.a_off - region) * 2
@@ -145,8 +150,9 @@ def replay(prog, w16, consts, cfg, pts, viewdirs, operand_precision: bool = Fals
             d = prog.is_[i]
             assert d.acc_col == sd.acc_col and d.a_off == sd.a_off and d.lo_off16 == sd.lo_off16
             assert d.flags_k == (sd.flags | (sd.ksteps << 16) | (sd.a_kind << 24))
-            assert d.b_lo_base == (n << 16) and d.b_inc == 2 * n
-            assert (d.idesc >> 17) & 0x3F == n >> 3 and (d.idesc >> 24) & 0x1F == 8 and (d.idesc >> 7) & 7 == int(bf16)
+            assert d.b_lo_base == (nh << 16) and d.b_inc == 2 * nh
+            assert (d.idesc >> 17) & 0x3F == n >> 3 and (d.idesc >> 24) & 0x1F == (16 if pair else 8)
+            assert (d.idesc >> 7) & 7 == int(bf16)
         n = ed.n
         v = acc[:, ed.acc_col:ed.acc_col + n] + consts[ed.bias_off:ed.bias_off + n][None]
         if ed.kind in (EPI_RELU_TO_A, EPI_LINEAR_TO_A):
@@ -207,6 +213,27 @@ def test_program_replay_matches_oracle_network(preset, over):
             assert_close(got[:, sl], ref[:, sl], rms(ref[:, sl]), f"{preset} {over} {name}", rel=tol)
 
 
+@pytest.mark.parametrize("preset,over", [("cfg2", {}), ("cfg3", {}), ("cfg1", dict(precision="bf16")),
+                                         ("cfg2", dict(D=5, W=128, num_classes=7, num_instances=3))])
+def test_pair_layout_replays_to_the_same_network(preset, over):
+    """PNR_PROGRAM_PAIR: every stage stored as two n/2-row images (one per CTA of a tcgen05 cta_group::2 pair).
+    Same network function, same program structure; only the weight stream order and the issue words differ."""
+    cfg = make_cfg(preset, **over)
+    net = S.init_network_weights(make_network(cfg), seed=4)
+    prog, w16, consts = build(cfg, net, pair=True)
+    single, w16_s, consts_s = build(cfg, net, pair=False)
+    assert prog.n_stages == single.n_stages and prog.n_steps == single.n_steps
+    assert w16.size == w16_s.size and np.array_equal(consts, consts_s)
+    assert np.array_equal(np.sort(w16), np.sort(w16_s))            # the same 16-bit words, re-ordered
+    g = torch.Generator().manual_seed(6)
+    pts = (torch.rand(130, 3, generator=g) * 2 - 1) * 4
+    vd = torch.nn.functional.normalize(torch.randn(130, 3, generator=g), dim=-1)
+    a, stages_of = replay(prog, w16, consts, cfg, pts, vd, pair=True)
+    b, _ = replay(single, w16_s, consts_s, cfg, pts, vd)
+    check_invariants(prog, stages_of)
+    assert np.array_equal(a, b)
+
+
 @pytest.mark.parametrize("precision,bound", [("fp16x3", 2e-5), ("bf16x3", 1e-4), ("fp16", 1e-2), ("bf16", 6e-2)])
 def test_operand_precision_of_each_mode(precision, bound):
     """The error the 16-bit operand split itself causes (activations AND weights rounded as the tensor cores see
@@ -239,8 +266,8 @@ def test_program_host_rejects_bad_input():
     ptrs = (C.c_void_p * 2)(w.data_ptr(), w.data_ptr())
     shp = (C.c_int64 * 4)(w.shape[0], w.shape[1], w.shape[0], 1)
     pb, wb, nc = C.c_size_t(), C.c_size_t(), C.c_size_t()
-    rc = L.pnr_program_host(C.byref(pc), ptrs, shp, 2, None, 0, C.byref(pb), None, 0, C.byref(wb), None, 0, C.byref(nc))
+    rc = L.pnr_program_host(C.byref(pc), ptrs, shp, 2, 0, None, 0, C.byref(pb), None, 0, C.byref(wb), None, 0, C.byref(nc))
     assert rc != 0 and b"tensors" in L.pnr_last_error()
     bad = _capi.PnrConfig(cfg.D, 100, cfg.xyz_res, cfg.view_res, 0, 0, _capi.PREC["fp16x3"], 0)
-    rc = L.pnr_program_host(C.byref(bad), ptrs, shp, 2, None, 0, C.byref(pb), None, 0, C.byref(wb), None, 0, C.byref(nc))
+    rc = L.pnr_program_host(C.byref(bad), ptrs, shp, 2, 0, None, 0, C.byref(pb), None, 0, C.byref(wb), None, 0, C.byref(nc))
     assert rc != 0 and b"W=100" in L.pnr_last_error()
