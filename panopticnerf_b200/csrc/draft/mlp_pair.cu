@@ -1,0 +1,662 @@
+// mlp_pair.cu — ROUND-2 DRAFT, NOT BUILT INTO libpnr.so (csrc/draft/ is outside _build.py's source list).
+//
+// The fused MLP kernel of mlp_tc05.cu re-organised around tcgen05.mma.cta_group::2: the two CTAs of a cluster
+// work on two tiles (256 samples) as ONE tensor-core unit.
+//   * tensor memory is allocated with cta_group::2; activations and accumulators stay in each CTA's own TMEM;
+//   * every weight stage is stored as two n/2-row images (Builder::pair / PNR_PROGRAM_PAIR, replayed on the CPU
+//     by tests/test_cpu_program.py); each CTA bulk-copies ITS image (16 KB) into its own 8-deep ring;
+//   * only the leader CTA (rank 0) runs the scout and the two issuer warps; its MMAs are M = 256 and drive both
+//     SMs, so each SM sees half the issue work and half the shared-memory weight traffic per unit of tensor work;
+//   * commits are multicast to both CTAs (acc_full, war_ok, ring empty, emb/dir empty);
+//   * the follower's epilogue / producer / "relay" warps signal the LEADER's barriers with remote arrives.
+// The MMA form itself is verified (tools/probe_pair_mma.cu).  Written without GPU access at the end of round 1:
+// compile-checked only (nvcc -c), to be brought up in round 2.
+#include <cstddef>
+#include "../common.cuh"
+#include "../mlp_program.h"
+#include "../tc05.cuh"
+
+namespace pnr {
+
+__constant__ MlpProgram c_prog;   // pair-mode program (Builder::pair = true)
+
+constexpr int kPairRing = 8;                       // ring slots per CTA
+constexpr int kPairSlotBytes = kStageBytes / 2;    // this CTA's image of a stage
+
+// ---- cluster helpers: the same shared-memory offset in the leader CTA (rank 0)
+__device__ __forceinline__ uint32_t mapa_rank0(uint32_t addr) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(addr));
+  return r;
+}
+// `count` arrivals on a barrier of another (or this) CTA of the cluster, release at cluster scope
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr, uint32_t count) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(count)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // waits fed by remote arrives
+  long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if ((++spins & 0x3FFu) == 0 && (clock64() - t0) > PNR_WATCHDOG_CYCLES) {
+      printf("pnr: pair mbarrier watchdog: block %d thread %d bar 0x%x parity %u\n", (int)blockIdx.x,
+             (int)threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+// tcgen05, CTA-pair forms
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_result_addr) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_result_addr), "n"(NCOLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+__device__ __forceinline__ void commit_pair(uint32_t bar) {   // arrives on this barrier offset in BOTH CTAs
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ts_lo_pair(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_desc_lo, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\t"
+      "mov.b64 bd, {%2, 0x4008};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], bd, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_desc_lo), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Write 8 consecutive K elements (one 16-byte core-matrix row) of this thread's row, split hi/lo.
+template <int PASSES, int FMT>
+__device__ __forceinline__ void store_core_row(uint8_t* hi_base, uint8_t* lo_base, int kcore, int row,
+                                               const float (&v)[8]) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) split_x2<FMT>(v[2 * j], v[2 * j + 1], h[j], l[j]);
+  const int off = (kcore * kTileM + row) * 16;
+  *reinterpret_cast<uint4*>(hi_base + off) = make_uint4(h[0], h[1], h[2], h[3]);
+  if (PASSES == 3) *reinterpret_cast<uint4*>(lo_base + off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// gamma(p) = [p, sin(2^0 p), cos(2^0 p), ...] padded with zeros to KPAD, streamed out 8 at a time.
+template <int PASSES, int FMT, int LMAX, int KPAD>
+__device__ __forceinline__ void encode_row(const float (&p)[3], int L, uint8_t* hi_base,
+                                           uint8_t* lo_base, int row) {
+  float v[KPAD];
+#pragma unroll
+  for (int i = 0; i < KPAD; ++i) v[i] = 0.f;
+  v[0] = p[0]; v[1] = p[1]; v[2] = p[2];
+  float f = 1.0f;
+#pragma unroll
+  for (int k = 0; k < LMAX; ++k) {
+    if (k < L) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float sn, cs;
+        sincosf(p[c] * f, &sn, &cs);
+        if (3 + 6 * k + c < KPAD) v[3 + 6 * k + c] = sn;
+        if (3 + 6 * k + 3 + c < KPAD) v[3 + 6 * k + 3 + c] = cs;
+      }
+    }
+    f *= 2.0f;
+  }
+#pragma unroll
+  for (int g = 0; g < KPAD / 8; ++g) {
+    float w8[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w8[j] = v[g * 8 + j];
+    store_core_row<PASSES, FMT>(hi_base, lo_base, g, row, w8);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Epilogue building blocks.  One thread owns one accumulator row (TMEM lane); groups are 16 columns.
+// ------------------------------------------------------------------------------------------------
+struct EpiCtx {
+  uint32_t tmem_lane;      // tmem base | lane offset of this thread's quarter
+  uint32_t bar_war;
+  uint32_t parity;
+};
+
+// activation -> next layer's A operand: v = act(acc + bias); [sigma += v . wsig]; split into hi / lo parts
+template <int PASSES, int FMT>
+__device__ __forceinline__ void epi_group_act(const uint32_t (&r)[16], int g, const EpiDesc& ed, float clamp_lo,
+                                              const float* bias, const float* wsig, float& sig,
+                                              uint32_t (&hi)[8], uint32_t (&lo)[8]) {
+  const float4* b4 = reinterpret_cast<const float4*>(bias + g * 16);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 b = b4[q];
+    const float v0 = fmaxf(__uint_as_float(r[4 * q + 0]) + b.x, clamp_lo);
+    const float v1 = fmaxf(__uint_as_float(r[4 * q + 1]) + b.y, clamp_lo);
+    const float v2 = fmaxf(__uint_as_float(r[4 * q + 2]) + b.z, clamp_lo);
+    const float v3 = fmaxf(__uint_as_float(r[4 * q + 3]) + b.w, clamp_lo);
+    if (ed.sigma) {
+      const float4 w = reinterpret_cast<const float4*>(wsig + g * 16)[q];
+      sig += v0 * w.x + v1 * w.y + v2 * w.z + v3 * w.w;
+    }
+    split_x2<FMT>(v0, v1, hi[2 * q], lo[2 * q]);
+    split_x2<FMT>(v2, v3, hi[2 * q + 1], lo[2 * q + 1]);
+  }
+}
+
+template <int PASSES>
+__device__ __forceinline__ void epi_group_store(int g, const EpiDesc& ed, const EpiCtx& cx,
+                                                const uint32_t (&hi)[8], const uint32_t (&lo)[8]) {
+  tmem_st8(cx.tmem_lane + ed.dst_col + g * 8, hi);
+  if (PASSES == 3) tmem_st8(cx.tmem_lane + ed.dst_lo_col + g * 8, lo);
+}
+
+__device__ __forceinline__ void epi_group_rgb(const uint32_t (&r)[16], int g, const EpiDesc& ed, const float* bias,
+                                              const float* wr, float& c0, float& c1, float& c2) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int c = g * 16 + j;
+    const float v = fmaxf(__uint_as_float(r[j]) + bias[c], 0.f);
+    c0 += v * wr[c];
+    c1 += v * wr[ed.n + c];
+    c2 += v * wr[2 * ed.n + c];
+  }
+}
+
+__device__ __forceinline__ void epi_group_logits(const uint32_t (&r)[16], int g, const EpiDesc& ed,
+                                                 const float* bias, float* dst) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    if (g * 16 + j < ed.n_valid) dst[g * 16 + j] = __uint_as_float(r[j]) + bias[g * 16 + j];
+}
+
+// CTAs run as clusters of two that stream the SAME weight stages in lock step: each CTA fetches half of every
+// stage from L2 and multicasts it into both shared memories, halving L2 -> SM weight traffic (the weight
+// stream, 29 B/clk/SM at full rate, was L2-latency bound with every SM fetching every byte).
+template <int PASSES, int FMT>
+__global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kMlpThreads, 1)
+mlp_pair_kernel(const MlpParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  // every CTA runs the same number of tile iterations (tiles past the end are dummies whose stores are
+  // masked) so that both CTAs of a cluster consume the shared weight stream the same number of times
+  const int tile_end = (int)(((p.num_tiles + (int)gridDim.x - 1) / (int)gridDim.x) * (int)gridDim.x);
+
+  float* consts = reinterpret_cast<float*>(smem + kSmemConsts);
+  float* part = reinterpret_cast<float*>(smem + kSmemPart);  // [2][128][4]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
+  const uint32_t ready_word = smem_u32(bars + 31);   // number of weight stages whose inputs are all ready
+
+  const bool leader = cta_rank == 0;
+  // barrier map (8-byte slots; 28.. are words): full[8] 0-7 (own image landed), empty[8] 8-15 (leader's MMAs
+  // done with the slot: committed to both CTAs), acc_full[2] 16-17, e_done[2] 18-19 (LEADER's copy counts both
+  // CTAs' epilogue warps), war 20, emb_full 21 / dir_full[2] 23-24 (LEADER's copy counts both CTAs' producer
+  // warps), emb_empty 22, dir_empty[2] 25-26
+  const uint32_t bar_full = smem_u32(&bars[0]);
+  const uint32_t bar_empty = smem_u32(&bars[kPairRing]);
+  const uint32_t bar_acc_full = smem_u32(&bars[16]);
+  const uint32_t bar_e_done = smem_u32(&bars[18]);
+  const uint32_t bar_war = smem_u32(&bars[20]);
+  const uint32_t bar_emb_full = smem_u32(&bars[21]);
+  const uint32_t bar_emb_empty = smem_u32(&bars[22]);
+  const uint32_t bar_dir_full = smem_u32(&bars[23]);
+  const uint32_t bar_dir_empty = smem_u32(&bars[25]);
+  // peer_full[8]: leader only, one per ring slot - the follower's relay arrives when ITS image of the stage in
+  // that slot has landed (same phase discipline as full[slot]; lives past the product's barrier block)
+  const uint32_t bar_peer_full = smem_u32(smem + kSmemTotal);
+
+  // ---- one-time setup: constants to shared memory, barriers, tensor memory
+  for (int i = threadIdx.x; i < c_prog.n_consts; i += blockDim.x) consts[i] = p.consts[i];
+  if (warp == 0) {
+    tmem_alloc_pair<512>(smem_u32(tmem_slot));
+  }
+  if (threadIdx.x == 32) {
+    for (int s = 0; s < kPairRing; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);              // one multicast commit of the leader's issuer
+    }
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(bar_acc_full + 8 * h, 1);
+      mbar_init(bar_e_done + 8 * h, 2 * kEpiWarps * 32);   // both CTAs' epilogue threads (used in the leader)
+      mbar_init(bar_dir_full + 8 * h, 2 * kProWarps * 32); // both CTAs' producer threads (used in the leader)
+      mbar_init(bar_dir_empty + 8 * h, 1);
+    }
+    mbar_init(bar_war, 1);
+    for (int s = 0; s < kPairRing; ++s) mbar_init(bar_peer_full + 8 * s, 1);
+    *reinterpret_cast<volatile uint32_t*>(bars + 31) = 0u;
+    *reinterpret_cast<volatile uint32_t*>(bars + 29) = 0u;
+    mbar_init(bar_emb_full, 2 * kProWarps * 32);
+    mbar_init(bar_emb_empty, 1);
+    fence_mbar_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();   // the peer's barriers must be initialised before anything is multicast into them
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int n_stages = c_prog.n_stages, n_steps = c_prog.n_steps;
+
+  if (warp < kEpiWarps) {
+    // =============================================================== epilogue warps
+    const int q = warp & 3, ch = warp >> 2;     // TMEM lane quarter ; which half of a column range
+    const int row = q * 32 + lane;
+    EpiCtx cx;
+    cx.tmem_lane = tmem + ((uint32_t)(q * 32) << 16);
+    cx.bar_war = bar_war;
+    uint32_t gstep = 0;
+    for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
+      const int64_t s = (int64_t)tile * kTileM + row;
+      const bool valid = s < p.S;
+      float sig = 0.f;
+      for (int st = 0; st < n_steps; ++st, ++gstep) {
+        const EpiDesc ed = c_prog.ep[st];
+        const uint32_t parity = gstep & 1u;
+        cx.parity = parity;
+        const float* bias = consts + ed.bias_off;
+        const float* aux = consts + ed.aux_off;
+        const bool to_a = ed.kind == EPI_RELU_TO_A || ed.kind == EPI_LINEAR_TO_A;
+        const float clamp_lo = ed.kind == EPI_RELU_TO_A ? 0.f : -INFINITY;
+        float* out_row = p.raw + (valid ? s : 0) * p.CH + ed.out_off;
+        bool war_pending = to_a;
+        float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+#ifdef PNR_TIMELINE
+          const bool rec = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && tile == 2 * (int)gridDim.x;
+          if (rec) p.dbg[4096 + (st * 2 + h) * 3 + 0] = clock64();
+#endif
+          mbar_wait_backoff(bar_acc_full + 8 * h, parity);
+          tc_fence_after();
+#ifdef PNR_TIMELINE
+          if (rec) p.dbg[4096 + (st * 2 + h) * 3 + 1] = clock64();
+#endif
+          const int gb_all = h == 0 ? 0 : (ed.n0 >> 4);
+          const int ge_all = h == 0 ? (ed.n0 >> 4) : (ed.n >> 4);
+          const int G = ge_all - gb_all;
+          constexpr int kCh = kEpiWarps / 4;                     // warps sharing one lane quarter
+          const int gb = gb_all + (ch * G + kCh - 1) / kCh;      // ceil(ch*G/kCh): near-equal contiguous shares
+          const int ge = gb_all + ((ch + 1) * G + kCh - 1) / kCh;
+          const uint32_t acc = cx.tmem_lane + ed.acc_col;
+          // software pipeline: the load of group g+1 is in flight while group g is processed
+          uint32_t ra[16], rb[16];
+          if (gb < ge) tmem_ld16(acc + gb * 16, ra);
+          if (to_a) {
+            // Two groups are converted before anything is stored: E0 reaches the write-after-read barrier
+            // (this step's MMAs still read the columns it overwrites) with two groups of work already done.
+#pragma unroll 1
+            for (int g = gb; g < ge; g += 2) {
+              uint32_t ha[8], la[8], hb[8], lb[8];
+              const bool two = g + 1 < ge;
+              tc_wait_ld();
+#ifdef PNR_TIMELINE
+              if (rec && h == 1 && g == gb) p.dbg[7168 + st * 4 + 0] = clock64();
+#endif
+              if (two) tmem_ld16(acc + (g + 1) * 16, rb);
+              epi_group_act<PASSES, FMT>(ra, g, ed, clamp_lo, bias, aux, sig, ha, la);
+#ifdef PNR_TIMELINE
+              if (rec && h == 1 && g == gb) p.dbg[7168 + st * 4 + 1] = clock64();
+#endif
+              if (two) {
+                tc_wait_ld();
+#ifdef PNR_TIMELINE
+                if (rec && h == 1 && g == gb) p.dbg[7168 + st * 4 + 2] = clock64();
+#endif
+                if (g + 2 < ge) tmem_ld16(acc + (g + 2) * 16, ra);
+                epi_group_act<PASSES, FMT>(rb, g + 1, ed, clamp_lo, bias, aux, sig, hb, lb);
+              }
+              if (war_pending) {  // the columns we are about to overwrite must have been consumed by the MMAs
+                mbar_wait_backoff(bar_war, parity);
+                tc_fence_after();
+                war_pending = false;
+              }
+              epi_group_store<PASSES>(g, ed, cx, ha, la);
+              if (two) epi_group_store<PASSES>(g + 1, ed, cx, hb, lb);
+            }
+          } else {
+#pragma unroll 1
+            for (int g = gb; g < ge; g += 2) {
+              tc_wait_ld();
+              if (g + 1 < ge) tmem_ld16(acc + (g + 1) * 16, rb);
+              if (ed.kind == EPI_VIEW_RGB) {
+                epi_group_rgb(ra, g, ed, bias, aux, c0, c1, c2);
+              } else if (valid) {
+                epi_group_logits(ra, g, ed, bias, out_row);
+              }
+              if (g + 1 < ge) {
+                tc_wait_ld();
+                if (g + 2 < ge) tmem_ld16(acc + (g + 2) * 16, ra);
+                if (ed.kind == EPI_VIEW_RGB) {
+                  epi_group_rgb(rb, g + 1, ed, bias, aux, c0, c1, c2);
+                } else if (valid) {
+                  epi_group_logits(rb, g + 1, ed, bias, out_row);
+                }
+              }
+            }
+          }
+          if (h == 0 && war_pending) {  // no columns of h0 for this thread: still consume the barrier phase
+            mbar_wait_backoff(bar_war, parity);
+            war_pending = false;
+          }
+          if (h == 1) {
+            if (ed.sigma) {
+              part[(ch * kTileM + row) * 4 + 3] = sig;
+              sig = 0.f;
+            }
+            if (ed.kind == EPI_VIEW_RGB) {
+              float* mine = part + (ch * kTileM + row) * 4;
+              mine[0] = c0; mine[1] = c1; mine[2] = c2;
+              named_bar_sync(1, kEpiWarps * 32);
+              if (ch == 0 && valid) {
+                const float* b3 = consts + c_prog.rgb_bias_off;
+                float o0 = c0, o1 = c1, o2 = c2, o3 = mine[3];
+#pragma unroll
+                for (int oc = 1; oc < kEpiWarps / 4; ++oc) {   // fixed order: deterministic sums
+                  const float* other = part + (oc * kTileM + row) * 4;
+                  o0 += other[0]; o1 += other[1]; o2 += other[2]; o3 += other[3];
+                }
+                o0 += b3[0]; o1 += b3[1]; o2 += b3[2]; o3 += consts[c_prog.sigma_bias_off];
+                float* dst = p.raw + s * p.CH;
+                if (p.CH == 4) {
+                  *reinterpret_cast<float4*>(dst) = make_float4(o0, o1, o2, o3);
+                } else {
+                  dst[0] = o0; dst[1] = o1; dst[2] = o2; dst[3] = o3;
+                }
+              }
+            }
+          }
+          if (to_a) tc_wait_st();
+          tc_fence_before();
+          __syncwarp();   // every lane's tensor-memory stores are complete and fenced
+          if (lane == 0) mbar_arrive_cluster(mapa_rank0(bar_e_done + 8 * h), 32u);
+#ifdef PNR_TIMELINE
+          if (rec) p.dbg[4096 + (st * 2 + h) * 3 + 2] = clock64();
+#endif
+        }
+      }
+    }
+  } else if (warp < kEpiWarps + kProWarps) {
+    // =============================================================== embedding producer warps
+    const int row = (warp - kEpiWarps) * 32 + lane;
+    uint8_t* emb_hi = smem + kSmemEmb;
+    uint8_t* emb_lo = emb_hi + kEmbPartBytes;
+    const int Lx = c_prog.Lx, Ld = c_prog.Ld;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
+      int64_t s = (int64_t)tile * kTileM + row;
+      if (s >= p.S) s = p.S - 1;  // clamp: tail rows compute on a valid sample, results are discarded
+      float x[3], d[3];
+      if (p.pts != nullptr) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { x[c] = p.pts[s * 3 + c]; d[c] = p.viewdirs[s * 3 + c]; }
+      } else {
+        const int64_t ray = s / p.N;
+        const float zi = p.z[s];
+        const float* rr = p.rays + ray * 6;
+        float dn2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float dc = rr[3 + c];
+          x[c] = __fadd_rn(rr[c], __fmul_rn(dc, zi));  // pts = o + d*z, separately rounded like the oracle
+          dn2 = (c == 0) ? __fmul_rn(dc, dc) : __fadd_rn(dn2, __fmul_rn(dc, dc));
+          d[c] = dc;
+        }
+        const float nrm = sqrtf(dn2);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) d[c] = __fdiv_rn(d[c], nrm);
+      }
+      mbar_wait_backoff(bar_emb_empty, (uint32_t)((it & 1) ^ 1));
+      encode_row<PASSES, FMT, 10, 64>(x, Lx, emb_hi, emb_lo, row);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_rank0(bar_emb_full), 32u);
+      const int b = it & 1;
+      uint8_t* dir_hi = smem + kSmemDir + b * 2 * kDirPartBytes;
+      mbar_wait_backoff(bar_dir_empty + 8 * b, (uint32_t)(((it >> 1) & 1) ^ 1));
+      encode_row<PASSES, FMT, 4, 32>(d, Ld, dir_hi, dir_hi + kDirPartBytes, row);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_rank0(bar_dir_full + 8 * b), 32u);
+    }
+  } else if (warp == kEpiWarps + kProWarps) {
+    // =============================================================== TMA producer (one elected thread)
+    if (elect_one()) {
+      uint32_t gs = 0;  // global stage counter
+      for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
+        for (int si = 0; si < n_stages; ++si, ++gs) {
+          const uint32_t slot = gs % kPairRing, ph = (gs / kPairRing) & 1;
+          const uint32_t gofs = c_prog.st[si].gofs, bytes = c_prog.st[si].bytes;
+          mbar_wait_backoff(bar_empty + 8 * slot, ph ^ 1);
+          // this CTA's image of the stage (rows [rank * n/2, (rank+1) * n/2), hi then lo) into its own ring slot
+          const uint32_t mine = bytes / 2;
+          mbar_arrive_expect_tx(bar_full + 8 * slot, mine);
+          bulk_g2s(smem_u32(smem + kSmemRing + slot * kPairSlotBytes), p.wpacked + gofs + cta_rank * mine, mine,
+                   bar_full + 8 * slot);
+        }
+      }
+    }
+  } else if (warp == kEpiWarps + kProWarps + 2) {
+    // =============================================================== scout (one elected thread)
+    // Does every wait the MMA issue depends on (epilogue hand-offs, embeddings, weight stage landed), in
+    // stage order, and publishes "stages ready" through a shared-memory counter.  The issuer never touches an
+    // mbarrier wait (each costs ~100 cycles even when already complete), it only polls that word.
+    if (elect_one()) {
+      uint32_t gs = 0;
+      int64_t gstep = -1;
+      int it = 0;
+      if (!leader) {
+        // follower: relay "my image of the stage in this slot has landed" to the leader's peer_full[slot]
+        const uint32_t peer = mapa_rank0(bar_peer_full);
+        for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
+#pragma unroll 1
+          for (int si = 0; si < n_stages; ++si, ++gs) {
+            const uint32_t slot = gs % kPairRing, ph = (gs / kPairRing) & 1;
+            mbar_wait(bar_full + 8 * slot, ph);
+            mbar_arrive_cluster(peer + 8 * slot, 1u);
+          }
+        }
+      } else {
+        for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
+          const int b = it & 1;
+#pragma unroll 1
+          for (int si = 0; si < n_stages; ++si, ++gs) {
+            const uint32_t flags = c_prog.st[si].flags;
+            if (flags & F_WAIT_E0) {
+              ++gstep;
+              if (gstep > 0) mbar_wait_cluster(bar_e_done, (uint32_t)((gstep - 1) & 1));
+            }
+            if ((flags & F_WAIT_E1) && gstep > 0) mbar_wait_cluster(bar_e_done + 8, (uint32_t)((gstep - 1) & 1));
+            if (flags & F_WAIT_EMB) mbar_wait_cluster(bar_emb_full, (uint32_t)(it & 1));
+            if (flags & F_WAIT_DIR) mbar_wait_cluster(bar_dir_full + 8 * b, (uint32_t)((it >> 1) & 1));
+            const uint32_t slot = gs % kPairRing, ph = (gs / kPairRing) & 1;
+            mbar_wait(bar_full + 8 * slot, ph);                 // my image
+            mbar_wait_cluster(bar_peer_full + 8 * slot, ph);    // the follower's image of the same stage
+            tc_fence_before();
+            st_release_smem(ready_word, gs + 1);
+          }
+        }
+      }
+    }
+  } else {
+    // =============================================================== MMA issuer
+    // The whole warp walks the stage list in lock step, so the loop state (stage words from __constant__
+    // memory, ring slot, descriptors) stays on the uniform datapath; only the tcgen05 instructions sit in an
+    // elect.sync branch.  The issue table (IssueDesc) holds every per-stage word ready to use: measured on
+    // a stand-alone replica (tools/probe_issue3.cu) this loop needs ~570 cycles per 12-MMA stage next to
+    // ALU-saturating warps, the field-by-field version it replaces ~1000 (the tensor work is 768).
+    //
+    // Two such warps (on different SM sub-partitions) take alternate stages.  The tensor pipe's queue is only a
+    // few MMAs deep, so the ~400-600 cycles one warp spends between two bursts (commits, next stage's words,
+    // loop) drain it; with two warps that work overlaps the other warp's burst.  The owner of stage g bursts
+    // only after the owner of g-1 has issued (shared counter `issued`): MMAs of one accumulator keep their
+    // order, and because the pipe retires a CTA's MMAs in issue order, the commit that follows a half's last
+    // stage also covers the stages the other warp issued for it.
+    if (leader) {
+    const uint32_t me = (warp == kEpiWarps + kProWarps + 1) ? 0u : 1u;
+    volatile uint32_t* issued_w = reinterpret_cast<volatile uint32_t*>(bars + 29);
+    uint32_t gs = 0, ready = 0, slot = 0, issued = 0;
+    int it = 0;
+    // (address field only: in a cluster the shared-window address of CTA rank > 0 carries the rank above it)
+    const uint32_t ring16 = (smem_u32(smem + kSmemRing) >> 4) & 0x3FFFu;
+    const uint32_t emb_hi = smem_u32(smem + kSmemEmb);
+    constexpr uint32_t kFullK = PASSES == 3 ? 4u : 8u;   // K16 steps of a full stage
+    for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
+      const int b = it & 1;
+      const uint32_t dir_hi = smem_u32(smem + kSmemDir + b * 2 * kDirPartBytes);
+#pragma unroll 1
+      for (int si = 0; si < n_stages; ++si, ++gs, slot = (slot + 1 == (uint32_t)kPairRing) ? 0u : slot + 1) {
+        if ((gs & 1u) != me) continue;
+        const uint32_t idesc = c_prog.is[si].idesc, b_lo_base = c_prog.is[si].b_lo_base;
+        const uint32_t b_inc = c_prog.is[si].b_inc, lo_off16 = c_prog.is[si].lo_off16;
+        const uint32_t acc_col = c_prog.is[si].acc_col, a_off = c_prog.is[si].a_off;
+        const uint32_t a_lo_off = c_prog.is[si].a_lo_off, fk = c_prog.is[si].flags_k;
+        const uint32_t flags = fk & 0xFFFFu, ksteps = (fk >> 16) & 0xFFu, a_kind = fk >> 24;
+#ifdef PNR_TIMELINE
+        const bool rec = p.dbg != nullptr && blockIdx.x == 0 && it == 2 && lane == 0;
+        if (rec) p.dbg[si * 5 + 0] = clock64();
+#endif
+        if (ready <= gs) {   // the scout may be several stages ahead: poll only when our copy is stale
+          ready = ld_acquire_smem(ready_word);
+          if (ready <= gs) {
+            long long t0 = clock64();
+            while ((ready = ld_acquire_smem(ready_word)) <= gs) {
+              if ((clock64() - t0) > PNR_WATCHDOG_CYCLES) {
+                if (lane == 0) printf("pnr: issuer watchdog: block %d stage %u\n", (int)blockIdx.x, gs);
+                __trap();
+              }
+            }
+          }
+        }
+#ifdef PNR_TIMELINE
+        if (rec) p.dbg[si * 5 + 1] = clock64();
+#endif
+        // low words of the weight-tile descriptors (K16 step 0; step ks adds ks * b_inc to the address field);
+        // the high word is the same for every operand: SBO = 128 B, descriptor version 1
+        const uint32_t b_hi0 = b_lo_base | (ring16 + slot * (uint32_t)(kPairSlotBytes >> 4));
+        const uint32_t b_lo0 = b_hi0 + lo_off16;
+        const uint32_t d_tmem = tmem + acc_col;
+        const uint32_t acc0 = (flags & F_FIRST) ? 0u : 1u;
+        const uint32_t a_hi = tmem + a_off, a_lo = tmem + a_lo_off;
+        const bool fast = a_kind == A_TMEM && ksteps == kFullK;
+        if (issued < gs) {   // the other warp must have issued stage gs-1
+          long long t0 = clock64();
+          while ((issued = *issued_w) < gs) {
+            if ((clock64() - t0) > PNR_WATCHDOG_CYCLES) {
+              if (lane == 0) printf("pnr: issuer hand-off watchdog: block %d stage %u\n", (int)blockIdx.x, gs);
+              __trap();
+            }
+          }
+        }
+        if (elect_one()) {
+          tc_fence_after();   // order our MMAs after the epilogue's tcgen05.ld / tcgen05.st (seen by the scout)
+          if (fast) {
+#pragma unroll
+            for (uint32_t ks = 0; ks < kFullK; ++ks) {
+              mma_ts_lo_pair(d_tmem, a_hi + ks * 8, b_hi0 + ks * b_inc, idesc, ks == 0 ? acc0 : 1u);
+              if (PASSES == 3) {
+                mma_ts_lo_pair(d_tmem, a_lo + ks * 8, b_hi0 + ks * b_inc, idesc, 1u);
+                mma_ts_lo_pair(d_tmem, a_hi + ks * 8, b_lo0 + ks * b_inc, idesc, 1u);
+              }
+            }
+          } else if (a_kind == A_TMEM) {
+#pragma unroll 1
+            for (uint32_t ks = 0; ks < ksteps; ++ks) {
+              mma_ts_lo_pair(d_tmem, a_hi + ks * 8, b_hi0 + ks * b_inc, idesc, ks == 0 ? acc0 : 1u);
+              if (PASSES == 3) {
+                mma_ts_lo_pair(d_tmem, a_lo + ks * 8, b_hi0 + ks * b_inc, idesc, 1u);
+                mma_ts_lo_pair(d_tmem, a_hi + ks * 8, b_lo0 + ks * b_inc, idesc, 1u);
+              }
+            }
+          } else {
+            const uint32_t a_base = (a_kind == A_EMB) ? emb_hi : dir_hi;
+            const uint32_t a_lo_delta = (a_kind == A_EMB) ? (uint32_t)kEmbPartBytes : (uint32_t)kDirPartBytes;
+            const uint64_t adesc0 = make_smem_desc_noswz(a_base, kTileM * 16, 128);
+            const uint64_t adesc0_lo = make_smem_desc_noswz(a_base + a_lo_delta, kTileM * 16, 128);
+            constexpr uint32_t a_inc = (2u * kTileM * 16u) >> 4;
+            const uint64_t bdesc0 = ((uint64_t)kDescHiWord << 32) | b_hi0;
+            const uint64_t bdesc0_lo = ((uint64_t)kDescHiWord << 32) | b_lo0;
+#pragma unroll 1
+            for (uint32_t ks = 0; ks < ksteps; ++ks) {
+              mma_ss_pair(d_tmem, adesc0 + (uint64_t)(ks * a_inc), bdesc0 + (uint64_t)(ks * b_inc), idesc, ks == 0 ? acc0 : 1u);
+              if (PASSES == 3) {
+                mma_ss_pair(d_tmem, adesc0_lo + (uint64_t)(ks * a_inc), bdesc0 + (uint64_t)(ks * b_inc), idesc, 1u);
+                mma_ss_pair(d_tmem, adesc0 + (uint64_t)(ks * a_inc), bdesc0_lo + (uint64_t)(ks * b_inc), idesc, 1u);
+              }
+            }
+          }
+          *issued_w = gs + 1;
+#ifdef PNR_TIMELINE
+          if (rec) p.dbg[si * 5 + 2] = clock64();
+#endif
+          commit_pair(bar_empty + 8 * slot);   // slot free in both CTAs
+          if (flags & (F_RELEASE_EMB | F_RELEASE_DIR | F_COMMIT_WAR | F_COMMIT_ACC0 | F_COMMIT_ACC1)) {
+            if (flags & F_RELEASE_EMB) commit_pair(bar_emb_empty);
+            if (flags & F_RELEASE_DIR) commit_pair(bar_dir_empty + 8 * b);
+            if (flags & F_COMMIT_WAR) commit_pair(bar_war);
+            if (flags & F_COMMIT_ACC0) commit_pair(bar_acc_full);
+            if (flags & F_COMMIT_ACC1) commit_pair(bar_acc_full + 8);
+          }
+#ifdef PNR_TIMELINE
+          if (rec) { p.dbg[si * 5 + 3] = clock64(); p.dbg[si * 5 + 4] = p.dbg[si * 5 + 3]; }
+#endif
+        }
+        __syncwarp();
+        issued = gs + 1;
+      }
+    }
+      }   // leader
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();   // no CTA may exit while its peer can still multicast into it or arrive on its barriers
+  if (warp == 0) tmem_dealloc_pair<512>(tmem);
+}
+
+// Launch (draft): grid = whole clusters; c_prog must hold a PAIR-mode program (Builder::pair) and p.wpacked the
+// matching stream.  Not wired into pnr_api.cu yet.
+template <int PASSES, int FMT>
+int launch_pair(const MlpParams& p, const MlpProgram* host_prog, cudaStream_t stream) {
+  int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  if (grid <= 0) return PNR_OK;
+  grid = (grid + 1) / 2 * 2;
+  if (grid > num_sms()) grid = num_sms() / 2 * 2;
+  PNR_CUDA(cudaMemcpyToSymbolAsync(c_prog, host_prog, sizeof(MlpProgram), 0, cudaMemcpyHostToDevice, stream));
+  PNR_CUDA(cudaFuncSetAttribute(mlp_pair_kernel<PASSES, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal + 256));
+  mlp_pair_kernel<PASSES, FMT><<<grid, kMlpThreads, kSmemTotal + 256, stream>>>(p);
+  PNR_LAUNCH_CHECK("mlp_pair_kernel");
+  return PNR_OK;
+}
+template int launch_pair<3, kFmtF16>(const MlpParams&, const MlpProgram*, cudaStream_t);
+template int launch_pair<3, kFmtBF16>(const MlpParams&, const MlpProgram*, cudaStream_t);
+template int launch_pair<1, kFmtF16>(const MlpParams&, const MlpProgram*, cudaStream_t);
+template int launch_pair<1, kFmtBF16>(const MlpParams&, const MlpProgram*, cudaStream_t);
+
+}  // namespace pnr
