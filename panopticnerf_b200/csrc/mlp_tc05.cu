@@ -3,11 +3,13 @@
 // One persistent CTA per SM walks 128-sample tiles.  Per tile the whole MLP runs on-chip:
 //   * 4 producer warps form pts = o + d*z, the positional encodings gamma(x), gamma(d), split them into
 //     16-bit hi/lo parts and write them into shared memory in the UMMA no-swizzle K-major operand layout;
-//   * 1 TMA warp streams the pre-packed weight stages (hi / lo images, <= 16 KB each) from L2 into an
-//     8-deep shared-memory ring with cp.async.bulk + mbarrier complete_tx;
-//   * 1 MMA warp (one elected thread) issues tcgen05.mma kind::f16, M=128, N<=128, K=16:
+//   * 1 TMA warp streams the pre-packed weight stages (<= 32 KB: hi image then lo image of a 128-row x 64-K
+//     tile) from L2 into a 4-deep shared-memory ring with cp.async.bulk + mbarrier complete_tx; the two CTAs
+//     of a cluster each fetch half of every stage and multicast it into both shared memories;
+//   * 2 MMA warps take alternate stages; one elected lane issues tcgen05.mma kind::f16, M=128, N<=128, K=16:
 //     the A operand is the embedding in shared memory (SS form) or the previous layer's activations
 //     in TENSOR MEMORY (TS form); accumulators are fp32 in tensor memory;
+//   * 1 scout thread does every mbarrier wait the issue depends on and publishes a "stages ready" counter;
 //   * 8 epilogue warps tcgen05.ld the accumulator, add bias, ReLU, split into hi/lo and tcgen05.st the
 //     result back to tensor memory as the next layer's A operand.  Activations never touch shared or
 //     global memory.  The sigma head (N=1) and rgb head (N=3) are CUDA-core dot products inside the
@@ -137,8 +139,8 @@ __device__ __forceinline__ void epi_group_logits(const uint32_t (&r)[16], int g,
 }
 
 // CTAs run as clusters of two that stream the SAME weight stages in lock step: each CTA fetches half of every
-// stage from L2 and multicasts it into both shared memories, halving L2 -> SM weight traffic (the weight
-// stream, 29 B/clk/SM at full rate, was L2-latency bound with every SM fetching every byte).
+// stage from L2 and multicasts it into both shared memories, halving L2 -> SM weight traffic (ncu: lts
+// throughput 28 % -> 16 %; the kernel time did not change - the weight stream is not what bounds it).
 template <int PASSES, int FMT>
 __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kMlpThreads, 1)
 mlp_fused_kernel(const MlpParams p) {
