@@ -2,7 +2,7 @@
 // weights are loaded, see pnr_api.cu) and the shared-memory / tensor-memory maps both sides agree on.
 //
 // A tile (128 samples) runs a fixed sequence of STEPS (one GEMM + epilogue each: trunk layers, heads,
-// feature layer, view branch).  Every step is issued as two N-HALVES (h0, h1) with separate accumulator
+// view branch with the feature layer folded in).  Every step is issued as two N-HALVES (h0, h1) with separate accumulator
 // column ranges, so that the epilogue of h0 (E0) overlaps the MMAs of h1, and the epilogue of h1 (E1)
 // overlaps the first K-chunks of the next step's h0 (which only need what E0 wrote).  Each half is a
 // list of weight STAGES (<= 32 KB: up to 128 rows x 64 K, hi image then lo image), streamed by TMA.

@@ -66,7 +66,7 @@ class Network(nn.Module):
         return (str(device), self.precision) + tuple((p.data_ptr(), p._version) for p in self.parameters())
 
     def pack(self, device=None) -> int:
-        """(Re)build the libpnr context: weights are split into bf16 hi/lo UMMA stage images once, and
+        """(Re)build the libpnr context: weights are split into 16-bit hi/lo UMMA stage images (fp16 or bf16 per cfg.precision) once, and
         again only when a parameter changed ('weight packer')."""
         device = torch.device(device if device is not None else next(self.parameters()).device)
         if device.type != "cuda":
