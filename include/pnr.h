@@ -162,6 +162,7 @@ int pnr_sample_pdf(const float* z, const float* weights, int64_t R, int32_t N, i
  * For the CPU test tier: tests/test_cpu_program.py replays the program on the host and compares it with
  * the oracle's Network.forward. */
 #define PNR_PROGRAM_PAIR 1 /* flags: CTA-pair weight layout (two n/2-row images per stage; host side only so far) */
+#define PNR_PROGRAM_SPLIT_WAR 2 /* flags: two write-after-read barriers per step (staged kernel variant -DPNR_SPLIT_WAR) */
 int pnr_program_host(const pnr_config* cfg, const float* const* tensors_host, const int64_t* shapes, int32_t n,
                      int32_t flags, void* program, size_t program_cap, size_t* program_bytes,
                      void* wpacked, size_t wpacked_cap, size_t* wpacked_bytes,

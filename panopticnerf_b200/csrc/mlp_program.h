@@ -47,7 +47,9 @@ enum : uint16_t {
   F_COMMIT_ACC0 = 8,    // last stage of h0: signal E0 when the MMAs so far retire
   F_COMMIT_ACC1 = 16,   // last stage of the step: signal E1
   F_COMMIT_WAR = 32,    // last stage reading the activation columns E0 of THIS step overwrites
-  F_WAIT_EMB = 64, F_RELEASE_EMB = 128, F_WAIT_DIR = 256, F_RELEASE_DIR = 512
+  F_WAIT_EMB = 64, F_RELEASE_EMB = 128, F_WAIT_DIR = 256, F_RELEASE_DIR = 512,
+  F_COMMIT_WAR1 = 1024  // split-war programs only: last stage reading the UPPER half of the columns E0 overwrites
+                        // (F_COMMIT_WAR then covers the lower half)
 };
 enum : uint8_t { EPI_RELU_TO_A = 0, EPI_LINEAR_TO_A = 1, EPI_VIEW_RGB = 2, EPI_LOGITS = 3 };
 

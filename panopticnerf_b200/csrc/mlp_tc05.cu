@@ -166,6 +166,9 @@ mlp_fused_kernel(const MlpParams p) {
   const uint32_t bar_emb_empty = smem_u32(&bars[2 * kRing + 6]);
   const uint32_t bar_dir_full = smem_u32(&bars[2 * kRing + 7]);   // [2]
   const uint32_t bar_dir_empty = smem_u32(&bars[2 * kRing + 9]);  // [2]
+#ifdef PNR_SPLIT_WAR
+  const uint32_t bar_war1 = smem_u32(&bars[2 * kRing + 11]);
+#endif
 
   // ---- one-time setup: constants to shared memory, barriers, tensor memory
   for (int i = threadIdx.x; i < c_prog.n_consts; i += blockDim.x) consts[i] = p.consts[i];
@@ -185,6 +188,9 @@ mlp_fused_kernel(const MlpParams p) {
       mbar_init(bar_dir_empty + 8 * h, 1);
     }
     mbar_init(bar_war, 1);
+#ifdef PNR_SPLIT_WAR
+    mbar_init(bar_war1, 1);
+#endif
     *reinterpret_cast<volatile uint32_t*>(bars + 31) = 0u;
     *reinterpret_cast<volatile uint32_t*>(bars + 29) = 0u;
     mbar_init(bar_emb_full, kProWarps * 32);
@@ -221,8 +227,30 @@ mlp_fused_kernel(const MlpParams p) {
         float* out_row = p.raw + (valid ? s : 0) * p.CH + ed.out_off;
         bool war_pending = to_a;
         float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+#ifdef PNR_SPLIT_WAR
+        // Staged for round 2 (not validated on a GPU yet): E0 runs as two blocks,
+        // the lower and the upper half of the activation columns it overwrites, each released by its own
+        // write-after-read barrier (war_ok after the LAST stage of half 1 that reads the lower block, war_ok1
+        // likewise for the upper block), so the first block is stored while half 1 is still on its first stages.
+        const int n0a = (((int)ed.n0 >> 4) >> 1) > 0 ? ((((int)ed.n0 >> 4) >> 1) << 4) : (int)ed.n0;
+#pragma unroll 1
+        for (int ph = 0; ph < 3; ++ph) {
+          const int h = ph == 2 ? 1 : 0;
+          const uint32_t my_war = ph == 0 ? bar_war : bar_war1;
+          if (ph < 2) war_pending = to_a;
+#ifdef PNR_TIMELINE
+          const bool rec = false;
+#endif
+          if (ph != 1) {
+            mbar_wait_backoff(bar_acc_full + 8 * h, parity);
+            tc_fence_after();
+          }
+          const int gb_all = (ph == 0 ? 0 : (ph == 1 ? n0a : (int)ed.n0)) >> 4;
+          const int ge_all = (ph == 0 ? n0a : (ph == 1 ? (int)ed.n0 : (int)ed.n)) >> 4;
+#else
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
+          const uint32_t my_war = bar_war;
 #ifdef PNR_TIMELINE
           const bool rec = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && tile == 2 * (int)gridDim.x;
           if (rec) p.dbg[4096 + (st * 2 + h) * 3 + 0] = clock64();
@@ -234,6 +262,7 @@ mlp_fused_kernel(const MlpParams p) {
 #endif
           const int gb_all = h == 0 ? 0 : (ed.n0 >> 4);
           const int ge_all = h == 0 ? (ed.n0 >> 4) : (ed.n >> 4);
+#endif
           const int G = ge_all - gb_all;
           constexpr int kCh = kEpiWarps / 4;                     // warps sharing one lane quarter
           const int gb = gb_all + (ch * G + kCh - 1) / kCh;      // ceil(ch*G/kCh): near-equal contiguous shares
@@ -267,7 +296,7 @@ mlp_fused_kernel(const MlpParams p) {
                 epi_group_act<PASSES, FMT>(rb, g + 1, ed, clamp_lo, bias, aux, sig, hb, lb);
               }
               if (war_pending) {  // the columns we are about to overwrite must have been consumed by the MMAs
-                mbar_wait_backoff(bar_war, parity);
+                mbar_wait_backoff(my_war, parity);
                 tc_fence_after();
                 war_pending = false;
               }
@@ -296,9 +325,12 @@ mlp_fused_kernel(const MlpParams p) {
             }
           }
           if (h == 0 && war_pending) {  // no columns of h0 for this thread: still consume the barrier phase
-            mbar_wait_backoff(bar_war, parity);
+            mbar_wait_backoff(my_war, parity);
             war_pending = false;
           }
+#ifdef PNR_SPLIT_WAR
+          if (ph == 0) continue;      // E0 signals once, after its second block
+#endif
           if (h == 1) {
             if (ed.sigma) {
               part[(ch * kTileM + row) * 4 + 3] = sig;
@@ -537,10 +569,17 @@ mlp_fused_kernel(const MlpParams p) {
           if (rec) p.dbg[si * 5 + 2] = clock64();
 #endif
           tc_commit_multicast(bar_empty + 8 * slot, (uint16_t)((1u << kClusterSize) - 1u));   // slot free in all CTAs
+#ifdef PNR_SPLIT_WAR
+          if (flags & (F_RELEASE_EMB | F_RELEASE_DIR | F_COMMIT_WAR | F_COMMIT_WAR1 | F_COMMIT_ACC0 | F_COMMIT_ACC1)) {
+#else
           if (flags & (F_RELEASE_EMB | F_RELEASE_DIR | F_COMMIT_WAR | F_COMMIT_ACC0 | F_COMMIT_ACC1)) {
+#endif
             if (flags & F_RELEASE_EMB) tc_commit(bar_emb_empty);
             if (flags & F_RELEASE_DIR) tc_commit(bar_dir_empty + 8 * b);
             if (flags & F_COMMIT_WAR) tc_commit(bar_war);
+#ifdef PNR_SPLIT_WAR
+            if (flags & F_COMMIT_WAR1) tc_commit(bar_war1);
+#endif
             if (flags & F_COMMIT_ACC0) tc_commit(bar_acc_full);
             if (flags & F_COMMIT_ACC1) tc_commit(bar_acc_full + 8);
           }

@@ -88,6 +88,13 @@ struct Builder {
   // for CTA 0 and [n/2, n) for CTA 1, each in the core-matrix layout of an n/2-row tile.  Host side only so
   // far (pnr_program_host + tests/test_cpu_program.py); the kernel that consumes it is not written yet.
   bool pair = false;
+  // E0's write-after-read barrier split in two (lower / upper half of the columns it overwrites): staged with the
+  // kernel's -DPNR_SPLIT_WAR variant for round 2, off in the product.
+#ifdef PNR_SPLIT_WAR
+  bool split_war = true;
+#else
+  bool split_war = false;
+#endif
   std::string err;
 
   Builder(int passes_, int fmt_) : passes(passes_), fmt(fmt_) { memset(&prog, 0, sizeof(prog)); }
@@ -236,13 +243,27 @@ struct Builder {
       // E0 of this step overwrites dst columns [dst, dst + n0/2) (hi and lo): last stage reading them
       const EpiDesc& e = prog.ep[s];
       int war = in.first_stage;
-      if (e.kind == EPI_RELU_TO_A || e.kind == EPI_LINEAR_TO_A) {
-        Foot f{0, 0, e.dst_col, e.dst_col + e.n0 / 2, 0, 0};
-        if (passes == 3) { f.lo0 = e.dst_lo_col; f.lo1 = e.dst_lo_col + e.n0 / 2; }
+      const bool to_a = e.kind == EPI_RELU_TO_A || e.kind == EPI_LINEAR_TO_A;
+      const int g0 = e.n0 / 16;
+      const int n0a = (split_war && g0 / 2 > 0) ? (g0 / 2) * 16 : e.n0;   // columns of E0's first block
+      if (to_a) {
+        Foot f{0, 0, e.dst_col, e.dst_col + n0a / 2, 0, 0};
+        if (passes == 3) { f.lo0 = e.dst_lo_col; f.lo1 = e.dst_lo_col + n0a / 2; }
         for (int i = in.first_stage; i < in.first_stage + in.n_stages; ++i)
           if (stage_touches(prog.st[i], f)) war = i;
       }
       prog.st[war].flags |= F_COMMIT_WAR;
+      if (split_war) {
+        int war1 = war;
+        if (to_a && n0a < e.n0) {
+          Foot f{0, 0, e.dst_col + n0a / 2, e.dst_col + e.n0 / 2, 0, 0};
+          if (passes == 3) { f.lo0 = e.dst_lo_col + n0a / 2; f.lo1 = e.dst_lo_col + e.n0 / 2; }
+          war1 = in.first_stage;
+          for (int i = in.first_stage; i < in.first_stage + in.n_stages; ++i)
+            if (stage_touches(prog.st[i], f)) war1 = i;
+        }
+        prog.st[war1].flags |= F_COMMIT_WAR1;
+      }
     }
     for (int i = 0; i < prog.n_stages; ++i) {   // issue table (flags are final now)
       const StageDesc& sd = prog.st[i];
@@ -476,9 +497,10 @@ extern "C" int pnr_program_host(const pnr_config* cfg, const float* const* t, co
                                 size_t* n_consts) {
   PNR_CHECK_ARG(cfg && t && shapes && program_bytes && wpacked_bytes && n_consts, "pnr_program_host: null pointer");
   if (const int rc = check_config(cfg)) return rc;
-  PNR_CHECK_ARG((flags & ~1) == 0, "pnr_program_host: unknown flags 0x%x", flags);
+  PNR_CHECK_ARG((flags & ~3) == 0, "pnr_program_host: unknown flags 0x%x", flags);
   Builder bld(precision_passes(cfg->precision), precision_fmt(cfg->precision));
   bld.pair = (flags & 1) != 0;
+  if (flags & 2) bld.split_war = true;
   const int rc = build_program(*cfg, t, shapes, n, bld);
   if (rc != PNR_OK) return rc;
   *program_bytes = sizeof(MlpProgram);

@@ -43,7 +43,7 @@ class MlpProgram(C.Structure):
                 ("ep", EpiDesc * K_MAX_STEPS)]
 
 
-def build(cfg, net, pair: bool = False):
+def build(cfg, net, pair: bool = False, flags: int = 0):
     host, shapes = [], []
     for lin in net._linears():
         w, b = lin.weight.detach().float().contiguous(), lin.bias.detach().float().contiguous()
@@ -55,13 +55,13 @@ def build(cfg, net, pair: bool = False):
     ptrs = (C.c_void_p * len(host))(*[t.data_ptr() for t in host])
     shp = (C.c_int64 * len(shapes))(*shapes)
     pb, wb, nc = C.c_size_t(), C.c_size_t(), C.c_size_t()
-    _capi.check(L.pnr_program_host(C.byref(pc), ptrs, shp, len(host), int(pair), None, 0, C.byref(pb), None, 0,
+    _capi.check(L.pnr_program_host(C.byref(pc), ptrs, shp, len(host), int(pair) | flags, None, 0, C.byref(pb), None, 0,
                                    C.byref(wb), None, 0, C.byref(nc)), "pnr_program_host (sizes)")
     assert pb.value == C.sizeof(MlpProgram), "MlpProgram layout in this test is out of date"
     prog = MlpProgram()
     w16 = np.zeros(wb.value // 2, dtype=np.uint16)
     consts = np.zeros(nc.value, dtype=np.float32)
-    _capi.check(L.pnr_program_host(C.byref(pc), ptrs, shp, len(host), int(pair), C.byref(prog), pb.value, C.byref(pb),
+    _capi.check(L.pnr_program_host(C.byref(pc), ptrs, shp, len(host), int(pair) | flags, C.byref(prog), pb.value, C.byref(pb),
                                    w16.ctypes.data, wb.value, C.byref(wb), consts.ctypes.data, nc.value, C.byref(nc)),
                 "pnr_program_host")
     return prog, w16, consts
