@@ -32,8 +32,15 @@ def test_reference_arm_prints_one_json_line():
     _check(_run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "1", "--ref-rows", "1"]), 1)
 
 
+def _free_port() -> int:
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
 def test_reference_arm_under_torchrun_only_rank0_reports():
     d = _run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-              "--master-addr", "127.0.0.1", "--master-port", "29541", "bench.py", "--impl", "reference",
+              "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), "bench.py", "--impl", "reference",
               "--gpus", "2", "--steps", "1", "--warmup", "1", "--ref-rows", "1"])
     _check(d, 2)
