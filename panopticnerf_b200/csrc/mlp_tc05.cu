@@ -183,7 +183,11 @@ mlp_fused_kernel(const MlpParams p) {
     }
     for (int h = 0; h < 2; ++h) {
       mbar_init(bar_acc_full + 8 * h, 1);
+#ifdef PNR_WARP_ARRIVE
+      mbar_init(bar_e_done + 8 * h, kEpiWarps);        // staged variant: one arrival per epilogue warp
+#else
       mbar_init(bar_e_done + 8 * h, kEpiWarps * 32);
+#endif
       mbar_init(bar_dir_full + 8 * h, kProWarps * 32);
       mbar_init(bar_dir_empty + 8 * h, 1);
     }
@@ -360,7 +364,14 @@ mlp_fused_kernel(const MlpParams p) {
           }
           if (to_a) tc_wait_st();
           tc_fence_before();
+#ifdef PNR_WARP_ARRIVE
+          // staged for round 2 (not validated on a GPU yet): 8 arrivals per hand-off
+          // instead of 256 - every lane's tensor-memory traffic is complete and fenced before the warp converges
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_e_done + 8 * h);
+#else
           mbar_arrive(bar_e_done + 8 * h);
+#endif
 #ifdef PNR_TIMELINE
           if (rec) p.dbg[4096 + (st * 2 + h) * 3 + 2] = clock64();
 #endif
