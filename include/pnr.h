@@ -12,8 +12,12 @@
  *  - all array arguments are DEVICE pointers unless the name ends in _host.
  *  - buffers are caller-owned; nothing is allocated on the stage entry points; all work is
  *    enqueued asynchronously on `stream` (a cudaStream_t passed as void*).
- *  - one context per device; a context is not thread-safe; outputs are deterministic
- *    (no atomics), so any ray sharding reproduces the single-GPU result bit for bit.
+ *  - a context belongs to one device (cfg.device); every entry point that takes a context makes that
+ *    device current for the call and restores the caller's current device before it returns; the
+ *    context-free stage entry points run on the caller's current device (the one their pointers and
+ *    stream belong to).  Several contexts, devices and streams may be used from one process; a single
+ *    context is not thread-safe.  Outputs are deterministic (no atomics on outputs), so any ray
+ *    sharding reproduces the single-GPU result bit for bit.
  */
 #ifndef PNR_H_
 #define PNR_H_
@@ -56,12 +60,21 @@ const char* pnr_last_error(void);
 int pnr_create(const pnr_config* cfg, pnr_ctx** out);
 int pnr_destroy(pnr_ctx* ctx);
 
+/* a8 range check: sticky status of the fused-MLP launches enqueued so far on `stream` (synchronises it).
+ * bit 0 (PNR_STATUS_RANGE): an activation left the range of the 16-bit operand format (fp16 modes: |x| > 65504)
+ * or was not finite - the outputs of that launch are not trustworthy, re-run with PNR_PREC_BF16X3.
+ * reset != 0 clears the word after reading it. */
+#define PNR_STATUS_RANGE 1u
+int pnr_status(pnr_ctx* ctx, uint32_t* status_host, int32_t reset, void* stream);
+
 /* a2: load a Network state_dict.  `tensors_host[i]` are HOST fp32 pointers in this fixed order:
  *   pts_linears.{0..D-1}.weight/.bias (interleaved w,b), alpha_linear.w/.b, feature_linear.w/.b,
  *   views_linears.0.w/.b, rgb_linear.w/.b, [semantic_linears.0.w/.b, semantic_linears.1.w/.b],
  *   [instance_linears.0.w/.b, instance_linears.1.w/.b]
  * `shapes[2*i], shapes[2*i+1]` = (out, in) for weights, (out, 1) for biases.  Weights are split
- * into bf16 hi/lo, laid out as no-swizzle K-major UMMA stage images and uploaded. */
+ * into 16-bit hi/lo parts of the context's operand format (fp16 or bf16, cfg.precision), laid out as
+ * no-swizzle K-major UMMA stage images and uploaded.  In the fp16 modes a weight with |w| > 65504 is
+ * rejected (PNR_ERR_UNSUPPORTED): use a bf16 mode. */
 int pnr_load_weights(pnr_ctx* ctx, const float* const* tensors_host, const int64_t* shapes, int32_t n);
 
 /* a5: ray / oriented-box slab test.  rays [R,6] (o||d); box_center, box_half [B,3]; box_rot [B,3,3]
@@ -86,6 +99,17 @@ int pnr_sample_stratified(const float* near, const float* far, const float* t_va
                           int64_t R, int32_t N, float perturb, const int32_t* box_id,
                           const float* t_in, const float* t_out, int32_t M, float* z,
                           int32_t* sample_box, void* stream);
+
+/* a6, interval mode: the N samples are placed inside the ray's hit intervals (clipped to [near, far]):
+ * n_m = floor(N * len_m / sum len) samples for interval m, the remainder one by one to the nearest intervals,
+ * sample j of an interval at a + (b-a)*(j+0.5)/n_m (or (j+u)/n_m when perturb > 0, u [R,N] per allocation slot),
+ * the depths sorted ascending; rays without a hit interval fall back to the uniform rule of pnr_sample_stratified.
+ * Same arguments as pnr_sample_stratified (box_id/t_in/t_out required).  The reference's own allocation rule is
+ * not in the mount (SURVEY 8(c) question 4): this one is chosen here and documented in DESIGN.md. */
+int pnr_sample_intervals(const float* near, const float* far, const float* t_vals, const float* u,
+                         int64_t R, int32_t N, float perturb, const int32_t* box_id,
+                         const float* t_in, const float* t_out, int32_t M, float* z,
+                         int32_t* sample_box, void* stream);
 
 /* a6: re-tag an existing depth array (after the coarse+fine merge). */
 int pnr_tag_samples(const float* z, int64_t R, int32_t N, const int32_t* box_id, const float* t_in,
@@ -161,15 +185,81 @@ int pnr_sample_pdf(const float* z, const float* weights, int64_t R, int32_t N, i
  * (each may be NULL to query sizes only).  `program` receives the MlpProgram struct of csrc/mlp_program.h.
  * For the CPU test tier: tests/test_cpu_program.py replays the program on the host and compares it with
  * the oracle's Network.forward. */
-#define PNR_PROGRAM_PAIR 1 /* flags: CTA-pair weight layout (two n/2-row images per stage; host side only so far) */
-#define PNR_PROGRAM_SPLIT_WAR 2 /* flags: two write-after-read barriers per step (staged kernel variant -DPNR_SPLIT_WAR) */
+#define PNR_PROGRAM_PAIR 1      /* flags: CTA-pair weight layout (two n/2-row images per stage; host side only) */
+#define PNR_PROGRAM_SPLIT_WAR 2 /* flags: E0 stores released in two blocks (two write-after-read barriers per step) */
+#define PNR_PROGRAM_SPLIT_E1 4  /* flags: E1 signalled in two blocks */
+#define PNR_PROGRAM_NO_SPLIT 8  /* flags: start from one-block epilogues instead of the precision's default */
 int pnr_program_host(const pnr_config* cfg, const float* const* tensors_host, const int64_t* shapes, int32_t n,
                      int32_t flags, void* program, size_t program_cap, size_t* program_bytes,
                      void* wpacked, size_t wpacked_cap, size_t* wpacked_bytes,
                      float* consts, size_t consts_cap, size_t* n_consts);
 
-/* Bytes of device scratch Renderer.render needs for R rays (z, raw, ids ...), for the caller to own. */
+/* a3/a4: Renderer.render / batchify_rays as ONE call.  Everything render_rays does for R rays - scene near/far,
+ * ray/primitive intersection, stratified sampling + per-sample ids, Network.forward, raw2outputs and, when
+ * Ni > 0, sample_pdf + merge + the fine pass - is enqueued on `stream` in ray chunks sized by the caller's
+ * workspace, so the big intermediate (raw [chunk, N+Ni, 4+C+K]) never exceeds it (size it with
+ * pnr_workspace_bytes: the default keeps `raw` L2-resident between the MLP and the compositing kernel).
+ * Results do not depend on the chunking (every kernel is per-ray and deterministic).
+ * All pointers are DEVICE pointers except aabb_host; outputs and most inputs are optional (NULL). */
+enum { PNR_SAMPLE_UNIFORM = 0,    /* z = near*(1-t) + far*t over [near, far], samples tagged with the interval they fall in */
+       PNR_SAMPLE_INTERVALS = 1   /* a6: the N samples are placed inside the ray's M hit intervals (pnr_sample_intervals) */ };
+typedef struct pnr_render_args {
+  const float* rays;            /* [R,6] origin || direction                                                      */
+  int64_t R;
+  const float* near;            /* [R] and                                                                        */
+  const float* far;             /* [R]; or both NULL: from aabb_host (pnr_scene_near_far) or near_min/far_default  */
+  const float* aabb_host;       /* {lo.xyz, hi.xyz} HOST floats, or NULL                                          */
+  float near_min, far_default;
+  const float* box_center;      /* [B,3]   bounding primitives (B = 0: none)                                      */
+  const float* box_half;        /* [B,3]                                                                          */
+  const float* box_rot;         /* [B,3,3]                                                                        */
+  const int32_t* box_sem;       /* [B] class id per primitive (fixed_semantic_map), nullable                      */
+  const int32_t* box_inst;      /* [B] instance id per primitive (fixed_instance_map), nullable                   */
+  int32_t B, M;                 /* M = hits kept per ray (<= 8)                                                   */
+  int32_t N, Ni;                /* coarse samples, importance samples (0: single pass)                            */
+  const float* t_vals;          /* [N] linspace(0,1,N) computed by the caller (host linspace, bit for bit)        */
+  const float* u;               /* [R,N] jitter, required when perturb > 0                                        */
+  float perturb;
+  const float* u_fine;          /* [R,Ni] (row stride u_fine_stride floats; 0 = one row shared by all rays)       */
+  int64_t u_fine_stride;
+  int32_t sample_mode;          /* PNR_SAMPLE_*                                                                   */
+  int32_t white_bkgd, sem_softmax, mask_outside, bound_by_primitives;
+  pnr_composite_out out;        /* maps of the final pass                                                         */
+  pnr_composite_out out0;       /* maps of the coarse pass (only used when Ni > 0)                                */
+  float* z_vals;                /* [R,N+Ni] depths of the final pass                                              */
+  float* z_vals0;               /* [R,N] coarse depths (Ni > 0)                                                   */
+  uint8_t* hit_mask;            /* [R]                                                                            */
+  int32_t* box_id;              /* [R,M]                                                                          */
+  float* t_in;                  /* [R,M]                                                                          */
+  float* t_out;                 /* [R,M]                                                                          */
+  int32_t* sample_box;          /* [R,N+Ni] primitive id per sample of the final pass (-1 = none)                 */
+  float* near_out;              /* [R] near / far actually used                                                   */
+  float* far_out;               /* [R]                                                                            */
+  void* workspace;              /* device scratch, caller-owned                                                   */
+  size_t workspace_bytes;
+} pnr_render_args;
+/* ctx_fine: the network of the fine pass (NULL = ctx). */
+int pnr_render_fused(pnr_ctx* ctx, pnr_ctx* ctx_fine, const pnr_render_args* args, void* stream);
+
+/* Bytes of device scratch pnr_render_fused wants for R rays: enough for one chunk of min(R, rays_per_chunk) rays
+ * with every optional output absent, where rays_per_chunk keeps `raw` near 96 MB (L2-resident on B200) but never
+ * below ~8 tiles of the fused MLP per SM.  Any workspace that holds at least one ray works (more chunks). */
 size_t pnr_workspace_bytes(const pnr_ctx* ctx, int64_t R, int32_t N, int32_t Ni);
+
+/* 8(e) multi-GPU entry: one NCCL communicator per rank (NCCL is bound at run time: pnr_comm_available() == 0
+ * when libnccl.so.2 cannot be loaded) and ONE all-gather of the rendered per-ray tiles.  Rays shard across ranks
+ * with no data-path collective; this gather of image / label tiles is the only exchange step of the path.
+ * Rank 0 creates the id with pnr_comm_unique_id and hands its PNR_COMM_ID_BYTES bytes to the other ranks over any
+ * out-of-band channel (the host application's launcher; torch.distributed.broadcast in the Python layer).
+ * pnr_allgather_outputs: recv [world * bytes_per_rank] <- each rank's send [bytes_per_rank], in rank order,
+ * asynchronously on `stream` (in place when send == recv + rank * bytes_per_rank). */
+#define PNR_COMM_ID_BYTES 128
+typedef struct pnr_comm pnr_comm;
+int pnr_comm_available(void);
+int pnr_comm_unique_id(uint8_t* id_out);
+int pnr_comm_init(pnr_comm** out, const uint8_t* id, int32_t rank, int32_t world, int32_t device);
+int pnr_comm_destroy(pnr_comm* comm);
+int pnr_allgather_outputs(pnr_comm* comm, const void* send, void* recv, size_t bytes_per_rank, void* stream);
 
 /* Number of kernels this library has launched on this thread since the last reset (bench evidence). */
 int64_t pnr_launch_count(int32_t reset);

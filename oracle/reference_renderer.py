@@ -184,6 +184,59 @@ def stratified_z(near, far, t_vals, perturb: float = 0.0, u: Optional[torch.Tens
     return z
 
 
+def interval_z(near, far, t_vals, box_id, t_in, t_out, perturb: float = 0.0, u: Optional[torch.Tensor] = None):
+    """SURVEY 8(a) a6, interval mode: "samples are placed inside the M hit intervals".  The reference's rule for
+    dividing the N samples between the intervals is not in the mount (8(c) question 4); the rule restated here is
+    the one chosen for this build ('chosen, unverified'), in the same fp32 operation order as the kernel:
+      1. valid intervals are clipped to [near, far] and kept when their length is positive;
+      2. L = sum of kept lengths (interval order); n_m = min(floor(N*len_m/L), samples still unassigned) in
+         interval order; the remainder goes one sample at a time to the kept intervals, nearest first (cyclic);
+      3. sample j of interval m: a + (b-a)*((j+c)/n_m), c = 0.5 or the jitter u of that allocation slot;
+      4. the N depths are sorted ascending.
+    Rays without a kept interval use the uniform rule of stratified_z."""
+    R, M = box_id.shape
+    N = t_vals.shape[0]
+    z_uniform = stratified_z(near, far, t_vals, perturb, u)
+    valid = box_id >= 0
+    a = torch.maximum(t_in, near[:, None])
+    b = torch.minimum(t_out, far[:, None])
+    ln = b - a
+    keep = valid & (ln > 0)
+    ln = torch.where(keep, ln, torch.zeros_like(ln))
+    L = torch.zeros(R)
+    seen = torch.zeros(R, dtype=torch.bool)
+    for m in range(M):                       # sequential fp32 sum over the kept intervals, first one copied
+        L = torch.where(keep[:, m], torch.where(seen, L + ln[:, m], ln[:, m]), L)
+        seen = seen | keep[:, m]
+    n = torch.zeros(R, M, dtype=torch.int64)
+    left = torch.full((R,), N, dtype=torch.int64)
+    Ls = torch.where(seen, L, torch.ones_like(L))
+    for m in range(M):
+        q = torch.floor((float(N) * ln[:, m]) / Ls).to(torch.int64)
+        q = torch.clamp(torch.minimum(q, left), min=0)
+        q = torch.where(keep[:, m], q, torch.zeros_like(q))
+        n[:, m] = q
+        left = left - q
+    while bool(((left > 0) & seen).any()):
+        for m in range(M):
+            give = keep[:, m] & (left > 0)
+            n[:, m] += give.to(torch.int64)
+            left = left - give.to(torch.int64)
+    first = torch.cumsum(n, 1) - n                                   # slot of each interval's first sample
+    k = torch.arange(N)[None, :].expand(R, N)
+    c = u if (perturb > 0.0 and u is not None) else torch.full((R, N), 0.5)
+    z = torch.zeros(R, N)
+    for m in range(M):
+        j = k - first[:, m:m + 1]
+        inside = (j >= 0) & (j < n[:, m:m + 1])
+        nm = torch.clamp(n[:, m:m + 1], min=1).to(torch.float32)
+        t = (j.to(torch.float32) + c) / nm
+        zm = a[:, m:m + 1] + (b[:, m:m + 1] - a[:, m:m + 1]) * t
+        z = torch.where(inside, zm, z)
+    z = torch.sort(z, -1).values
+    return torch.where(seen[:, None], z, z_uniform)
+
+
 def tag_samples(z, box_id, t_in, t_out):
     """a6: each sample carries the id of the first (nearest) hit interval containing it, else -1."""
     R, N = z.shape
@@ -301,13 +354,22 @@ def _composite_onehot(weights, sample_box, table, n):
 # --------------------------------------------------------------------------------------------
 # a10  sample_pdf
 # --------------------------------------------------------------------------------------------
-def sample_pdf(bins, weights, N_importance: int, det: bool = True, u: Optional[torch.Tensor] = None):
+def sample_pdf(bins, weights, N_importance: int, det: bool = True, u: Optional[torch.Tensor] = None,
+               pdf_norm: str = "cumsum"):
     """SURVEY 8(a) a10.  bins [R,Nb] (= mid points), weights [R,Nb-1] (= coarse weights[1:-1]).
     Returns z_f [R,Ni] and the searchsorted indices idx [R,Ni] (int64).
-    Normalisation uses the running sum's last element so the operation order is fully specified."""
+    pdf_norm: how the pdf is normalised.  "cumsum" (default; what the CUDA kernel reproduces bit for bit) divides by
+    the last element of the running sum, so the operation order is fully specified.  "sum" divides by
+    torch.sum(w, -1) as nerf-pytorch does: torch's blocked fp32 reduction differs from the running sum in the last
+    ulp, which can move a searchsorted index when u falls within an ulp of a cdf entry
+    (tests/test_cpu_oracle.py::test_sample_pdf_sum_variant counts how often).  Kept so that the variant the real
+    reference uses can be switched on the day its source is mounted."""
     w = weights + 1e-5
-    csum = torch.cumsum(w, -1)
-    pdf = w / csum[:, -1:]
+    if pdf_norm == "sum":
+        pdf = w / torch.sum(w, -1, keepdim=True)
+    else:
+        csum = torch.cumsum(w, -1)
+        pdf = w / csum[:, -1:]
     cdf = torch.cumsum(pdf, -1)
     cdf = torch.cat([torch.zeros_like(cdf[:, :1]), cdf], -1)       # [R,Nb]
     if u is None:
@@ -379,7 +441,10 @@ class Renderer:
                 far = torch.where(hit, torch.minimum(far, last), far)
         t_vals = torch.linspace(0.0, 1.0, N)
         u = batch["u"][sl] if "u" in batch else None
-        z = stratified_z(near, far, t_vals, perturb, u)
+        if has_boxes and str(getattr(cfg, "sample_mode", "uniform")) == "intervals":
+            z = interval_z(near, far, t_vals, box_id, t_in, t_out, perturb, u)
+        else:
+            z = stratified_z(near, far, t_vals, perturb, u)
         kw = dict(raw_noise_std=0.0, white_bkgd=bool(getattr(cfg, "white_bkgd", False)),
                   num_classes=C, num_instances=K,
                   sem_activation=str(getattr(cfg, "sem_activation", "none")),

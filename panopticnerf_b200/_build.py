@@ -14,7 +14,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libpnr.so"
-SOURCES = ["pnr_api.cu", "ray_kernels.cu", "stream_kernels.cu", "mlp_tc05.cu"]
+SOURCES = ["pnr_api.cu", "ray_kernels.cu", "stream_kernels.cu", "mlp_tc05.cu", "render.cu", "comm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"] + os.environ.get("PNR_NVCC_FLAGS", "").split()   # e.g. -DPNR_TIMELINE
 
@@ -41,19 +41,28 @@ def is_fresh() -> bool:
     return LIB.exists() and stamp.exists() and stamp.read_text().strip() == _digest()
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile csrc/*.cu -> panopticnerf_b200/libpnr.so.  Cross-compiles without a GPU."""
+def build(force: bool = False, verbose: bool = False, out: Path = None, extra_flags=()) -> Path:
+    """Compile csrc/*.cu -> panopticnerf_b200/libpnr.so.  Cross-compiles without a GPU.
+    `out` + `extra_flags`: a development variant next to the product library (e.g. the -DPNR_TIMELINE build that
+    tools/timeline.py loads through PNR_LIB); the product library and its stamp are left alone."""
+    if out is not None:
+        return _compile(Path(out), list(extra_flags), verbose, PKG.parent / "build" / Path(out).stem)
     if not force and is_fresh():
         return LIB
+    _compile(LIB, [], verbose, PKG.parent / "build" / "libpnr")
+    (PKG / "libpnr.stamp").write_text(_digest())
+    return LIB
+
+
+def _compile(lib: Path, extra_flags, verbose: bool, objdir: Path) -> Path:
     nvcc = _nvcc()
-    objdir = PKG.parent / "build" / "libpnr"
     objdir.mkdir(parents=True, exist_ok=True)
     procs = []
     objs = []
     for src in SOURCES:
         obj = objdir / (src[:-3] + ".o")
         objs.append(str(obj))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-c", str(CSRC / src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -63,14 +72,17 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
         if verbose and out:
             print(out)
-    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *objs,
-            "-cudart", "shared"]
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(lib), *objs,
+            "-cudart", "shared", "-ldl"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
-    (PKG / "libpnr.stamp").write_text(_digest())
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force=True, verbose=True))
+    import sys
+    if "--timeline" in sys.argv:
+        print(build(out=PKG / "libpnr_timeline.so", extra_flags=["-DPNR_TIMELINE"]))
+    else:
+        print(build(force=True, verbose=True))

@@ -6,12 +6,14 @@ There is no CPU or PyTorch fallback: if libpnr.so is missing or a call fails, th
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 from typing import Optional
 
 import torch
 
-_LIB_PATH = Path(__file__).resolve().parent / "libpnr.so"
+# PNR_LIB: load a development variant of the library (tools/timeline.py: the -DPNR_TIMELINE build)
+_LIB_PATH = Path(os.environ.get("PNR_LIB") or Path(__file__).resolve().parent / "libpnr.so")
 _lib: Optional[C.CDLL] = None
 
 PREC = {"bf16x3": 0, "bf16": 1, "fp16x3": 2, "fp16": 3}
@@ -39,6 +41,25 @@ class PnrCompositeGrads(C.Structure):
                  "instance_map", "fixed_semantic_map", "fixed_instance_map")]
 
 
+class PnrRenderArgs(C.Structure):
+    """pnr_render_args of include/pnr.h (same field order)."""
+    _fields_ = [("rays", C.c_void_p), ("R", C.c_int64), ("near", C.c_void_p), ("far", C.c_void_p),
+                ("aabb_host", C.POINTER(C.c_float)), ("near_min", C.c_float), ("far_default", C.c_float),
+                ("box_center", C.c_void_p), ("box_half", C.c_void_p), ("box_rot", C.c_void_p),
+                ("box_sem", C.c_void_p), ("box_inst", C.c_void_p), ("B", C.c_int32), ("M", C.c_int32),
+                ("N", C.c_int32), ("Ni", C.c_int32), ("t_vals", C.c_void_p), ("u", C.c_void_p),
+                ("perturb", C.c_float), ("u_fine", C.c_void_p), ("u_fine_stride", C.c_int64),
+                ("sample_mode", C.c_int32), ("white_bkgd", C.c_int32), ("sem_softmax", C.c_int32),
+                ("mask_outside", C.c_int32), ("bound_by_primitives", C.c_int32),
+                ("out", PnrCompositeOut), ("out0", PnrCompositeOut), ("z_vals", C.c_void_p), ("z_vals0", C.c_void_p),
+                ("hit_mask", C.c_void_p), ("box_id", C.c_void_p), ("t_in", C.c_void_p), ("t_out", C.c_void_p),
+                ("sample_box", C.c_void_p), ("near_out", C.c_void_p), ("far_out", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
+SAMPLE_MODE = {"uniform": 0, "intervals": 1}
+COMM_ID_BYTES = 128
+
 # name -> (restype, argtypes); mirrors include/pnr.h one to one
 _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 SIGNATURES = {
@@ -46,11 +67,13 @@ SIGNATURES = {
     "pnr_last_error": (C.c_char_p, []),
     "pnr_create": (C.c_int, [C.POINTER(PnrConfig), C.POINTER(_vp)]),
     "pnr_destroy": (C.c_int, [_vp]),
+    "pnr_status": (C.c_int, [_vp, C.POINTER(C.c_uint32), _i32, _vp]),
     "pnr_load_weights": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_i64), _i32]),
     "pnr_intersect": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "pnr_scene_near_far": (C.c_int, [_vp, _i64, C.POINTER(_f32), _f32, _f32, _vp, _vp, _vp]),
     "pnr_bound_by_primitives": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "pnr_sample_stratified": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "pnr_sample_intervals": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "pnr_tag_samples": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp]),
     "pnr_generate_rays": (C.c_int, [_i32, _i32, _i32, _i32, _i32, C.POINTER(_f32), C.POINTER(_f32), _vp, _vp]),
     "pnr_encode": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
@@ -64,7 +87,13 @@ SIGNATURES = {
     "pnr_program_host": (C.c_int, [C.POINTER(PnrConfig), C.POINTER(_vp), C.POINTER(_i64), _i32, _i32, _vp, C.c_size_t,
                                    C.POINTER(C.c_size_t), _vp, C.c_size_t, C.POINTER(C.c_size_t), _vp, C.c_size_t,
                                    C.POINTER(C.c_size_t)]),
+    "pnr_render_fused": (C.c_int, [_vp, _vp, C.POINTER(PnrRenderArgs), _vp]),
     "pnr_workspace_bytes": (C.c_size_t, [_vp, _i64, _i32, _i32]),
+    "pnr_comm_available": (C.c_int, []),
+    "pnr_comm_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
+    "pnr_comm_init": (C.c_int, [C.POINTER(_vp), C.POINTER(C.c_uint8), _i32, _i32, _i32]),
+    "pnr_comm_destroy": (C.c_int, [_vp]),
+    "pnr_allgather_outputs": (C.c_int, [_vp, _vp, _vp, C.c_size_t, _vp]),
     "pnr_launch_count": (_i64, [_i32]),
 }
 

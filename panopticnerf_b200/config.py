@@ -19,6 +19,9 @@ _DEFAULTS = dict(
     # sampling / rendering (a5, a6, a9, a10)
     N_samples=64, N_importance=0, perturb=0.0, white_bkgd=False, raw_noise_std=0.0,
     near=0.05, far=80.0, max_hits=4, bound_by_primitives=False, mask_outside=False,
+    # a6: "uniform" = near..far, samples tagged with the hit interval they fall in; "intervals" = the N samples are
+    # placed inside the ray's hit intervals (rule in oracle/reference_renderer.py::interval_z / DESIGN.md)
+    sample_mode="uniform",
     sem_activation="none", chunk=32768, return_raw=False,
     # image shape (KITTI-360 perspective)
     H=376, W_img=1408, fx=552.554, fy=552.554, cx=682.05, cy=238.77, camera="pinhole",
@@ -26,6 +29,12 @@ _DEFAULTS = dict(
     # tensor-core operand format x passes: "fp16x3" (default; ~2^-21 per product, meets the 1e-4 tolerance
     # with margin, needs |activation| < 65504) | "bf16x3" (~2^-17, fp32 range) | "fp16" / "bf16" (1 pass, fast)
     precision="fp16x3",
+    # Renderer.render: "fused" = one pnr_render_fused call per frame (chunked inside by the workspace, `raw` never
+    # materialised for the frame); "staged" = one libpnr call per stage from Python (implied by return_raw).
+    # workspace_mb = 0: pnr_workspace_bytes' default (raw ~96 MB per chunk, L2-resident).
+    render_path="fused", workspace_mb=0,
+    # raise if the fp16 operands overflowed in this render (costs one 4-byte D2H read per render)
+    check_range=True,
 )
 
 # BASELINE.json "configs", in order.

@@ -2,12 +2,21 @@
 // weights are loaded, see pnr_api.cu) and the shared-memory / tensor-memory maps both sides agree on.
 //
 // A tile (128 samples) runs a fixed sequence of STEPS (one GEMM + epilogue each: trunk layers, heads,
-// view branch with the feature layer folded in).  Every step is issued as two N-HALVES (h0, h1) with separate accumulator
-// column ranges, so that the epilogue of h0 (E0) overlaps the MMAs of h1, and the epilogue of h1 (E1)
+// view branch with the feature layer folded in).  Every step is issued as two N-HALVES (h0, h1) with separate
+// accumulator column ranges, so that the epilogue of h0 (E0) overlaps the MMAs of h1, and the epilogue of h1 (E1)
 // overlaps the first K-chunks of the next step's h0 (which only need what E0 wrote).  Each half is a
 // list of weight STAGES (<= 32 KB: up to 128 rows x 64 K, hi image then lo image), streamed by TMA.
-// The program lives in __constant__ memory so the single MMA-issuing thread reads it through the uniform
-// datapath (no register->uniform moves on the issue path).
+//
+// Each half-epilogue works in two PARTS (column blocks a, b; part b may be empty):
+//   E0 part a / b are released by their own write-after-read barriers (war_ok[0/1]: the MMAs of h1 that still
+//     read the activation columns the part overwrites have retired), so E0 stores its first block while h1 is
+//     still on its first stages;
+//   E1 part a / b are SIGNALLED separately, so the next step's third K-chunk can start when half of E1 is done.
+// Epilogue -> MMA hand-offs are three monotonic shared-memory counters (E0 done, E1 part a done, E1 done), bumped
+// once per epilogue warp and polled by the MMA-issuing warps themselves: every stage carries the counts it needs.
+//
+// The program travels as a __grid_constant__ kernel parameter (constant bank, uniform datapath for the issuing
+// thread; nothing shared between contexts, streams, devices or graph replays).
 #pragma once
 #include <stdint.h>
 
@@ -20,7 +29,7 @@ constexpr int kEpiWarps = 8;              // TMEM->reg->TMEM activation warps (2
 constexpr int kProWarps = 4;              // positional-encoding producer warps (one thread per row)
 constexpr int kMlpThreads = (kEpiWarps + kProWarps + 4) * 32;   // + TMA warp, MMA issuer, scout, second MMA issuer = 512
 constexpr int kClusterSize = 2;           // CTAs sharing one weight stream by TMA multicast
-constexpr int kMaxStages = 384;
+constexpr int kMaxStages = 256;
 constexpr int kMaxSteps = 24;
 constexpr int kMaxConsts = 4096;          // floats: biases + sigma / rgb weights
 
@@ -42,16 +51,16 @@ constexpr int kSmemProg = kSmemDir + 4 * kDirPartBytes;
 enum : uint8_t { A_TMEM = 0, A_EMB = 1, A_DIR = 2 };
 enum : uint16_t {
   F_FIRST = 1,          // first MMA of this half overwrites the accumulator
-  F_WAIT_E0 = 2,        // first stage of a step: wait for E0 of the previous step
-  F_WAIT_E1 = 4,        // first stage that touches anything E1 of the previous step reads or writes
+  F_WAIT_E0 = 2,        // first stage of a step: needs E0 of the previous step
+  F_WAIT_E1 = 4,        // first stage that touches anything E1 part b of the previous step reads or writes
   F_COMMIT_ACC0 = 8,    // last stage of h0: signal E0 when the MMAs so far retire
   F_COMMIT_ACC1 = 16,   // last stage of the step: signal E1
-  F_COMMIT_WAR = 32,    // last stage reading the activation columns E0 of THIS step overwrites
+  F_COMMIT_WAR = 32,    // last stage reading the activation columns E0 part a of THIS step overwrites
   F_WAIT_EMB = 64, F_RELEASE_EMB = 128, F_WAIT_DIR = 256, F_RELEASE_DIR = 512,
-  F_COMMIT_WAR1 = 1024  // split-war programs only: last stage reading the UPPER half of the columns E0 overwrites
-                        // (F_COMMIT_WAR then covers the lower half)
+  F_COMMIT_WAR1 = 1024, // last stage reading the columns E0 part b overwrites (= F_COMMIT_WAR's stage when E0 is one block)
+  F_WAIT_E1A = 2048     // first stage that touches anything E1 part a of the previous step reads or writes
 };
-enum : uint8_t { EPI_RELU_TO_A = 0, EPI_LINEAR_TO_A = 1, EPI_VIEW_RGB = 2, EPI_LOGITS = 3 };
+enum : uint8_t { EPI_RELU_TO_A = 0, EPI_VIEW_RGB = 2, EPI_LOGITS = 3 };   // (1 was a linear hand-over: feature_linear is folded now)
 
 struct StageDesc {     // one weight stage = one bulk copy + its MMAs
   uint32_t gofs;       // byte offset into the packed weight stream
@@ -74,6 +83,9 @@ struct IssueDesc {     // the same stage, pre-digested for the MMA-issuing warp:
   uint32_t acc_col;
   uint32_t a_off, a_lo_off;
   uint32_t flags_k;    // flags | ksteps << 16 | a_kind << 24
+  uint32_t needs;      // epilogue hand-offs this stage needs, as step counts + 1 relative to the tile's first step:
+                       // E0 | E1 part a << 8 | E1 << 16  (v: the first v-1 steps of this tile - and every earlier
+                       // tile - have finished that epilogue part; v = 0: the previous tile's last step may lack it)
 };
 
 struct EpiDesc {
@@ -88,6 +100,8 @@ struct EpiDesc {
   uint16_t bias_off;   // float offset into consts (16-byte aligned)
   uint16_t aux_off;    // sigma weights (EPI_*_TO_A with sigma) or rgb weights [3][n] (EPI_VIEW_RGB)
   uint16_t out_off;    // EPI_LOGITS: channel offset in the raw row
+  uint16_t n0a;        // E0 part a = columns [0, n0a), part b = [n0a, n0)        (multiples of 16; n0a = n0: one block)
+  uint16_t n1a;        // E1 part a = columns [n0, n1a), part b = [n1a, n)        (n1a = n: one block)
 };
 
 struct MlpProgram {
@@ -102,7 +116,6 @@ struct MlpProgram {
 
 // Launch arguments of the fused kernel (device pointers).
 struct MlpParams {
-  const MlpProgram* prog;
   const uint8_t* wpacked;
   const float* consts;
   const float* pts;       // [S,3] or null
@@ -114,10 +127,18 @@ struct MlpParams {
   int32_t CH;             // raw row width 4 + C + K
   float* raw;
   int32_t num_tiles;
+  uint32_t* status;       // sticky device word: bit 0 = a non-finite / out-of-range activation was seen (may be null)
   long long* dbg;         // optional clock64 timeline of block 0 (development aid), else null
 };
 
-constexpr int kSmemConsts = kSmemProg;   // (the program itself is in __constant__ memory)
+// What a launch carries: arguments + the context's program, as ONE __grid_constant__ kernel parameter.
+struct MlpLaunch {
+  MlpParams p;
+  MlpProgram prog;
+};
+static_assert(sizeof(MlpLaunch) <= 32764, "kernel parameter space is 32764 bytes");
+
+constexpr int kSmemConsts = kSmemProg;   // (the program itself is in the kernel's parameter bank)
 constexpr int kSmemPart = kSmemConsts + kMaxConsts * 4;      // [kEpiWarps/4][128][4] floats
 constexpr int kSmemBars = kSmemPart + (kEpiWarps / 4) * kTileM * 4 * 4;
 constexpr int kSmemTotal = kSmemBars + 256;

@@ -9,7 +9,8 @@
 //   * 2 MMA warps take alternate stages; one elected lane issues tcgen05.mma kind::f16, M=128, N<=128, K=16:
 //     the A operand is the embedding in shared memory (SS form) or the previous layer's activations
 //     in TENSOR MEMORY (TS form); accumulators are fp32 in tensor memory;
-//   * 1 scout thread does every mbarrier wait the issue depends on and publishes a "stages ready" counter;
+//   * 1 scout thread does the mbarrier waits for "weight stage landed" / "embedding written" and publishes a
+//     "stages ready" counter, so the issuers never execute an mbarrier wait;
 //   * 8 epilogue warps tcgen05.ld the accumulator, add bias, ReLU, split into hi/lo and tcgen05.st the
 //     result back to tensor memory as the next layer's A operand.  Activations never touch shared or
 //     global memory.  The sigma head (N=1) and rgb head (N=3) are CUDA-core dot products inside the
@@ -17,22 +18,28 @@
 //
 // Overlap: every step (layer) is issued as two N-halves h0, h1 with separate accumulator columns.
 // E0 (epilogue of h0) runs while the tensor pipe works on h1; E1 runs while the next step's h0 consumes
-// the K-chunks E0 already produced.  Hazards are tracked with five mbarriers that each complete once
-// per step: acc_full[0/1] (MMA -> epilogue), war_ok (MMA -> E0: the activation columns E0 overwrites
-// have been read), e_done[0/1] (epilogue -> MMA).
+// the K-chunks E0 already produced.  Hazards:
+//   MMA -> epilogue   acc_full[0/1]  mbarriers (tcgen05.commit), one phase per step;
+//   MMA -> E0 stores  war_ok[0/1]    mbarriers: the activation columns part a / part b of E0 overwrite have
+//                                    been read by the last MMA of this step that needs them;
+//   epilogue -> MMA   three monotonic shared-memory counters (E0 done, E1 part a done, E1 done), +1 per
+//                     epilogue warp (red.release after tcgen05.wait::st + fence), polled with ld.acquire by
+//                     the issuing warps: the hand-off costs one shared-memory round trip instead of
+//                     256 mbarrier arrivals -> scout wake-up -> ready word -> issuer (~560 cycles, timeline v10).
 //
 // Precision: operands are 16-bit (fp16 or bf16), accumulation fp32.  The "x3" modes compute every product
 // as A_hi*B_hi + A_lo*B_hi + A_hi*B_lo with x = hi + lo split in the operand format: ~2^-21 relative
 // per product for fp16x3 (default; what the 1e-4 parity tolerance needs with margin), ~2^-17 for
 // bf16x3 (fp32 exponent range).  The 1-pass modes keep the first term only (fast, out of tolerance).
+// An activation outside the operand format's range (|x| > 65504 in the fp16 modes, non-finite in any) sets
+// bit 0 of the context's sticky status word: overflow is reported (pnr_status), never silent.
 #include <cstddef>
+#include <mutex>
 #include "common.cuh"
 #include "mlp_program.h"
 #include "tc05.cuh"
 
 namespace pnr {
-
-__constant__ MlpProgram c_prog;   // the program of the context being launched (uploaded when it changes)
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -84,39 +91,39 @@ __device__ __forceinline__ void encode_row(const float (&p)[3], int L, uint8_t* 
 // ------------------------------------------------------------------------------------------------
 // Epilogue building blocks.  One thread owns one accumulator row (TMEM lane); groups are 16 columns.
 // ------------------------------------------------------------------------------------------------
-struct EpiCtx {
-  uint32_t tmem_lane;      // tmem base | lane offset of this thread's quarter
-  uint32_t bar_war;
-  uint32_t parity;
-};
 
-// activation -> next layer's A operand: v = act(acc + bias); [sigma += v . wsig]; split into hi / lo parts
+// activation -> next layer's A operand: v = act(acc + bias); [sigma += v . wsig]; split into hi / lo parts.
+// `vmax` collects the largest |v| bit pattern seen (range check of the 16-bit operand format).
 template <int PASSES, int FMT>
-__device__ __forceinline__ void epi_group_act(const uint32_t (&r)[16], int g, const EpiDesc& ed, float clamp_lo,
-                                              const float* bias, const float* wsig, float& sig,
+__device__ __forceinline__ void epi_group_act(const uint32_t (&r)[16], int g, const EpiDesc& ed,
+                                              const float* bias, const float* wsig, float& sig, uint32_t& vmax,
                                               uint32_t (&hi)[8], uint32_t (&lo)[8]) {
   const float4* b4 = reinterpret_cast<const float4*>(bias + g * 16);
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const float4 b = b4[q];
-    const float v0 = fmaxf(__uint_as_float(r[4 * q + 0]) + b.x, clamp_lo);
-    const float v1 = fmaxf(__uint_as_float(r[4 * q + 1]) + b.y, clamp_lo);
-    const float v2 = fmaxf(__uint_as_float(r[4 * q + 2]) + b.z, clamp_lo);
-    const float v3 = fmaxf(__uint_as_float(r[4 * q + 3]) + b.w, clamp_lo);
+    const float v0 = fmaxf(__uint_as_float(r[4 * q + 0]) + b.x, 0.f);
+    const float v1 = fmaxf(__uint_as_float(r[4 * q + 1]) + b.y, 0.f);
+    const float v2 = fmaxf(__uint_as_float(r[4 * q + 2]) + b.z, 0.f);
+    const float v3 = fmaxf(__uint_as_float(r[4 * q + 3]) + b.w, 0.f);
     if (ed.sigma) {
       const float4 w = reinterpret_cast<const float4*>(wsig + g * 16)[q];
       sig += v0 * w.x + v1 * w.y + v2 * w.z + v3 * w.w;
     }
+    // v >= 0 after the ReLU, so the fp32 bit patterns order like the values (+inf on top; fmaxf turns a NaN
+    // accumulator into 0, but a NaN can only follow an overflow that was flagged where it happened)
+    vmax = __vimax3_u32(vmax, __float_as_uint(v0), __float_as_uint(v1));
+    vmax = __vimax3_u32(vmax, __float_as_uint(v2), __float_as_uint(v3));
     split_x2<FMT>(v0, v1, hi[2 * q], lo[2 * q]);
     split_x2<FMT>(v2, v3, hi[2 * q + 1], lo[2 * q + 1]);
   }
 }
 
 template <int PASSES>
-__device__ __forceinline__ void epi_group_store(int g, const EpiDesc& ed, const EpiCtx& cx,
+__device__ __forceinline__ void epi_group_store(int g, const EpiDesc& ed, uint32_t tmem_lane,
                                                 const uint32_t (&hi)[8], const uint32_t (&lo)[8]) {
-  tmem_st8(cx.tmem_lane + ed.dst_col + g * 8, hi);
-  if (PASSES == 3) tmem_st8(cx.tmem_lane + ed.dst_lo_col + g * 8, lo);
+  tmem_st8(tmem_lane + ed.dst_col + g * 8, hi);
+  if (PASSES == 3) tmem_st8(tmem_lane + ed.dst_lo_col + g * 8, lo);
 }
 
 __device__ __forceinline__ void epi_group_rgb(const uint32_t (&r)[16], int g, const EpiDesc& ed, const float* bias,
@@ -138,13 +145,21 @@ __device__ __forceinline__ void epi_group_logits(const uint32_t (&r)[16], int g,
     if (g * 16 + j < ed.n_valid) dst[g * 16 + j] = __uint_as_float(r[j]) + bias[g * 16 + j];
 }
 
+// Largest finite magnitude of the operand format, as fp32 bits: 65504 (fp16) / FLT_MAX (bf16 shares fp32's range).
+template <int FMT>
+__device__ __forceinline__ constexpr uint32_t range_limit_bits() {
+  return FMT == kFmtF16 ? 0x477FE000u : 0x7F7FFFFFu;
+}
+
 // CTAs run as clusters of two that stream the SAME weight stages in lock step: each CTA fetches half of every
 // stage from L2 and multicasts it into both shared memories, halving L2 -> SM weight traffic (ncu: lts
 // throughput 28 % -> 16 %; the kernel time did not change - the weight stream is not what bounds it).
 template <int PASSES, int FMT>
 __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kMlpThreads, 1)
-mlp_fused_kernel(const MlpParams p) {
+mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  const MlpParams& p = L.p;
+  const MlpProgram& prog = L.prog;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = cluster_ctarank();
   // every CTA runs the same number of tile iterations (tiles past the end are dummies whose stores are
@@ -154,24 +169,25 @@ mlp_fused_kernel(const MlpParams p) {
   float* consts = reinterpret_cast<float*>(smem + kSmemConsts);
   float* part = reinterpret_cast<float*>(smem + kSmemPart);  // [2][128][4]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBars);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
-  const uint32_t ready_word = smem_u32(bars + 31);   // number of weight stages whose inputs are all ready
 
   const uint32_t bar_full = smem_u32(&bars[0]);                 // [kRing]
   const uint32_t bar_empty = smem_u32(&bars[kRing]);            // [kRing]
   const uint32_t bar_acc_full = smem_u32(&bars[2 * kRing]);     // [2]
-  const uint32_t bar_e_done = smem_u32(&bars[2 * kRing + 2]);   // [2]
-  const uint32_t bar_war = smem_u32(&bars[2 * kRing + 4]);
-  const uint32_t bar_emb_full = smem_u32(&bars[2 * kRing + 5]);
-  const uint32_t bar_emb_empty = smem_u32(&bars[2 * kRing + 6]);
-  const uint32_t bar_dir_full = smem_u32(&bars[2 * kRing + 7]);   // [2]
-  const uint32_t bar_dir_empty = smem_u32(&bars[2 * kRing + 9]);  // [2]
-#ifdef PNR_SPLIT_WAR
-  const uint32_t bar_war1 = smem_u32(&bars[2 * kRing + 11]);
-#endif
+  const uint32_t bar_war = smem_u32(&bars[2 * kRing + 2]);      // [2]  E0 part a / part b may store
+  const uint32_t bar_emb_full = smem_u32(&bars[2 * kRing + 4]);
+  const uint32_t bar_emb_empty = smem_u32(&bars[2 * kRing + 5]);
+  const uint32_t bar_dir_full = smem_u32(&bars[2 * kRing + 6]);   // [2]
+  const uint32_t bar_dir_empty = smem_u32(&bars[2 * kRing + 8]);  // [2]
+  // 32-bit words (each in its own 8-byte slot)
+  const uint32_t cnt_e0 = smem_u32(&bars[24]);      // epilogue -> MMA counters: +1 per epilogue warp and part
+  const uint32_t cnt_e1a = smem_u32(&bars[25]);
+  const uint32_t cnt_e1 = smem_u32(&bars[26]);
+  volatile uint32_t* issued_w = reinterpret_cast<volatile uint32_t*>(bars + 29);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
+  const uint32_t ready_word = smem_u32(bars + 31);   // number of weight stages whose operands have all landed
 
   // ---- one-time setup: constants to shared memory, barriers, tensor memory
-  for (int i = threadIdx.x; i < c_prog.n_consts; i += blockDim.x) consts[i] = p.consts[i];
+  for (int i = threadIdx.x; i < prog.n_consts; i += blockDim.x) consts[i] = p.consts[i];
   if (warp == 0) {
     tmem_alloc<512>(smem_u32(tmem_slot));
     tmem_relinquish();
@@ -183,20 +199,11 @@ mlp_fused_kernel(const MlpParams p) {
     }
     for (int h = 0; h < 2; ++h) {
       mbar_init(bar_acc_full + 8 * h, 1);
-#ifdef PNR_WARP_ARRIVE
-      mbar_init(bar_e_done + 8 * h, kEpiWarps);        // staged variant: one arrival per epilogue warp
-#else
-      mbar_init(bar_e_done + 8 * h, kEpiWarps * 32);
-#endif
+      mbar_init(bar_war + 8 * h, 1);
       mbar_init(bar_dir_full + 8 * h, kProWarps * 32);
       mbar_init(bar_dir_empty + 8 * h, 1);
     }
-    mbar_init(bar_war, 1);
-#ifdef PNR_SPLIT_WAR
-    mbar_init(bar_war1, 1);
-#endif
-    *reinterpret_cast<volatile uint32_t*>(bars + 31) = 0u;
-    *reinterpret_cast<volatile uint32_t*>(bars + 29) = 0u;
+    for (int w = 24; w < 32; ++w) bars[w] = 0ull;
     mbar_init(bar_emb_full, kProWarps * 32);
     mbar_init(bar_emb_empty, 1);
     fence_mbar_init();
@@ -206,135 +213,119 @@ mlp_fused_kernel(const MlpParams p) {
   cluster_sync();   // the peer's barriers must be initialised before anything is multicast into them
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const int n_stages = c_prog.n_stages, n_steps = c_prog.n_steps;
+  const int n_stages = prog.n_stages, n_steps = prog.n_steps;
 
   if (warp < kEpiWarps) {
     // =============================================================== epilogue warps
-    const int q = warp & 3, ch = warp >> 2;     // TMEM lane quarter ; which half of a column range
+    const int q = warp & 3, ch = warp >> 2;     // TMEM lane quarter ; which share of a column block
+    constexpr int kCh = kEpiWarps / 4;          // warps sharing one lane quarter
     const int row = q * 32 + lane;
-    EpiCtx cx;
-    cx.tmem_lane = tmem + ((uint32_t)(q * 32) << 16);
-    cx.bar_war = bar_war;
+    const uint32_t tmem_lane = tmem + ((uint32_t)(q * 32) << 16);
     uint32_t gstep = 0;
+    uint32_t vmax = 0;                          // largest activation magnitude (fp32 bits) this thread produced
     for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
       const int64_t s = (int64_t)tile * kTileM + row;
       const bool valid = s < p.S;
       float sig = 0.f;
       for (int st = 0; st < n_steps; ++st, ++gstep) {
-        const EpiDesc ed = c_prog.ep[st];
+        const EpiDesc ed = prog.ep[st];
         const uint32_t parity = gstep & 1u;
-        cx.parity = parity;
         const float* bias = consts + ed.bias_off;
         const float* aux = consts + ed.aux_off;
-        const bool to_a = ed.kind == EPI_RELU_TO_A || ed.kind == EPI_LINEAR_TO_A;
-        const float clamp_lo = ed.kind == EPI_RELU_TO_A ? 0.f : -INFINITY;
+        const bool to_a = ed.kind == EPI_RELU_TO_A;
         float* out_row = p.raw + (valid ? s : 0) * p.CH + ed.out_off;
-        bool war_pending = to_a;
         float c0 = 0.f, c1 = 0.f, c2 = 0.f;
-#ifdef PNR_SPLIT_WAR
-        // Staged for round 2 (not validated on a GPU yet): E0 runs as two blocks,
-        // the lower and the upper half of the activation columns it overwrites, each released by its own
-        // write-after-read barrier (war_ok after the LAST stage of half 1 that reads the lower block, war_ok1
-        // likewise for the upper block), so the first block is stored while half 1 is still on its first stages.
-        const int n0a = (((int)ed.n0 >> 4) >> 1) > 0 ? ((((int)ed.n0 >> 4) >> 1) << 4) : (int)ed.n0;
-#pragma unroll 1
-        for (int ph = 0; ph < 3; ++ph) {
-          const int h = ph == 2 ? 1 : 0;
-          const uint32_t my_war = ph == 0 ? bar_war : bar_war1;
-          if (ph < 2) war_pending = to_a;
-#ifdef PNR_TIMELINE
-          const bool rec = false;
-#endif
-          if (ph != 1) {
-            mbar_wait_backoff(bar_acc_full + 8 * h, parity);
-            tc_fence_after();
-          }
-          const int gb_all = (ph == 0 ? 0 : (ph == 1 ? n0a : (int)ed.n0)) >> 4;
-          const int ge_all = (ph == 0 ? n0a : (ph == 1 ? (int)ed.n0 : (int)ed.n)) >> 4;
-#else
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
-          const uint32_t my_war = bar_war;
 #ifdef PNR_TIMELINE
           const bool rec = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && tile == 2 * (int)gridDim.x;
           if (rec) p.dbg[4096 + (st * 2 + h) * 3 + 0] = clock64();
 #endif
+          // column blocks (in 16-column groups) of this half: part a = [pa0, pa1), part b = [pa1, pb1)
+          const int pa0 = (h == 0 ? 0 : (int)ed.n0) >> 4;
+          const int pa1 = (h == 0 ? (int)ed.n0a : (int)ed.n1a) >> 4;
+          const int pb1 = (h == 0 ? (int)ed.n0 : (int)ed.n) >> 4;
+          // this warp's near-equal contiguous share of each part
+          const int a_lo = pa0 + (ch * (pa1 - pa0) + kCh - 1) / kCh, a_hi = pa0 + ((ch + 1) * (pa1 - pa0) + kCh - 1) / kCh;
+          const int b_lo = pa1 + (ch * (pb1 - pa1) + kCh - 1) / kCh, b_hi = pa1 + ((ch + 1) * (pb1 - pa1) + kCh - 1) / kCh;
+          const int na = a_hi - a_lo, cnt = na + (b_hi - b_lo);
+          auto group_of = [&](int i) { return i < na ? a_lo + i : b_lo + (i - na); };
+          // hand-off after part a of E1 (part a of E0 is not signalled: the next step's first MMA overwrites
+          // accumulator columns that part b still reads)
+          // (relaxed add: what is handed over lives in tensor memory - complete after tcgen05.wait::st and ordered
+          //  by the tcgen05 fences on both sides; a release here is a MEMBAR.ALL.CTA per hand-off for nothing)
+          auto signal = [&](uint32_t counter) {
+            if (to_a) tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) red_add_smem(counter, 1u);
+          };
           mbar_wait_backoff(bar_acc_full + 8 * h, parity);
           tc_fence_after();
 #ifdef PNR_TIMELINE
           if (rec) p.dbg[4096 + (st * 2 + h) * 3 + 1] = clock64();
 #endif
-          const int gb_all = h == 0 ? 0 : (ed.n0 >> 4);
-          const int ge_all = h == 0 ? (ed.n0 >> 4) : (ed.n >> 4);
-#endif
-          const int G = ge_all - gb_all;
-          constexpr int kCh = kEpiWarps / 4;                     // warps sharing one lane quarter
-          const int gb = gb_all + (ch * G + kCh - 1) / kCh;      // ceil(ch*G/kCh): near-equal contiguous shares
-          const int ge = gb_all + ((ch + 1) * G + kCh - 1) / kCh;
-          const uint32_t acc = cx.tmem_lane + ed.acc_col;
-          // software pipeline: the load of group g+1 is in flight while group g is processed
+          if (h == 1 && na == 0) signal(cnt_e1a);
+          const uint32_t acc = tmem_lane + ed.acc_col;
+          // software pipeline: the load of group i+1 is in flight while group i is processed
           uint32_t ra[16], rb[16];
-          if (gb < ge) tmem_ld16(acc + gb * 16, ra);
+          if (cnt > 0) tmem_ld16(acc + group_of(0) * 16, ra);
+          bool war_a = !(to_a && h == 0), war_b = war_a;   // "may store" state of part a / part b
           if (to_a) {
-            // Two groups are converted before anything is stored: E0 reaches the write-after-read barrier
+            // Two groups are converted before anything is stored: E0 reaches its write-after-read barrier
             // (this step's MMAs still read the columns it overwrites) with two groups of work already done.
 #pragma unroll 1
-            for (int g = gb; g < ge; g += 2) {
+            for (int i = 0; i < cnt; i += 2) {
               uint32_t ha[8], la[8], hb[8], lb[8];
-              const bool two = g + 1 < ge;
+              const bool two = i + 1 < cnt;
+              const int g0 = group_of(i), g1 = group_of(i + 1);
               tc_wait_ld();
-#ifdef PNR_TIMELINE
-              if (rec && h == 1 && g == gb) p.dbg[7168 + st * 4 + 0] = clock64();
-#endif
-              if (two) tmem_ld16(acc + (g + 1) * 16, rb);
-              epi_group_act<PASSES, FMT>(ra, g, ed, clamp_lo, bias, aux, sig, ha, la);
-#ifdef PNR_TIMELINE
-              if (rec && h == 1 && g == gb) p.dbg[7168 + st * 4 + 1] = clock64();
-#endif
+              if (two) tmem_ld16(acc + g1 * 16, rb);
+              epi_group_act<PASSES, FMT>(ra, g0, ed, bias, aux, sig, vmax, ha, la);
               if (two) {
                 tc_wait_ld();
-#ifdef PNR_TIMELINE
-                if (rec && h == 1 && g == gb) p.dbg[7168 + st * 4 + 2] = clock64();
-#endif
-                if (g + 2 < ge) tmem_ld16(acc + (g + 2) * 16, ra);
-                epi_group_act<PASSES, FMT>(rb, g + 1, ed, clamp_lo, bias, aux, sig, hb, lb);
+                if (i + 2 < cnt) tmem_ld16(acc + group_of(i + 2) * 16, ra);
+                epi_group_act<PASSES, FMT>(rb, g1, ed, bias, aux, sig, vmax, hb, lb);
               }
-              if (war_pending) {  // the columns we are about to overwrite must have been consumed by the MMAs
-                mbar_wait_backoff(my_war, parity);
-                tc_fence_after();
-                war_pending = false;
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                if (k == 1 && !two) break;
+                const int idx = i + k;
+                const bool in_a = idx < na;
+                if (!(in_a ? war_a : war_b)) {  // the columns we are about to overwrite must have been consumed by the MMAs
+                  mbar_wait_backoff(bar_war + (in_a ? 0 : 8), parity);
+                  tc_fence_after();
+                  if (in_a) war_a = true; else war_b = true;
+                }
+                if (k == 0) epi_group_store<PASSES>(g0, ed, tmem_lane, ha, la);
+                else epi_group_store<PASSES>(g1, ed, tmem_lane, hb, lb);
+                if (h == 1 && idx + 1 == na) signal(cnt_e1a);
               }
-              epi_group_store<PASSES>(g, ed, cx, ha, la);
-              if (two) epi_group_store<PASSES>(g + 1, ed, cx, hb, lb);
             }
           } else {
 #pragma unroll 1
-            for (int g = gb; g < ge; g += 2) {
+            for (int i = 0; i < cnt; i += 2) {
+              const int g0 = group_of(i), g1 = group_of(i + 1);
               tc_wait_ld();
-              if (g + 1 < ge) tmem_ld16(acc + (g + 1) * 16, rb);
+              if (i + 1 < cnt) tmem_ld16(acc + g1 * 16, rb);
               if (ed.kind == EPI_VIEW_RGB) {
-                epi_group_rgb(ra, g, ed, bias, aux, c0, c1, c2);
+                epi_group_rgb(ra, g0, ed, bias, aux, c0, c1, c2);
               } else if (valid) {
-                epi_group_logits(ra, g, ed, bias, out_row);
+                epi_group_logits(ra, g0, ed, bias, out_row);
               }
-              if (g + 1 < ge) {
+              if (h == 1 && i + 1 == na) signal(cnt_e1a);
+              if (i + 1 < cnt) {
                 tc_wait_ld();
-                if (g + 2 < ge) tmem_ld16(acc + (g + 2) * 16, ra);
+                if (i + 2 < cnt) tmem_ld16(acc + group_of(i + 2) * 16, ra);
                 if (ed.kind == EPI_VIEW_RGB) {
-                  epi_group_rgb(rb, g + 1, ed, bias, aux, c0, c1, c2);
+                  epi_group_rgb(rb, g1, ed, bias, aux, c0, c1, c2);
                 } else if (valid) {
-                  epi_group_logits(rb, g + 1, ed, bias, out_row);
+                  epi_group_logits(rb, g1, ed, bias, out_row);
                 }
+                if (h == 1 && i + 2 == na) signal(cnt_e1a);
               }
             }
           }
-          if (h == 0 && war_pending) {  // no columns of h0 for this thread: still consume the barrier phase
-            mbar_wait_backoff(my_war, parity);
-            war_pending = false;
-          }
-#ifdef PNR_SPLIT_WAR
-          if (ph == 0) continue;      // E0 signals once, after its second block
-#endif
           if (h == 1) {
             if (ed.sigma) {
               part[(ch * kTileM + row) * 4 + 3] = sig;
@@ -345,14 +336,14 @@ mlp_fused_kernel(const MlpParams p) {
               mine[0] = c0; mine[1] = c1; mine[2] = c2;
               named_bar_sync(1, kEpiWarps * 32);
               if (ch == 0 && valid) {
-                const float* b3 = consts + c_prog.rgb_bias_off;
+                const float* b3 = consts + prog.rgb_bias_off;
                 float o0 = c0, o1 = c1, o2 = c2, o3 = mine[3];
 #pragma unroll
                 for (int oc = 1; oc < kEpiWarps / 4; ++oc) {   // fixed order: deterministic sums
                   const float* other = part + (oc * kTileM + row) * 4;
                   o0 += other[0]; o1 += other[1]; o2 += other[2]; o3 += other[3];
                 }
-                o0 += b3[0]; o1 += b3[1]; o2 += b3[2]; o3 += consts[c_prog.sigma_bias_off];
+                o0 += b3[0]; o1 += b3[1]; o2 += b3[2]; o3 += consts[prog.sigma_bias_off];
                 float* dst = p.raw + s * p.CH;
                 if (p.CH == 4) {
                   *reinterpret_cast<float4*>(dst) = make_float4(o0, o1, o2, o3);
@@ -362,28 +353,20 @@ mlp_fused_kernel(const MlpParams p) {
               }
             }
           }
-          if (to_a) tc_wait_st();
-          tc_fence_before();
-#ifdef PNR_WARP_ARRIVE
-          // staged for round 2 (not validated on a GPU yet): 8 arrivals per hand-off
-          // instead of 256 - every lane's tensor-memory traffic is complete and fenced before the warp converges
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_e_done + 8 * h);
-#else
-          mbar_arrive(bar_e_done + 8 * h);
-#endif
+          signal(h == 0 ? cnt_e0 : cnt_e1);
 #ifdef PNR_TIMELINE
           if (rec) p.dbg[4096 + (st * 2 + h) * 3 + 2] = clock64();
 #endif
         }
       }
     }
+    if (p.status != nullptr && vmax > range_limit_bits<FMT>()) atomicOr(p.status, 1u);
   } else if (warp < kEpiWarps + kProWarps) {
     // =============================================================== embedding producer warps
     const int row = (warp - kEpiWarps) * 32 + lane;
     uint8_t* emb_hi = smem + kSmemEmb;
     uint8_t* emb_lo = emb_hi + kEmbPartBytes;
-    const int Lx = c_prog.Lx, Ld = c_prog.Ld;
+    const int Lx = prog.Lx, Ld = prog.Ld;
     int it = 0;
     for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
       int64_t s = (int64_t)tile * kTileM + row;
@@ -426,7 +409,7 @@ mlp_fused_kernel(const MlpParams p) {
       for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
         for (int si = 0; si < n_stages; ++si, ++gs) {
           const uint32_t slot = gs % kRing, ph = (gs / kRing) & 1;
-          const uint32_t gofs = c_prog.st[si].gofs, bytes = c_prog.st[si].bytes;
+          const uint32_t gofs = prog.st[si].gofs, bytes = prog.st[si].bytes;
           mbar_wait_backoff(bar_empty + 8 * slot, ph ^ 1);
 #ifdef PNR_TIMELINE
           if (p.dbg != nullptr && blockIdx.x == 0 && tile == 2 * (int)gridDim.x) p.dbg[6144 + si] = clock64();
@@ -443,36 +426,52 @@ mlp_fused_kernel(const MlpParams p) {
     }
   } else if (warp == kEpiWarps + kProWarps + 2) {
     // =============================================================== scout (one elected thread)
-    // Does every wait the MMA issue depends on (epilogue hand-offs, embeddings, weight stage landed), in
-    // stage order, and publishes "stages ready" through a shared-memory counter.  The issuer never touches an
-    // mbarrier wait (each costs ~100 cycles even when already complete), it only polls that word.
+    // Does every wait the MMA issue depends on, in stage order, and publishes "stages ready" through ONE
+    // shared-memory word, so the issuers never execute an mbarrier wait (each costs ~100 cycles even when
+    // already complete) and poll a single word.  Operands that arrive through the async proxy (weight stage
+    // landed, embeddings written) are checked first - they are ready long before they are needed - then the
+    // scout spins on the epilogue hand-off counters: epilogue warp -> counter -> scout -> ready word -> issuer
+    // is two shared-memory round trips (~100 cycles; the mbarrier relay it replaces took ~560, timeline v10).
     if (elect_one()) {
       uint32_t gs = 0;
-      int64_t gstep = -1;
+      uint32_t have_e0 = 0, have_e1a = 0, have_e1 = 0;   // last values read from the hand-off counters
+      auto spin = [&](uint32_t addr, uint32_t target, uint32_t& have, const char* what) {
+        if ((int32_t)(have - target) >= 0) return;
+        const long long t0 = clock64();
+        while ((int32_t)((have = ld_volatile_smem(addr)) - target) < 0) {
+          if ((clock64() - t0) > PNR_WATCHDOG_CYCLES) {
+            printf("pnr: scout watchdog (%s): block %d stage %u\n", what, (int)blockIdx.x, gs);
+            __trap();
+          }
+        }
+      };
       int it = 0;
       for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
         const int b = it & 1;
+        const uint32_t step_base = (uint32_t)(it * n_steps) - 1u;   // needs are stored + 1
+        uint32_t needs = prog.is[0].needs;
 #pragma unroll 1
         for (int si = 0; si < n_stages; ++si, ++gs) {
-          const uint32_t flags = c_prog.st[si].flags;
-          if (flags & F_WAIT_E0) {
-            ++gstep;
-            if (gstep > 0) mbar_wait(bar_e_done, (uint32_t)((gstep - 1) & 1));
-          }
-          if ((flags & F_WAIT_E1) && gstep > 0) mbar_wait(bar_e_done + 8, (uint32_t)((gstep - 1) & 1));
+          const uint32_t flags = prog.st[si].flags;
+          const uint32_t needs_next = prog.is[si + 1 < n_stages ? si + 1 : 0].needs;   // (in flight during the waits)
           if (flags & F_WAIT_EMB) mbar_wait(bar_emb_full, (uint32_t)(it & 1));
           if (flags & F_WAIT_DIR) mbar_wait(bar_dir_full + 8 * b, (uint32_t)((it >> 1) & 1));
           const uint32_t slot = gs % kRing, ph = (gs / kRing) & 1;
           mbar_wait(bar_full + 8 * slot, ph);
+          // kEpiWarps arrivals per completed epilogue part
+          spin(cnt_e0, (step_base + (needs & 0xFFu)) * kEpiWarps, have_e0, "E0");
+          spin(cnt_e1a, (step_base + ((needs >> 8) & 0xFFu)) * kEpiWarps, have_e1a, "E1a");
+          spin(cnt_e1, (step_base + ((needs >> 16) & 0xFFu)) * kEpiWarps, have_e1, "E1");
           tc_fence_before();
           st_release_smem(ready_word, gs + 1);
+          needs = needs_next;
         }
       }
     }
   } else {
     // =============================================================== MMA issuer
-    // The whole warp walks the stage list in lock step, so the loop state (stage words from __constant__
-    // memory, ring slot, descriptors) stays on the uniform datapath; only the tcgen05 instructions sit in an
+    // The whole warp walks the stage list in lock step, so the loop state (stage words from the parameter
+    // bank, ring slot, descriptors) stays on the uniform datapath; only the tcgen05 instructions sit in an
     // elect.sync branch.  The issue table (IssueDesc) holds every per-stage word ready to use: measured on
     // a stand-alone replica (tools/probe_issue3.cu) this loop needs ~570 cycles per 12-MMA stage next to
     // ALU-saturating warps, the field-by-field version it replaces ~1000 (the tensor work is 768).
@@ -482,9 +481,8 @@ mlp_fused_kernel(const MlpParams p) {
     // loop) drain it; with two warps that work overlaps the other warp's burst.  The owner of stage g bursts
     // only after the owner of g-1 has issued (shared counter `issued`): MMAs of one accumulator keep their
     // order, and because the pipe retires a CTA's MMAs in issue order, the commit that follows a half's last
-    // stage also covers the stages the other warp issued for it.
+    // stage also covers the stages the other warp issued for it (hardware assumption).
     const uint32_t me = (warp == kEpiWarps + kProWarps + 1) ? 0u : 1u;
-    volatile uint32_t* issued_w = reinterpret_cast<volatile uint32_t*>(bars + 29);
     uint32_t gs = 0, ready = 0, slot = 0, issued = 0;
     int it = 0;
     // (address field only: in a cluster the shared-window address of CTA rank > 0 carries the rank above it)
@@ -497,10 +495,10 @@ mlp_fused_kernel(const MlpParams p) {
 #pragma unroll 1
       for (int si = 0; si < n_stages; ++si, ++gs, slot = (slot + 1 == (uint32_t)kRing) ? 0u : slot + 1) {
         if ((gs & 1u) != me) continue;
-        const uint32_t idesc = c_prog.is[si].idesc, b_lo_base = c_prog.is[si].b_lo_base;
-        const uint32_t b_inc = c_prog.is[si].b_inc, lo_off16 = c_prog.is[si].lo_off16;
-        const uint32_t acc_col = c_prog.is[si].acc_col, a_off = c_prog.is[si].a_off;
-        const uint32_t a_lo_off = c_prog.is[si].a_lo_off, fk = c_prog.is[si].flags_k;
+        const uint32_t idesc = prog.is[si].idesc, b_lo_base = prog.is[si].b_lo_base;
+        const uint32_t b_inc = prog.is[si].b_inc, lo_off16 = prog.is[si].lo_off16;
+        const uint32_t acc_col = prog.is[si].acc_col, a_off = prog.is[si].a_off;
+        const uint32_t a_lo_off = prog.is[si].a_lo_off, fk = prog.is[si].flags_k;
         const uint32_t flags = fk & 0xFFFFu, ksteps = (fk >> 16) & 0xFFu, a_kind = fk >> 24;
 #ifdef PNR_TIMELINE
         const bool rec = p.dbg != nullptr && blockIdx.x == 0 && it == 2 && lane == 0;
@@ -509,7 +507,7 @@ mlp_fused_kernel(const MlpParams p) {
         if (ready <= gs) {   // the scout may be several stages ahead: poll only when our copy is stale
           ready = ld_acquire_smem(ready_word);
           if (ready <= gs) {
-            long long t0 = clock64();
+            const long long t0 = clock64();
             while ((ready = ld_acquire_smem(ready_word)) <= gs) {
               if ((clock64() - t0) > PNR_WATCHDOG_CYCLES) {
                 if (lane == 0) printf("pnr: issuer watchdog: block %d stage %u\n", (int)blockIdx.x, gs);
@@ -580,17 +578,11 @@ mlp_fused_kernel(const MlpParams p) {
           if (rec) p.dbg[si * 5 + 2] = clock64();
 #endif
           tc_commit_multicast(bar_empty + 8 * slot, (uint16_t)((1u << kClusterSize) - 1u));   // slot free in all CTAs
-#ifdef PNR_SPLIT_WAR
           if (flags & (F_RELEASE_EMB | F_RELEASE_DIR | F_COMMIT_WAR | F_COMMIT_WAR1 | F_COMMIT_ACC0 | F_COMMIT_ACC1)) {
-#else
-          if (flags & (F_RELEASE_EMB | F_RELEASE_DIR | F_COMMIT_WAR | F_COMMIT_ACC0 | F_COMMIT_ACC1)) {
-#endif
             if (flags & F_RELEASE_EMB) tc_commit(bar_emb_empty);
             if (flags & F_RELEASE_DIR) tc_commit(bar_dir_empty + 8 * b);
             if (flags & F_COMMIT_WAR) tc_commit(bar_war);
-#ifdef PNR_SPLIT_WAR
-            if (flags & F_COMMIT_WAR1) tc_commit(bar_war1);
-#endif
+            if (flags & F_COMMIT_WAR1) tc_commit(bar_war + 8);
             if (flags & F_COMMIT_ACC0) tc_commit(bar_acc_full);
             if (flags & F_COMMIT_ACC1) tc_commit(bar_acc_full + 8);
           }
@@ -609,36 +601,43 @@ mlp_fused_kernel(const MlpParams p) {
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
+// Per-device launch state: the > 48 KB dynamic shared-memory opt-in is a per-device function attribute, and so
+// is the SM count the persistent grid is sized by.
+struct DeviceState {
+  bool attr_done[2][2] = {{false, false}, {false, false}};
+  int sms = 0;
+};
+static DeviceState g_dev[kMaxDevices];
+static std::mutex g_dev_mutex;
+
 template <int PASSES, int FMT>
-static int launch_one(const MlpParams& p, int grid, cudaStream_t stream) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    PNR_CUDA(cudaFuncSetAttribute(mlp_fused_kernel<PASSES, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  kSmemTotal));
-    attr_done = true;
+static int launch_one(const MlpLaunch& L, int dev, int grid, cudaStream_t stream) {
+  {
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
+    bool& done = g_dev[dev].attr_done[PASSES == 3][FMT == kFmtBF16];
+    if (!done) {
+      PNR_CUDA(cudaFuncSetAttribute(mlp_fused_kernel<PASSES, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kSmemTotal));
+      done = true;
+    }
   }
-  mlp_fused_kernel<PASSES, FMT><<<grid, kMlpThreads, kSmemTotal, stream>>>(p);
+  mlp_fused_kernel<PASSES, FMT><<<grid, kMlpThreads, kSmemTotal, stream>>>(L);
   PNR_LAUNCH_CHECK("mlp_fused_kernel");
   return PNR_OK;
 }
 
-// `host_prog` / `prog_id`: the context's program; it is copied to __constant__ memory (stream-ordered) only
-// when it differs from the one last uploaded on this device.
-int launch_mlp(const MlpParams& p, const MlpProgram* host_prog, uint64_t prog_id, int passes, int fmt,
-               cudaStream_t stream) {
-  int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  if (grid <= 0) return PNR_OK;
-  grid = (grid + kClusterSize - 1) / kClusterSize * kClusterSize;   // whole clusters (spare CTAs run dummy tiles)
-  if (grid > num_sms()) grid = num_sms() / kClusterSize * kClusterSize;
-  static uint64_t loaded_id[64] = {0};
+// Launches on the CURRENT device (the caller has made the context's device current).
+int launch_mlp(const MlpLaunch& L, int passes, int fmt, cudaStream_t stream) {
   int dev = 0;
   PNR_CUDA(cudaGetDevice(&dev));
-  if (loaded_id[dev & 63] != prog_id) {
-    PNR_CUDA(cudaMemcpyToSymbolAsync(c_prog, host_prog, sizeof(MlpProgram), 0, cudaMemcpyHostToDevice, stream));
-    loaded_id[dev & 63] = prog_id;
-  }
-  if (fmt == kFmtF16) return passes == 3 ? launch_one<3, kFmtF16>(p, grid, stream) : launch_one<1, kFmtF16>(p, grid, stream);
-  return passes == 3 ? launch_one<3, kFmtBF16>(p, grid, stream) : launch_one<1, kFmtBF16>(p, grid, stream);
+  PNR_CHECK_ARG(dev >= 0 && dev < kMaxDevices, "launch_mlp: device ordinal %d >= %d", dev, kMaxDevices);
+  const int sms = num_sms(dev);
+  int grid = L.p.num_tiles < sms ? L.p.num_tiles : sms;
+  if (grid <= 0) return PNR_OK;
+  grid = (grid + kClusterSize - 1) / kClusterSize * kClusterSize;   // whole clusters (spare CTAs run dummy tiles)
+  if (grid > sms) grid = sms / kClusterSize * kClusterSize;
+  if (fmt == kFmtF16) return passes == 3 ? launch_one<3, kFmtF16>(L, dev, grid, stream) : launch_one<1, kFmtF16>(L, dev, grid, stream);
+  return passes == 3 ? launch_one<3, kFmtBF16>(L, dev, grid, stream) : launch_one<1, kFmtBF16>(L, dev, grid, stream);
 }
 
 }  // namespace pnr

@@ -1,5 +1,6 @@
 // pnr_api.cu — context management, weight packing / MLP program construction and the
 // pnr_mlp_forward entry point of the C ABI (include/pnr.h).
+#include <cstdlib>
 #include <cstring>
 #include <cuda_fp16.h>
 #include <string>
@@ -23,8 +24,7 @@ int set_error(int code, const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches += n; }
 
-int launch_mlp(const MlpParams& p, const MlpProgram* host_prog, uint64_t prog_id, int passes, int fmt,
-               cudaStream_t stream);  // mlp_tc05.cu
+int launch_mlp(const MlpLaunch& L, int passes, int fmt, cudaStream_t stream);  // mlp_tc05.cu
 
 }  // namespace pnr
 
@@ -35,10 +35,12 @@ struct pnr_ctx {
   int passes = 3;
   int fmt = 0;   // 0 = fp16, 1 = bf16 (instruction-descriptor encoding)
   bool loaded = false;
-  MlpProgram h_prog;            // uploaded to __constant__ memory at launch when it is not the resident one
-  uint64_t prog_id = 0;
+  MlpLaunch launch;             // launch.prog = this context's program; launch.p is filled per call.  The whole
+                                // struct travels as the kernel's __grid_constant__ parameter: nothing is shared
+                                // between contexts, streams, devices or CUDA-graph replays.
   uint8_t* d_wpacked = nullptr;
   float* d_consts = nullptr;
+  uint32_t* d_status = nullptr; // sticky range-check word of the fused MLP (bit 0: activation out of operand range)
   size_t wpacked_bytes = 0;
 };
 
@@ -88,16 +90,22 @@ struct Builder {
   // for CTA 0 and [n/2, n) for CTA 1, each in the core-matrix layout of an n/2-row tile.  Host side only so
   // far (pnr_program_host + tests/test_cpu_program.py); the kernel that consumes it is not written yet.
   bool pair = false;
-  // E0's write-after-read barrier split in two (lower / upper half of the columns it overwrites): staged with the
-  // kernel's -DPNR_SPLIT_WAR variant for round 2, off in the product.
-#ifdef PNR_SPLIT_WAR
-  bool split_war = true;
-#else
-  bool split_war = false;
-#endif
+  // Epilogue parts (mlp_program.h): E0 in two blocks with their own write-after-read barriers, E1 in two blocks
+  // signalled separately.  Both only pay off when a half spans several weight stages (the x3 modes, K = 64 per
+  // stage); PNR_SPLIT_WAR / PNR_SPLIT_E1 = 0 / 1 in the environment override the default (tuning aid).
+  bool split_war, split_e1;
+  bool out_of_fp16_range = false;   // a weight (after the feature_linear fold) exceeds 65504 or is not finite
   std::string err;
 
-  Builder(int passes_, int fmt_) : passes(passes_), fmt(fmt_) { memset(&prog, 0, sizeof(prog)); }
+  static bool env_flag(const char* name, bool dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? (*v != '0') : dflt;
+  }
+  Builder(int passes_, int fmt_) : passes(passes_), fmt(fmt_) {
+    memset(&prog, 0, sizeof(prog));
+    split_war = env_flag("PNR_SPLIT_WAR", passes == 3);
+    split_e1 = env_flag("PNR_SPLIT_E1", passes == 3);
+  }
 
   int add_consts(const float* src, int n_valid, int n_pad) {
     const int off = (int)consts.size();
@@ -117,6 +125,7 @@ struct Builder {
           const int n = row0 + nn;
           const int k = k0 + kc * 8 + e;
           const float w = (n < m.out && k < kvalid) ? m.w[(size_t)n * m.in + col0 + k] : 0.f;
+          if (!(w >= -65504.f && w <= 65504.f)) out_of_fp16_range = true;   // also catches NaN
           uint16_t v;
           if (fmt == 1) {
             const uint16_t h = f2bf(w);
@@ -195,6 +204,9 @@ struct Builder {
     ed.n = (uint16_t)n_pad;
     ed.n0 = (uint16_t)n0;
     ed.acc_col = (uint16_t)acc_col;
+    const int g0 = n0 / 16, g1 = (n_pad - n0) / 16;
+    ed.n0a = (uint16_t)((split_war && g0 >= 2) ? (g0 / 2) * 16 : n0);
+    ed.n1a = (uint16_t)(n0 + ((split_e1 && g1 >= 2) ? (g1 / 2) * 16 : (n_pad - n0)));
     prog.ep[prog.n_steps++] = ed;
     return true;
   }
@@ -203,12 +215,13 @@ struct Builder {
 
   // Tensor-memory footprints (column intervals) used to place the cross-step hazard flags.
   struct Foot { int acc0, acc1, hi0, hi1, lo0, lo1; };
-  Foot e1_foot(int s) const {   // what E1 of step s reads (acc) and writes (activation columns)
+  // what the columns [c0, c1) of step s's epilogue read (accumulator) and write (activation columns)
+  Foot epi_foot(int s, int c0, int c1) const {
     const EpiDesc& e = prog.ep[s];
-    Foot f{e.acc_col + e.n0, e.acc_col + e.n, 0, 0, 0, 0};
-    if ((e.kind == EPI_RELU_TO_A || e.kind == EPI_LINEAR_TO_A) && e.n0 < e.n) {
-      f.hi0 = e.dst_col + e.n0 / 2; f.hi1 = e.dst_col + e.n / 2;
-      if (passes == 3) { f.lo0 = e.dst_lo_col + e.n0 / 2; f.lo1 = e.dst_lo_col + e.n / 2; }
+    Foot f{e.acc_col + c0, e.acc_col + c1, 0, 0, 0, 0};
+    if (e.kind == EPI_RELU_TO_A && c0 < c1) {
+      f.hi0 = e.dst_col + c0 / 2; f.hi1 = e.dst_col + c1 / 2;
+      if (passes == 3) { f.lo0 = e.dst_lo_col + c0 / 2; f.lo1 = e.dst_lo_col + c1 / 2; }
     }
     return f;
   }
@@ -226,44 +239,52 @@ struct Builder {
     return false;
   }
 
-  // Place F_WAIT_E1 (against the previous step, cyclically: the first step of a tile follows the last
-  // step of the previous tile) and F_COMMIT_WAR (against this step's own E0 destination).
+  // Place the waits on the previous step's E1 parts (cyclically: the first step of a tile follows the last step
+  // of the previous tile), the write-after-read commits for this step's own E0 parts, and the per-stage
+  // hand-off counts of the issue table.
   void finalize() {
     const int S = prog.n_steps;
+    std::vector<int> at_a(S), at_b(S);
     for (int s = 0; s < S; ++s) {
       const StepInfo& in = steps[s];
-      const Foot prev = e1_foot((s + S - 1) % S);
-      int at = -1;
-      for (int i = in.first_stage; i < in.first_stage + in.n_stages && at < 0; ++i)
-        if (stage_touches(prog.st[i], prev)) at = i;
-      const bool split = in.n0_stage < in.first_stage + in.n_stages;
-      if (at < 0) at = split ? in.n0_stage : in.first_stage;
-      else if (split && at > in.n0_stage) at = in.n0_stage;   // never later than the first stage of h1
-      prog.st[at].flags |= F_WAIT_E1;
-      // E0 of this step overwrites dst columns [dst, dst + n0/2) (hi and lo): last stage reading them
+      const int end = in.first_stage + in.n_stages;
+      const EpiDesc& pe = prog.ep[(s + S - 1) % S];
+      const bool split = in.n0_stage < end;
+      auto first_touch = [&](const Foot& f) {
+        int at = -1;
+        for (int i = in.first_stage; i < end && at < 0; ++i)
+          if (stage_touches(prog.st[i], f)) at = i;
+        if (at < 0) at = split ? in.n0_stage : in.first_stage;
+        else if (split && at > in.n0_stage) at = in.n0_stage;   // never later than the first stage of h1
+        return at;
+      };
+      const int prev = (s + S - 1) % S;
+      at_b[s] = first_touch(pe.n1a < pe.n ? epi_foot(prev, pe.n1a, pe.n) : epi_foot(prev, pe.n0, pe.n));
+      at_a[s] = pe.n1a < pe.n ? first_touch(epi_foot(prev, pe.n0, pe.n1a)) : at_b[s];
+      if (at_a[s] > at_b[s]) at_a[s] = at_b[s];                 // "E1 done" implies "E1 part a done"
+      prog.st[at_a[s]].flags |= F_WAIT_E1A;
+      prog.st[at_b[s]].flags |= F_WAIT_E1;
+      // E0 of this step overwrites dst columns [dst, dst + n0/2) (hi and lo) in two blocks: last stage reading each
       const EpiDesc& e = prog.ep[s];
-      int war = in.first_stage;
-      const bool to_a = e.kind == EPI_RELU_TO_A || e.kind == EPI_LINEAR_TO_A;
-      const int g0 = e.n0 / 16;
-      const int n0a = (split_war && g0 / 2 > 0) ? (g0 / 2) * 16 : e.n0;   // columns of E0's first block
-      if (to_a) {
-        Foot f{0, 0, e.dst_col, e.dst_col + n0a / 2, 0, 0};
-        if (passes == 3) { f.lo0 = e.dst_lo_col; f.lo1 = e.dst_lo_col + n0a / 2; }
-        for (int i = in.first_stage; i < in.first_stage + in.n_stages; ++i)
-          if (stage_touches(prog.st[i], f)) war = i;
-      }
+      const bool to_a = e.kind == EPI_RELU_TO_A;
+      auto last_touch = [&](int c0, int c1) {
+        int last = in.first_stage;
+        Foot f = epi_foot(s, c0, c1);
+        f.acc0 = f.acc1 = 0;   // stores only: the loads of E0 are ordered by acc_full
+        for (int i = in.first_stage; i < end; ++i)
+          if (stage_touches(prog.st[i], f)) last = i;
+        return last;
+      };
+      const int war = to_a ? last_touch(0, e.n0a) : in.first_stage;
+      const int war1 = (to_a && e.n0a < e.n0) ? last_touch(e.n0a, e.n0) : war;
       prog.st[war].flags |= F_COMMIT_WAR;
-      if (split_war) {
-        int war1 = war;
-        if (to_a && n0a < e.n0) {
-          Foot f{0, 0, e.dst_col + n0a / 2, e.dst_col + e.n0 / 2, 0, 0};
-          if (passes == 3) { f.lo0 = e.dst_lo_col + n0a / 2; f.lo1 = e.dst_lo_col + e.n0 / 2; }
-          war1 = in.first_stage;
-          for (int i = in.first_stage; i < in.first_stage + in.n_stages; ++i)
-            if (stage_touches(prog.st[i], f)) war1 = i;
-        }
-        prog.st[war1].flags |= F_COMMIT_WAR1;
-      }
+      prog.st[war1].flags |= F_COMMIT_WAR1;
+    }
+    for (int s = 0; s < S; ++s) {
+      const StepInfo& in = steps[s];
+      for (int i = in.first_stage; i < in.first_stage + in.n_stages; ++i)
+        prog.is[i].needs = (uint32_t)(s + 1) | ((uint32_t)(i >= at_a[s] ? s + 1 : s) << 8) |
+                           ((uint32_t)(i >= at_b[s] ? s + 1 : s) << 16);
     }
     for (int i = 0; i < prog.n_stages; ++i) {   // issue table (flags are final now)
       const StageDesc& sd = prog.st[i];
@@ -322,20 +343,43 @@ extern "C" int pnr_create(const pnr_config* cfg, pnr_ctx** out) {
   if (prop.major != 10)
     return set_error(PNR_ERR_UNSUPPORTED, "pnr_create: device %d is sm_%d%d; libpnr is sm_100a only (no fallback path)",
                      cfg->device, prop.major, prop.minor);
-  PNR_CUDA(cudaSetDevice(cfg->device));
+  PNR_CHECK_ARG(cfg->device < kMaxDevices, "pnr_create: device ordinal %d >= %d", cfg->device, kMaxDevices);
+  DeviceGuard guard(cfg->device);   // the caller's current device is restored on return
   pnr_ctx* c = new pnr_ctx();
   c->cfg = *cfg;
   c->passes = precision_passes(cfg->precision);
   c->fmt = precision_fmt(cfg->precision);
+  memset(&c->launch, 0, sizeof(c->launch));
+  cudaError_t e = cudaMalloc(&c->d_status, sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMemset(c->d_status, 0, sizeof(uint32_t));
+  if (e != cudaSuccess) {
+    delete c;
+    return set_error(PNR_ERR_CUDA, "pnr_create: status word: %s", cudaGetErrorString(e));
+  }
   *out = c;
   return PNR_OK;
 }
 
 extern "C" int pnr_destroy(pnr_ctx* ctx) {
   if (!ctx) return PNR_OK;
+  DeviceGuard guard(ctx->cfg.device);
   cudaFree(ctx->d_wpacked);
   cudaFree(ctx->d_consts);
+  cudaFree(ctx->d_status);
   delete ctx;
+  return PNR_OK;
+}
+
+// Sticky status of the fused MLP launches enqueued so far on `stream` (synchronises that stream): bit 0 = an
+// activation left the range of the 16-bit operand format (fp16 modes: |x| > 65504) or was not finite - the
+// results of that launch are not trustworthy; re-run with PNR_PREC_BF16X3.  reset != 0 clears the word.
+extern "C" int pnr_status(pnr_ctx* ctx, uint32_t* status_host, int32_t reset, void* stream) {
+  PNR_CHECK_ARG(ctx && status_host, "pnr_status: null pointer");
+  DeviceGuard guard(ctx->cfg.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  PNR_CUDA(cudaMemcpyAsync(status_host, ctx->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  if (reset) PNR_CUDA(cudaMemsetAsync(ctx->d_status, 0, sizeof(uint32_t), st));
+  PNR_CUDA(cudaStreamSynchronize(st));
   return PNR_OK;
 }
 
@@ -464,6 +508,9 @@ static int build_program(const pnr_config& c, const float* const* t, const int64
   if (!ok) return set_error(PNR_ERR_UNSUPPORTED, "pnr_load_weights: program build failed: %s", bld.err.c_str());
   if ((int)bld.consts.size() > kMaxConsts)
     return set_error(PNR_ERR_UNSUPPORTED, "pnr_load_weights: %d constants > %d", (int)bld.consts.size(), kMaxConsts);
+  if (bld.out_of_fp16_range && bld.fmt == kFmtF16)
+    return set_error(PNR_ERR_UNSUPPORTED, "pnr_load_weights: a weight is outside the fp16 range (|w| > 65504 or not "
+                     "finite): use precision bf16x3");
   bld.prog.n_consts = (int)bld.consts.size();
   bld.finalize();
   return PNR_OK;
@@ -476,15 +523,15 @@ extern "C" int pnr_load_weights(pnr_ctx* ctx, const float* const* t, const int64
   const int rc = build_program(c, t, shapes, n, bld);
   if (rc != PNR_OK) return rc;
 
-  PNR_CUDA(cudaSetDevice(c.device));
+  DeviceGuard guard(c.device);
+  // (plain cudaFree / cudaMemcpy: they synchronise with the device, so no launch still reads the old buffers)
   cudaFree(ctx->d_wpacked); cudaFree(ctx->d_consts);
   ctx->d_wpacked = nullptr; ctx->d_consts = nullptr;
+  ctx->loaded = false;
   ctx->wpacked_bytes = bld.wbuf.size() * 2;
   PNR_CUDA(cudaMalloc(&ctx->d_wpacked, ctx->wpacked_bytes));
   PNR_CUDA(cudaMalloc(&ctx->d_consts, bld.consts.size() * 4));
-  static uint64_t next_id = 0;
-  ctx->h_prog = bld.prog;
-  ctx->prog_id = ++next_id;
+  ctx->launch.prog = bld.prog;
   PNR_CUDA(cudaMemcpy(ctx->d_wpacked, bld.wbuf.data(), ctx->wpacked_bytes, cudaMemcpyHostToDevice));
   PNR_CUDA(cudaMemcpy(ctx->d_consts, bld.consts.data(), bld.consts.size() * 4, cudaMemcpyHostToDevice));
   ctx->loaded = true;
@@ -497,10 +544,12 @@ extern "C" int pnr_program_host(const pnr_config* cfg, const float* const* t, co
                                 size_t* n_consts) {
   PNR_CHECK_ARG(cfg && t && shapes && program_bytes && wpacked_bytes && n_consts, "pnr_program_host: null pointer");
   if (const int rc = check_config(cfg)) return rc;
-  PNR_CHECK_ARG((flags & ~3) == 0, "pnr_program_host: unknown flags 0x%x", flags);
+  PNR_CHECK_ARG((flags & ~15) == 0, "pnr_program_host: unknown flags 0x%x", flags);
   Builder bld(precision_passes(cfg->precision), precision_fmt(cfg->precision));
-  bld.pair = (flags & 1) != 0;
-  if (flags & 2) bld.split_war = true;
+  bld.pair = (flags & PNR_PROGRAM_PAIR) != 0;
+  if (flags & PNR_PROGRAM_NO_SPLIT) bld.split_war = bld.split_e1 = false;
+  if (flags & PNR_PROGRAM_SPLIT_WAR) bld.split_war = true;
+  if (flags & PNR_PROGRAM_SPLIT_E1) bld.split_e1 = true;
   const int rc = build_program(*cfg, t, shapes, n, bld);
   if (rc != PNR_OK) return rc;
   *program_bytes = sizeof(MlpProgram);
@@ -544,22 +593,28 @@ static int mlp_forward_impl(pnr_ctx* ctx, const float* pts, const float* viewdir
   const int64_t S = R * (int64_t)N;
   if (S == 0) return PNR_OK;
   PNR_CHECK_ARG((S + kTileM - 1) / kTileM < (int64_t)1 << 31, "pnr_mlp_forward: too many samples");
-  MlpParams p;
-  p.prog = nullptr; p.wpacked = ctx->d_wpacked; p.consts = ctx->d_consts;
+  MlpParams& p = ctx->launch.p;
+  p.wpacked = ctx->d_wpacked; p.consts = ctx->d_consts;
   p.pts = pts; p.viewdirs = viewdirs; p.rays = rays; p.z = z;
   p.S = S; p.N = N; p.CH = 4 + ctx->cfg.num_classes + ctx->cfg.num_instances; p.raw = raw;
   p.num_tiles = (int32_t)((S + kTileM - 1) / kTileM);
+  p.status = ctx->d_status;
   p.dbg = dbg;
-  return launch_mlp(p, &ctx->h_prog, ctx->prog_id, ctx->passes, ctx->fmt, (cudaStream_t)stream);
+  DeviceGuard guard(ctx->cfg.device);   // launch on the context's device whatever the caller's current one is
+  return launch_mlp(ctx->launch, ctx->passes, ctx->fmt, (cudaStream_t)stream);
 }
 
+namespace pnr {
+size_t workspace_bytes_for(int64_t R, int N, int Ni, int CH);   // render.cu
+int ctx_channels(const pnr_ctx* ctx) { return 4 + ctx->cfg.num_classes + ctx->cfg.num_instances; }
+int ctx_classes(const pnr_ctx* ctx, int* C, int* K) {
+  *C = ctx->cfg.num_classes;
+  *K = ctx->cfg.num_instances;
+  return PNR_OK;
+}
+}  // namespace pnr
+
 extern "C" size_t pnr_workspace_bytes(const pnr_ctx* ctx, int64_t R, int32_t N, int32_t Ni) {
-  if (!ctx || R <= 0) return 0;
-  const size_t CH = 4 + ctx->cfg.num_classes + ctx->cfg.num_instances;
-  const size_t Nt = (size_t)N + (size_t)(Ni > 0 ? Ni : 0);
-  size_t b = 0;
-  b += (size_t)R * Nt * CH * 4;          // raw
-  b += (size_t)R * Nt * (4 + 4 + 4);     // z, weights, sample_box
-  b += (size_t)R * (8 + 1 + 8 * 12);     // near/far, hit mask, hit list (M <= 8)
-  return b;
+  if (!ctx || R <= 0 || N < 1) return 0;
+  return workspace_bytes_for(R, N, Ni > 0 ? Ni : 0, ctx_channels(ctx));
 }

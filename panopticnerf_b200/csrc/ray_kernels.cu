@@ -129,6 +129,57 @@ __global__ void __launch_bounds__(256) stratified_kernel(
   }
 }
 
+// a6, interval mode (ray_math.h: pnr_interval_plan): one warp per ray; every lane builds the ray's (tiny) plan
+// from the same <= 8 intervals, lanes stride the allocation slots, the warp bitonic-sorts the depths in shared
+// memory and tags them.
+constexpr int kIvWarps = 8;
+constexpr int kIvMaxN = 256;
+
+__global__ void __launch_bounds__(kIvWarps * 32) interval_kernel(
+    const float* __restrict__ near, const float* __restrict__ far, const float* __restrict__ t_vals,
+    const float* __restrict__ u, int64_t R, int N, float perturb, const int32_t* __restrict__ box_id,
+    const float* __restrict__ t_in, const float* __restrict__ t_out, int M, float* __restrict__ z,
+    int32_t* __restrict__ sample_box) {
+  __shared__ float s_all[kIvWarps][kIvMaxN];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * kIvWarps + warp;
+  if (r >= R) return;
+  const float nr = near[r], fr = far[r];
+  PnrIntervalPlan P;
+  pnr_interval_plan(nr, fr, box_id + r * M, t_in + r * M, t_out + r * M, M, N, &P);
+  float* all = s_all[warp];
+  if (P.kept == 0) {   // no primitive on this ray: the uniform rule (already ascending)
+    for (int i = lane; i < N; i += 32) {
+      const int64_t idx = r * N + i;
+      z[idx] = (perturb > 0.f) ? pnr_strat_z_jitter(nr, fr, t_vals, i, N, u[idx]) : pnr_strat_z(nr, fr, t_vals[i]);
+      if (sample_box != nullptr) sample_box[idx] = -1;
+    }
+    return;
+  }
+  int Pw = 1;
+  while (Pw < N) Pw <<= 1;
+  for (int k = lane; k < Pw; k += 32)
+    all[k] = k < N ? pnr_interval_z(&P, k, (perturb > 0.f) ? u[r * N + k] : 0.5f) : __int_as_float(0x7f800000);
+  __syncwarp();
+  for (int k = 2; k <= Pw; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < Pw; i += 32) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const bool asc = (i & k) == 0;
+          const float a = all[i], b = all[ixj];
+          if ((a > b) == asc) { all[i] = b; all[ixj] = a; }
+        }
+      }
+      __syncwarp();
+    }
+  for (int i = lane; i < N; i += 32) {
+    const float zi = all[i];
+    z[r * N + i] = zi;
+    if (sample_box != nullptr) sample_box[r * N + i] = pnr_tag(zi, box_id + r * M, t_in + r * M, t_out + r * M, M);
+  }
+}
+
 // Re-tag an existing depth array (used after the fine-sample merge).
 __global__ void __launch_bounds__(256) tag_kernel(const float* __restrict__ z, int64_t R, int N,
                                                   const int32_t* __restrict__ box_id,
@@ -151,7 +202,7 @@ constexpr int kPdfMaxAll = 512;   // coarse + fine, padded to a power of two
 
 __global__ void __launch_bounds__(kPdfWarps * 32) sample_pdf_kernel(
     const float* __restrict__ z, const float* __restrict__ weights, int64_t R, int N, int Ni,
-    const float* __restrict__ u, float* __restrict__ z_fine, int64_t* __restrict__ idx_out,
+    const float* __restrict__ u, int64_t u_stride, float* __restrict__ z_fine, int64_t* __restrict__ idx_out,
     float* __restrict__ z_all) {
   __shared__ float s_w[kPdfWarps][kPdfMaxN];
   __shared__ float s_z[kPdfWarps][kPdfMaxN];
@@ -175,7 +226,7 @@ __global__ void __launch_bounds__(kPdfWarps * 32) sample_pdf_kernel(
   int P = 1;
   while (P < N + Ni) P <<= 1;
   for (int j = lane; j < Ni; j += 32) {
-    const float uj = u[r * Ni + j];
+    const float uj = u[r * u_stride + j];
     int idx;
     const float zf = pnr_pdf_sample(zz, cdf, Nb, uj, &idx);
     if (z_fine != nullptr) z_fine[r * Ni + j] = zf;
@@ -271,6 +322,20 @@ extern "C" int pnr_sample_stratified(const float* near, const float* far, const 
   return PNR_OK;
 }
 
+extern "C" int pnr_sample_intervals(const float* near, const float* far, const float* t_vals, const float* u,
+                                    int64_t R, int32_t N, float perturb, const int32_t* box_id, const float* t_in,
+                                    const float* t_out, int32_t M, float* z, int32_t* sample_box, void* stream) {
+  if (R == 0) return PNR_OK;
+  PNR_CHECK_ARG(near && far && t_vals && z, "pnr_sample_intervals: null pointer");
+  PNR_CHECK_ARG(N >= 1 && N <= kIvMaxN, "pnr_sample_intervals: N=%d outside [1,%d]", N, kIvMaxN);
+  PNR_CHECK_ARG(!(perturb > 0.f) || u, "pnr_sample_intervals: perturb > 0 needs u");
+  PNR_CHECK_ARG(box_id && t_in && t_out && M >= 1 && M <= PNR_MAX_HITS, "pnr_sample_intervals: bad interval table");
+  interval_kernel<<<blocks_for(R, kIvWarps), kIvWarps * 32, 0, (cudaStream_t)stream>>>(
+      near, far, t_vals, u, R, N, perturb, box_id, t_in, t_out, M, z, sample_box);
+  PNR_LAUNCH_CHECK("interval_kernel");
+  return PNR_OK;
+}
+
 extern "C" int pnr_tag_samples(const float* z, int64_t R, int32_t N, const int32_t* box_id,
                                const float* t_in, const float* t_out, int32_t M, int32_t* sample_box,
                                void* stream) {
@@ -286,6 +351,12 @@ extern "C" int pnr_tag_samples(const float* z, int64_t R, int32_t N, const int32
 
 extern "C" int pnr_sample_pdf(const float* z, const float* weights, int64_t R, int32_t N, int32_t Ni,
                               const float* u, float* z_fine, int64_t* idx, float* z_all, void* stream) {
+  return pnr::sample_pdf_strided(z, weights, R, N, Ni, u, Ni, z_fine, idx, z_all, stream);
+}
+
+// u row stride in floats (0: every ray reads the same row - the deterministic sampler without an [R,Ni] tensor)
+int pnr::sample_pdf_strided(const float* z, const float* weights, int64_t R, int32_t N, int32_t Ni, const float* u,
+                            int64_t u_stride, float* z_fine, int64_t* idx, float* z_all, void* stream) {
   if (R == 0) return PNR_OK;
   PNR_CHECK_ARG(z && weights && u, "pnr_sample_pdf: null pointer (u is required; for the deterministic\n"
                 "                 sampler pass torch.linspace(0,1,Ni) broadcast over rays)");
@@ -293,7 +364,7 @@ extern "C" int pnr_sample_pdf(const float* z, const float* weights, int64_t R, i
   PNR_CHECK_ARG(Ni >= 1 && N + Ni <= kPdfMaxAll, "pnr_sample_pdf: N+Ni=%d > %d", N + Ni, kPdfMaxAll);
   if (R == 0) return PNR_OK;
   sample_pdf_kernel<<<blocks_for(R, kPdfWarps), kPdfWarps * 32, 0, (cudaStream_t)stream>>>(
-      z, weights, R, N, Ni, u, z_fine, idx, z_all);
+      z, weights, R, N, Ni, u, u_stride, z_fine, idx, z_all);
   PNR_LAUNCH_CHECK("sample_pdf_kernel");
   return PNR_OK;
 }

@@ -104,6 +104,77 @@ PNR_HD int32_t pnr_tag(float z, const int32_t* box_id, const float* t_in, const 
   return -1;
 }
 
+// a6, interval mode: the N samples of a ray are placed INSIDE its hit intervals (the reference samples inside
+// ray/primitive intersections; how it divides the samples is not in the mount - SURVEY 8(c) question 4 - so the
+// rule below is chosen here and stated in DESIGN.md as "chosen, unverified"):
+//   1. every valid interval m (box_id >= 0) is clipped to [near, far]: a = max(t_in, near), b = min(t_out, far),
+//      len = b - a, kept when len > 0;
+//   2. L = sum of the kept lengths in interval order (nearest first); interval m gets
+//      n_m = min(floor(N * len_m / L), samples still unassigned) samples, in interval order; what is left after
+//      that goes one sample at a time to the kept intervals, nearest first (cyclically);
+//   3. sample j of interval m sits at a + (b - a) * ((j + c) / n_m), c = 0.5 (or the jitter u of that sample slot
+//      when perturb > 0);
+//   4. the N depths are sorted ascending (pnr_tag then names the first interval containing each).
+// A ray with no kept interval falls back to the uniform near..far rule.  All arithmetic is individually rounded fp32.
+struct PnrIntervalPlan {
+  float a[PNR_MAX_HITS], b[PNR_MAX_HITS];
+  int n[PNR_MAX_HITS];      // samples per interval (0 for dropped ones)
+  int first[PNR_MAX_HITS];  // slot of its first sample in allocation order
+  int kept;                 // number of kept intervals (0 -> uniform fallback)
+};
+PNR_HD void pnr_interval_plan(float near, float far, const int32_t* box_id, const float* t_in, const float* t_out,
+                              int M, int N, PnrIntervalPlan* P) {
+  float len[PNR_MAX_HITS];
+  float L = 0.f;
+  P->kept = 0;
+#pragma unroll
+  for (int m = 0; m < PNR_MAX_HITS; ++m) {
+    P->a[m] = 0.f; P->b[m] = 0.f; P->n[m] = 0; P->first[m] = 0; len[m] = 0.f;
+    if (m < M && box_id[m] >= 0) {
+      const float a = pnr_max_nan(t_in[m], near), b = pnr_min_nan(t_out[m], far);
+      const float l = PNR_SUB(b, a);
+      if (l > 0.f) {
+        P->a[m] = a; P->b[m] = b; len[m] = l;
+        L = (P->kept == 0) ? l : PNR_ADD(L, l);
+        P->kept += 1;
+      }
+    }
+  }
+  if (P->kept == 0) return;
+  int left = N;
+#pragma unroll
+  for (int m = 0; m < PNR_MAX_HITS; ++m) {
+    if (len[m] > 0.f) {
+      int q = (int)floorf(PNR_DIV(PNR_MUL((float)N, len[m]), L));
+      if (q > left) q = left;
+      if (q < 0) q = 0;
+      P->n[m] = q;
+      left -= q;
+    }
+  }
+  while (left > 0) {   // at most `kept` passes are ever needed in exact arithmetic; cyclic for safety
+#pragma unroll
+    for (int m = 0; m < PNR_MAX_HITS; ++m)
+      if (len[m] > 0.f && left > 0) { P->n[m] += 1; left -= 1; }
+  }
+  int off = 0;
+#pragma unroll
+  for (int m = 0; m < PNR_MAX_HITS; ++m) { P->first[m] = off; off += P->n[m]; }
+}
+// depth of allocation slot k (before the sort); c = 0.5 or the slot's jitter
+PNR_HD float pnr_interval_z(const PnrIntervalPlan* P, int k, float c) {
+  float z = 0.f;
+#pragma unroll
+  for (int m = 0; m < PNR_MAX_HITS; ++m) {
+    const int j = k - P->first[m];
+    if (j >= 0 && j < P->n[m]) {
+      const float t = PNR_DIV(PNR_ADD((float)j, c), (float)P->n[m]);
+      z = PNR_ADD(P->a[m], PNR_MUL(PNR_SUB(P->b[m], P->a[m]), t));
+    }
+  }
+  return z;
+}
+
 // a10: cdf over the Nb = N-1 bin edges from coarse weights[0..N-1] (uses weights[1..N-2]).
 // Sequential running sums with a double accumulator rounded to fp32 per element (= torch.cumsum CPU).
 PNR_HD void pnr_pdf_cdf(const float* weights, int N, float* cdf /* [N-1] */) {

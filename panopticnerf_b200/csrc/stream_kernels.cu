@@ -5,6 +5,7 @@
 //   composite : one warp per ray; lanes stride the sample axis; transmittance is an exclusive
 //               product scan done with warp shuffles; per-class logits are accumulated with lanes
 //               striding the (contiguous) channel axis so every raw row is read once, coalesced.
+#include <mutex>
 #include "common.cuh"
 
 namespace pnr {
@@ -431,10 +432,17 @@ extern "C" int pnr_encode(const float* x, int64_t n, int32_t L, float* out, void
   PNR_CHECK_ARG(L >= 0 && L <= 16, "pnr_encode: L=%d outside [0,16]", L);
   if (n == 0) return PNR_OK;
   const size_t smem = (size_t)kEncTile * (3 + 6 * L) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    PNR_CUDA(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr_set = true;
+  {   // the > 48 KB dynamic shared-memory opt-in is a per-device function attribute
+    static bool attr_set[kMaxDevices] = {false};
+    static std::mutex mu;
+    int dev = 0;
+    PNR_CUDA(cudaGetDevice(&dev));
+    PNR_CHECK_ARG(dev >= 0 && dev < kMaxDevices, "pnr_encode: device ordinal %d >= %d", dev, kMaxDevices);
+    std::lock_guard<std::mutex> lock(mu);
+    if (!attr_set[dev]) {
+      PNR_CUDA(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      attr_set[dev] = true;
+    }
   }
   encode_kernel<<<(unsigned)((n + kEncTile - 1) / kEncTile), kEncTile, smem, (cudaStream_t)stream>>>(
       x, n, L, out);

@@ -90,6 +90,15 @@ __device__ __forceinline__ uint32_t ld_acquire_smem(uint32_t addr) {
   asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
   return v;
 }
+// Monotonic hand-off counter in shared memory (epilogue warps -> scout): relaxed add, no return value.
+__device__ __forceinline__ void red_add_smem(uint32_t addr, uint32_t v) {
+  asm volatile("red.relaxed.cta.shared::cta.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_volatile_smem(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
 
 // ---------------------------------------------------------------- proxies / bulk copy
 __device__ __forceinline__ void fence_proxy_async_smem() {

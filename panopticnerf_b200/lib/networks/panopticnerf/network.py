@@ -48,6 +48,27 @@ class Network(nn.Module):
         self._ctx: Optional[int] = None
         self._ctx_key = None
 
+    # The libpnr handle is a raw pointer owned by THIS object: copies (copy.deepcopy for EMA weights, pickling /
+    # torch.save of the module, DataParallel replicas) must not share it - the copy would destroy the context the
+    # original still uses.  A copy starts without a context and packs its own on first use.
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_ctx"], state["_ctx_key"] = None, None
+        return state
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = None if k in ("_ctx", "_ctx_key") else copy.deepcopy(v, memo)
+        return new
+
+    def _replicate_for_data_parallel(self):
+        replica = super()._replicate_for_data_parallel()
+        replica._ctx, replica._ctx_key = None, None
+        return replica
+
     # ------------------------------------------------------------------ libpnr context
     @property
     def out_channels(self) -> int:
@@ -118,10 +139,11 @@ class Network(nn.Module):
         v = viewdirs.reshape(-1, 3).to(torch.float32).contiguous()
         ctx = self.pack(p.device if p.is_cuda else None)
         raw = torch.empty(p.shape[0], self.out_channels, device=p.device, dtype=torch.float32)
-        _capi.check(_capi.lib().pnr_mlp_forward(ctx, _capi.ptr(p, torch.float32, "pts"),
-                                                _capi.ptr(v, torch.float32, "viewdirs"), None, None,
-                                                p.shape[0], 1, _capi.ptr(raw), _capi.stream_ptr()),
-                    "pnr_mlp_forward")
+        with torch.cuda.device(p.device):        # the stream handed to libpnr is the tensors' device's current one
+            _capi.check(_capi.lib().pnr_mlp_forward(ctx, _capi.ptr(p, torch.float32, "pts"),
+                                                    _capi.ptr(v, torch.float32, "viewdirs"), None, None,
+                                                    p.shape[0], 1, _capi.ptr(raw), _capi.stream_ptr()),
+                        "pnr_mlp_forward")
         return raw.reshape(*pts.shape[:-1], self.out_channels)
 
     def forward_rays(self, rays: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
@@ -129,7 +151,28 @@ class Network(nn.Module):
         R, N = z.shape
         ctx = self.pack(rays.device if rays.is_cuda else None)
         raw = torch.empty(R, N, self.out_channels, device=rays.device, dtype=torch.float32)
-        _capi.check(_capi.lib().pnr_mlp_forward(ctx, None, None, _capi.ptr(rays, torch.float32, "rays"),
-                                                _capi.ptr(z, torch.float32, "z"), R, N, _capi.ptr(raw),
-                                                _capi.stream_ptr()), "pnr_mlp_forward")
+        with torch.cuda.device(rays.device):
+            _capi.check(_capi.lib().pnr_mlp_forward(ctx, None, None, _capi.ptr(rays, torch.float32, "rays"),
+                                                    _capi.ptr(z, torch.float32, "z"), R, N, _capi.ptr(raw),
+                                                    _capi.stream_ptr()), "pnr_mlp_forward")
         return raw
+
+    def range_status(self, reset: bool = True) -> int:
+        """Sticky range-check word of this network's fused-MLP launches (synchronises the current stream).
+        Bit 0 set: an activation left the range of the 16-bit operand format (fp16 modes: |x| > 65504) or was not
+        finite - those outputs are wrong; use precision='bf16x3' for this network."""
+        if self._ctx is None:
+            return 0
+        dev = torch.device(self._ctx_key[0])
+        out = C.c_uint32(0)
+        with torch.cuda.device(dev):
+            _capi.check(_capi.lib().pnr_status(self._ctx, C.byref(out), int(bool(reset)), _capi.stream_ptr()),
+                        "pnr_status")
+        return int(out.value)
+
+    def check_range(self) -> None:
+        """Raise if a launch since the last check overflowed the operand format (never silent)."""
+        if self.range_status(reset=True) & 1:
+            raise _capi.PnrError(
+                f"Network: an activation left the range of the {self.precision} tensor-core operands (|x| > 65504 "
+                "or non-finite) - the MLP outputs of this call are invalid; use cfg.precision = 'bf16x3'")

@@ -9,6 +9,7 @@ CPU tensors raise: there is no CPU path in the product.
 from __future__ import annotations
 
 import ctypes as C
+import functools
 from typing import Dict, Optional
 
 import torch
@@ -16,6 +17,7 @@ import torch
 from panopticnerf_b200 import _capi
 
 _F32, _I32 = torch.float32, torch.int32
+MAX_SAMPLES_PER_RAY = 256      # pnr_composite: 32 lanes x 8 samples
 
 
 def _f(t: torch.Tensor, name: str) -> torch.Tensor:
@@ -24,9 +26,30 @@ def _f(t: torch.Tensor, name: str) -> torch.Tensor:
     return t.to(_F32).contiguous()
 
 
+def _on_tensor_device(fn):
+    """Run a stage wrapper with the device of its first tensor argument current: the stream handed to libpnr
+    (torch's current stream) and the kernels it launches then belong to the device the buffers live on, whatever
+    the caller's current device is (several GPUs driven from one process)."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kw):
+        t = next((a for a in args if torch.is_tensor(a)), None)
+        if t is None or not t.is_cuda:
+            return fn(*args, **kw)          # the wrapper's own checks raise the "GPU-only" error
+        with torch.cuda.device(t.device):
+            return fn(*args, **kw)
+    return wrapper
+
+
+def _same_device(ref: torch.Tensor, **tensors) -> None:
+    for name, t in tensors.items():
+        if t is not None and t.device != ref.device:
+            raise _capi.PnrError(f"{name} is on {t.device}, expected {ref.device}")
+
+
 # ------------------------------------------------------------------------------------------------
 # stage wrappers (one libpnr call each)
 # ------------------------------------------------------------------------------------------------
+@_on_tensor_device
 def intersect(rays, box_center, box_half, box_rot, max_hits: int):
     """a5 -> hit_mask [R] bool, box_id [R,M] i32, t_in, t_out [R,M]."""
     rays = _f(rays, "rays")
@@ -43,6 +66,7 @@ def intersect(rays, box_center, box_half, box_rot, max_hits: int):
     return hit.bool(), box_id, t_in, t_out
 
 
+@_on_tensor_device
 def scene_near_far(rays, aabb, near_min: float, far_default: float):
     rays = _f(rays, "rays")
     R = rays.shape[0]
@@ -55,6 +79,7 @@ def scene_near_far(rays, aabb, near_min: float, far_default: float):
     return near, far
 
 
+@_on_tensor_device
 def bound_by_primitives(hit, box_id, t_in, t_out, near, far):
     hit8 = hit.to(torch.uint8).contiguous()
     near, far = near.clone(), far.clone()
@@ -65,6 +90,7 @@ def bound_by_primitives(hit, box_id, t_in, t_out, near, far):
     return near, far
 
 
+@_on_tensor_device
 def stratified_z(near, far, t_vals, perturb: float = 0.0, u: Optional[torch.Tensor] = None,
                  box_id=None, t_in=None, t_out=None, want_tags: bool = False):
     """a6 -> z [R,N] (and sample_box [R,N] i32 when want_tags)."""
@@ -83,6 +109,25 @@ def stratified_z(near, far, t_vals, perturb: float = 0.0, u: Optional[torch.Tens
     return (z, sb) if want_tags else z
 
 
+@_on_tensor_device
+def interval_z(near, far, t_vals, box_id, t_in, t_out, perturb: float = 0.0, u: Optional[torch.Tensor] = None):
+    """a6 interval mode -> (z [R,N] ascending, sample_box [R,N] i32): the N samples sit inside the ray's hit
+    intervals (n_m ~ N * len_m / sum len, remainder to the nearest; rays without a hit use the uniform rule)."""
+    near, far, t_vals = _f(near, "near"), _f(far, "far"), _f(t_vals, "t_vals")
+    R, N = near.shape[0], t_vals.shape[0]
+    if perturb > 0.0 and u is None:
+        u = torch.rand(R, N, device=near.device, dtype=_F32)
+    u = _f(u, "u") if (u is not None and perturb > 0.0) else None
+    z = torch.empty(R, N, dtype=_F32, device=near.device)
+    sb = torch.empty(R, N, dtype=_I32, device=near.device)
+    _capi.check(_capi.lib().pnr_sample_intervals(
+        _capi.ptr(near), _capi.ptr(far), _capi.ptr(t_vals), _capi.ptr(u), R, N, float(perturb),
+        _capi.ptr(box_id, _I32), _capi.ptr(t_in), _capi.ptr(t_out), box_id.shape[1], _capi.ptr(z), _capi.ptr(sb),
+        _capi.stream_ptr()), "pnr_sample_intervals")
+    return z, sb
+
+
+@_on_tensor_device
 def tag_samples(z, box_id, t_in, t_out):
     z = _f(z, "z")
     sb = torch.empty(z.shape, dtype=_I32, device=z.device)
@@ -105,6 +150,7 @@ def generate_rays(H: int, W: int, intr, c2w: torch.Tensor, camera: str = "pinhol
     return rays
 
 
+@_on_tensor_device
 def embed(x: torch.Tensor, L: int) -> torch.Tensor:
     """a7 standalone positional encoding (the Renderer uses the copy fused into the MLP kernel)."""
     xf = _f(x.reshape(-1, 3), "x")
@@ -114,6 +160,19 @@ def embed(x: torch.Tensor, L: int) -> torch.Tensor:
     return out.reshape(*x.shape[:-1], 3 + 6 * L)
 
 
+def _box_table_size(raw, sample_box, box_sem, box_inst) -> int:
+    """One B bounds both id tables in the kernel (sample_box indexes them): they must have the same length and
+    live on raw's device."""
+    _same_device(raw, sample_box=sample_box, box_sem=box_sem, box_inst=box_inst)
+    if sample_box is None:
+        return 0
+    sizes = {int(t.shape[0]) for t in (box_sem, box_inst) if t is not None}
+    if len(sizes) > 1:
+        raise ValueError(f"box_sem and box_inst must have one entry per primitive each, got lengths {sorted(sizes)}")
+    return sizes.pop() if sizes else 0
+
+
+@_on_tensor_device
 def raw2outputs(raw, z_vals, rays_d, raw_noise_std: float = 0.0, white_bkgd: bool = False,
                 num_classes: int = 0, num_instances: int = 0, sem_activation: str = "none",
                 sample_box: Optional[torch.Tensor] = None, box_sem: Optional[torch.Tensor] = None,
@@ -142,13 +201,11 @@ def raw2outputs(raw, z_vals, rays_d, raw_noise_std: float = 0.0, white_bkgd: boo
         out["semantic_map"] = torch.empty(R, Cn, dtype=_F32, device=dev)
     if Kn > 0:
         out["instance_map"] = torch.empty(R, Kn, dtype=_F32, device=dev)
-    B = 0
+    B = _box_table_size(raw, sample_box, box_sem, box_inst)
     if sample_box is not None and box_sem is not None and Cn > 0:
         out["fixed_semantic_map"] = torch.empty(R, Cn, dtype=_F32, device=dev)
-        B = box_sem.shape[0]
     if sample_box is not None and box_inst is not None and Kn > 0:
         out["fixed_instance_map"] = torch.empty(R, Kn, dtype=_F32, device=dev)
-        B = box_inst.shape[0]
     co = _capi.PnrCompositeOut(**{k: _capi.ptr(out[k]) if k in out else None
                                   for k, _ in _capi.PnrCompositeOut._fields_})
     sb = sample_box.to(_I32).contiguous() if sample_box is not None else None
@@ -161,6 +218,7 @@ def raw2outputs(raw, z_vals, rays_d, raw_noise_std: float = 0.0, white_bkgd: boo
     return out
 
 
+@_on_tensor_device
 def raw2outputs_backward(raw, z_vals, rays_d, grads: Dict[str, torch.Tensor], white_bkgd: bool = False,
                          num_classes: int = 0, num_instances: int = 0, sem_activation: str = "none",
                          sample_box: Optional[torch.Tensor] = None, box_sem: Optional[torch.Tensor] = None,
@@ -192,11 +250,7 @@ def raw2outputs_backward(raw, z_vals, rays_d, grads: Dict[str, torch.Tensor], wh
         held[k] = g
     cg = _capi.PnrCompositeGrads(**{k: _capi.ptr(held[k]) if k in held else None
                                     for k, _ in _capi.PnrCompositeGrads._fields_})
-    B = 0
-    if sample_box is not None and box_sem is not None:
-        B = box_sem.shape[0]
-    if sample_box is not None and box_inst is not None:
-        B = box_inst.shape[0]
+    B = _box_table_size(raw, sample_box, box_sem, box_inst)
     sb = sample_box.to(_I32).contiguous() if sample_box is not None else None
     bs = box_sem.to(_I32).contiguous() if box_sem is not None else None
     bi = box_inst.to(_I32).contiguous() if box_inst is not None else None
@@ -255,6 +309,7 @@ def raw2outputs_autograd(raw, z_vals, rays_d, white_bkgd: bool = False, num_clas
     return out
 
 
+@_on_tensor_device
 def sample_pdf(z, weights, N_importance: int, det: bool = True, u: Optional[torch.Tensor] = None,
                want_idx: bool = False):
     """a10 on coarse depths z [R,N] and coarse weights [R,N] (bins = mid points, pdf = weights[1:-1]).
@@ -289,6 +344,11 @@ class Renderer:
         self.cfg, self.net = cfg, net
         self.net_fine = net_fine if net_fine is not None else net
         self._t_vals = {}
+        self._ws = {}                 # pnr_render_fused scratch, one buffer per device
+        N, Ni = int(cfg.N_samples), int(getattr(cfg, "N_importance", 0))
+        if N < 1 or N + Ni > MAX_SAMPLES_PER_RAY:
+            raise ValueError(f"Renderer: N_samples + N_importance = {N} + {Ni} exceeds the {MAX_SAMPLES_PER_RAY} samples "
+                             "per ray the compositing kernel handles")
 
     def _tv(self, N: int, device) -> torch.Tensor:
         key = (N, str(device))
@@ -336,9 +396,12 @@ class Renderer:
             if bool(getattr(cfg, "bound_by_primitives", False)):
                 near, far = bound_by_primitives(hit, box_id, t_in, t_out, near, far)
         u = batch["u"][sl] if "u" in batch else None
-        res = stratified_z(near, far, self._tv(N, rays.device), perturb, u, box_id, t_in, t_out,
-                           want_tags=has_boxes)
-        z, sb = res if has_boxes else (res, None)
+        if has_boxes and str(getattr(cfg, "sample_mode", "uniform")) == "intervals":
+            z, sb = interval_z(near, far, self._tv(N, rays.device), box_id, t_in, t_out, perturb, u)
+        else:
+            res = stratified_z(near, far, self._tv(N, rays.device), perturb, u, box_id, t_in, t_out,
+                               want_tags=has_boxes)
+            z, sb = res if has_boxes else (res, None)
         kw = dict(white_bkgd=bool(getattr(cfg, "white_bkgd", False)), num_classes=Cn, num_instances=Kn,
                   sem_activation=str(getattr(cfg, "sem_activation", "none")),
                   mask_outside=bool(getattr(cfg, "mask_outside", False)))
@@ -381,7 +444,122 @@ class Renderer:
         else:
             near = torch.full((rays.shape[0],), float(cfg.near), dtype=_F32, device=rays.device)
             far = torch.full((rays.shape[0],), float(cfg.far), dtype=_F32, device=rays.device)
-        chunk = getattr(cfg, "gpu_chunk", None) or self._auto_chunk(rays)
-        out = self.batchify_rays(rays, near, far, batch, chunk)
-        out["near"], out["far"] = near, far
+        staged = str(getattr(cfg, "render_path", "fused")) == "staged" or bool(getattr(cfg, "return_raw", False))
+        with torch.cuda.device(rays.device):
+            if staged:     # stage by stage from Python (one libpnr call per stage and chunk; keeps `raw`)
+                chunk = getattr(cfg, "gpu_chunk", None) or self._auto_chunk(rays)
+                out = self.batchify_rays(rays, near, far, batch, chunk)
+                out["near"], out["far"] = near, far
+            else:          # the whole frame in ONE libpnr call (pnr_render_fused), chunked inside by the workspace
+                out = self.render_fused(rays, near, far, batch)
+            if bool(getattr(cfg, "check_range", True)):
+                self.net.check_range()
+                if self.net_fine is not self.net:
+                    self.net_fine.check_range()
+        return out
+
+    # -- a3/a4 through the single C-ABI entry point
+    def _workspace(self, ctx, R: int, N: int, Ni: int, device) -> torch.Tensor:
+        want = int(getattr(self.cfg, "workspace_mb", 0)) << 20
+        chunk = int(getattr(self.cfg, "gpu_chunk", 0) or 0)
+        if want <= 0 and chunk > 0:     # rays per chunk given instead of bytes
+            one = int(_capi.lib().pnr_workspace_bytes(ctx, 1, N, Ni))
+            want = int(_capi.lib().pnr_workspace_bytes(ctx, min(chunk, 1 << 16), N, Ni))
+            want += max(0, chunk - (1 << 16)) * one
+        if want <= 0:
+            want = int(_capi.lib().pnr_workspace_bytes(ctx, R, N, Ni))
+        ws = self._ws.get(str(device))
+        if ws is None or ws.numel() < want:
+            ws = torch.empty(want, dtype=torch.uint8, device=device)
+            self._ws[str(device)] = ws
+        return ws
+
+    def render_fused(self, rays, near, far, batch) -> Dict[str, torch.Tensor]:
+        cfg = self.cfg
+        dev = rays.device
+        R = rays.shape[0]
+        N, Ni = int(cfg.N_samples), int(getattr(cfg, "N_importance", 0))
+        Nt = N + Ni
+        Cn, Kn = int(getattr(cfg, "num_classes", 0)), int(getattr(cfg, "num_instances", 0))
+        M = int(getattr(cfg, "max_hits", 4))
+        perturb = float(batch.get("perturb", getattr(cfg, "perturb", 0.0)))
+        has_boxes = "box_center" in batch and batch["box_center"].shape[0] > 0
+        ctx = self.net.pack(dev)
+        ctx_fine = self.net_fine.pack(dev) if self.net_fine is not self.net else None
+        e = lambda *shape, dtype=_F32: torch.empty(*shape, dtype=dtype, device=dev)
+
+        def maps(n_samples):
+            m = {"rgb_map": e(R, 3), "depth_map": e(R), "acc_map": e(R), "disp_map": e(R), "weights": e(R, n_samples)}
+            if Cn > 0:
+                m["semantic_map"] = e(R, Cn)
+            if Kn > 0:
+                m["instance_map"] = e(R, Kn)
+            if has_boxes and batch.get("box_sem") is not None and Cn > 0:
+                m["fixed_semantic_map"] = e(R, Cn)
+            if has_boxes and batch.get("box_inst") is not None and Kn > 0:
+                m["fixed_instance_map"] = e(R, Kn)
+            return m
+
+        def cstruct(m):
+            return _capi.PnrCompositeOut(**{k: _capi.ptr(m[k]) if k in m else None
+                                            for k, _ in _capi.PnrCompositeOut._fields_})
+        final, coarse = maps(Nt), (maps(N) if Ni > 0 else {})
+        keep = [rays, near, far]                      # tensors the call reads: alive until it is enqueued
+        a = _capi.PnrRenderArgs()
+        a.rays, a.R, a.near, a.far = _capi.ptr(rays), R, _capi.ptr(near), _capi.ptr(far)
+        a.near_min, a.far_default = float(cfg.near), float(cfg.far)
+        out: Dict[str, torch.Tensor] = {}
+        if has_boxes:
+            bc, bh, br = _f(batch["box_center"], "box_center"), _f(batch["box_half"], "box_half"), _f(batch["box_rot"], "box_rot")
+            bs = batch["box_sem"].to(dev, _I32).contiguous() if batch.get("box_sem") is not None else None
+            bi = batch["box_inst"].to(dev, _I32).contiguous() if batch.get("box_inst") is not None else None
+            _box_table_size(rays, torch.empty(0, device=dev), bs, bi)
+            keep += [bc, bh, br, bs, bi]
+            a.box_center, a.box_half, a.box_rot = _capi.ptr(bc), _capi.ptr(bh), _capi.ptr(br)
+            a.box_sem, a.box_inst, a.B, a.M = _capi.ptr(bs), _capi.ptr(bi), bc.shape[0], M
+            hit8 = e(R, dtype=torch.uint8)
+            out.update(box_id=e(R, M, dtype=_I32), t_in=e(R, M), t_out=e(R, M), sample_box=e(R, Nt, dtype=_I32))
+            a.hit_mask, a.box_id, a.t_in, a.t_out = _capi.ptr(hit8), _capi.ptr(out["box_id"]), _capi.ptr(out["t_in"]), _capi.ptr(out["t_out"])
+            a.sample_box = _capi.ptr(out["sample_box"])
+        a.N, a.Ni = N, Ni
+        tv = self._tv(N, dev)
+        a.t_vals = _capi.ptr(tv)
+        if perturb > 0.0:
+            u = _f(batch["u"], "u") if "u" in batch else torch.rand(R, N, device=dev, dtype=_F32)
+            keep.append(u)
+            a.u = _capi.ptr(u)
+        a.perturb = perturb
+        if Ni > 0:
+            if "u_fine" in batch:
+                uf = _f(batch["u_fine"], "u_fine")
+                a.u_fine_stride = Ni
+            elif perturb == 0.0:
+                uf = self._tv(Ni, dev)                 # deterministic sampler: one host-linspace row for every ray
+                a.u_fine_stride = 0
+            else:
+                uf = torch.rand(R, Ni, device=dev, dtype=_F32)
+                a.u_fine_stride = Ni
+            keep.append(uf)
+            a.u_fine = _capi.ptr(uf)
+        a.sample_mode = _capi.SAMPLE_MODE[str(getattr(cfg, "sample_mode", "uniform"))] if has_boxes else 0
+        a.white_bkgd = int(bool(getattr(cfg, "white_bkgd", False)))
+        a.sem_softmax = int(str(getattr(cfg, "sem_activation", "none")) == "softmax")
+        a.mask_outside = int(bool(getattr(cfg, "mask_outside", False)))
+        a.bound_by_primitives = int(bool(getattr(cfg, "bound_by_primitives", False)))
+        a.out, a.out0 = cstruct(final), cstruct(coarse)
+        out["z_vals"] = e(R, Nt)
+        a.z_vals = _capi.ptr(out["z_vals"])
+        if Ni > 0:
+            out["z_vals_0"] = e(R, N)
+            a.z_vals0 = _capi.ptr(out["z_vals_0"])
+        out["near"], out["far"] = e(R), e(R)
+        a.near_out, a.far_out = _capi.ptr(out["near"]), _capi.ptr(out["far"])
+        ws = self._workspace(ctx, R, N, Ni, dev)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        _capi.check(_capi.lib().pnr_render_fused(ctx, ctx_fine, C.byref(a), _capi.stream_ptr()), "pnr_render_fused")
+        del keep
+        if has_boxes:
+            out["hit_mask"] = hit8.bool()
+        out.update({k + "_0": v for k, v in coarse.items()})
+        out.update(final)
         return out

@@ -39,6 +39,31 @@ void emu_stratified(const float* near, const float* far, const float* t_vals, co
     }
 }
 
+void emu_intervals(const float* near, const float* far, const float* t_vals, const float* u, int64_t R, int N,
+                   float perturb, const int32_t* box_id, const float* t_in, const float* t_out, int M, float* z,
+                   int32_t* sb) {
+  for (int64_t r = 0; r < R; ++r) {
+    PnrIntervalPlan P;
+    pnr_interval_plan(near[r], far[r], box_id + r * M, t_in + r * M, t_out + r * M, M, N, &P);
+    float* zr = z + r * N;
+    if (P.kept == 0) {
+      for (int i = 0; i < N; ++i)
+        zr[i] = perturb > 0.f ? pnr_strat_z_jitter(near[r], far[r], t_vals, i, N, u[r * N + i])
+                              : pnr_strat_z(near[r], far[r], t_vals[i]);
+    } else {
+      for (int k = 0; k < N; ++k) zr[k] = pnr_interval_z(&P, k, perturb > 0.f ? u[r * N + k] : 0.5f);
+      for (int i = 1; i < N; ++i) {   // insertion sort: the kernel's bitonic network yields the same sorted array
+        const float v = zr[i];
+        int j = i - 1;
+        while (j >= 0 && zr[j] > v) { zr[j + 1] = zr[j]; --j; }
+        zr[j + 1] = v;
+      }
+    }
+    for (int i = 0; i < N; ++i)
+      sb[r * N + i] = P.kept == 0 ? -1 : pnr_tag(zr[i], box_id + r * M, t_in + r * M, t_out + r * M, M);
+  }
+}
+
 void emu_sample_pdf(const float* z, const float* w, int64_t R, int N, int Ni, const float* u, float* z_f,
                     int64_t* idx) {
   float cdf[256];

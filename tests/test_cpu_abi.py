@@ -83,3 +83,35 @@ def test_state_dict_is_drop_in():
                [(k, tuple(v.shape)) for k, v in b.state_dict().items()]
         a.load_state_dict(b.state_dict())
         assert 2 * sum(p.numel() for n, p in a.named_parameters() if n.endswith("weight")) == O.mlp_flops_per_sample(cfg)
+
+
+def test_network_copies_do_not_share_the_native_handle(tmp_path):
+    """The libpnr context is a raw pointer owned by one Network object: deepcopy (EMA weights), pickle / torch.save
+    of the module and DataParallel-style replicas must start WITHOUT it, or the copy's release() / __del__ would
+    destroy the context the original still uses (use-after-free / double free)."""
+    import copy
+    import pickle
+    import panopticnerf_b200 as PN
+    net = PN.make_network(PN.make_cfg("cfg1"))
+    net._ctx, net._ctx_key = 0xDEAD0000, ("cuda:0", "fp16x3")   # pretend a context exists (never dereferenced here)
+    try:
+        dup = copy.deepcopy(net)
+        assert dup._ctx is None and dup._ctx_key is None and net._ctx == 0xDEAD0000
+        assert all(torch.equal(a, b) and a.data_ptr() != b.data_ptr()
+                   for a, b in zip(net.state_dict().values(), dup.state_dict().values()))
+        back = pickle.loads(pickle.dumps(net))
+        assert back._ctx is None and back._ctx_key is None
+        torch.save(net, tmp_path / "net.pt")
+        loaded = torch.load(tmp_path / "net.pt", weights_only=False)
+        assert loaded._ctx is None
+        rep = net._replicate_for_data_parallel()
+        assert rep._ctx is None and net._ctx == 0xDEAD0000
+    finally:
+        net._ctx, net._ctx_key = None, None                      # nothing to destroy
+
+
+def test_renderer_rejects_too_many_samples_up_front():
+    import panopticnerf_b200 as PN
+    cfg = PN.make_cfg("cfg2", N_samples=192, N_importance=128)
+    with pytest.raises(ValueError, match="samples"):
+        PN.make_renderer(cfg, PN.make_network(cfg))

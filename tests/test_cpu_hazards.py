@@ -1,19 +1,21 @@
 """CPU tier: tensor-memory hazard check of the fused MLP program (Builder::finalize in csrc/pnr_api.cu).
 
 The kernel keeps accumulators, activations (16-bit hi / lo parts) and head activations in overlapping tensor-memory
-column ranges and orders the MMA stages against the two half-epilogues of every step with five barriers whose
-placement (F_WAIT_E0 / F_WAIT_E1 / F_COMMIT_ACC0 / F_COMMIT_ACC1 / F_COMMIT_WAR) is computed on the host.
-This test rebuilds the happens-before graph those flags imply, over two consecutive tiles, and requires that every
-pair of events that touch overlapping columns with at least one write is ordered by it."""
+column ranges and orders the MMA stages against the epilogue parts of every step with
+  * tcgen05.commit -> mbarrier:  acc_full[0/1] (F_COMMIT_ACC0/1), war_ok[0/1] (F_COMMIT_WAR / F_COMMIT_WAR1),
+  * three monotonic counters epilogue -> MMA issuer (E0 done, E1 part a done, E1 done): every stage of the issue
+    table carries the counts it needs (IssueDesc.needs).
+Their placement is computed on the host.  This test rebuilds the happens-before graph they imply, over two
+consecutive tiles, and requires that every pair of events that touch overlapping columns with at least one write
+is ordered by it."""
 import itertools
 
 import pytest
 
 from panopticnerf_b200 import make_cfg, make_network, synthetic as S
-from test_cpu_program import (A_TMEM, EPI_LINEAR_TO_A, EPI_RELU_TO_A, F_COMMIT_ACC0, F_COMMIT_ACC1, F_COMMIT_WAR,
-                              F_WAIT_E0, F_WAIT_E1, build)
-
-F_COMMIT_WAR1 = 1024   # split-war programs (PNR_PROGRAM_SPLIT_WAR): second write-after-read barrier of a step
+from test_cpu_program import (A_TMEM, EPI_RELU_TO_A, F_COMMIT_ACC0, F_COMMIT_ACC1, F_COMMIT_WAR,
+                              F_COMMIT_WAR1, F_WAIT_E0, F_WAIT_E1, F_WAIT_E1A, PROGRAM_NO_SPLIT, PROGRAM_SPLIT_E1,
+                              PROGRAM_SPLIT_WAR, build)
 
 
 def overlap(a, b):
@@ -21,25 +23,37 @@ def overlap(a, b):
 
 
 def events_and_edges(prog, tiles=2):
-    """Events: ('S', t, i) MMA stage i of tile t; ('L0', t, s) loads of E0 of step s; ('W0', t, s) / ('W0b', t, s) its
-    stores to the lower / upper half of the columns it overwrites (one barrier each in split-war programs, the same
-    barrier otherwise); ('E1', t, s) loads + stores of E1.  Returns (reads, writes, edges)."""
+    """Events of step s of tile t (aggregated over the epilogue warps):
+      ('S', t, i)    MMA stage i
+      ('L0', t, s)   E0's accumulator loads            (after acc_full[0])
+      ('W0', t, s) / ('W0b', t, s)  E0's stores, part a / part b   (after war_ok[0] / war_ok[1])
+      ('E1a', t, s) / ('E1b', t, s) E1's loads + stores, part a / b (after acc_full[1])
+      ('D0', t, s), ('D1a', t, s), ('D1', t, s)   the three hand-off counters reaching this step's count
+    Returns (reads, writes, edges)."""
     x3 = prog.passes == 3
-    split_war = any(prog.st[i].flags & F_COMMIT_WAR1 for i in range(prog.n_stages))
     steps = []
     for i in range(prog.n_stages):
         if prog.st[i].flags & F_WAIT_E0:
             steps.append([])
         steps[-1].append(i)
+    n_steps = len(steps)
     reads, writes, edges = {}, {}, []
-    order = []            # (tile, step) in execution order
-    for t in range(tiles):
-        for s in range(len(steps)):
-            order.append((t, s))
+    order = [(t, s) for t in range(tiles) for s in range(n_steps)]
+    gidx = {ts: k for k, ts in enumerate(order)}
+
+    def cols(ed, c0, c1, to_a):
+        """(accumulator interval read, activation intervals written) of epilogue columns [c0, c1)."""
+        r = [(ed.acc_col + c0, ed.acc_col + c1)] if c0 < c1 else []
+        w = []
+        if to_a and c0 < c1:
+            w = [(ed.dst_col + c0 // 2, ed.dst_col + c1 // 2)] + (
+                [(ed.dst_lo_col + c0 // 2, ed.dst_lo_col + c1 // 2)] if x3 else [])
+        return r, w
+
     prev_stage = None
     for t, s in order:
         ed = prog.ep[s]
-        to_a = ed.kind in (EPI_RELU_TO_A, EPI_LINEAR_TO_A)
+        to_a = ed.kind == EPI_RELU_TO_A
         for i in steps[s]:
             sd = prog.st[i]
             ev = ("S", t, i)
@@ -52,46 +66,36 @@ def events_and_edges(prog, tiles=2):
             if prev_stage is not None:
                 edges.append((prev_stage, ev))        # the tensor pipe retires MMAs in issue order
             prev_stage = ev
-            if sd.flags & F_COMMIT_ACC0:
-                edges.append((ev, ("L0", t, s)))
+            if sd.flags & F_COMMIT_ACC0:     # a warp stores only after it has passed acc_full[0] itself
+                edges += [(ev, ("L0", t, s)), (ev, ("W0", t, s)), (ev, ("W0b", t, s))]
             if sd.flags & F_COMMIT_ACC1:
-                edges.append((ev, ("E1", t, s)))
+                edges += [(ev, ("E1a", t, s)), (ev, ("E1b", t, s))]
             if sd.flags & F_COMMIT_WAR:
                 edges.append((ev, ("W0", t, s)))
-                if not split_war:
-                    edges.append((ev, ("W0b", t, s)))
             if sd.flags & F_COMMIT_WAR1:
                 edges.append((ev, ("W0b", t, s)))
-        split = ed.n0 < ed.n
-        # a step issued as one half signals only acc_full[1]; its E0 then has all the columns and starts with E1
+            # hand-off counts: v - 1 steps of this tile (and all earlier tiles) have completed that part
+            needs = prog.is_[i].needs
+            for shift, name in ((0, "D0"), (8, "D1a"), (16, "D1")):
+                g = t * n_steps + ((needs >> shift) & 0xFF) - 2       # global index of the last step required
+                if g >= 0:
+                    edges.append(((name,) + order[g], ev))
+        # a step issued as one half signals acc_full[0] and [1] from its last stage
         if not any(prog.st[i].flags & F_COMMIT_ACC0 for i in steps[s]):
-            last = ("S", t, steps[s][-1])
-            edges.append((last, ("L0", t, s)))
-        reads[("L0", t, s)], writes[("L0", t, s)] = [(ed.acc_col, ed.acc_col + ed.n0)], []
-        g0 = ed.n0 // 16
-        n0a = (g0 // 2) * 16 if g0 // 2 > 0 else ed.n0          # the kernel's first E0 block (same formula)
-        w0, w0b = [], []
-        if to_a:
-            w0 = [(ed.dst_col, ed.dst_col + n0a // 2)] + ([(ed.dst_lo_col, ed.dst_lo_col + n0a // 2)] if x3 else [])
-            w0b = [(ed.dst_col + n0a // 2, ed.dst_col + ed.n0 // 2)] + (
-                [(ed.dst_lo_col + n0a // 2, ed.dst_lo_col + ed.n0 // 2)] if x3 else [])
-        reads[("W0", t, s)], writes[("W0", t, s)] = [], w0
-        reads[("W0b", t, s)], writes[("W0b", t, s)] = [], w0b
-        r1 = [(ed.acc_col + ed.n0, ed.acc_col + ed.n)] if split else []
-        w1 = []
-        if to_a and split:
-            w1 = [(ed.dst_col + ed.n0 // 2, ed.dst_col + ed.n // 2)] + (
-                [(ed.dst_lo_col + ed.n0 // 2, ed.dst_lo_col + ed.n // 2)] if x3 else [])
-        reads[("E1", t, s)], writes[("E1", t, s)] = r1, w1
-        edges += [(("L0", t, s), ("W0", t, s)), (("W0", t, s), ("W0b", t, s)), (("W0b", t, s), ("E1", t, s))]  # same warps
-    for (t, s), (t2, s2) in zip(order, order[1:]):
-        edges.append((("E1", t, s), ("L0", t2, s2)))
-        for i in steps[s2]:
-            sd = prog.st[i]
-            if sd.flags & F_WAIT_E0:
-                edges.append((("W0b", t, s), ("S", t2, i)))
-            if sd.flags & F_WAIT_E1:
-                edges.append((("E1", t, s), ("S", t2, i)))
+            edges += [(("S", t, steps[s][-1]), (e, t, s)) for e in ("L0", "W0", "W0b")]
+        reads[("L0", t, s)], writes[("L0", t, s)] = cols(ed, 0, ed.n0, False)[0], []
+        reads[("W0", t, s)], writes[("W0", t, s)] = [], cols(ed, 0, ed.n0a, to_a)[1]
+        reads[("W0b", t, s)], writes[("W0b", t, s)] = [], cols(ed, ed.n0a, ed.n0, to_a)[1]
+        reads[("E1a", t, s)], writes[("E1a", t, s)] = cols(ed, ed.n0, ed.n1a, to_a)
+        reads[("E1b", t, s)], writes[("E1b", t, s)] = cols(ed, ed.n1a, ed.n, to_a)
+        for d in ("D0", "D1a", "D1"):
+            reads[(d, t, s)], writes[(d, t, s)] = [], []
+        edges += [(("L0", t, s), ("D0", t, s)), (("W0", t, s), ("D0", t, s)), (("W0b", t, s), ("D0", t, s)),
+                  (("E1a", t, s), ("D1a", t, s)), (("E1b", t, s), ("D1", t, s)),
+                  # every warp bumps its counters in program order, so a count implies the earlier ones
+                  (("D0", t, s), ("D1a", t, s)), (("D1a", t, s), ("D1", t, s))]
+        if gidx[(t, s)] + 1 < len(order):
+            edges.append((("D1", t, s), ("D0",) + order[gidx[(t, s)] + 1]))
     return reads, writes, edges
 
 
@@ -113,17 +117,11 @@ def reachability(nodes, edges):
     return idx, reach
 
 
-@pytest.mark.parametrize("preset,over", [
-    ("cfg1", {}), ("cfg2", {}), ("cfg3", {}), ("cfg2", dict(precision="fp16")),
-    ("cfg2", dict(D=5, W=128, num_classes=7, num_instances=3)), ("cfg3", dict(precision="bf16x3", W=128)),
-    ("cfg1", dict(D=3, num_classes=45))])
-def test_every_tensor_memory_conflict_is_ordered(preset, over):
-    cfg = make_cfg(preset, **over)
-    prog, _, _ = build(cfg, S.init_network_weights(make_network(cfg), seed=0))
+def unordered_conflicts(prog):
     reads, writes, edges = events_and_edges(prog)
     nodes = list(reads)
     idx, reach = reachability(nodes, edges)
-    checked = 0
+    checked, bad = 0, []
     for a, b in itertools.combinations(nodes, 2):
         if a[0] == "S" and b[0] == "S":
             continue                                    # MMAs are ordered among themselves by construction
@@ -132,55 +130,57 @@ def test_every_tensor_memory_conflict_is_ordered(preset, over):
         if not conflict:
             continue
         checked += 1
-        assert idx[b] in reach[idx[a]] or idx[a] in reach[idx[b]], \
-            f"{preset} {over}: {a} and {b} touch overlapping tensor-memory columns but are not ordered"
+        if not (idx[b] in reach[idx[a]] or idx[a] in reach[idx[b]]):
+            bad.append((a, b))
+    return checked, bad
+
+
+CASES = [("cfg1", {}), ("cfg2", {}), ("cfg3", {}), ("cfg2", dict(precision="fp16")),
+         ("cfg2", dict(D=5, W=128, num_classes=7, num_instances=3)), ("cfg3", dict(precision="bf16x3", W=128)),
+         ("cfg1", dict(D=3, num_classes=45))]
+
+
+@pytest.mark.parametrize("preset,over", CASES)
+@pytest.mark.parametrize("flags", [0, PROGRAM_NO_SPLIT, PROGRAM_NO_SPLIT | PROGRAM_SPLIT_WAR,
+                                   PROGRAM_NO_SPLIT | PROGRAM_SPLIT_E1, PROGRAM_SPLIT_WAR | PROGRAM_SPLIT_E1])
+def test_every_tensor_memory_conflict_is_ordered(preset, over, flags):
+    """Default program of the precision, one-block epilogues, and each split on its own / together."""
+    cfg = make_cfg(preset, **over)
+    prog, _, _ = build(cfg, S.init_network_weights(make_network(cfg), seed=0), flags=flags)
+    checked, bad = unordered_conflicts(prog)
     assert checked > 20
+    assert not bad, f"{preset} {over} flags={flags}: unordered tensor-memory conflicts, e.g. {bad[:3]}"
 
 
-@pytest.mark.parametrize("preset,over", [("cfg1", {}), ("cfg2", {}), ("cfg3", {}), ("cfg2", dict(precision="fp16")),
-                                         ("cfg2", dict(D=5, W=128, num_classes=7, num_instances=3))])
-def test_split_war_programs_are_ordered_too(preset, over):
-    """PNR_PROGRAM_SPLIT_WAR (staged kernel variant): E0's stores are released in two blocks; the lower block's
-    barrier must come no later than the single barrier of the product program."""
+@pytest.mark.parametrize("preset,over", [("cfg2", {}), ("cfg3", {}), ("cfg2", dict(D=5, W=128, num_classes=7, num_instances=3))])
+def test_split_programs_release_earlier(preset, over):
+    """With the splits on, part a of E0 is released no later than the single write-after-read barrier of the
+    one-block program (earlier wherever a half spans several weight stages), part b where that barrier was, and
+    the wait on E1 part a comes no later than the wait on all of E1."""
     cfg = make_cfg(preset, **over)
     net = S.init_network_weights(make_network(cfg), seed=0)
-    prog, _, _ = build(cfg, net, flags=2)
-    base, _, _ = build(cfg, net)
-    reads, writes, edges = events_and_edges(prog)
-    nodes = list(reads)
-    idx, reach = reachability(nodes, edges)
-    for a, b in itertools.combinations(nodes, 2):
-        if a[0] == "S" and b[0] == "S":
-            continue
-        conflict = any(overlap(x, y) for x in writes[a] for y in reads[b] + writes[b]) or \
-                   any(overlap(x, y) for x in writes[b] for y in reads[a])
-        if conflict:
-            assert idx[b] in reach[idx[a]] or idx[a] in reach[idx[b]], f"{preset} {over}: {a} / {b} unordered"
-    war = [i for i in range(prog.n_stages) if prog.st[i].flags & F_COMMIT_WAR]
-    war1 = [i for i in range(prog.n_stages) if prog.st[i].flags & F_COMMIT_WAR1]
-    war_base = [i for i in range(base.n_stages) if base.st[i].flags & F_COMMIT_WAR]
+    prog, _, _ = build(cfg, net, flags=PROGRAM_SPLIT_WAR | PROGRAM_SPLIT_E1)
+    base, _, _ = build(cfg, net, flags=PROGRAM_NO_SPLIT)
+    assert prog.n_stages == base.n_stages
+
+    def where(p, flag):
+        return [i for i in range(p.n_stages) if p.st[i].flags & flag]
+    war, war1, war_base = where(prog, F_COMMIT_WAR), where(prog, F_COMMIT_WAR1), where(base, F_COMMIT_WAR)
     assert len(war) == len(war1) == len(war_base) == prog.n_steps
-    assert all(a <= b for a, b in zip(war, war_base))
-    if cfg.W >= 256 and cfg.precision.endswith("x3"):    # otherwise one weight stage (K = 64 / 128) covers a whole block
-        assert any(a < b for a, b in zip(war, war_base))
-    assert war1 == war_base                              # the upper block is released where the single barrier was
+    assert all(a <= b for a, b in zip(war, war_base)) and war1 == war_base
+    assert where(base, F_COMMIT_WAR1) == war_base and where(base, F_WAIT_E1A) == where(base, F_WAIT_E1)
+    e1a, e1, e1_base = where(prog, F_WAIT_E1A), where(prog, F_WAIT_E1), where(base, F_WAIT_E1)
+    assert all(a <= b for a, b in zip(e1a, e1)) and all(b >= c for b, c in zip(e1, e1_base))
+    if cfg.W >= 256:     # a 256-wide x3 layer has 4 weight stages per half: both splits move something
+        assert any(a < b for a, b in zip(war, war_base)) and any(b > c for b, c in zip(e1, e1_base))
 
 
 def test_the_checker_sees_a_missing_wait():
-    """Remove one F_WAIT_E1 and the same analysis must find an unordered conflict (the check is not vacuous)."""
+    """Drop one stage's wait on E1 and the same analysis must find an unordered conflict (the check is not vacuous)."""
     cfg = make_cfg("cfg2")
     prog, _, _ = build(cfg, S.init_network_weights(make_network(cfg), seed=0))
     victim = next(i for i in range(prog.n_stages) if prog.st[i].flags & F_WAIT_E1 and not prog.st[i].flags & F_WAIT_E0)
-    prog.st[victim].flags &= ~F_WAIT_E1
-    reads, writes, edges = events_and_edges(prog)
-    nodes = list(reads)
-    idx, reach = reachability(nodes, edges)
-    bad = 0
-    for a, b in itertools.combinations(nodes, 2):
-        if a[0] == "S" and b[0] == "S":
-            continue
-        conflict = any(overlap(x, y) for x in writes[a] for y in reads[b] + writes[b]) or \
-                   any(overlap(x, y) for x in writes[b] for y in reads[a])
-        if conflict and not (idx[b] in reach[idx[a]] or idx[a] in reach[idx[b]]):
-            bad += 1
-    assert bad > 0
+    needs = prog.is_[victim].needs
+    prog.is_[victim].needs = (needs & 0xFF00FFFF) | ((((needs >> 16) & 0xFF) - 1) << 16)
+    _, bad = unordered_conflicts(prog)
+    assert bad

@@ -14,10 +14,12 @@ from oracle import reference_renderer as O
 from panopticnerf_b200 import _capi, make_cfg, make_network, synthetic as S
 from util import assert_close, rms
 
-K_MAX_STAGES, K_MAX_STEPS = 384, 24
+K_MAX_STAGES, K_MAX_STEPS = 256, 24
 A_TMEM, A_EMB, A_DIR = 0, 1, 2
 F_FIRST, F_WAIT_E0, F_WAIT_E1, F_COMMIT_ACC0, F_COMMIT_ACC1, F_COMMIT_WAR = 1, 2, 4, 8, 16, 32
-EPI_RELU_TO_A, EPI_LINEAR_TO_A, EPI_VIEW_RGB, EPI_LOGITS = 0, 1, 2, 3
+F_COMMIT_WAR1, F_WAIT_E1A = 1024, 2048
+PROGRAM_PAIR, PROGRAM_SPLIT_WAR, PROGRAM_SPLIT_E1, PROGRAM_NO_SPLIT = 1, 2, 4, 8
+EPI_RELU_TO_A, EPI_VIEW_RGB, EPI_LOGITS = 0, 2, 3
 COL_A_HI, COL_HEAD_HI = 256, 128
 
 
@@ -28,12 +30,13 @@ class StageDesc(C.Structure):
 
 
 class IssueDesc(C.Structure):
-    _fields_ = [(k, C.c_uint32) for k in ("idesc", "b_lo_base", "b_inc", "lo_off16", "acc_col", "a_off", "a_lo_off", "flags_k")]
+    _fields_ = [(k, C.c_uint32) for k in ("idesc", "b_lo_base", "b_inc", "lo_off16", "acc_col", "a_off", "a_lo_off", "flags_k",
+                                          "needs")]
 
 
 class EpiDesc(C.Structure):
     _fields_ = [("kind", C.c_uint8), ("sigma", C.c_uint8)] + [(k, C.c_uint16) for k in
-                ("n", "n0", "n_valid", "acc_col", "dst_col", "dst_lo_col", "bias_off", "aux_off", "out_off")]
+                ("n", "n0", "n_valid", "acc_col", "dst_col", "dst_lo_col", "bias_off", "aux_off", "out_off", "n0a", "n1a")]
 
 
 class MlpProgram(C.Structure):
@@ -155,9 +158,8 @@ def replay(prog, w16, consts, cfg, pts, viewdirs, operand_precision: bool = Fals
             assert (d.idesc >> 7) & 7 == int(bf16)
         n = ed.n
         v = acc[:, ed.acc_col:ed.acc_col + n] + consts[ed.bias_off:ed.bias_off + n][None]
-        if ed.kind in (EPI_RELU_TO_A, EPI_LINEAR_TO_A):
-            if ed.kind == EPI_RELU_TO_A:
-                v = np.maximum(v, 0.0)
+        if ed.kind == EPI_RELU_TO_A:
+            v = np.maximum(v, 0.0)
             if ed.sigma:
                 sig = v @ consts[ed.aux_off:ed.aux_off + n].astype(np.float64)
             act[ed.dst_col][:, :n] = v
@@ -177,13 +179,28 @@ def check_invariants(prog, stages_of):
     for idxs in stages_of:
         fl = [prog.st[i].flags for i in idxs]
         assert sum(bool(f & F_WAIT_E0) for f in fl) == 1 and fl[0] & F_WAIT_E0
-        assert sum(bool(f & F_WAIT_E1) for f in fl) == 1
+        assert sum(bool(f & F_WAIT_E1) for f in fl) == 1 and sum(bool(f & F_WAIT_E1A) for f in fl) == 1
+        assert sum(bool(f & F_COMMIT_WAR1) for f in fl) == 1
         assert sum(bool(f & F_COMMIT_ACC1) for f in fl) == 1 and fl[-1] & F_COMMIT_ACC1
         assert sum(bool(f & F_COMMIT_ACC0) for f in fl) <= 1
         assert sum(bool(f & F_COMMIT_WAR) for f in fl) == 1
         for i in idxs:
             sd = prog.st[i]
             assert sd.bytes <= 32768 and sd.n % 16 == 0 and 16 <= sd.n <= 128 and 1 <= sd.ksteps <= 8
+    # hand-off counts of the issue table: E0 of every earlier step of the tile, E1 parts one step behind until the
+    # stage that carries the matching wait flag
+    for s, idxs in enumerate(stages_of):
+        ed = prog.ep[s]
+        assert 0 < ed.n0a <= ed.n0 <= ed.n1a <= ed.n and ed.n0a % 16 == 0 and ed.n1a % 16 == 0
+        seen_a = seen_b = False
+        for i in idxs:
+            f = prog.st[i].flags
+            seen_a |= bool(f & F_WAIT_E1A)
+            seen_b |= bool(f & F_WAIT_E1)
+            needs = prog.is_[i].needs
+            assert needs & 0xFF == s + 1
+            assert (needs >> 8) & 0xFF == s + int(seen_a) and (needs >> 16) & 0xFF == s + int(seen_b)
+            assert not (seen_b and not seen_a)            # "E1 done" is never required before "E1 part a done"
 
 
 @pytest.mark.parametrize("preset,over", [

@@ -64,6 +64,34 @@ def test_stratified_order(emu, N, perturb):
     assert torch.equal(z, z_ref) and torch.equal(sb, sb_ref)
 
 
+@pytest.mark.parametrize("N,perturb,M", [(64, 0.0, 4), (64, 1.0, 4), (192, 0.0, 8), (7, 1.0, 2), (32, 0.0, 1)])
+def test_interval_sampling_order(emu, N, perturb, M):
+    """a6 interval mode: allocation counts, depths and ids equal the oracle's bit for bit (rays with several
+    overlapping hits, rays with none, intervals cut by near/far)."""
+    cfg = make_cfg("cfg2")
+    rays = S.make_rays(cfg, rows=3, row0=150)
+    near, far = O.scene_near_far(rays[:, :3], rays[:, 3:], torch.tensor(S.SCENE_AABB), cfg.near, cfg.far)
+    far = torch.minimum(far, torch.full_like(far, 40.0))        # cut some intervals short
+    bx = S.make_boxes(12, 45, 64, seed=2)                       # few boxes: some rays hit none
+    _, bid, tin, tout = O.intersect(rays[:, :3], rays[:, 3:], bx["box_center"], bx["box_half"], bx["box_rot"], M)
+    t = torch.linspace(0, 1, N)
+    u = torch.rand(rays.shape[0], N, generator=torch.Generator().manual_seed(0))
+    z_ref = O.interval_z(near, far, t, bid, tin, tout, perturb, u)
+    sb_ref = O.tag_samples(z_ref, bid, tin, tout)
+    z = torch.zeros_like(z_ref)
+    sb = torch.zeros_like(sb_ref)
+    emu.emu_intervals(_p(near), _p(far), _p(t), _p(u), C.c_int64(rays.shape[0]), N, C.c_float(perturb),
+                      _p(bid), _p(tin), _p(tout), M, _p(z), _p(sb))
+    assert torch.equal(z, z_ref)
+    # rays without a kept interval carry -1 everywhere in both (their samples lie in no interval by construction)
+    assert torch.equal(sb, sb_ref)
+    hit_rays = (bid >= 0).any(1)
+    assert hit_rays.any() and (~hit_rays).any()
+    inside = (sb_ref[hit_rays] >= 0).float().mean()
+    assert inside > 0.95            # the point of the mode: (almost) every sample of a hit ray lies in a primitive
+    assert (z_ref[:, 1:] >= z_ref[:, :-1]).all()
+
+
 @pytest.mark.parametrize("N,Ni,det", [(64, 128, True), (64, 128, False), (3, 4, True), (192, 64, False)])
 def test_sample_pdf_order(emu, N, Ni, det):
     g = torch.Generator().manual_seed(1)

@@ -1,0 +1,194 @@
+"""GPU: the single-call frame renderer (pnr_render_fused), the interval sampler (8(a) a6), the range
+check of the fp16 operands, several devices driven from one process and the NCCL entry points of the C ABI."""
+import ctypes as C
+
+import pytest
+import torch
+
+import panopticnerf_b200 as PN
+from oracle import reference_renderer as O
+from panopticnerf_b200 import _capi, parallel, synthetic as S
+from panopticnerf_b200.lib.networks.renderer import panopticnerf_renderer as P
+from util import check_render_outputs
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _same(a, b, what=""):
+    assert a.keys() == b.keys(), (sorted(a), sorted(b))
+    for k in a:
+        x, y = a[k], b[k]
+        assert x.shape == y.shape and x.dtype == y.dtype, f"{what}{k}: {x.shape} {x.dtype} vs {y.shape} {y.dtype}"
+        assert torch.equal(torch.nan_to_num(x.float()), torch.nan_to_num(y.float())), f"{what}{k} differs"
+
+
+@pytest.mark.parametrize("preset,over,rows", [
+    ("cfg1", {}, None), ("cfg1", dict(num_classes=5, num_instances=6, N_importance=16), None),
+    ("cfg3", {}, 3), ("cfg3", dict(sample_mode="intervals", bound_by_primitives=True, mask_outside=True), 2),
+    ("cfg2", dict(white_bkgd=True), 5)])
+def test_fused_render_equals_staged_bit_for_bit(preset, over, rows):
+    """One pnr_render_fused call == the stage-by-stage path from Python, for every returned key, whatever the
+    workspace (one chunk, the default, a workspace that forces ~20 ragged chunks) - and with jitter."""
+    cfg = PN.make_cfg(preset, **over)
+    net = S.init_network_weights(PN.make_network(cfg), seed=2).to(DEV)
+    batch = {k: v.to(DEV) for k, v in S.make_batch(cfg, rows=rows).items()}
+    R = batch["rays"].shape[0]
+    staged = PN.make_renderer(PN.make_cfg(preset, render_path="staged", **over), net).render(batch)
+    _same(PN.make_renderer(cfg, net).render(batch), staged)
+    _same(PN.make_renderer(PN.make_cfg(preset, gpu_chunk=R // 20 + 3, **over), net).render(batch), staged, "chunked: ")
+    g = torch.Generator().manual_seed(1)
+    jit = dict(batch, perturb=1.0, u=torch.rand(R, cfg.N_samples, generator=g).to(DEV))
+    if cfg.N_importance:
+        jit["u_fine"] = torch.rand(R, cfg.N_importance, generator=g).to(DEV)
+    _same(PN.make_renderer(PN.make_cfg(preset, gpu_chunk=R // 3 + 1, **over), net).render(jit),
+          PN.make_renderer(PN.make_cfg(preset, render_path="staged", **over), net).render(jit), "jitter: ")
+
+
+@pytest.mark.parametrize("N,perturb,M,B", [(64, 0.0, 4, 64), (64, 1.0, 4, 12), (192, 0.0, 8, 64), (7, 1.0, 2, 12),
+                                           (256, 0.0, 1, 5)])
+def test_interval_sampler_bit_exact(N, perturb, M, B):
+    cfg = PN.make_cfg("cfg2")
+    rays = S.make_rays(cfg, rows=3, row0=150)
+    near, far = O.scene_near_far(rays[:, :3], rays[:, 3:], torch.tensor(S.SCENE_AABB), cfg.near, cfg.far)
+    far = torch.minimum(far, torch.full_like(far, 40.0))
+    bx = S.make_boxes(B, 45, 64, seed=2)
+    _, bid, tin, tout = O.intersect(rays[:, :3], rays[:, 3:], bx["box_center"], bx["box_half"], bx["box_rot"], M)
+    t = torch.linspace(0, 1, N)
+    u = torch.rand(rays.shape[0], N, generator=torch.Generator().manual_seed(0))
+    z_ref = O.interval_z(near, far, t, bid, tin, tout, perturb, u)
+    d = lambda x: x.to(DEV)
+    z, sb = P.interval_z(d(near), d(far), d(t), d(bid), d(tin), d(tout), perturb, d(u))
+    assert torch.equal(z.cpu(), z_ref) and torch.equal(sb.cpu(), O.tag_samples(z_ref, bid, tin, tout))
+
+
+def test_interval_mode_render_end_to_end():
+    """cfg3 (heads, coarse + fine) with the samples placed inside the primitives, against the oracle."""
+    cfg = PN.make_cfg("cfg3", sample_mode="intervals", W=64, D=4)
+    net = S.init_network_weights(PN.make_network(cfg), seed=3)
+    batch = S.make_batch(cfg, row0=200, rows=1)
+    batch["rays"] = batch["rays"][::7].contiguous()
+    onet = O.Network(cfg)
+    onet.load_state_dict(net.state_dict())
+    ref = O.make_renderer(cfg, onet).render(batch)
+    out = PN.make_renderer(cfg, net.to(DEV)).render({k: v.to(DEV) for k, v in batch.items()})
+    for k in ("hit_mask", "box_id", "z_vals_0"):
+        assert torch.equal(out[k].cpu().to(ref[k].dtype), ref[k]), k
+    assert float((ref["sample_box"][ref["hit_mask"]] >= 0).float().mean()) > 0.9
+    # the fine depths are discontinuous in the coarse weights: compare what does not depend on them
+    check_render_outputs(out, {k: v for k, v in ref.items() if k.endswith("_0") or k in ("near", "far", "t_in", "t_out")},
+                         float(ref["far"].max()))
+
+
+def _scaled(net, s):
+    with torch.no_grad():
+        for lin in net.pts_linears:
+            lin.weight.mul_(s)
+    return net
+
+
+def test_fp16_overflow_is_reported_and_bf16x3_handles_it():
+    """Trunk weights x8 per layer: activations pass 65504 after a few layers.  fp16x3 must flag it (status bit,
+    Renderer.render raises), bf16x3 must run the same network within tolerance (per-tensor RMS floor)."""
+    cfg = PN.make_cfg("cfg2")
+    g = torch.Generator().manual_seed(4)
+    pts = (torch.rand(3000, 3, generator=g) * 2 - 1) * 4
+    vd = torch.nn.functional.normalize(torch.randn(3000, 3, generator=g), dim=-1)
+    base = _scaled(S.init_network_weights(PN.make_network(cfg), seed=5), 8.0)
+    onet = O.Network(cfg)
+    onet.load_state_dict(base.state_dict())
+    with torch.no_grad():
+        ref = onet(pts, vd)
+    assert float(ref[:, 3].abs().max()) > 1e5                 # the scale really is out of fp16's range
+    net16 = PN.make_network(cfg)
+    net16.load_state_dict(base.state_dict())
+    net16 = net16.to(DEV)
+    assert net16.range_status() == 0
+    with torch.no_grad():
+        net16(pts.to(DEV), vd.to(DEV))
+    assert net16.range_status(reset=False) & 1 and net16.range_status() & 1 and net16.range_status() == 0
+    with pytest.raises(_capi.PnrError, match="range"):
+        batch = {k: v.to(DEV) for k, v in S.make_batch(cfg, rows=1).items()}
+        PN.make_renderer(cfg, net16).render(batch)
+    cfgb = PN.make_cfg("cfg2", precision="bf16x3")
+    netb = PN.make_network(cfgb)
+    netb.load_state_dict(base.state_dict())
+    netb = netb.to(DEV)
+    with torch.no_grad():
+        got = netb(pts.to(DEV), vd.to(DEV)).cpu()
+    assert netb.range_status() == 0
+    from util import assert_close, rms
+    assert_close(got[:, :3], ref[:, :3], rms(ref[:, :3]), "rgb (bf16x3, x8 weights)", rel=2e-4)
+    assert_close(got[:, 3:4], ref[:, 3:4], rms(ref[:, 3:4]), "sigma (bf16x3, x8 weights)", rel=2e-4)
+
+
+@pytest.mark.parametrize("scale,shift", [(2.0, -3.0), (1.5, 0.5)])
+def test_trained_like_statistics_within_tolerance(scale, shift):
+    """Larger-than-init weights (x1.5 / x2 per trunk layer: activations up to ~1e3) and a shifted sigma bias, the
+    statistics a trained scene network has: fp16x3 stays inside 1e-4 of the per-tensor RMS and reports no overflow."""
+    from util import assert_close, rms
+    cfg = PN.make_cfg("cfg3")
+    base = _scaled(S.init_network_weights(PN.make_network(cfg), seed=6), scale)
+    with torch.no_grad():
+        base.alpha_linear.bias.add_(shift)
+    g = torch.Generator().manual_seed(7)
+    pts = (torch.rand(2000, 3, generator=g) * 2 - 1) * 8
+    vd = torch.nn.functional.normalize(torch.randn(2000, 3, generator=g), dim=-1)
+    onet = O.Network(cfg)
+    onet.load_state_dict(base.state_dict())
+    with torch.no_grad():
+        ref = onet(pts, vd)
+    net = base.to(DEV)
+    with torch.no_grad():
+        got = net(pts.to(DEV), vd.to(DEV)).cpu()
+    assert net.range_status() == 0
+    for name, sl in (("rgb", slice(0, 3)), ("sigma", slice(3, 4)), ("sem", slice(4, 49)), ("inst", slice(49, 113))):
+        assert_close(got[:, sl], ref[:, sl], rms(ref[:, sl]), f"{name} (x{scale} weights)")
+
+
+def test_bf16x3_render_end_to_end():
+    cfg = PN.make_cfg("cfg1", precision="bf16x3", num_classes=5, num_instances=6)
+    net = S.init_network_weights(PN.make_network(cfg), seed=8)
+    batch = S.make_batch(cfg, rows=16)
+    onet = O.Network(cfg)
+    onet.load_state_dict(net.state_dict())
+    ref = O.make_renderer(cfg, onet).render(batch)
+    out = PN.make_renderer(cfg, net.to(DEV)).render({k: v.to(DEV) for k, v in batch.items()})
+    check_render_outputs(out, ref, float(ref["far"].max()), rel=2e-4)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_second_device_from_one_process():
+    """Contexts on two devices driven from one process and one thread: per-device kernel attributes,
+    launches on the context's device whatever the current device is, and the caller's device left untouched."""
+    cfg = PN.make_cfg("cfg1", num_classes=5, num_instances=6, N_importance=16)
+    net = S.init_network_weights(PN.make_network(cfg), seed=2)
+    batch = S.make_batch(cfg)
+    import copy
+    n0, n1 = copy.deepcopy(net).to("cuda:0"), copy.deepcopy(net).to("cuda:1")
+    torch.cuda.set_device(0)
+    a = PN.make_renderer(cfg, n0).render({k: v.to("cuda:0") for k, v in batch.items()})
+    b = PN.make_renderer(cfg, n1).render({k: v.to("cuda:1") for k, v in batch.items()})
+    assert torch.cuda.current_device() == 0 and b["rgb_map"].device.index == 1
+    _same(a, {k: v.to("cuda:0") for k, v in b.items()})
+    e = P.embed(torch.rand(1000, 3, device="cuda:1"), 10)       # > 48 KB shared-memory opt-in on the second device
+    assert e.device.index == 1 and torch.isfinite(e).all()
+
+
+def test_comm_single_rank_allgather():
+    """pnr_comm_* through ctypes with world = 1 (the 2-rank case: tests/test_gpu_comm2.py under torchrun)."""
+    L = _capi.lib()
+    if not L.pnr_comm_available():
+        pytest.skip("libnccl.so.2 not loadable")
+    uid = (C.c_uint8 * _capi.COMM_ID_BYTES)()
+    _capi.check(L.pnr_comm_unique_id(uid), "pnr_comm_unique_id")
+    comm = C.c_void_p()
+    _capi.check(L.pnr_comm_init(C.byref(comm), uid, 0, 1, 0), "pnr_comm_init")
+    src = torch.arange(1000, dtype=torch.float32, device=DEV)
+    dst = torch.zeros_like(src)
+    _capi.check(L.pnr_allgather_outputs(comm, src.data_ptr(), dst.data_ptr(), src.numel() * 4, _capi.stream_ptr()),
+                "pnr_allgather_outputs")
+    torch.cuda.synchronize()
+    assert torch.equal(src, dst)
+    _capi.check(L.pnr_comm_destroy(comm), "pnr_comm_destroy")
+    assert L.pnr_comm_init(C.byref(comm), uid, 3, 2, 0) != 0 and b"rank" in L.pnr_last_error()

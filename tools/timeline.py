@@ -1,4 +1,5 @@
-"""Dump the clock64 timeline of one tile of the fused MLP kernel (block 0, third tile)."""
+"""Dump the clock64 timeline of one tile of the fused MLP kernel (block 0, third tile).
+Needs the -DPNR_TIMELINE build: python -m panopticnerf_b200._build --timeline ; PNR_LIB=panopticnerf_b200/libpnr_timeline.so python tools/timeline.py"""
 import sys
 from pathlib import Path
 import torch
@@ -36,9 +37,3 @@ for k in range(48):
     if w > 0:
         print(f"{k // 2:3d} h{k % 2} {w - t0:8d} {a - t0:8d} {d - t0:8d}   wait {a - w:6d} work {d - a:6d}")
 
-print("E1 fine: acc_ready -> first ld done -> group0 processed -> second ld done")
-for st in range(12):
-    q = t[7168 + st * 4:7168 + st * 4 + 3]
-    a = t[4096 + (st * 2 + 1) * 3 + 1]
-    if q[0] > 0:
-        print(f"{st:3d}  ld0 {q[0] - a:5d}  proc0 {q[1] - q[0]:5d}  ld1-wait {q[2] - q[1]:5d}")
