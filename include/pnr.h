@@ -155,6 +155,14 @@ int pnr_composite(const float* raw, const float* z, const float* rays, int64_t R
                   const int32_t* sample_box, const int32_t* box_sem, const int32_t* box_inst,
                   int32_t B, const pnr_composite_out* out, void* stream);
 
+/* 8(e) label tiles / 8(f) rank 4 (panoptic label fusion): what a rank contributes to the all-gather when labels,
+ * not logits, are wanted - rgb8 [R,3] u8 = round(255*clamp(rgb)), depth_out [R] f32, sem_label / inst_label [R] i16 =
+ * argmax of the composited semantic / instance maps (ties -> lowest index, NaN counts as -inf).
+ * 13 bytes per ray instead of 4*(5+C+K).  Any output pointer may be NULL. */
+int pnr_label_tiles(const float* rgb_map, const float* depth_map, const float* semantic_map,
+                    const float* instance_map, int64_t R, int32_t C, int32_t K, uint8_t* rgb8,
+                    float* depth_out, int16_t* sem_label, int16_t* inst_label, void* stream);
+
 /* a9 backward (first stage of the backward chain): d(loss)/d(raw) [R,N,4+C+K] from the
  * gradients of the composited maps (any pointer may be NULL = zero gradient; disp_map is not differentiated).
  * Same arguments as pnr_composite.  sem_softmax != 0 returns PNR_ERR_UNSUPPORTED. */

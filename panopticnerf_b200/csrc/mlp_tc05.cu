@@ -112,8 +112,10 @@ __device__ __forceinline__ void epi_group_act(const uint32_t (&r)[16], int g, co
     }
     // v >= 0 after the ReLU, so the fp32 bit patterns order like the values (+inf on top; fmaxf turns a NaN
     // accumulator into 0, but a NaN can only follow an overflow that was flagged where it happened)
+#ifndef PNR_ABL_NOVMAX
     vmax = __vimax3_u32(vmax, __float_as_uint(v0), __float_as_uint(v1));
     vmax = __vimax3_u32(vmax, __float_as_uint(v2), __float_as_uint(v3));
+#endif
     split_x2<FMT>(v0, v1, hi[2 * q], lo[2 * q]);
     split_x2<FMT>(v2, v3, hi[2 * q + 1], lo[2 * q + 1]);
   }
@@ -248,10 +250,7 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
           // this warp's near-equal contiguous share of each part
           const int a_lo = pa0 + (ch * (pa1 - pa0) + kCh - 1) / kCh, a_hi = pa0 + ((ch + 1) * (pa1 - pa0) + kCh - 1) / kCh;
           const int b_lo = pa1 + (ch * (pb1 - pa1) + kCh - 1) / kCh, b_hi = pa1 + ((ch + 1) * (pb1 - pa1) + kCh - 1) / kCh;
-          const int na = a_hi - a_lo, cnt = na + (b_hi - b_lo);
-          auto group_of = [&](int i) { return i < na ? a_lo + i : b_lo + (i - na); };
-          // hand-off after part a of E1 (part a of E0 is not signalled: the next step's first MMA overwrites
-          // accumulator columns that part b still reads)
+          const int na = a_hi - a_lo, nb = b_hi - b_lo;
           // (relaxed add: what is handed over lives in tensor memory - complete after tcgen05.wait::st and ordered
           //  by the tcgen05 fences on both sides; a release here is a MEMBAR.ALL.CTA per hand-off for nothing)
           auto signal = [&](uint32_t counter) {
@@ -265,66 +264,72 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
 #ifdef PNR_TIMELINE
           if (rec) p.dbg[4096 + (st * 2 + h) * 3 + 1] = clock64();
 #endif
-          if (h == 1 && na == 0) signal(cnt_e1a);
           const uint32_t acc = tmem_lane + ed.acc_col;
-          // software pipeline: the load of group i+1 is in flight while group i is processed
+          // software pipeline: the load of the next group is in flight while a group is processed - also across
+          // the part boundary, so signalling part a does not restart the load pipeline
           uint32_t ra[16], rb[16];
-          if (cnt > 0) tmem_ld16(acc + group_of(0) * 16, ra);
-          bool war_a = !(to_a && h == 0), war_b = war_a;   // "may store" state of part a / part b
-          if (to_a) {
-            // Two groups are converted before anything is stored: E0 reaches its write-after-read barrier
-            // (this step's MMAs still read the columns it overwrites) with two groups of work already done.
-#pragma unroll 1
-            for (int i = 0; i < cnt; i += 2) {
-              uint32_t ha[8], la[8], hb[8], lb[8];
-              const bool two = i + 1 < cnt;
-              const int g0 = group_of(i), g1 = group_of(i + 1);
-              tc_wait_ld();
-              if (two) tmem_ld16(acc + g1 * 16, rb);
-              epi_group_act<PASSES, FMT>(ra, g0, ed, bias, aux, sig, vmax, ha, la);
-              if (two) {
-                tc_wait_ld();
-                if (i + 2 < cnt) tmem_ld16(acc + group_of(i + 2) * 16, ra);
-                epi_group_act<PASSES, FMT>(rb, g1, ed, bias, aux, sig, vmax, hb, lb);
-              }
+          if (na > 0) tmem_ld16(acc + a_lo * 16, ra);
+          else if (nb > 0) tmem_ld16(acc + b_lo * 16, ra);
 #pragma unroll
-              for (int k = 0; k < 2; ++k) {
-                if (k == 1 && !two) break;
-                const int idx = i + k;
-                const bool in_a = idx < na;
-                if (!(in_a ? war_a : war_b)) {  // the columns we are about to overwrite must have been consumed by the MMAs
-                  mbar_wait_backoff(bar_war + (in_a ? 0 : 8), parity);
-                  tc_fence_after();
-                  if (in_a) war_a = true; else war_b = true;
-                }
-                if (k == 0) epi_group_store<PASSES>(g0, ed, tmem_lane, ha, la);
-                else epi_group_store<PASSES>(g1, ed, tmem_lane, hb, lb);
-                if (h == 1 && idx + 1 == na) signal(cnt_e1a);
-              }
-            }
-          } else {
+          for (int pi = 0; pi < 2; ++pi) {
+            const int lo = pi == 0 ? a_lo : b_lo, hi = pi == 0 ? a_hi : b_hi;
+            const int nxt = (pi == 0 && nb > 0) ? b_lo : -1;   // first group of the part that follows
+            // E0 only: this part's stores wait for its write-after-read barrier (once)
+            bool war_pending = to_a && h == 0 && lo < hi;
+            if (to_a) {
+              // Two groups are converted before anything is stored: E0 reaches its write-after-read barrier
+              // (this step's MMAs still read the columns it overwrites) with two groups of work already done.
 #pragma unroll 1
-            for (int i = 0; i < cnt; i += 2) {
-              const int g0 = group_of(i), g1 = group_of(i + 1);
-              tc_wait_ld();
-              if (i + 1 < cnt) tmem_ld16(acc + g1 * 16, rb);
-              if (ed.kind == EPI_VIEW_RGB) {
-                epi_group_rgb(ra, g0, ed, bias, aux, c0, c1, c2);
-              } else if (valid) {
-                epi_group_logits(ra, g0, ed, bias, out_row);
-              }
-              if (h == 1 && i + 1 == na) signal(cnt_e1a);
-              if (i + 1 < cnt) {
+              for (int g = lo; g < hi; g += 2) {
+                uint32_t ha[8], la[8], hb[8], lb[8];
+                const bool two = g + 1 < hi;
+                const int after = (g + 2 < hi) ? g + 2 : nxt;
                 tc_wait_ld();
-                if (i + 2 < cnt) tmem_ld16(acc + group_of(i + 2) * 16, ra);
-                if (ed.kind == EPI_VIEW_RGB) {
-                  epi_group_rgb(rb, g1, ed, bias, aux, c0, c1, c2);
-                } else if (valid) {
-                  epi_group_logits(rb, g1, ed, bias, out_row);
+                if (two) tmem_ld16(acc + (g + 1) * 16, rb);
+                epi_group_act<PASSES, FMT>(ra, g, ed, bias, aux, sig, vmax, ha, la);
+                if (two) {
+                  tc_wait_ld();
+                  if (after >= 0) tmem_ld16(acc + after * 16, ra);
+                  epi_group_act<PASSES, FMT>(rb, g + 1, ed, bias, aux, sig, vmax, hb, lb);
+                } else if (after >= 0) {
+                  tmem_ld16(acc + after * 16, ra);
                 }
-                if (h == 1 && i + 2 == na) signal(cnt_e1a);
+                if (war_pending) {  // the columns we are about to overwrite must have been consumed by the MMAs
+                  mbar_wait_backoff(bar_war + 8 * pi, parity);
+                  tc_fence_after();
+                  war_pending = false;
+                }
+                epi_group_store<PASSES>(g, ed, tmem_lane, ha, la);
+                if (two) epi_group_store<PASSES>(g + 1, ed, tmem_lane, hb, lb);
+              }
+            } else {
+#pragma unroll 1
+              for (int g = lo; g < hi; g += 2) {
+                const bool two = g + 1 < hi;
+                const int after = (g + 2 < hi) ? g + 2 : nxt;
+                tc_wait_ld();
+                if (two) tmem_ld16(acc + (g + 1) * 16, rb);
+                if (ed.kind == EPI_VIEW_RGB) {
+                  epi_group_rgb(ra, g, ed, bias, aux, c0, c1, c2);
+                } else if (valid) {
+                  epi_group_logits(ra, g, ed, bias, out_row);
+                }
+                if (two) {
+                  tc_wait_ld();
+                  if (after >= 0) tmem_ld16(acc + after * 16, ra);
+                  if (ed.kind == EPI_VIEW_RGB) {
+                    epi_group_rgb(rb, g + 1, ed, bias, aux, c0, c1, c2);
+                  } else if (valid) {
+                    epi_group_logits(rb, g + 1, ed, bias, out_row);
+                  }
+                } else if (after >= 0) {
+                  tmem_ld16(acc + after * 16, ra);
+                }
               }
             }
+            // hand-off after part a of E1 (part a of E0 is not signalled: the next step's first MMA overwrites
+            // accumulator columns that part b still reads)
+            if (pi == 0 && h == 1) signal(cnt_e1a);
           }
           if (h == 1) {
             if (ed.sigma) {

@@ -303,6 +303,10 @@ struct Builder {
 };
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+inline int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
 
 }  // namespace
 
@@ -503,7 +507,12 @@ static int build_program(const pnr_config& c, const float* const* t, const int64
     std::vector<Seg> segs;
     segs.push_back(seg_tmem(m_fold, 0, W, kColAHi, kColALo));
     segs.push_back(Seg{A_DIR, m_fold, W, Ed, 32, 0, 0, true});
-    ok = bld.add_step(segs, W2, kColAcc, ed, false);
+    // The view step accumulates in the UPPER half of the accumulator region when it fits: the next tile's first
+    // layer (h0 -> lower half) can then be issued right behind the view MMAs instead of waiting until both view
+    // epilogues have drained the lower half (timeline r2: ~2500 idle cycles per tile).  The head activations that
+    // live up there (kColHeadHi/Lo) are dead by now; tests/test_cpu_hazards.py checks the ordering.
+    const int view_acc = (W2 <= 128 && env_int("PNR_VIEW_UPPER", 1)) ? kColAcc + 256 - W2 : kColAcc;
+    ok = bld.add_step(segs, W2, view_acc, ed, false);
   }
   if (!ok) return set_error(PNR_ERR_UNSUPPORTED, "pnr_load_weights: program build failed: %s", bld.err.c_str());
   if ((int)bld.consts.size() > kMaxConsts)

@@ -387,6 +387,68 @@ __global__ void __launch_bounds__(kCompWarps * 32) composite_backward_kernel(Com
 
 using namespace pnr;
 
+// ------------------------------------------------------------------------------------ label tiles
+// 8(e) / 8(f) rank 4: the per-ray tile a rank contributes to the all-gather when labels, not logits, are wanted:
+// rgb as u8, depth as f32, semantic / instance label = argmax over the composited maps (ties -> lowest index)
+// as i16.  13 bytes per ray instead of 4*(5+C+K) (cfg3: 456 -> 13).  One warp per ray; lanes stride channels.
+struct LabelArgs {
+  const float* rgb; const float* depth; const float* sem; const float* inst;
+  int64_t R; int C, K;
+  uint8_t* rgb8; float* depth_out; int16_t* sem_label; int16_t* inst_label;
+};
+
+// argmax over v[0..n) with lanes striding the channels; NaN counts as -inf; ties -> lowest index; -1 when n == 0
+__device__ __forceinline__ int warp_argmax(const float* __restrict__ v, int n, int lane) {
+  float best = -INFINITY;
+  int arg = 0x7fffffff;
+  for (int c = lane; c < n; c += 32) {
+    float x = v[c];
+    if (x != x) x = -INFINITY;
+    if (x > best || arg == 0x7fffffff) { best = x; arg = c; }   // ascending c: the first maximum is kept
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, d);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, d);
+    if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+  }
+  return arg == 0x7fffffff ? -1 : arg;
+}
+
+__global__ void __launch_bounds__(256) label_tiles_kernel(LabelArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= a.R) return;
+  if (a.rgb8 != nullptr && lane < 3) {
+    const float c = fminf(fmaxf(a.rgb[r * 3 + lane], 0.f), 1.f);
+    a.rgb8[r * 3 + lane] = (uint8_t)__float2int_rn(c * 255.0f);
+  }
+  if (a.depth_out != nullptr && lane == 3) a.depth_out[r] = a.depth[r];
+  if (a.sem_label != nullptr) {
+    const int s = warp_argmax(a.sem + r * a.C, a.C, lane);
+    if (lane == 0) a.sem_label[r] = (int16_t)s;
+  }
+  if (a.inst_label != nullptr) {
+    const int s = warp_argmax(a.inst + r * a.K, a.K, lane);
+    if (lane == 0) a.inst_label[r] = (int16_t)s;
+  }
+}
+
+extern "C" int pnr_label_tiles(const float* rgb_map, const float* depth_map, const float* semantic_map,
+                               const float* instance_map, int64_t R, int32_t C, int32_t K, uint8_t* rgb8,
+                               float* depth_out, int16_t* sem_label, int16_t* inst_label, void* stream) {
+  if (R == 0) return PNR_OK;
+  PNR_CHECK_ARG(R > 0 && C >= 0 && K >= 0 && C < 32768 && K < 32768, "pnr_label_tiles: bad sizes");
+  PNR_CHECK_ARG(!rgb8 || rgb_map, "pnr_label_tiles: rgb8 wanted without rgb_map");
+  PNR_CHECK_ARG(!depth_out || depth_map, "pnr_label_tiles: depth wanted without depth_map");
+  PNR_CHECK_ARG(!sem_label || (semantic_map && C > 0), "pnr_label_tiles: semantic labels wanted without semantic_map");
+  PNR_CHECK_ARG(!inst_label || (instance_map && K > 0), "pnr_label_tiles: instance labels wanted without instance_map");
+  LabelArgs a{rgb_map, depth_map, semantic_map, instance_map, R, C, K, rgb8, depth_out, sem_label, inst_label};
+  label_tiles_kernel<<<(unsigned)((R + 7) / 8), 256, 0, (cudaStream_t)stream>>>(a);
+  PNR_LAUNCH_CHECK("label_tiles_kernel");
+  return PNR_OK;
+}
+
 extern "C" int pnr_composite_backward(const float* raw, const float* z, const float* rays, int64_t R, int32_t N,
                                       int32_t C, int32_t K, int32_t white_bkgd, int32_t sem_softmax,
                                       int32_t mask_outside, const int32_t* sample_box, const int32_t* box_sem,

@@ -138,22 +138,21 @@ class Network(nn.Module):
         p = pts.reshape(-1, 3).to(torch.float32).contiguous()
         v = viewdirs.reshape(-1, 3).to(torch.float32).contiguous()
         ctx = self.pack(p.device if p.is_cuda else None)
+        pp, vp = _capi.ptr(p, torch.float32, "pts"), _capi.ptr(v, torch.float32, "viewdirs")   # CPU tensors raise here
         raw = torch.empty(p.shape[0], self.out_channels, device=p.device, dtype=torch.float32)
         with torch.cuda.device(p.device):        # the stream handed to libpnr is the tensors' device's current one
-            _capi.check(_capi.lib().pnr_mlp_forward(ctx, _capi.ptr(p, torch.float32, "pts"),
-                                                    _capi.ptr(v, torch.float32, "viewdirs"), None, None,
-                                                    p.shape[0], 1, _capi.ptr(raw), _capi.stream_ptr()),
-                        "pnr_mlp_forward")
+            _capi.check(_capi.lib().pnr_mlp_forward(ctx, pp, vp, None, None, p.shape[0], 1, _capi.ptr(raw),
+                                                    _capi.stream_ptr()), "pnr_mlp_forward")
         return raw.reshape(*pts.shape[:-1], self.out_channels)
 
     def forward_rays(self, rays: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
         """Fused form used by the Renderer: pts = o + d*z and viewdirs = d/|d| are formed in-kernel."""
         R, N = z.shape
         ctx = self.pack(rays.device if rays.is_cuda else None)
+        rp, zp = _capi.ptr(rays, torch.float32, "rays"), _capi.ptr(z, torch.float32, "z")       # CPU tensors raise here
         raw = torch.empty(R, N, self.out_channels, device=rays.device, dtype=torch.float32)
         with torch.cuda.device(rays.device):
-            _capi.check(_capi.lib().pnr_mlp_forward(ctx, None, None, _capi.ptr(rays, torch.float32, "rays"),
-                                                    _capi.ptr(z, torch.float32, "z"), R, N, _capi.ptr(raw),
+            _capi.check(_capi.lib().pnr_mlp_forward(ctx, None, None, rp, zp, R, N, _capi.ptr(raw),
                                                     _capi.stream_ptr()), "pnr_mlp_forward")
         return raw
 

@@ -552,8 +552,7 @@ class Renderer:
         if Ni > 0:
             out["z_vals_0"] = e(R, N)
             a.z_vals0 = _capi.ptr(out["z_vals_0"])
-        out["near"], out["far"] = e(R), e(R)
-        a.near_out, a.far_out = _capi.ptr(out["near"]), _capi.ptr(out["far"])
+        out["near"], out["far"] = near, far          # as given (bound_by_primitives works on a private copy)
         ws = self._workspace(ctx, R, N, Ni, dev)
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
         _capi.check(_capi.lib().pnr_render_fused(ctx, ctx_fine, C.byref(a), _capi.stream_ptr()), "pnr_render_fused")

@@ -192,3 +192,43 @@ def test_comm_single_rank_allgather():
     assert torch.equal(src, dst)
     _capi.check(L.pnr_comm_destroy(comm), "pnr_comm_destroy")
     assert L.pnr_comm_init(C.byref(comm), uid, 3, 2, 0) != 0 and b"rank" in L.pnr_last_error()
+
+
+def test_label_tiles_kernel():
+    """pnr_label_tiles: rgb -> u8, argmax labels with ties to the lowest index and NaN treated as -inf."""
+    g = torch.Generator().manual_seed(3)
+    R, Cn, Kn = 1000, 45, 64
+    rgb, depth = torch.rand(R, 3, generator=g), torch.rand(R, generator=g) * 50
+    sem, inst = torch.randn(R, Cn, generator=g), torch.randn(R, Kn, generator=g)
+    sem[5] = 0.25                        # all equal: label 0
+    sem[6, 7] = sem[6, 30] = 9.0         # tie: lowest index
+    inst[7, :10] = float("nan")
+    g_rgb, g_depth, g_sem, g_inst = rgb.to(DEV), depth.to(DEV), sem.to(DEV), inst.to(DEV)   # kept alive over the call
+    rgb8 = torch.empty(R, 3, dtype=torch.uint8, device=DEV)
+    dep = torch.empty(R, device=DEV)
+    sl = torch.empty(R, dtype=torch.int16, device=DEV)
+    il = torch.empty(R, dtype=torch.int16, device=DEV)
+    _capi.check(_capi.lib().pnr_label_tiles(g_rgb.data_ptr(), g_depth.data_ptr(), g_sem.data_ptr(), g_inst.data_ptr(),
+                                            R, Cn, Kn, rgb8.data_ptr(), dep.data_ptr(), sl.data_ptr(), il.data_ptr(),
+                                            _capi.stream_ptr()), "pnr_label_tiles")
+    torch.cuda.synchronize()
+    assert torch.equal(rgb8.cpu().float(), torch.round(rgb * 255)) and torch.equal(dep.cpu(), depth)
+    assert torch.equal(sl.cpu().long(), sem.argmax(-1)) and int(sl[5]) == 0 and int(sl[6]) == 7
+    assert torch.equal(il.cpu().long(), torch.nan_to_num(inst, nan=-float("inf")).argmax(-1))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_rank_tile_gather():
+    import socket
+    import subprocess
+    import sys
+    from pathlib import Path
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    worker = Path(__file__).parent / "comm2_worker.py"
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(worker)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "COMM2 OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
