@@ -193,8 +193,6 @@ int pnr_sample_pdf(const float* z, const float* weights, int64_t R, int32_t N, i
  * (each may be NULL to query sizes only).  `program` receives the MlpProgram struct of csrc/mlp_program.h.
  * For the CPU test tier: tests/test_cpu_program.py replays the program on the host and compares it with
  * the oracle's Network.forward. */
-#define PNR_PROGRAM_PAIR 1      /* flags: CTA-pair weight layout (two n/2-row images per stage; host side only) */
-#define PNR_PROGRAM_SPLIT_WAR 2 /* flags: E0 stores released in two blocks (two write-after-read barriers per step) */
 #define PNR_PROGRAM_SPLIT_E1 4  /* flags: E1 signalled in two blocks */
 #define PNR_PROGRAM_NO_SPLIT 8  /* flags: start from one-block epilogues instead of the precision's default */
 int pnr_program_host(const pnr_config* cfg, const float* const* tensors_host, const int64_t* shapes, int32_t n,
@@ -206,7 +204,7 @@ int pnr_program_host(const pnr_config* cfg, const float* const* tensors_host, co
  * ray/primitive intersection, stratified sampling + per-sample ids, Network.forward, raw2outputs and, when
  * Ni > 0, sample_pdf + merge + the fine pass - is enqueued on `stream` in ray chunks sized by the caller's
  * workspace, so the big intermediate (raw [chunk, N+Ni, 4+C+K]) never exceeds it (size it with
- * pnr_workspace_bytes: the default keeps `raw` L2-resident between the MLP and the compositing kernel).
+ * pnr_workspace_bytes).
  * Results do not depend on the chunking (every kernel is per-ray and deterministic).
  * All pointers are DEVICE pointers except aabb_host; outputs and most inputs are optional (NULL). */
 enum { PNR_SAMPLE_UNIFORM = 0,    /* z = near*(1-t) + far*t over [near, far], samples tagged with the interval they fall in */
@@ -250,8 +248,9 @@ typedef struct pnr_render_args {
 int pnr_render_fused(pnr_ctx* ctx, pnr_ctx* ctx_fine, const pnr_render_args* args, void* stream);
 
 /* Bytes of device scratch pnr_render_fused wants for R rays: enough for one chunk of min(R, rays_per_chunk) rays
- * with every optional output absent, where rays_per_chunk keeps `raw` near 96 MB (L2-resident on B200) but never
- * below ~8 tiles of the fused MLP per SM.  Any workspace that holds at least one ray works (more chunks). */
+ * with every optional output absent, where rays_per_chunk puts `raw` near 1.5 GB and never below ~64 tiles of the
+ * fused MLP per SM (smaller chunks cost more in kernel ramp-up than they save).  Any workspace that holds at
+ * least one ray works (more chunks). */
 size_t pnr_workspace_bytes(const pnr_ctx* ctx, int64_t R, int32_t N, int32_t Ni);
 
 /* 8(e) multi-GPU entry: one NCCL communicator per rank (NCCL is bound at run time: pnr_comm_available() == 0

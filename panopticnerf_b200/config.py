@@ -31,7 +31,7 @@ _DEFAULTS = dict(
     precision="fp16x3",
     # Renderer.render: "fused" = one pnr_render_fused call per frame (chunked inside by the workspace, `raw` never
     # materialised for the frame); "staged" = one libpnr call per stage from Python (implied by return_raw).
-    # workspace_mb = 0: pnr_workspace_bytes' default (raw ~96 MB per chunk, L2-resident).
+    # workspace_mb = 0: pnr_workspace_bytes' default (raw ~1.5 GB per chunk).
     render_path="fused", workspace_mb=0,
     # raise if the fp16 operands overflowed in this render (costs one 4-byte D2H read per render)
     check_range=True,

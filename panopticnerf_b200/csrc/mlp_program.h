@@ -7,13 +7,11 @@
 // overlaps the first K-chunks of the next step's h0 (which only need what E0 wrote).  Each half is a
 // list of weight STAGES (<= 32 KB: up to 128 rows x 64 K, hi image then lo image), streamed by TMA.
 //
-// Each half-epilogue works in two PARTS (column blocks a, b; part b may be empty):
-//   E0 part a / b are released by their own write-after-read barriers (war_ok[0/1]: the MMAs of h1 that still
-//     read the activation columns the part overwrites have retired), so E0 stores its first block while h1 is
-//     still on its first stages;
-//   E1 part a / b are SIGNALLED separately, so the next step's third K-chunk can start when half of E1 is done.
+// E1 works in two PARTS (column blocks a, b; part b may be empty) that are SIGNALLED separately, so the next step's
+// third K-chunk can start when half of E1 is done (timeline r2: 75.4 k -> 71.5 k cycles per tile).  (Releasing E0's
+// stores in two blocks with two write-after-read barriers was measured as well: no gain, removed.)
 // Epilogue -> MMA hand-offs are three monotonic shared-memory counters (E0 done, E1 part a done, E1 done), bumped
-// once per epilogue warp and polled by the MMA-issuing warps themselves: every stage carries the counts it needs.
+// once per epilogue warp and watched by the scout thread: every stage carries the counts it needs.
 //
 // The program travels as a __grid_constant__ kernel parameter (constant bank, uniform datapath for the issuing
 // thread; nothing shared between contexts, streams, devices or graph replays).
@@ -55,10 +53,9 @@ enum : uint16_t {
   F_WAIT_E1 = 4,        // first stage that touches anything E1 part b of the previous step reads or writes
   F_COMMIT_ACC0 = 8,    // last stage of h0: signal E0 when the MMAs so far retire
   F_COMMIT_ACC1 = 16,   // last stage of the step: signal E1
-  F_COMMIT_WAR = 32,    // last stage reading the activation columns E0 part a of THIS step overwrites
+  F_COMMIT_WAR = 32,    // last stage reading the activation columns E0 of THIS step overwrites
   F_WAIT_EMB = 64, F_RELEASE_EMB = 128, F_WAIT_DIR = 256, F_RELEASE_DIR = 512,
-  F_COMMIT_WAR1 = 1024, // last stage reading the columns E0 part b overwrites (= F_COMMIT_WAR's stage when E0 is one block)
-  F_WAIT_E1A = 2048     // first stage that touches anything E1 part a of the previous step reads or writes
+  F_WAIT_E1A = 1024     // first stage that touches anything E1 part a of the previous step reads or writes
 };
 enum : uint8_t { EPI_RELU_TO_A = 0, EPI_VIEW_RGB = 2, EPI_LOGITS = 3 };   // (1 was a linear hand-over: feature_linear is folded now)
 
@@ -100,8 +97,7 @@ struct EpiDesc {
   uint16_t bias_off;   // float offset into consts (16-byte aligned)
   uint16_t aux_off;    // sigma weights (EPI_*_TO_A with sigma) or rgb weights [3][n] (EPI_VIEW_RGB)
   uint16_t out_off;    // EPI_LOGITS: channel offset in the raw row
-  uint16_t n0a;        // E0 part a = columns [0, n0a), part b = [n0a, n0)        (multiples of 16; n0a = n0: one block)
-  uint16_t n1a;        // E1 part a = columns [n0, n1a), part b = [n1a, n)        (n1a = n: one block)
+  uint16_t n1a;        // E1 part a = columns [n0, n1a), part b = [n1a, n)   (multiple of 16; n1a = n: one block)
 };
 
 struct MlpProgram {

@@ -20,8 +20,8 @@
 // E0 (epilogue of h0) runs while the tensor pipe works on h1; E1 runs while the next step's h0 consumes
 // the K-chunks E0 already produced.  Hazards:
 //   MMA -> epilogue   acc_full[0/1]  mbarriers (tcgen05.commit), one phase per step;
-//   MMA -> E0 stores  war_ok[0/1]    mbarriers: the activation columns part a / part b of E0 overwrite have
-//                                    been read by the last MMA of this step that needs them;
+//   MMA -> E0 stores  war_ok         mbarrier: the activation columns E0 overwrites have been read by the last
+//                                    MMA of this step that needs them;
 //   epilogue -> MMA   three monotonic shared-memory counters (E0 done, E1 part a done, E1 done), +1 per
 //                     epilogue warp (red.release after tcgen05.wait::st + fence), polled with ld.acquire by
 //                     the issuing warps: the hand-off costs one shared-memory round trip instead of
@@ -93,7 +93,7 @@ __device__ __forceinline__ void encode_row(const float (&p)[3], int L, uint8_t* 
 // ------------------------------------------------------------------------------------------------
 
 // activation -> next layer's A operand: v = act(acc + bias); [sigma += v . wsig]; split into hi / lo parts.
-// `vmax` collects the largest |v| bit pattern seen (range check of the 16-bit operand format).
+// `vmax` collects the largest hi-part bit patterns seen (two 16-bit lanes; range check of the operand format).
 template <int PASSES, int FMT>
 __device__ __forceinline__ void epi_group_act(const uint32_t (&r)[16], int g, const EpiDesc& ed,
                                               const float* bias, const float* wsig, float& sig, uint32_t& vmax,
@@ -110,14 +110,15 @@ __device__ __forceinline__ void epi_group_act(const uint32_t (&r)[16], int g, co
       const float4 w = reinterpret_cast<const float4*>(wsig + g * 16)[q];
       sig += v0 * w.x + v1 * w.y + v2 * w.z + v3 * w.w;
     }
-    // v >= 0 after the ReLU, so the fp32 bit patterns order like the values (+inf on top; fmaxf turns a NaN
-    // accumulator into 0, but a NaN can only follow an overflow that was flagged where it happened)
-#ifndef PNR_ABL_NOVMAX
-    vmax = __vimax3_u32(vmax, __float_as_uint(v0), __float_as_uint(v1));
-    vmax = __vimax3_u32(vmax, __float_as_uint(v2), __float_as_uint(v3));
-#endif
     split_x2<FMT>(v0, v1, hi[2 * q], lo[2 * q]);
     split_x2<FMT>(v2, v3, hi[2 * q + 1], lo[2 * q + 1]);
+    // Range check on the packed hi parts (one 3-input 16x2 max per four values): v >= 0 after the ReLU, so the
+    // 16-bit patterns order like the values, with +inf (what an overflowing conversion yields) and NaN on top.
+    // (fmaxf turns a NaN accumulator into 0, but a NaN can only follow an overflow that was flagged where it
+    // happened - which is why the check sits in every layer and not only on the outputs.)
+#ifndef PNR_ABL_NOVMAX
+    vmax = __vimax3_u16x2(vmax, hi[2 * q], hi[2 * q + 1]);
+#endif
   }
 }
 
@@ -147,10 +148,10 @@ __device__ __forceinline__ void epi_group_logits(const uint32_t (&r)[16], int g,
     if (g * 16 + j < ed.n_valid) dst[g * 16 + j] = __uint_as_float(r[j]) + bias[g * 16 + j];
 }
 
-// Largest finite magnitude of the operand format, as fp32 bits: 65504 (fp16) / FLT_MAX (bf16 shares fp32's range).
+// Bit pattern of +inf in the operand format: a hi part >= this is an overflowed (or NaN) activation.
 template <int FMT>
-__device__ __forceinline__ constexpr uint32_t range_limit_bits() {
-  return FMT == kFmtF16 ? 0x477FE000u : 0x7F7FFFFFu;
+__device__ __forceinline__ constexpr uint32_t inf_bits16() {
+  return FMT == kFmtF16 ? 0x7C00u : 0x7F80u;
 }
 
 // CTAs run as clusters of two that stream the SAME weight stages in lock step: each CTA fetches half of every
@@ -175,7 +176,7 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
   const uint32_t bar_full = smem_u32(&bars[0]);                 // [kRing]
   const uint32_t bar_empty = smem_u32(&bars[kRing]);            // [kRing]
   const uint32_t bar_acc_full = smem_u32(&bars[2 * kRing]);     // [2]
-  const uint32_t bar_war = smem_u32(&bars[2 * kRing + 2]);      // [2]  E0 part a / part b may store
+  const uint32_t bar_war = smem_u32(&bars[2 * kRing + 2]);      // E0 may store
   const uint32_t bar_emb_full = smem_u32(&bars[2 * kRing + 4]);
   const uint32_t bar_emb_empty = smem_u32(&bars[2 * kRing + 5]);
   const uint32_t bar_dir_full = smem_u32(&bars[2 * kRing + 6]);   // [2]
@@ -201,10 +202,10 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
     }
     for (int h = 0; h < 2; ++h) {
       mbar_init(bar_acc_full + 8 * h, 1);
-      mbar_init(bar_war + 8 * h, 1);
       mbar_init(bar_dir_full + 8 * h, kProWarps * 32);
       mbar_init(bar_dir_empty + 8 * h, 1);
     }
+    mbar_init(bar_war, 1);
     for (int w = 24; w < 32; ++w) bars[w] = 0ull;
     mbar_init(bar_emb_full, kProWarps * 32);
     mbar_init(bar_emb_empty, 1);
@@ -224,7 +225,7 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
     const int row = q * 32 + lane;
     const uint32_t tmem_lane = tmem + ((uint32_t)(q * 32) << 16);
     uint32_t gstep = 0;
-    uint32_t vmax = 0;                          // largest activation magnitude (fp32 bits) this thread produced
+    uint32_t vmax = 0;                          // largest hi-part bit patterns this thread produced (16x2)
     for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
       const int64_t s = (int64_t)tile * kTileM + row;
       const bool valid = s < p.S;
@@ -243,9 +244,9 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
           const bool rec = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && tile == 2 * (int)gridDim.x;
           if (rec) p.dbg[4096 + (st * 2 + h) * 3 + 0] = clock64();
 #endif
-          // column blocks (in 16-column groups) of this half: part a = [pa0, pa1), part b = [pa1, pb1)
+          // column blocks (in 16-column groups) of this half: part a = [pa0, pa1), part b = [pa1, pb1) (E1 only)
           const int pa0 = (h == 0 ? 0 : (int)ed.n0) >> 4;
-          const int pa1 = (h == 0 ? (int)ed.n0a : (int)ed.n1a) >> 4;
+          const int pa1 = (h == 0 ? (int)ed.n0 : (int)ed.n1a) >> 4;
           const int pb1 = (h == 0 ? (int)ed.n0 : (int)ed.n) >> 4;
           // this warp's near-equal contiguous share of each part
           const int a_lo = pa0 + (ch * (pa1 - pa0) + kCh - 1) / kCh, a_hi = pa0 + ((ch + 1) * (pa1 - pa0) + kCh - 1) / kCh;
@@ -274,7 +275,7 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
           for (int pi = 0; pi < 2; ++pi) {
             const int lo = pi == 0 ? a_lo : b_lo, hi = pi == 0 ? a_hi : b_hi;
             const int nxt = (pi == 0 && nb > 0) ? b_lo : -1;   // first group of the part that follows
-            // E0 only: this part's stores wait for its write-after-read barrier (once)
+            // E0 only (one part): the stores wait for the write-after-read barrier (once)
             bool war_pending = to_a && h == 0 && lo < hi;
             if (to_a) {
               // Two groups are converted before anything is stored: E0 reaches its write-after-read barrier
@@ -295,7 +296,7 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
                   tmem_ld16(acc + after * 16, ra);
                 }
                 if (war_pending) {  // the columns we are about to overwrite must have been consumed by the MMAs
-                  mbar_wait_backoff(bar_war + 8 * pi, parity);
+                  mbar_wait_backoff(bar_war, parity);
                   tc_fence_after();
                   war_pending = false;
                 }
@@ -327,9 +328,7 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
                 }
               }
             }
-            // hand-off after part a of E1 (part a of E0 is not signalled: the next step's first MMA overwrites
-            // accumulator columns that part b still reads)
-            if (pi == 0 && h == 1) signal(cnt_e1a);
+            if (pi == 0 && h == 1) signal(cnt_e1a);   // hand-off after part a of E1
           }
           if (h == 1) {
             if (ed.sigma) {
@@ -365,7 +364,8 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
         }
       }
     }
-    if (p.status != nullptr && vmax > range_limit_bits<FMT>()) atomicOr(p.status, 1u);
+    if (p.status != nullptr && ((vmax & 0xFFFFu) >= inf_bits16<FMT>() || (vmax >> 16) >= inf_bits16<FMT>()))
+      atomicOr(p.status, 1u);
   } else if (warp < kEpiWarps + kProWarps) {
     // =============================================================== embedding producer warps
     const int row = (warp - kEpiWarps) * 32 + lane;
@@ -583,11 +583,10 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
           if (rec) p.dbg[si * 5 + 2] = clock64();
 #endif
           tc_commit_multicast(bar_empty + 8 * slot, (uint16_t)((1u << kClusterSize) - 1u));   // slot free in all CTAs
-          if (flags & (F_RELEASE_EMB | F_RELEASE_DIR | F_COMMIT_WAR | F_COMMIT_WAR1 | F_COMMIT_ACC0 | F_COMMIT_ACC1)) {
+          if (flags & (F_RELEASE_EMB | F_RELEASE_DIR | F_COMMIT_WAR | F_COMMIT_ACC0 | F_COMMIT_ACC1)) {
             if (flags & F_RELEASE_EMB) tc_commit(bar_emb_empty);
             if (flags & F_RELEASE_DIR) tc_commit(bar_dir_empty + 8 * b);
             if (flags & F_COMMIT_WAR) tc_commit(bar_war);
-            if (flags & F_COMMIT_WAR1) tc_commit(bar_war + 8);
             if (flags & F_COMMIT_ACC0) tc_commit(bar_acc_full);
             if (flags & F_COMMIT_ACC1) tc_commit(bar_acc_full + 8);
           }

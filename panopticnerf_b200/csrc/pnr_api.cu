@@ -86,25 +86,15 @@ struct Builder {
   std::vector<uint16_t> wbuf;   // packed weight stream (bf16 elements)
   std::vector<float> consts;
   int passes, fmt;
-  // CTA-pair layout (round 2, tcgen05.mma.cta_group::2): every stage is stored as two images, rows [0, n/2)
-  // for CTA 0 and [n/2, n) for CTA 1, each in the core-matrix layout of an n/2-row tile.  Host side only so
-  // far (pnr_program_host + tests/test_cpu_program.py); the kernel that consumes it is not written yet.
-  bool pair = false;
-  // Epilogue parts (mlp_program.h): E0 in two blocks with their own write-after-read barriers, E1 in two blocks
-  // signalled separately.  Both only pay off when a half spans several weight stages (the x3 modes, K = 64 per
-  // stage); PNR_SPLIT_WAR / PNR_SPLIT_E1 = 0 / 1 in the environment override the default (tuning aid).
-  bool split_war, split_e1;
+  // E1 in two blocks signalled separately (mlp_program.h).  Pays off when a half spans several weight stages
+  // (the x3 modes, K = 64 per stage: 75.4 k -> 71.5 k cycles per tile); the 1-pass modes keep one block.
+  bool split_e1;
   bool out_of_fp16_range = false;   // a weight (after the feature_linear fold) exceeds 65504 or is not finite
   std::string err;
 
-  static bool env_flag(const char* name, bool dflt) {
-    const char* v = getenv(name);
-    return (v && *v) ? (*v != '0') : dflt;
-  }
   Builder(int passes_, int fmt_) : passes(passes_), fmt(fmt_) {
     memset(&prog, 0, sizeof(prog));
-    split_war = env_flag("PNR_SPLIT_WAR", passes == 3);
-    split_e1 = env_flag("PNR_SPLIT_E1", passes == 3);
+    split_e1 = passes == 3;
   }
 
   int add_consts(const float* src, int n_valid, int n_pad) {
@@ -170,7 +160,7 @@ struct Builder {
             sd.acc_col = (uint16_t)(acc_col + r0);
             sd.a_off = (uint16_t)(sg.a_hi + k0 / 2);
             sd.a_lo_off = (uint16_t)(sg.a_lo + k0 / 2);
-            sd.lo_off16 = (uint16_t)((pair ? (r1 - r0) / 2 : (r1 - r0)) * kcores);
+            sd.lo_off16 = (uint16_t)((r1 - r0) * kcores);
             sd.ksteps = (uint8_t)(kcores / 2);
             sd.a_kind = sg.kind;
             const bool seg_first = (k0 == 0);
@@ -180,14 +170,7 @@ struct Builder {
             if (sg.kind == A_EMB && seg_last && sg.release && last_half) sd.flags |= F_RELEASE_EMB;
             if (sg.kind == A_DIR && seg_first && h == 0) sd.flags |= F_WAIT_DIR;
             if (sg.kind == A_DIR && seg_last && sg.release && last_half) sd.flags |= F_RELEASE_DIR;
-            if (!pair) {
-              for (int part = 0; part < parts; ++part) pack_stage(sg.m, r0, r1 - r0, sg.col0, sg.kvalid, k0, kcores, part);
-            } else {
-              const int nh = (r1 - r0) / 2;
-              for (int cta = 0; cta < 2; ++cta)
-                for (int part = 0; part < parts; ++part)
-                  pack_stage(sg.m, r0 + cta * nh, nh, sg.col0, sg.kvalid, k0, kcores, part);
-            }
+            for (int part = 0; part < parts; ++part) pack_stage(sg.m, r0, r1 - r0, sg.col0, sg.kvalid, k0, kcores, part);
           }
         }
       }
@@ -204,8 +187,7 @@ struct Builder {
     ed.n = (uint16_t)n_pad;
     ed.n0 = (uint16_t)n0;
     ed.acc_col = (uint16_t)acc_col;
-    const int g0 = n0 / 16, g1 = (n_pad - n0) / 16;
-    ed.n0a = (uint16_t)((split_war && g0 >= 2) ? (g0 / 2) * 16 : n0);
+    const int g1 = (n_pad - n0) / 16;
     ed.n1a = (uint16_t)(n0 + ((split_e1 && g1 >= 2) ? (g1 / 2) * 16 : (n_pad - n0)));
     prog.ep[prog.n_steps++] = ed;
     return true;
@@ -240,8 +222,8 @@ struct Builder {
   }
 
   // Place the waits on the previous step's E1 parts (cyclically: the first step of a tile follows the last step
-  // of the previous tile), the write-after-read commits for this step's own E0 parts, and the per-stage
-  // hand-off counts of the issue table.
+  // of the previous tile), the write-after-read commit for this step's own E0, and the per-stage hand-off counts
+  // of the issue table.
   void finalize() {
     const int S = prog.n_steps;
     std::vector<int> at_a(S), at_b(S);
@@ -264,21 +246,16 @@ struct Builder {
       if (at_a[s] > at_b[s]) at_a[s] = at_b[s];                 // "E1 done" implies "E1 part a done"
       prog.st[at_a[s]].flags |= F_WAIT_E1A;
       prog.st[at_b[s]].flags |= F_WAIT_E1;
-      // E0 of this step overwrites dst columns [dst, dst + n0/2) (hi and lo) in two blocks: last stage reading each
+      // E0 of this step overwrites dst columns [dst, dst + n0/2) (hi and lo): last stage reading them
       const EpiDesc& e = prog.ep[s];
-      const bool to_a = e.kind == EPI_RELU_TO_A;
-      auto last_touch = [&](int c0, int c1) {
-        int last = in.first_stage;
-        Foot f = epi_foot(s, c0, c1);
+      int war = in.first_stage;
+      if (e.kind == EPI_RELU_TO_A) {
+        Foot f = epi_foot(s, 0, e.n0);
         f.acc0 = f.acc1 = 0;   // stores only: the loads of E0 are ordered by acc_full
         for (int i = in.first_stage; i < end; ++i)
-          if (stage_touches(prog.st[i], f)) last = i;
-        return last;
-      };
-      const int war = to_a ? last_touch(0, e.n0a) : in.first_stage;
-      const int war1 = (to_a && e.n0a < e.n0) ? last_touch(e.n0a, e.n0) : war;
+          if (stage_touches(prog.st[i], f)) war = i;
+      }
       prog.st[war].flags |= F_COMMIT_WAR;
-      prog.st[war1].flags |= F_COMMIT_WAR1;
     }
     for (int s = 0; s < S; ++s) {
       const StepInfo& in = steps[s];
@@ -289,8 +266,8 @@ struct Builder {
     for (int i = 0; i < prog.n_stages; ++i) {   // issue table (flags are final now)
       const StageDesc& sd = prog.st[i];
       IssueDesc& d = prog.is[i];
-      const uint32_t rows = pair ? sd.n / 2u : sd.n;     // rows of the weight tile one CTA holds
-      d.idesc = make_idesc_f32acc(pair ? 2 * kTileM : kTileM, sd.n, fmt);   // fmt: 0 = fp16, 1 = bf16
+      const uint32_t rows = sd.n;                         // rows of the weight tile
+      d.idesc = make_idesc_f32acc(kTileM, sd.n, fmt);     // fmt: 0 = fp16, 1 = bf16
       d.b_lo_base = (uint32_t)(((rows * 16u) >> 4) & 0x3FFFu) << 16;
       d.b_inc = (2u * rows * 16u) >> 4;
       d.lo_off16 = sd.lo_off16;
@@ -303,10 +280,7 @@ struct Builder {
 };
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
-inline int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return (v && *v) ? atoi(v) : dflt;
-}
+
 
 }  // namespace
 
@@ -507,12 +481,10 @@ static int build_program(const pnr_config& c, const float* const* t, const int64
     std::vector<Seg> segs;
     segs.push_back(seg_tmem(m_fold, 0, W, kColAHi, kColALo));
     segs.push_back(Seg{A_DIR, m_fold, W, Ed, 32, 0, 0, true});
-    // The view step accumulates in the UPPER half of the accumulator region when it fits: the next tile's first
-    // layer (h0 -> lower half) can then be issued right behind the view MMAs instead of waiting until both view
-    // epilogues have drained the lower half (timeline r2: ~2500 idle cycles per tile).  The head activations that
-    // live up there (kColHeadHi/Lo) are dead by now; tests/test_cpu_hazards.py checks the ordering.
-    const int view_acc = (W2 <= 128 && env_int("PNR_VIEW_UPPER", 1)) ? kColAcc + 256 - W2 : kColAcc;
-    ok = bld.add_step(segs, W2, view_acc, ed, false);
+    // (Accumulating the view step in the UPPER half of the accumulator region, so that the next tile's first layer
+    // can be issued right behind the view MMAs, was measured: the stall only moves in front of the view step -
+    // the tile boundary is bound by the serial epilogues of view + layer 0, 71.6 k vs 71.9 k cycles per tile.)
+    ok = bld.add_step(segs, W2, kColAcc, ed, false);
   }
   if (!ok) return set_error(PNR_ERR_UNSUPPORTED, "pnr_load_weights: program build failed: %s", bld.err.c_str());
   if ((int)bld.consts.size() > kMaxConsts)
@@ -553,11 +525,10 @@ extern "C" int pnr_program_host(const pnr_config* cfg, const float* const* t, co
                                 size_t* n_consts) {
   PNR_CHECK_ARG(cfg && t && shapes && program_bytes && wpacked_bytes && n_consts, "pnr_program_host: null pointer");
   if (const int rc = check_config(cfg)) return rc;
-  PNR_CHECK_ARG((flags & ~15) == 0, "pnr_program_host: unknown flags 0x%x", flags);
+  PNR_CHECK_ARG((flags & ~(PNR_PROGRAM_SPLIT_E1 | PNR_PROGRAM_NO_SPLIT)) == 0,
+                "pnr_program_host: unknown flags 0x%x", flags);
   Builder bld(precision_passes(cfg->precision), precision_fmt(cfg->precision));
-  bld.pair = (flags & PNR_PROGRAM_PAIR) != 0;
-  if (flags & PNR_PROGRAM_NO_SPLIT) bld.split_war = bld.split_e1 = false;
-  if (flags & PNR_PROGRAM_SPLIT_WAR) bld.split_war = true;
+  if (flags & PNR_PROGRAM_NO_SPLIT) bld.split_e1 = false;
   if (flags & PNR_PROGRAM_SPLIT_E1) bld.split_e1 = true;
   const int rc = build_program(*cfg, t, shapes, n, bld);
   if (rc != PNR_OK) return rc;

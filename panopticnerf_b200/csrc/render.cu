@@ -1,8 +1,7 @@
 // render.cu — pnr_render_fused: Renderer.render / batchify_rays / render_rays as one
 // C-ABI call.  The host side only sequences the stage kernels of this library over ray chunks; the chunk size
 // follows from the caller's workspace, so the one large intermediate - raw [chunk, N+Ni, 4+C+K] - is bounded
-// (and, at the default workspace, stays in L2 between the fused MLP that writes it and the compositing kernel
-// that reads it) instead of being materialised for the whole frame.
+// (~1.5 GB at the default workspace) instead of being materialised for the whole frame (46 GB at config 3).
 #include <cstring>
 #include "common.cuh"
 #include "ray_math.h"   // PNR_MAX_HITS
@@ -89,12 +88,15 @@ __global__ void __launch_bounds__(256) fill2_kernel(float* __restrict__ a, float
   if (i < n) { a[i] = va; b[i] = vb; }
 }
 
-// rays per chunk that keep raw near 96 MB but never below ~8 tiles of the fused MLP per SM
+// Rays per chunk by default: raw of ~1.5 GB, never below ~64 tiles of the fused MLP per SM and pass.  (Measured,
+// B200: chunks small enough to keep raw L2-resident - 96 MB, ~1 200 rays of config 3 - leave the persistent MLP
+// kernel 4-12 tiles per SM and launch, and its ramp-up / tail then costs far more than the HBM round trip of raw
+// saves: 633 ms per config-3 frame against ~430.)
 int64_t default_chunk_rays(int Nt, int CH) {
   const size_t raw_per_ray = (size_t)Nt * CH * 4;
-  int64_t by_l2 = (int64_t)((96ull << 20) / raw_per_ray);
-  const int64_t by_tiles = ((int64_t)148 * 8 * 128 + Nt - 1) / Nt;
-  return by_l2 > by_tiles ? by_l2 : by_tiles;
+  int64_t by_bytes = (int64_t)((1536ull << 20) / raw_per_ray);
+  const int64_t by_tiles = ((int64_t)148 * 64 * 128 + Nt - 1) / Nt;
+  return by_bytes > by_tiles ? by_bytes : by_tiles;
 }
 
 size_t workspace_bytes_for(int64_t R, int N, int Ni, int CH) {

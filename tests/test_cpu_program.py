@@ -17,8 +17,8 @@ from util import assert_close, rms
 K_MAX_STAGES, K_MAX_STEPS = 256, 24
 A_TMEM, A_EMB, A_DIR = 0, 1, 2
 F_FIRST, F_WAIT_E0, F_WAIT_E1, F_COMMIT_ACC0, F_COMMIT_ACC1, F_COMMIT_WAR = 1, 2, 4, 8, 16, 32
-F_COMMIT_WAR1, F_WAIT_E1A = 1024, 2048
-PROGRAM_PAIR, PROGRAM_SPLIT_WAR, PROGRAM_SPLIT_E1, PROGRAM_NO_SPLIT = 1, 2, 4, 8
+F_WAIT_E1A = 1024
+PROGRAM_SPLIT_E1, PROGRAM_NO_SPLIT = 4, 8
 EPI_RELU_TO_A, EPI_VIEW_RGB, EPI_LOGITS = 0, 2, 3
 COL_A_HI, COL_HEAD_HI = 256, 128
 
@@ -36,7 +36,7 @@ class IssueDesc(C.Structure):
 
 class EpiDesc(C.Structure):
     _fields_ = [("kind", C.c_uint8), ("sigma", C.c_uint8)] + [(k, C.c_uint16) for k in
-                ("n", "n0", "n_valid", "acc_col", "dst_col", "dst_lo_col", "bias_off", "aux_off", "out_off", "n0a", "n1a")]
+                ("n", "n0", "n_valid", "acc_col", "dst_col", "dst_lo_col", "bias_off", "aux_off", "out_off", "n1a")]
 
 
 class MlpProgram(C.Structure):
@@ -46,7 +46,7 @@ class MlpProgram(C.Structure):
                 ("ep", EpiDesc * K_MAX_STEPS)]
 
 
-def build(cfg, net, pair: bool = False, flags: int = 0):
+def build(cfg, net, flags: int = 0):
     host, shapes = [], []
     for lin in net._linears():
         w, b = lin.weight.detach().float().contiguous(), lin.bias.detach().float().contiguous()
@@ -58,13 +58,13 @@ def build(cfg, net, pair: bool = False, flags: int = 0):
     ptrs = (C.c_void_p * len(host))(*[t.data_ptr() for t in host])
     shp = (C.c_int64 * len(shapes))(*shapes)
     pb, wb, nc = C.c_size_t(), C.c_size_t(), C.c_size_t()
-    _capi.check(L.pnr_program_host(C.byref(pc), ptrs, shp, len(host), int(pair) | flags, None, 0, C.byref(pb), None, 0,
+    _capi.check(L.pnr_program_host(C.byref(pc), ptrs, shp, len(host), flags, None, 0, C.byref(pb), None, 0,
                                    C.byref(wb), None, 0, C.byref(nc)), "pnr_program_host (sizes)")
     assert pb.value == C.sizeof(MlpProgram), "MlpProgram layout in this test is out of date"
     prog = MlpProgram()
     w16 = np.zeros(wb.value // 2, dtype=np.uint16)
     consts = np.zeros(nc.value, dtype=np.float32)
-    _capi.check(L.pnr_program_host(C.byref(pc), ptrs, shp, len(host), int(pair) | flags, C.byref(prog), pb.value, C.byref(pb),
+    _capi.check(L.pnr_program_host(C.byref(pc), ptrs, shp, len(host), flags, C.byref(prog), pb.value, C.byref(pb),
                                    w16.ctypes.data, wb.value, C.byref(wb), consts.ctypes.data, nc.value, C.byref(nc)),
                 "pnr_program_host")
     return prog, w16, consts
@@ -85,7 +85,7 @@ def split16(x: np.ndarray, bf16: bool):
     return hi.double().numpy(), lo.double().numpy()
 
 
-def replay(prog, w16, consts, cfg, pts, viewdirs, operand_precision: bool = False, pair: bool = False):
+def replay(prog, w16, consts, cfg, pts, viewdirs, operand_precision: bool = False):
     """What the kernel computes for these samples, from the packed program.  Default: exact activations, float64
     (tests the program).  operand_precision=True also rounds the A operands like the tensor cores see them:
     fp32 activations split into 16-bit hi (+ lo in the x3 modes), products hi*Whi (+ lo*Whi + hi*Wlo)."""
@@ -115,20 +115,14 @@ def replay(prog, w16, consts, cfg, pts, viewdirs, operand_precision: bool = Fals
             base = sd.gofs // 2
             parts = 2 if prog.passes == 3 else 1
             assert sd.bytes == parts * n * kc * 16
-            images = 2 if pair else 1                               # one image per CTA of the pair
-            nh = n // images
+            nh = n
             assert sd.lo_off16 == nh * kc
-            Ws, Wlos = [], []
-            for c in range(images):
-                b0 = base + c * parts * nh * kc * 8
-                hi = to_f32(w16[b0:b0 + nh * kc * 8], bf16).reshape(kc, nh, 8).astype(np.float64)
-                lo = np.zeros_like(hi)
-                if parts == 2:
-                    lo0 = b0 + sd.lo_off16 * 8
-                    lo = to_f32(w16[lo0:lo0 + nh * kc * 8], bf16).reshape(kc, nh, 8).astype(np.float64)
-                Ws.append(hi.transpose(1, 0, 2).reshape(nh, kc * 8))   # [row, k]
-                Wlos.append(lo.transpose(1, 0, 2).reshape(nh, kc * 8))
-            W, Wlo = np.concatenate(Ws, 0), np.concatenate(Wlos, 0)
+            hi = to_f32(w16[base:base + nh * kc * 8], bf16).reshape(kc, nh, 8).astype(np.float64)
+            lo = np.zeros_like(hi)
+            if parts == 2:
+                lo0 = base + sd.lo_off16 * 8
+                lo = to_f32(w16[lo0:lo0 + nh * kc * 8], bf16).reshape(kc, nh, 8).astype(np.float64)
+            W, Wlo = hi.transpose(1, 0, 2).reshape(nh, kc * 8), lo.transpose(1, 0, 2).reshape(nh, kc * 8)   # [row, k]
             if sd.a_kind == A_TMEM:
                 region = COL_A_HI if sd.a_off >= COL_A_HI else COL_HEAD_HI
                 k0 = (sd.a_off - region) * 2
@@ -154,7 +148,7 @@ def replay(prog, w16, consts, cfg, pts, viewdirs, operand_precision: bool = Fals
             assert d.acc_col == sd.acc_col and d.a_off == sd.a_off and d.lo_off16 == sd.lo_off16
             assert d.flags_k == (sd.flags | (sd.ksteps << 16) | (sd.a_kind << 24))
             assert d.b_lo_base == (nh << 16) and d.b_inc == 2 * nh
-            assert (d.idesc >> 17) & 0x3F == n >> 3 and (d.idesc >> 24) & 0x1F == (16 if pair else 8)
+            assert (d.idesc >> 17) & 0x3F == n >> 3 and (d.idesc >> 24) & 0x1F == 8
             assert (d.idesc >> 7) & 7 == int(bf16)
         n = ed.n
         v = acc[:, ed.acc_col:ed.acc_col + n] + consts[ed.bias_off:ed.bias_off + n][None]
@@ -180,7 +174,6 @@ def check_invariants(prog, stages_of):
         fl = [prog.st[i].flags for i in idxs]
         assert sum(bool(f & F_WAIT_E0) for f in fl) == 1 and fl[0] & F_WAIT_E0
         assert sum(bool(f & F_WAIT_E1) for f in fl) == 1 and sum(bool(f & F_WAIT_E1A) for f in fl) == 1
-        assert sum(bool(f & F_COMMIT_WAR1) for f in fl) == 1
         assert sum(bool(f & F_COMMIT_ACC1) for f in fl) == 1 and fl[-1] & F_COMMIT_ACC1
         assert sum(bool(f & F_COMMIT_ACC0) for f in fl) <= 1
         assert sum(bool(f & F_COMMIT_WAR) for f in fl) == 1
@@ -191,7 +184,7 @@ def check_invariants(prog, stages_of):
     # stage that carries the matching wait flag
     for s, idxs in enumerate(stages_of):
         ed = prog.ep[s]
-        assert 0 < ed.n0a <= ed.n0 <= ed.n1a <= ed.n and ed.n0a % 16 == 0 and ed.n1a % 16 == 0
+        assert 0 < ed.n0 <= ed.n1a <= ed.n and ed.n1a % 16 == 0
         seen_a = seen_b = False
         for i in idxs:
             f = prog.st[i].flags
@@ -228,27 +221,6 @@ def test_program_replay_matches_oracle_network(preset, over):
     for name, sl in (("rgb", slice(0, 3)), ("sigma", slice(3, 4)), ("sem", slice(4, 4 + C_)), ("inst", slice(4 + C_, 4 + C_ + K_))):
         if ref[:, sl].numel():
             assert_close(got[:, sl], ref[:, sl], rms(ref[:, sl]), f"{preset} {over} {name}", rel=tol)
-
-
-@pytest.mark.parametrize("preset,over", [("cfg2", {}), ("cfg3", {}), ("cfg1", dict(precision="bf16")),
-                                         ("cfg2", dict(D=5, W=128, num_classes=7, num_instances=3))])
-def test_pair_layout_replays_to_the_same_network(preset, over):
-    """PNR_PROGRAM_PAIR: every stage stored as two n/2-row images (one per CTA of a tcgen05 cta_group::2 pair).
-    Same network function, same program structure; only the weight stream order and the issue words differ."""
-    cfg = make_cfg(preset, **over)
-    net = S.init_network_weights(make_network(cfg), seed=4)
-    prog, w16, consts = build(cfg, net, pair=True)
-    single, w16_s, consts_s = build(cfg, net, pair=False)
-    assert prog.n_stages == single.n_stages and prog.n_steps == single.n_steps
-    assert w16.size == w16_s.size and np.array_equal(consts, consts_s)
-    assert np.array_equal(np.sort(w16), np.sort(w16_s))            # the same 16-bit words, re-ordered
-    g = torch.Generator().manual_seed(6)
-    pts = (torch.rand(130, 3, generator=g) * 2 - 1) * 4
-    vd = torch.nn.functional.normalize(torch.randn(130, 3, generator=g), dim=-1)
-    a, stages_of = replay(prog, w16, consts, cfg, pts, vd, pair=True)
-    b, _ = replay(single, w16_s, consts_s, cfg, pts, vd)
-    check_invariants(prog, stages_of)
-    assert np.array_equal(a, b)
 
 
 @pytest.mark.parametrize("precision,bound", [("fp16x3", 2e-5), ("bf16x3", 1e-4), ("fp16", 1e-2), ("bf16", 6e-2)])

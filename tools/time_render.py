@@ -1,4 +1,5 @@
-"""Whole-frame Renderer.render time for a BASELINE preset (CUDA events, L2 flushed between runs)."""
+"""Renderer.render time for BASELINE presets (CUDA events, L2 flushed between runs):
+    python tools/time_render.py [preset[:rows] ...]      e.g.  cfg2 cfg3   or   cfg3:32  (a 32-row strip)"""
 import json, sys
 from pathlib import Path
 import torch
@@ -9,10 +10,11 @@ from panopticnerf_b200 import synthetic as S
 dev = "cuda:0"
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 res = {}
-for preset in sys.argv[1:] or ["cfg2", "cfg3"]:
+for spec in sys.argv[1:] or ["cfg2", "cfg3"]:
+    preset, _, rows = spec.partition(":")
     cfg = PN.make_cfg(preset)
     net = S.init_network_weights(PN.make_network(cfg)).to(dev)
-    batch = {k: v.to(dev) for k, v in S.make_batch(cfg).items()}
+    batch = {k: v.to(dev) for k, v in S.make_batch(cfg, rows=int(rows) if rows else None).items()}
     ren = PN.make_renderer(cfg, net)
     ts = []
     for i in range(5):
@@ -22,8 +24,8 @@ for preset in sys.argv[1:] or ["cfg2", "cfg3"]:
         if i >= 2: ts.append(a.elapsed_time(b))
     R = batch["rays"].shape[0]
     ms = sum(ts) / len(ts)
-    res[preset] = dict(ms=ms, rays_per_s=R / ms * 1e3, peak_mem_gb=torch.cuda.max_memory_allocated() / 2**30)
-    print(preset, res[preset], flush=True)
+    res[spec] = dict(ms=ms, rays_per_s=R / ms * 1e3, peak_mem_gb=torch.cuda.max_memory_allocated() / 2**30)
+    print(spec, res[spec], flush=True)
     del out, batch, net, ren
     torch.cuda.empty_cache(); torch.cuda.reset_peak_memory_stats()
 (ROOT / "gpurun_out").mkdir(exist_ok=True)
