@@ -59,7 +59,7 @@ WORKLOADS = {
 def metric_name(cfg) -> str:
     if cfg.preset == "cfg2":
         return "rays/sec at 376x1408x64 samples (8x256 MLP, rgb+sigma)"
-    n = cfg.N_samples + (f"+{cfg.N_importance}" if cfg.N_importance else "")
+    n = f"{cfg.N_samples}" + (f"+{cfg.N_importance}" if cfg.N_importance else "")
     return f"rays/sec at {cfg.H}x{cfg.W_img}x{n} samples (8x256 MLP + semantic/instance heads)"
 
 
@@ -329,8 +329,11 @@ def main():
 
     L = _capi.lib()
     sampler = ClockSampler(local_rank)
+    out = gathered = None
     for _ in range(args.warmup):
-        step()
+        out, gathered = step()      # bound like in the timed loop: the previous step's outputs stay alive while the
+                                    # next ones are allocated, so the caching allocator reaches its steady state here
+                                    # (otherwise the 2nd timed step pays a cudaMalloc: 94 / 224 ms outliers, r2 logs)
     barrier()
     sampler.start()
     L.pnr_launch_count(1)

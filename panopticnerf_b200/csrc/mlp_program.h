@@ -96,7 +96,9 @@ struct EpiDesc {
   uint16_t dst_lo_col;
   uint16_t bias_off;   // float offset into consts (16-byte aligned)
   uint16_t aux_off;    // sigma weights (EPI_*_TO_A with sigma) or rgb weights [3][n] (EPI_VIEW_RGB)
-  uint16_t out_off;    // EPI_LOGITS: channel offset in the raw row
+  uint16_t out_off;    // EPI_LOGITS: channel offset in the raw row of column 0 (columns [0, n0), n_valid real ones)
+  uint16_t out_off1;   //             and of column n0 (columns [n0, n), n_valid1 real ones) when the second half is a
+  uint16_t n_valid1;   //             layer of its own (two logit layers issued as the two halves of one step)
   uint16_t n1a;        // E1 part a = columns [n0, n1a), part b = [n1a, n)   (multiple of 16; n1a = n: one block)
 };
 

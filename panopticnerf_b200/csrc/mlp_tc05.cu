@@ -141,11 +141,15 @@ __device__ __forceinline__ void epi_group_rgb(const uint32_t (&r)[16], int g, co
   }
 }
 
-__device__ __forceinline__ void epi_group_logits(const uint32_t (&r)[16], int g, const EpiDesc& ed,
+// logits straight to the raw row.  `dst` / `n_valid` / `c0` describe the half the group lies in: channel of column c
+// = (c - c0) relative to dst, real while < n_valid.
+__device__ __forceinline__ void epi_group_logits(const uint32_t (&r)[16], int g, int c0, int n_valid,
                                                  const float* bias, float* dst) {
 #pragma unroll
-  for (int j = 0; j < 16; ++j)
-    if (g * 16 + j < ed.n_valid) dst[g * 16 + j] = __uint_as_float(r[j]) + bias[g * 16 + j];
+  for (int j = 0; j < 16; ++j) {
+    const int ch = g * 16 + j - c0;
+    if (ch < n_valid) dst[ch] = __uint_as_float(r[j]) + bias[g * 16 + j];
+  }
 }
 
 // Bit pattern of +inf in the operand format: a hi part >= this is an overflowed (or NaN) activation.
@@ -236,7 +240,7 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
         const float* bias = consts + ed.bias_off;
         const float* aux = consts + ed.aux_off;
         const bool to_a = ed.kind == EPI_RELU_TO_A;
-        float* out_row = p.raw + (valid ? s : 0) * p.CH + ed.out_off;
+        float* raw_row = p.raw + (valid ? s : 0) * p.CH;
         float c0 = 0.f, c1 = 0.f, c2 = 0.f;
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
@@ -266,6 +270,10 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
           if (rec) p.dbg[4096 + (st * 2 + h) * 3 + 1] = clock64();
 #endif
           const uint32_t acc = tmem_lane + ed.acc_col;
+          // EPI_LOGITS: where this half's columns go (the second half may be a logit layer of its own)
+          const bool own_half = h == 1 && ed.n_valid1 > 0;
+          float* out_row = raw_row + (own_half ? ed.out_off1 : ed.out_off);
+          const int out_c0 = own_half ? (int)ed.n0 : 0, out_valid = own_half ? (int)ed.n_valid1 : (int)ed.n_valid;
           // software pipeline: the load of the next group is in flight while a group is processed - also across
           // the part boundary, so signalling part a does not restart the load pipeline
           uint32_t ra[16], rb[16];
@@ -313,7 +321,7 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
                 if (ed.kind == EPI_VIEW_RGB) {
                   epi_group_rgb(ra, g, ed, bias, aux, c0, c1, c2);
                 } else if (valid) {
-                  epi_group_logits(ra, g, ed, bias, out_row);
+                  epi_group_logits(ra, g, out_c0, out_valid, bias, out_row);
                 }
                 if (two) {
                   tc_wait_ld();
@@ -321,7 +329,7 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
                   if (ed.kind == EPI_VIEW_RGB) {
                     epi_group_rgb(rb, g + 1, ed, bias, aux, c0, c1, c2);
                   } else if (valid) {
-                    epi_group_logits(rb, g + 1, ed, bias, out_row);
+                    epi_group_logits(rb, g + 1, out_c0, out_valid, bias, out_row);
                   }
                 } else if (after >= 0) {
                   tmem_ld16(acc + after * 16, ra);

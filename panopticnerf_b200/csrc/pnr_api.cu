@@ -133,18 +133,23 @@ struct Builder {
 
   // One GEMM step: acc[:, acc_col:acc_col+n_pad) = sum_seg A_seg * W_seg^T, then epilogue `ed`.
   // Issued as two N-halves (rows [0,n0) then [n0,n_pad)) when n_pad >= 64, each its own stage list.
-  bool add_step(std::vector<Seg> segs, int n_pad, int acc_col, EpiDesc ed, bool first_of_tile) {
+  // `segs_h1` + `n0_split`: the second half is a GEMM of its own (own matrices, rows counted from 0, own K range) -
+  // two small layers that share nothing but the step, e.g. the two logit layers (block-diagonal, zero blocks skipped).
+  bool add_step(std::vector<Seg> segs, int n_pad, int acc_col, EpiDesc ed, bool first_of_tile,
+                const std::vector<Seg>* segs_h1 = nullptr, int n0_split = 0) {
     if (prog.n_steps >= kMaxSteps) { err = "too many steps"; return false; }
-    const int n0 = n_pad >= 64 ? n_pad / 2 : n_pad;
+    const int n0 = n0_split > 0 ? n0_split : (n_pad >= 64 ? n_pad / 2 : n_pad);
     const int halves = n0 < n_pad ? 2 : 1;
     StepInfo info{prog.n_stages, 0, 0};
     bool emb_waited = false;
     for (int h = 0; h < halves; ++h) {
       const int r0 = h == 0 ? 0 : n0, r1 = h == 0 ? n0 : n_pad;
+      const std::vector<Seg>& hsegs = (h == 1 && segs_h1) ? *segs_h1 : segs;
+      const int mrow0 = (h == 1 && segs_h1) ? 0 : r0;     // first row of the half in its weight matrix
       const int half_first = prog.n_stages;
       if (h == 1) info.n0_stage = prog.n_stages;
-      for (size_t si = 0; si < segs.size(); ++si) {
-        const Seg& sg = segs[si];
+      for (size_t si = 0; si < hsegs.size(); ++si) {
+        const Seg& sg = hsegs[si];
         // K per stage: 64 with hi+lo images (x3), 128 with the hi image only (1-pass): <= 32 KB either way
         const int chunk = passes == 3 ? 64 : 128;
         for (int k0 = 0; k0 < sg.kpad; k0 += chunk) {
@@ -170,7 +175,7 @@ struct Builder {
             if (sg.kind == A_EMB && seg_last && sg.release && last_half) sd.flags |= F_RELEASE_EMB;
             if (sg.kind == A_DIR && seg_first && h == 0) sd.flags |= F_WAIT_DIR;
             if (sg.kind == A_DIR && seg_last && sg.release && last_half) sd.flags |= F_RELEASE_DIR;
-            for (int part = 0; part < parts; ++part) pack_stage(sg.m, r0, r1 - r0, sg.col0, sg.kvalid, k0, kcores, part);
+            for (int part = 0; part < parts; ++part) pack_stage(sg.m, mrow0, r1 - r0, sg.col0, sg.kvalid, k0, kcores, part);
           }
         }
       }
@@ -436,24 +441,6 @@ static int build_program(const pnr_config& c, const float* const* t, const int64
     }
     ok = bld.add_step(segs, W, kColAcc, ed, i == 0);
   }
-  // heads: hidden layer -> (upper half of the accumulator region) -> logits
-  auto add_head = [&](const Mat& m1, const float* b1, const Mat& m2, const float* b2, int nout, int out_off) {
-    EpiDesc e1{};
-    e1.kind = EPI_RELU_TO_A;
-    e1.dst_col = kColHeadHi;
-    e1.dst_lo_col = kColHeadLo;
-    e1.bias_off = (uint16_t)bld.add_consts(b1, W2, W2);
-    ok = ok && bld.add_step({seg_tmem(m1, 0, W, kColAHi, kColALo)}, W2, kColAcc, e1, false);
-    const int npad = round_up(nout, 16);
-    EpiDesc e2{};
-    e2.kind = EPI_LOGITS;
-    e2.n_valid = (uint16_t)nout;
-    e2.out_off = (uint16_t)out_off;
-    e2.bias_off = (uint16_t)bld.add_consts(b2, nout, npad);
-    ok = ok && bld.add_step({seg_tmem(m2, 0, W2, kColHeadHi, kColHeadLo)}, npad, kColAcc, e2, false);
-  };
-  if (ok && C > 0) add_head(m_s1, b_s1, m_s2, b_s2, C, 4);
-  if (ok && K > 0) add_head(m_i1, b_i1, m_i2, b_i2, K, 4 + C);
   // feature_linear has no activation, so it is folded into the view layer when the weights are loaded
   // (exact algebra, done in double):  W_view [feat ; gamma(d)] + b_view  with  feat = W_feat h + b_feat
   //   = (W_view[:, :W] W_feat) h + W_view[:, W:] gamma(d) + (W_view[:, :W] b_feat + b_view).
@@ -473,7 +460,7 @@ static int build_program(const pnr_config& c, const float* const* t, const int64
     fold_b[n_] = (float)accb;
   }
   const Mat m_fold{fold.data(), W2, W + Ed};
-  if (ok) {  // view branch [h, gamma(d)] -> relu -> rgb (CUDA cores) ; writes rgb + sigma
+  auto add_view = [&]() {  // view branch [h, gamma(d)] -> relu -> rgb (CUDA cores) ; writes rgb + sigma
     EpiDesc ed{};
     ed.kind = EPI_VIEW_RGB;
     ed.bias_off = (uint16_t)bld.add_consts(fold_b.data(), W2, W2);
@@ -484,7 +471,62 @@ static int build_program(const pnr_config& c, const float* const* t, const int64
     // (Accumulating the view step in the UPPER half of the accumulator region, so that the next tile's first layer
     // can be issued right behind the view MMAs, was measured: the stall only moves in front of the view step -
     // the tile boundary is bound by the serial epilogues of view + layer 0, 71.6 k vs 71.9 k cycles per tile.)
-    ok = bld.add_step(segs, W2, kColAcc, ed, false);
+    ok = ok && bld.add_step(segs, W2, kColAcc, ed, false);
+  };
+  // heads: hidden layer -> logits
+  auto add_head = [&](const Mat& m1, const float* b1, const Mat& m2, const float* b2, int nout, int out_off) {
+    EpiDesc e1{};
+    e1.kind = EPI_RELU_TO_A;
+    e1.dst_col = kColHeadHi;        // head hidden activations (K <= 128) live in the upper half of the
+    e1.dst_lo_col = kColHeadLo;     // accumulator region while it is free
+    e1.bias_off = (uint16_t)bld.add_consts(b1, W2, W2);
+    ok = ok && bld.add_step({seg_tmem(m1, 0, W, kColAHi, kColALo)}, W2, kColAcc, e1, false);
+    const int npad = round_up(nout, 16);
+    EpiDesc e2{};
+    e2.kind = EPI_LOGITS;
+    e2.n_valid = (uint16_t)nout;
+    e2.out_off = (uint16_t)out_off;
+    e2.bias_off = (uint16_t)bld.add_consts(b2, nout, npad);
+    ok = ok && bld.add_step({seg_tmem(m2, 0, W2, kColHeadHi, kColHeadLo)}, npad, kColAcc, e2, false);
+  };
+  std::vector<float> hid_w, hid_b;   // must outlive add_step (Mat holds a pointer)
+  if (C > 0 && K > 0 && 2 * W2 == W && W >= 128) {
+    // Both heads: the view step runs first (it is the last reader of the trunk output), then ONE W-wide hidden
+    // step computes both heads' hidden layers ([W_s1 ; W_i1], ReLU) in place of the trunk activations - a full-size
+    // layer at trunk efficiency instead of two N = W/2 steps whose halves are issue-bound - and ONE logits step whose
+    // halves are the two (block-diagonal) logit layers, zero blocks skipped: h0 = semantic logits from hidden
+    // columns [0, W/2), h1 = instance logits from [W/2, W).  Per tile: 11 steps instead of 13, and the serial chain
+    // hidden -> epilogue -> logits -> epilogue runs once, not twice (r2 timeline: ~30 k of a cfg3 tile's ~99 k
+    // cycles went into the two head chains for ~10 k cycles of tensor work).
+    add_view();
+    hid_w.resize((size_t)W * W);
+    hid_b.resize(W);
+    memcpy(hid_w.data(), m_s1.w, sizeof(float) * (size_t)W2 * W);
+    memcpy(hid_w.data() + (size_t)W2 * W, m_i1.w, sizeof(float) * (size_t)W2 * W);
+    memcpy(hid_b.data(), b_s1, sizeof(float) * W2);
+    memcpy(hid_b.data() + W2, b_i1, sizeof(float) * W2);
+    const Mat m_hid{hid_w.data(), W, W};
+    EpiDesc eh{};
+    eh.kind = EPI_RELU_TO_A;
+    eh.dst_col = kColAHi;
+    eh.dst_lo_col = kColALo;
+    eh.bias_off = (uint16_t)bld.add_consts(hid_b.data(), W, W);
+    ok = ok && bld.add_step({seg_tmem(m_hid, 0, W, kColAHi, kColALo)}, W, kColAcc, eh, false);
+    const int n_s = round_up(C, 16), n_i = round_up(K, 16);
+    EpiDesc el{};
+    el.kind = EPI_LOGITS;
+    el.n_valid = (uint16_t)C;
+    el.out_off = 4;
+    el.n_valid1 = (uint16_t)K;
+    el.out_off1 = (uint16_t)(4 + C);
+    el.bias_off = (uint16_t)bld.add_consts(b_s2, C, n_s);
+    bld.add_consts(b_i2, K, n_i);                         // contiguous: bias of column n_s + j
+    const std::vector<Seg> seg_i{seg_tmem(m_i2, 0, W2, kColAHi + W2 / 2, kColALo + W2 / 2)};
+    ok = ok && bld.add_step({seg_tmem(m_s2, 0, W2, kColAHi, kColALo)}, n_s + n_i, kColAcc, el, false, &seg_i, n_s);
+  } else {
+    if (ok && C > 0) add_head(m_s1, b_s1, m_s2, b_s2, C, 4);
+    if (ok && K > 0) add_head(m_i1, b_i1, m_i2, b_i2, K, 4 + C);
+    add_view();
   }
   if (!ok) return set_error(PNR_ERR_UNSUPPORTED, "pnr_load_weights: program build failed: %s", bld.err.c_str());
   if ((int)bld.consts.size() > kMaxConsts)

@@ -143,3 +143,24 @@ def test_flop_counts_match_baseline_md():
     assert O.mlp_flops_per_sample(make_cfg("cfg1")) == 55040
     assert O.mlp_flops_per_sample(make_cfg("cfg2")) == 1186816
     assert O.mlp_flops_per_sample(make_cfg("cfg3")) == 1345792
+
+
+def test_sample_pdf_sum_variant():
+    """VERDICT r1 (weak item 1): the oracle normalises the pdf by the running sum's last element (fully specified
+    order, what the kernel reproduces bit for bit); nerf-pytorch divides by torch.sum.  Both variants are kept.
+    They agree in every index except where u falls within an ulp of a cdf entry: count it, and bound it."""
+    g = torch.Generator().manual_seed(3)
+    R, N, Ni = 4000, 64, 128
+    z = torch.sort(torch.rand(R, N, generator=g) * 30 + 0.05, -1).values
+    w = torch.rand(R, N, generator=g) ** 4 * (torch.rand(R, N, generator=g) > 0.5)
+    bins, wi = 0.5 * (z[:, 1:] + z[:, :-1]), w[:, 1:-1]
+    za, ia = O.sample_pdf(bins, wi, Ni, det=True)
+    zb, ib = O.sample_pdf(bins, wi, Ni, det=True, pdf_norm="sum")
+    differ = int((ia != ib).sum())
+    assert differ <= 0.001 * ia.numel(), f"{differ} of {ia.numel()} searchsorted indices differ between the variants"
+    same = ia == ib
+    dz = (za[same] - zb[same]).abs()
+    # an ulp of the cdf is amplified by 1/(cdf[above]-cdf[below]) where a bin carries almost no mass
+    assert float(torch.quantile(dz, 0.999)) < 1e-3 and float(dz.max()) < 0.5
+    print(f"sample_pdf: {differ} of {ia.numel()} indices differ between pdf_norm='cumsum' and 'sum'; "
+          f"depths with equal index differ by at most {float(dz.max()):.2e} (99.9 %: {float(torch.quantile(dz, 0.999)):.2e})")

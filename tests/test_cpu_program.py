@@ -36,7 +36,7 @@ class IssueDesc(C.Structure):
 
 class EpiDesc(C.Structure):
     _fields_ = [("kind", C.c_uint8), ("sigma", C.c_uint8)] + [(k, C.c_uint16) for k in
-                ("n", "n0", "n_valid", "acc_col", "dst_col", "dst_lo_col", "bias_off", "aux_off", "out_off", "n1a")]
+                ("n", "n0", "n_valid", "acc_col", "dst_col", "dst_lo_col", "bias_off", "aux_off", "out_off", "out_off1", "n_valid1", "n1a")]
 
 
 class MlpProgram(C.Structure):
@@ -164,6 +164,8 @@ def replay(prog, w16, consts, cfg, pts, viewdirs, operand_precision: bool = Fals
             out[:, 3] = sig + consts[prog.sigma_bias_off]
         else:
             out[:, ed.out_off:ed.out_off + ed.n_valid] = v[:, :ed.n_valid]
+            if ed.n_valid1:        # the second half is a logit layer of its own (columns [n0, n))
+                out[:, ed.out_off1:ed.out_off1 + ed.n_valid1] = v[:, ed.n0:ed.n0 + ed.n_valid1]
     return out, stages_of
 
 
