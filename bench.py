@@ -365,18 +365,23 @@ def main():
     # With a fine pass the fine launch (N + Ni samples, heads) is the dominant one.
     z = out["z_vals"]
     Nz = z.shape[1]
+    # (the stand-alone launch materialises raw [R_m, Nz, 4+C+K]: a ray subset when that would exceed ~2 GB - a cfg5
+    #  frame's raw is 170 GB - still hundreds of tiles per SM)
+    raw_per_ray = Nz * (4 + cfg.num_classes + cfg.num_instances) * 4
+    R_m = R if R * raw_per_ray <= (4 << 30) else max(1, (2 << 30) // raw_per_ray)
+    m_rays, m_z = batch["rays"][:R_m].contiguous(), z[:R_m].contiguous()
     mlp_ms = []
     for i in range(3 + min(args.steps, 10)):
         flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        net.forward_rays(batch["rays"], z)
+        net.forward_rays(m_rays, m_z)
         b.record()
         torch.cuda.synchronize()
         if i >= 3:
             mlp_ms.append(a.elapsed_time(b))
     clocks = sampler.stop()
-    mlp_t = sum(mlp_ms) / len(mlp_ms)
+    mlp_t = sum(mlp_ms) / len(mlp_ms) * (R / R_m)          # scaled to the rank's whole share when a subset was timed
     pk = peaks()
     alg_flop = flops_per_sample(cfg) * R * Nz
     achieved = alg_flop / (mlp_t / 1e3) / 1e12
@@ -396,6 +401,7 @@ def main():
                 "peak_source": f"bf16_tflops_sustained, {pk['_src']}", "kernel_ms": mlp_t,
                 "kernel_share_of_step": min(1.0, mlp_per_step / (total_ms / args.steps)),
                 "alg_flop_per_launch": alg_flop, "samples_per_launch": R * Nz,
+                "timed_on_rays": R_m,
                 "passes": 3 if args.precision.endswith("x3") else 1,
                 "executed_flop_per_launch_one_pass": (flops_per_sample(cfg) - 2 * cfg.W * cfg.W) * R * Nz,
                 "note": "achieved = the reference network's algorithmic FLOPs (true layer shapes, 1 pass) / time; "

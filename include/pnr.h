@@ -163,6 +163,18 @@ int pnr_label_tiles(const float* rgb_map, const float* depth_map, const float* s
                     const float* instance_map, int64_t R, int32_t C, int32_t K, uint8_t* rgb8,
                     float* depth_out, int16_t* sem_label, int16_t* inst_label, void* stream);
 
+/* a8 + a9 in ONE kernel: Network.forward with the compositing done in the MLP's epilogue - per-sample alpha /
+ * transmittance / weight right after the sigma-producing layer, colours and logits reduced on chip per ray - so the
+ * network outputs `raw` [R,N,4+C+K] (456 B per sample with both heads) are never written to memory; only
+ * out->weights [R,N] (REQUIRED) and the per-ray maps leave the SM.  Same maps as pnr_mlp_forward + pnr_composite
+ * (weights bit-identical, sums in a different but fixed order); fixed_* maps come from the weights and the id
+ * tables (a small second kernel).  Needs N % 32 == 0 and rays mode; sem_softmax is not available here
+ * (PNR_ERR_UNSUPPORTED: use the two-call path). */
+int pnr_mlp_composite(pnr_ctx* ctx, const float* rays, const float* z, int64_t R, int32_t N,
+                      int32_t white_bkgd, int32_t mask_outside, const int32_t* sample_box,
+                      const int32_t* box_sem, const int32_t* box_inst, int32_t B,
+                      const pnr_composite_out* out, void* stream);
+
 /* a9 backward (first stage of the backward chain): d(loss)/d(raw) [R,N,4+C+K] from the
  * gradients of the composited maps (any pointer may be NULL = zero gradient; disp_map is not differentiated).
  * Same arguments as pnr_composite.  sem_softmax != 0 returns PNR_ERR_UNSUPPORTED. */

@@ -10,6 +10,9 @@ namespace pnr {
 
 int set_error(int code, const char* fmt, ...);   // stores a thread-local message, returns code
 void count_launch(int n = 1);
+// fixed (bounding-box) one-hot maps from per-sample weights (stream_kernels.cu; used by pnr_mlp_composite)
+int launch_fixed_maps(const float* weights, const int32_t* sample_box, const int32_t* box_sem, const int32_t* box_inst,
+                      int64_t R, int N, int C, int K, int B, float* fsem, float* finst, cudaStream_t stream);
 // pnr_sample_pdf with an explicit row stride for u (ray_kernels.cu; used by pnr_render_fused)
 int sample_pdf_strided(const float* z, const float* weights, int64_t R, int32_t N, int32_t Ni, const float* u,
                        int64_t u_stride, float* z_fine, int64_t* idx, float* z_all, void* stream);

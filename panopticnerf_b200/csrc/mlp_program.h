@@ -127,6 +127,18 @@ struct MlpParams {
   int32_t num_tiles;
   uint32_t* status;       // sticky device word: bit 0 = a non-finite / out-of-range activation was seen (may be null)
   long long* dbg;         // optional clock64 timeline of block 0 (development aid), else null
+  // ---- compositing epilogue (COMPOSITE kernels only: rays mode, N % 32 == 0; `raw` is not written)
+  int64_t rays_per_cta;   // every CTA owns a contiguous range of whole rays (carries stay on chip)
+  const int32_t* sample_box;   // [S] primitive id per sample, or null (only read when mask_outside)
+  int32_t mask_outside, white_bkgd;
+  int32_t C, K;           // semantic / instance channels of the network
+  float* weights;         // [S]   per-sample compositing weights (always written)
+  float* rgb_map;         // [R,3] nullable, like the rest
+  float* depth_map;       // [R]
+  float* acc_map;         // [R]
+  float* disp_map;        // [R]
+  float* sem_map;         // [R,C]
+  float* inst_map;        // [R,K]
 };
 
 // What a launch carries: arguments + the context's program, as ONE __grid_constant__ kernel parameter.
@@ -140,6 +152,15 @@ constexpr int kSmemConsts = kSmemProg;   // (the program itself is in the kernel
 constexpr int kSmemPart = kSmemConsts + kMaxConsts * 4;      // [kEpiWarps/4][128][4] floats
 constexpr int kSmemBars = kSmemPart + (kEpiWarps / 4) * kTileM * 4 * 4;
 constexpr int kSmemTotal = kSmemBars + 256;
-static_assert(kSmemTotal <= 232448, "shared-memory map exceeds the 227 KB per-CTA limit");
+// compositing epilogue: weights of the tile's rows, per-quarter transmittance products and the carried transmittance
+// (double-buffered by tile parity), per-quarter partial sums of every composited channel (double-buffered)
+constexpr int kCompMaxCh = 5 + 128 + 128;                       // rgb(3) depth acc + C + K
+constexpr int kCompChPad = (kCompMaxCh + 31) / 32 * 32;         // 288
+constexpr int kSmemCompW = kSmemTotal;                          // float w_row[128]
+constexpr int kSmemCompQ = kSmemCompW + kTileM * 4;             // float qprod[2][4]; float carry[2]; (64 bytes)
+constexpr int kSmemCompS = kSmemCompQ + 64;                     // float qsum[2][4][kCompChPad]
+constexpr int kSmemCompR = kSmemCompS + 2 * 4 * kCompChPad * 4; // float racc[kCompChPad]: running sums of the open ray
+constexpr int kSmemTotalComp = kSmemCompR + kCompChPad * 4;
+static_assert(kSmemTotalComp <= 232448, "shared-memory map exceeds the 227 KB per-CTA limit");
 
 }  // namespace pnr

@@ -36,6 +36,7 @@
 #include <cstddef>
 #include <mutex>
 #include "common.cuh"
+#include "composite_math.cuh"
 #include "mlp_program.h"
 #include "tc05.cuh"
 
@@ -152,6 +153,42 @@ __device__ __forceinline__ void epi_group_logits(const uint32_t (&r)[16], int g,
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Compositing epilogue building blocks (COMP kernels).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum32(float v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+// x[j] = this lane's (= this sample's) value of column j.  Returns the sum over the 32 lanes of column
+// comp_col_of_lane(lane), by a fixed exchange tree (16 shuffles): lanes swap the half of the columns they give up.
+__device__ __forceinline__ float comp_reduce16(const float (&x)[16], int lane) {
+  float y[8], z[4], u[2];
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) y[j] = (b4 ? x[j + 8] : x[j]) + __shfl_xor_sync(0xffffffffu, b4 ? x[j] : x[j + 8], 16);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) z[j] = (b3 ? y[j + 4] : y[j]) + __shfl_xor_sync(0xffffffffu, b3 ? y[j] : y[j + 4], 8);
+#pragma unroll
+  for (int j = 0; j < 2; ++j) u[j] = (b2 ? z[j + 2] : z[j]) + __shfl_xor_sync(0xffffffffu, b2 ? z[j] : z[j + 2], 4);
+  float v = (b1 ? u[1] : u[0]) + __shfl_xor_sync(0xffffffffu, b1 ? u[0] : u[1], 2);
+  return v + __shfl_xor_sync(0xffffffffu, v, 1);
+}
+__device__ __forceinline__ int comp_col_of_lane(int lane) { return (lane >> 1) & 15; }   // 8*b4 + 4*b3 + 2*b2 + b1
+
+// logits of one 16-column group, weighted by this sample's compositing weight and summed over the warp's 32 samples
+// (one aligned group of a ray); the even lanes write the per-quarter partial sums.
+__device__ __forceinline__ void epi_group_logits_comp(const uint32_t (&r)[16], int g, int c0, int n_valid, int ch_base,
+                                                      const float* bias, float w, int lane, float* qsum_q) {
+  float x[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) x[j] = w * (__uint_as_float(r[j]) + bias[g * 16 + j]);
+  const float tot = comp_reduce16(x, lane);
+  const int ch = g * 16 + comp_col_of_lane(lane) - c0;
+  if ((lane & 1) == 0 && ch < n_valid) qsum_q[ch_base + ch] = tot;
+}
+
 // Bit pattern of +inf in the operand format: a hi part >= this is an overflowed (or NaN) activation.
 template <int FMT>
 __device__ __forceinline__ constexpr uint32_t inf_bits16() {
@@ -161,7 +198,14 @@ __device__ __forceinline__ constexpr uint32_t inf_bits16() {
 // CTAs run as clusters of two that stream the SAME weight stages in lock step: each CTA fetches half of every
 // stage from L2 and multicasts it into both shared memories, halving L2 -> SM weight traffic (ncu: lts
 // throughput 28 % -> 16 %; the kernel time did not change - the weight stream is not what bounds it).
-template <int PASSES, int FMT>
+//
+// COMP = false: tiles are dealt round-robin to the CTAs and the network outputs go to `raw`.
+// COMP = true : every CTA owns a contiguous range of whole rays and walks it tile by tile; the epilogue warps
+// composite on chip - per-sample alpha / transmittance / weight right after the sigma-producing layer (warp scan
+// over aligned groups of 32 samples, carried across groups, tiles and warps through shared memory), logits and
+// colours reduced per group with a fixed shuffle tree and accumulated per ray in ray order - and only weights and
+// the per-ray maps leave the SM: `raw` (456 B per sample with both heads) is never written.
+template <int PASSES, int FMT, bool COMP>
 __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kMlpThreads, 1)
 mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -171,7 +215,19 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
   const uint32_t cta_rank = cluster_ctarank();
   // every CTA runs the same number of tile iterations (tiles past the end are dummies whose stores are
   // masked) so that both CTAs of a cluster consume the shared weight stream the same number of times
-  const int tile_end = (int)(((p.num_tiles + (int)gridDim.x - 1) / (int)gridDim.x) * (int)gridDim.x);
+  const int n_iter = COMP ? (int)((p.rays_per_cta * p.N + kTileM - 1) / kTileM)
+                          : (p.num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  // first sample of this CTA's tile `it`, and the end of the samples it owns (nothing 64-bit is kept live in the
+  // round-robin variant: everything is recomputed from blockIdx / gridDim / launch constants)
+  auto cta_first = [&]() -> int64_t { return COMP ? (int64_t)blockIdx.x * p.rays_per_cta * p.N : 0; };
+  auto tile_base = [&](int it) -> int64_t {
+    return COMP ? cta_first() + (int64_t)it * kTileM : (int64_t)((int)blockIdx.x + it * (int)gridDim.x) * kTileM;
+  };
+  auto cta_end = [&]() -> int64_t {
+    if (!COMP) return p.S;
+    const int64_t e = cta_first() + p.rays_per_cta * p.N;
+    return e < p.S ? e : p.S;
+  };
 
   float* consts = reinterpret_cast<float*>(smem + kSmemConsts);
   float* part = reinterpret_cast<float*>(smem + kSmemPart);  // [2][128][4]
@@ -230,9 +286,26 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
     const uint32_t tmem_lane = tmem + ((uint32_t)(q * 32) << 16);
     uint32_t gstep = 0;
     uint32_t vmax = 0;                          // largest hi-part bit patterns this thread produced (16x2)
-    for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
-      const int64_t s = (int64_t)tile * kTileM + row;
-      const bool valid = s < p.S;
+    // compositing state (COMP): see mlp_program.h for the shared-memory map
+    float* w_row = reinterpret_cast<float*>(smem + kSmemCompW);
+    float* qprod = reinterpret_cast<float*>(smem + kSmemCompQ);   // [2][4]
+    float* carry = qprod + 8;                                       // [2]
+    float* qsum = reinterpret_cast<float*>(smem + kSmemCompS);     // [2][4][kCompChPad]
+    float* racc = reinterpret_cast<float*>(smem + kSmemCompR);     // [kCompChPad]
+    const int nch = 5 + p.C + p.K;
+    if (COMP) {
+      for (int c = threadIdx.x; c < kCompChPad; c += kEpiWarps * 32) racc[c] = 0.f;
+      if (threadIdx.x == 0) carry[0] = 1.0f;
+      named_bar_sync(2, kEpiWarps * 32);
+    }
+    for (int it = 0; it < n_iter; ++it) {
+      const int64_t s_base = tile_base(it);
+      const int64_t s = s_base + row;
+      const int64_t s_end = cta_end();
+      const bool valid = s < s_end;
+      const int par = it & 1;
+      float* qsum_q = qsum + (par * 4 + q) * kCompChPad;             // this quarter's partial sums of this tile
+      float w_mine = 0.f;                                            // this row's compositing weight (COMP)
       float sig = 0.f;
       for (int st = 0; st < n_steps; ++st, ++gstep) {
         const EpiDesc ed = prog.ep[st];
@@ -245,7 +318,7 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
 #ifdef PNR_TIMELINE
-          const bool rec = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && tile == 2 * (int)gridDim.x;
+          const bool rec = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && it == 2;
           if (rec) p.dbg[4096 + (st * 2 + h) * 3 + 0] = clock64();
 #endif
           // column blocks (in 16-column groups) of this half: part a = [pa0, pa1), part b = [pa1, pb1) (E1 only)
@@ -274,6 +347,7 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
           const bool own_half = h == 1 && ed.n_valid1 > 0;
           float* out_row = raw_row + (own_half ? ed.out_off1 : ed.out_off);
           const int out_c0 = own_half ? (int)ed.n0 : 0, out_valid = own_half ? (int)ed.n_valid1 : (int)ed.n_valid;
+          const int out_ch = (own_half ? (int)ed.out_off1 : (int)ed.out_off) + 1;   // composited channel of column out_c0
           // software pipeline: the load of the next group is in flight while a group is processed - also across
           // the part boundary, so signalling part a does not restart the load pipeline
           uint32_t ra[16], rb[16];
@@ -320,6 +394,8 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
                 if (two) tmem_ld16(acc + (g + 1) * 16, rb);
                 if (ed.kind == EPI_VIEW_RGB) {
                   epi_group_rgb(ra, g, ed, bias, aux, c0, c1, c2);
+                } else if (COMP) {
+                  epi_group_logits_comp(ra, g, out_c0, out_valid, out_ch, bias, w_mine, lane, qsum_q);
                 } else if (valid) {
                   epi_group_logits(ra, g, out_c0, out_valid, bias, out_row);
                 }
@@ -328,6 +404,8 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
                   if (after >= 0) tmem_ld16(acc + after * 16, ra);
                   if (ed.kind == EPI_VIEW_RGB) {
                     epi_group_rgb(rb, g + 1, ed, bias, aux, c0, c1, c2);
+                  } else if (COMP) {
+                    epi_group_logits_comp(rb, g + 1, out_c0, out_valid, out_ch, bias, w_mine, lane, qsum_q);
                   } else if (valid) {
                     epi_group_logits(rb, g + 1, out_c0, out_valid, bias, out_row);
                   }
@@ -347,7 +425,7 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
               float* mine = part + (ch * kTileM + row) * 4;
               mine[0] = c0; mine[1] = c1; mine[2] = c2;
               named_bar_sync(1, kEpiWarps * 32);
-              if (ch == 0 && valid) {
+              if (ch == 0 && (COMP || valid)) {
                 const float* b3 = consts + prog.rgb_bias_off;
                 float o0 = c0, o1 = c1, o2 = c2, o3 = mine[3];
 #pragma unroll
@@ -356,11 +434,18 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
                   o0 += other[0]; o1 += other[1]; o2 += other[2]; o3 += other[3];
                 }
                 o0 += b3[0]; o1 += b3[1]; o2 += b3[2]; o3 += consts[prog.sigma_bias_off];
-                float* dst = p.raw + s * p.CH;
-                if (p.CH == 4) {
-                  *reinterpret_cast<float4*>(dst) = make_float4(o0, o1, o2, o3);
+                if (COMP) {   // colours weighted and summed over this aligned group of 32 samples (w = 0 on dummy rows)
+                  const float r0 = warp_sum32(w_mine * comp_sigmoid(o0));
+                  const float r1 = warp_sum32(w_mine * comp_sigmoid(o1));
+                  const float r2 = warp_sum32(w_mine * comp_sigmoid(o2));
+                  if (lane == 0) { qsum_q[0] = r0; qsum_q[1] = r1; qsum_q[2] = r2; }
                 } else {
-                  dst[0] = o0; dst[1] = o1; dst[2] = o2; dst[3] = o3;
+                  float* dst = p.raw + s * p.CH;
+                  if (p.CH == 4) {
+                    *reinterpret_cast<float4*>(dst) = make_float4(o0, o1, o2, o3);
+                  } else {
+                    dst[0] = o0; dst[1] = o1; dst[2] = o2; dst[3] = o3;
+                  }
                 }
               }
             }
@@ -369,6 +454,91 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
 #ifdef PNR_TIMELINE
           if (rec) p.dbg[4096 + (st * 2 + h) * 3 + 2] = clock64();
 #endif
+        }
+        if (COMP && ed.sigma) {
+          // ---- per-sample weights of this tile, right after the sigma-producing layer handed over (the MMAs go on
+          // with the view / head steps meanwhile).  sigma = the two column shares' partial dot products + bias, in
+          // the order the raw-writing kernel uses.  One warp per lane quarter = one aligned group of 32 samples.
+          named_bar_sync(2, kEpiWarps * 32);            // both shares of every row's sigma are in shared memory
+          if (ch == 0) {
+            const int64_t sq = s_base + q * 32;         // first sample of this quarter; live or dummy as a whole
+            const bool live = sq < s_end;
+            float alpha = 0.f, zi = 0.f, t = 1.0f;
+            if (live) {
+              const int64_t r = sq / p.N;
+              const int i = (int)(sq - r * p.N) + lane;
+              zi = p.z[sq + lane];
+              const bool has_next = i + 1 < p.N;
+              const float z_next = has_next ? p.z[sq + lane + 1] : 0.f;
+              const float* rr = p.rays + r * 6;
+              const float dist = comp_dist(zi, z_next, has_next, comp_dnorm(rr[3], rr[4], rr[5]));
+              float sraw = part[row * 4 + 3];
+              sraw += part[(kTileM + row) * 4 + 3];
+              sraw += consts[prog.sigma_bias_off];
+              const bool masked = p.mask_outside && p.sample_box != nullptr && p.sample_box[sq + lane] < 0;
+              alpha = comp_alpha(sraw, dist, masked);
+              t = 1.0f - alpha + 1e-10f;
+            }
+            float total;
+            const float excl = comp_scan32(t, lane, &total);
+            if (lane == 0) qprod[par * 4 + q] = total;
+            named_bar_sync(3, 4 * 32);                  // the four quarter products
+            // transmittance at this quarter's first sample: carried in from the previous tile, restarted where a
+            // ray starts, multiplied through the earlier quarters in order (the order is fixed by the sample index)
+            float prefix = carry[par];
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+              if (qq <= q) {
+                if ((s_base + 32 * qq) % p.N == 0) prefix = 1.0f;
+                if (qq < q) prefix *= qprod[par * 4 + qq];
+              }
+            }
+            const float wi = live ? alpha * (prefix * excl) : 0.f;
+            w_row[row] = wi;
+            if (live) p.weights[sq + lane] = wi;
+            const float sd = warp_sum32(wi * zi), sa = warp_sum32(wi);
+            if (lane == 0) {
+              qsum_q[3] = sd;
+              qsum_q[4] = sa;
+              if (q == 3) carry[par ^ 1] = prefix * total;   // transmittance behind the tile's last sample
+            }
+          }
+          named_bar_sync(2, kEpiWarps * 32);            // w_row is visible to both column shares
+          w_mine = w_row[row];
+        }
+      }
+      if (COMP) {
+        // ---- end of tile: fold this tile's per-quarter sums into the running sums of the open ray, in ray order;
+        // a ray is written out when the next one starts (or the CTA's range ends).  One warp, lanes stride channels.
+        named_bar_sync(2, kEpiWarps * 32);              // every quarter's partial sums are in shared memory
+        if (warp == 0) {
+          auto flush = [&](int64_t r) {
+            const float depth = racc[3], acc = racc[4];
+            __syncwarp();
+            for (int c = lane; c < nch; c += 32) {
+              const float v = racc[c];
+              if (c < 3) { if (p.rgb_map) p.rgb_map[r * 3 + c] = v + (p.white_bkgd ? (1.0f - acc) : 0.f); }
+              else if (c == 3) {
+                if (p.depth_map) p.depth_map[r] = v;
+                if (p.disp_map) p.disp_map[r] = comp_disp(depth, acc);
+              }
+              else if (c == 4) { if (p.acc_map) p.acc_map[r] = v; }
+              else if (c < 5 + p.C) { if (p.sem_map) p.sem_map[r * p.C + (c - 5)] = v; }
+              else { if (p.inst_map) p.inst_map[r * p.K + (c - 5 - p.C)] = v; }
+              racc[c] = 0.f;
+            }
+            __syncwarp();
+          };
+#pragma unroll 1
+          for (int qq = 0; qq < 4; ++qq) {
+            const int64_t sq = s_base + 32 * qq;
+            if (sq >= s_end) break;
+            if (sq > cta_first() && sq % p.N == 0) flush(sq / p.N - 1);    // the previous ray ended right before sq
+            const float* src = qsum + (par * 4 + qq) * kCompChPad;
+            for (int c = lane; c < nch; c += 32) racc[c] += src[c];
+            __syncwarp();
+          }
+          if (s_base < s_end && s_base + kTileM >= s_end) flush(s_end / p.N - 1);   // the CTA's last ray
         }
       }
     }
@@ -380,9 +550,8 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
     uint8_t* emb_hi = smem + kSmemEmb;
     uint8_t* emb_lo = emb_hi + kEmbPartBytes;
     const int Lx = prog.Lx, Ld = prog.Ld;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
-      int64_t s = (int64_t)tile * kTileM + row;
+    for (int it = 0; it < n_iter; ++it) {
+      int64_t s = tile_base(it) + row;
       if (s >= p.S) s = p.S - 1;  // clamp: tail rows compute on a valid sample, results are discarded
       float x[3], d[3];
       if (p.pts != nullptr) {
@@ -419,13 +588,13 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
     // =============================================================== TMA producer (one elected thread)
     if (elect_one()) {
       uint32_t gs = 0;  // global stage counter
-      for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
+      for (int it = 0; it < n_iter; ++it) {
         for (int si = 0; si < n_stages; ++si, ++gs) {
           const uint32_t slot = gs % kRing, ph = (gs / kRing) & 1;
           const uint32_t gofs = prog.st[si].gofs, bytes = prog.st[si].bytes;
           mbar_wait_backoff(bar_empty + 8 * slot, ph ^ 1);
 #ifdef PNR_TIMELINE
-          if (p.dbg != nullptr && blockIdx.x == 0 && tile == 2 * (int)gridDim.x) p.dbg[6144 + si] = clock64();
+          if (p.dbg != nullptr && blockIdx.x == 0 && it == 2) p.dbg[6144 + si] = clock64();
 #endif
           // our barrier expects the whole stage; we fetch our 1/kClusterSize of it and multicast that part into
           // every CTA of the cluster (same shared-memory offset, same barrier offset in each of them)
@@ -458,8 +627,7 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
           }
         }
       };
-      int it = 0;
-      for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
+      for (int it = 0; it < n_iter; ++it) {
         const int b = it & 1;
         const uint32_t step_base = (uint32_t)(it * n_steps) - 1u;   // needs are stored + 1
         uint32_t needs = prog.is[0].needs;
@@ -497,12 +665,11 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
     // stage also covers the stages the other warp issued for it (hardware assumption).
     const uint32_t me = (warp == kEpiWarps + kProWarps + 1) ? 0u : 1u;
     uint32_t gs = 0, ready = 0, slot = 0, issued = 0;
-    int it = 0;
     // (address field only: in a cluster the shared-window address of CTA rank > 0 carries the rank above it)
     const uint32_t ring16 = (smem_u32(smem + kSmemRing) >> 4) & 0x3FFFu;
     const uint32_t emb_hi = smem_u32(smem + kSmemEmb);
     constexpr uint32_t kFullK = PASSES == 3 ? 4u : 8u;   // K16 steps of a full stage
-    for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
+    for (int it = 0; it < n_iter; ++it) {
       const int b = it & 1;
       const uint32_t dir_hi = smem_u32(smem + kSmemDir + b * 2 * kDirPartBytes);
 #pragma unroll 1
@@ -616,30 +783,32 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
 // Per-device launch state: the > 48 KB dynamic shared-memory opt-in is a per-device function attribute, and so
 // is the SM count the persistent grid is sized by.
 struct DeviceState {
-  bool attr_done[2][2] = {{false, false}, {false, false}};
-  int sms = 0;
+  bool attr_done[2][2][2] = {};
 };
 static DeviceState g_dev[kMaxDevices];
 static std::mutex g_dev_mutex;
 
-template <int PASSES, int FMT>
+template <int PASSES, int FMT, bool COMP>
 static int launch_one(const MlpLaunch& L, int dev, int grid, cudaStream_t stream) {
+  constexpr int kSmem = COMP ? kSmemTotalComp : kSmemTotal;
   {
     std::lock_guard<std::mutex> lock(g_dev_mutex);
-    bool& done = g_dev[dev].attr_done[PASSES == 3][FMT == kFmtBF16];
+    bool& done = g_dev[dev].attr_done[PASSES == 3][FMT == kFmtBF16][COMP];
     if (!done) {
-      PNR_CUDA(cudaFuncSetAttribute(mlp_fused_kernel<PASSES, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    kSmemTotal));
+      PNR_CUDA(cudaFuncSetAttribute(mlp_fused_kernel<PASSES, FMT, COMP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kSmem));
       done = true;
     }
   }
-  mlp_fused_kernel<PASSES, FMT><<<grid, kMlpThreads, kSmemTotal, stream>>>(L);
+  mlp_fused_kernel<PASSES, FMT, COMP><<<grid, kMlpThreads, kSmem, stream>>>(L);
   PNR_LAUNCH_CHECK("mlp_fused_kernel");
   return PNR_OK;
 }
 
-// Launches on the CURRENT device (the caller has made the context's device current).
-int launch_mlp(const MlpLaunch& L, int passes, int fmt, cudaStream_t stream) {
+// Launches on the CURRENT device (the caller has made the context's device current).  `composite`: the
+// compositing-epilogue variant; the launch's rays_per_cta is set here (whole rays per CTA, a multiple of the
+// 128 / gcd(N, 128) rays that make whole tiles, so that every CTA's range starts on a 32-sample boundary).
+int launch_mlp(MlpLaunch& L, int passes, int fmt, bool composite, cudaStream_t stream) {
   int dev = 0;
   PNR_CUDA(cudaGetDevice(&dev));
   PNR_CHECK_ARG(dev >= 0 && dev < kMaxDevices, "launch_mlp: device ordinal %d >= %d", dev, kMaxDevices);
@@ -648,8 +817,14 @@ int launch_mlp(const MlpLaunch& L, int passes, int fmt, cudaStream_t stream) {
   if (grid <= 0) return PNR_OK;
   grid = (grid + kClusterSize - 1) / kClusterSize * kClusterSize;   // whole clusters (spare CTAs run dummy tiles)
   if (grid > sms) grid = sms / kClusterSize * kClusterSize;
-  if (fmt == kFmtF16) return passes == 3 ? launch_one<3, kFmtF16>(L, dev, grid, stream) : launch_one<1, kFmtF16>(L, dev, grid, stream);
-  return passes == 3 ? launch_one<3, kFmtBF16>(L, dev, grid, stream) : launch_one<1, kFmtBF16>(L, dev, grid, stream);
+  if (composite) {
+    const int64_t R = L.p.S / L.p.N;
+    L.p.rays_per_cta = (R + grid - 1) / grid;
+  }
+#define PNR_LAUNCH(P, F) (composite ? launch_one<P, F, true>(L, dev, grid, stream) : launch_one<P, F, false>(L, dev, grid, stream))
+  if (fmt == kFmtF16) return passes == 3 ? PNR_LAUNCH(3, kFmtF16) : PNR_LAUNCH(1, kFmtF16);
+  return passes == 3 ? PNR_LAUNCH(3, kFmtBF16) : PNR_LAUNCH(1, kFmtBF16);
+#undef PNR_LAUNCH
 }
 
 }  // namespace pnr

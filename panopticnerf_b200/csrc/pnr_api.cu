@@ -24,7 +24,7 @@ int set_error(int code, const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches += n; }
 
-int launch_mlp(const MlpLaunch& L, int passes, int fmt, cudaStream_t stream);  // mlp_tc05.cu
+int launch_mlp(MlpLaunch& L, int passes, int fmt, bool composite, cudaStream_t stream);  // mlp_tc05.cu
 
 }  // namespace pnr
 
@@ -623,7 +623,44 @@ static int mlp_forward_impl(pnr_ctx* ctx, const float* pts, const float* viewdir
   p.status = ctx->d_status;
   p.dbg = dbg;
   DeviceGuard guard(ctx->cfg.device);   // launch on the context's device whatever the caller's current one is
-  return launch_mlp(ctx->launch, ctx->passes, ctx->fmt, (cudaStream_t)stream);
+  return launch_mlp(ctx->launch, ctx->passes, ctx->fmt, false, (cudaStream_t)stream);
+}
+
+extern "C" int pnr_mlp_composite(pnr_ctx* ctx, const float* rays, const float* z, int64_t R, int32_t N,
+                                 int32_t white_bkgd, int32_t mask_outside, const int32_t* sample_box,
+                                 const int32_t* box_sem, const int32_t* box_inst, int32_t B,
+                                 const pnr_composite_out* out, void* stream) {
+  if (R == 0) return PNR_OK;
+  PNR_CHECK_ARG(ctx && rays && z && out, "pnr_mlp_composite: null pointer");
+  if (!ctx->loaded) return set_error(PNR_ERR_STATE, "pnr_mlp_composite: pnr_load_weights has not been called");
+  PNR_CHECK_ARG(R > 0 && N >= 1, "pnr_mlp_composite: bad sizes R=%lld N=%d", (long long)R, N);
+  if (N % 32 != 0)
+    return set_error(PNR_ERR_UNSUPPORTED, "pnr_mlp_composite: N=%d is not a multiple of 32 (use pnr_mlp_forward + pnr_composite)", N);
+  PNR_CHECK_ARG(out->weights, "pnr_mlp_composite: out->weights is required");
+  PNR_CHECK_ARG(!mask_outside || sample_box, "pnr_mlp_composite: mask_outside needs sample_box");
+  const int C = ctx->cfg.num_classes, K = ctx->cfg.num_instances;
+  const int64_t S = R * (int64_t)N;
+  PNR_CHECK_ARG((S + kTileM - 1) / kTileM < (int64_t)1 << 31, "pnr_mlp_composite: too many samples");
+  MlpParams& p = ctx->launch.p;
+  p.wpacked = ctx->d_wpacked; p.consts = ctx->d_consts;
+  p.pts = nullptr; p.viewdirs = nullptr; p.rays = rays; p.z = z;
+  p.S = S; p.N = N; p.CH = 4 + C + K; p.raw = nullptr;
+  p.num_tiles = (int32_t)((S + kTileM - 1) / kTileM);
+  p.status = ctx->d_status;
+  p.dbg = nullptr;
+  p.sample_box = sample_box; p.mask_outside = mask_outside; p.white_bkgd = white_bkgd;
+  p.C = C; p.K = K;
+  p.weights = out->weights; p.rgb_map = out->rgb_map; p.depth_map = out->depth_map; p.acc_map = out->acc_map;
+  p.disp_map = out->disp_map; p.sem_map = C > 0 ? out->semantic_map : nullptr; p.inst_map = K > 0 ? out->instance_map : nullptr;
+  DeviceGuard guard(ctx->cfg.device);
+  if (const int rc = launch_mlp(ctx->launch, ctx->passes, ctx->fmt, true, (cudaStream_t)stream)) return rc;
+  const bool fs = C > 0 && out->fixed_semantic_map && sample_box && box_sem;
+  const bool fi = K > 0 && out->fixed_instance_map && sample_box && box_inst;
+  if (fs || fi)
+    return launch_fixed_maps(out->weights, sample_box, box_sem, box_inst, R, N, C, K, B,
+                             fs ? out->fixed_semantic_map : nullptr, fi ? out->fixed_instance_map : nullptr,
+                             (cudaStream_t)stream);
+  return PNR_OK;
 }
 
 namespace pnr {

@@ -2,6 +2,7 @@
 // C-ABI call.  The host side only sequences the stage kernels of this library over ray chunks; the chunk size
 // follows from the caller's workspace, so the one large intermediate - raw [chunk, N+Ni, 4+C+K] - is bounded
 // (~1.5 GB at the default workspace) instead of being materialised for the whole frame (46 GB at config 3).
+#include <cstdlib>
 #include <cstring>
 #include "common.cuh"
 #include "ray_math.h"   // PNR_MAX_HITS
@@ -21,25 +22,37 @@ inline size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
 // Per-ray scratch layout of one chunk.  `have_*`: the caller supplies the full-frame array, no scratch needed.
 struct Layout {
   int N, Ni, Nt, CH, M;
-  bool boxes, have_z, have_z0, have_w0, have_sb, have_hits, have_nf;
-  size_t raw, z0, zall, w0, sb, near, far, hit, bid, tin, tout;   // bytes per ray
-  size_t per_ray() const { return raw + z0 + zall + w0 + sb + near + far + hit + bid + tin + tout; }
+  bool boxes, have_z, have_z0, have_w0, have_w1, have_sb, have_hits, have_nf;
+  bool comp0, comp1;   // the pass runs as ONE kernel (MLP with compositing epilogue): no raw
+  size_t raw, z0, zall, w0, w1, sb, near, far, hit, bid, tin, tout;   // bytes per ray
+  size_t per_ray() const { return raw + z0 + zall + w0 + w1 + sb + near + far + hit + bid + tin + tout; }
 };
+
+// the compositing epilogue needs aligned groups of 32 samples per ray and composites logits, not softmax(logits)
+inline bool comp_ok(int n_samples, const pnr_render_args* a) {
+  static const bool off = getenv("PNR_NO_COMP") != nullptr;   // tuning aid: force the two-kernel path
+  return !off && n_samples % 32 == 0 && (!a || !a->sem_softmax);
+}
 
 Layout make_layout(int N, int Ni, int CH, int M, bool boxes, const pnr_render_args* a) {
   Layout L{};
   L.N = N; L.Ni = Ni; L.Nt = N + Ni; L.CH = CH; L.M = M; L.boxes = boxes;
   const bool fine = Ni > 0;
+  L.comp0 = comp_ok(N, a);
+  L.comp1 = fine ? comp_ok(N + Ni, a) : L.comp0;
+  L.have_w1 = a && a->out.weights;
   L.have_z = a && a->z_vals;
   L.have_z0 = a && a->z_vals0;
   L.have_w0 = a && a->out0.weights;
   L.have_sb = a && a->sample_box;
   L.have_hits = a && a->hit_mask && a->box_id && a->t_in && a->t_out;
   L.have_nf = a && a->near_out && a->far_out;
-  L.raw = (size_t)L.Nt * CH * 4;
+  L.raw = (L.comp0 && L.comp1) ? 0 : (size_t)((fine && L.comp1) ? N : L.Nt) * CH * 4;   // only for two-kernel passes
   L.zall = L.have_z ? 0 : (size_t)L.Nt * 4;
   L.z0 = (fine && !L.have_z0) ? (size_t)N * 4 : 0;
   L.w0 = (fine && !L.have_w0) ? (size_t)N * 4 : 0;
+  L.w1 = L.have_w1 ? 0 : (size_t)L.Nt * 4;          // the last pass's weights (required by the one-kernel path)
+  if (!fine) { L.w0 = L.w1; L.w1 = 0; }             // single pass: its weights are "w0"
   L.sb = (boxes && !L.have_sb) ? (size_t)L.Nt * 4 : 0;
   L.near = L.have_nf ? 0 : 4;
   L.far = L.have_nf ? 0 : 4;
@@ -50,7 +63,7 @@ Layout make_layout(int N, int Ni, int CH, int M, bool boxes, const pnr_render_ar
 // bytes of a chunk of Rc rays (each sub-buffer aligned)
 size_t chunk_bytes(const Layout& L, int64_t Rc) {
   size_t b = 0;
-  for (size_t per : {L.raw, L.z0, L.zall, L.w0, L.sb, L.near, L.far, L.hit, L.bid, L.tin, L.tout})
+  for (size_t per : {L.raw, L.z0, L.zall, L.w0, L.w1, L.sb, L.near, L.far, L.hit, L.bid, L.tin, L.tout})
     if (per) b += align_up(per * (size_t)Rc);
   return b;
 }
@@ -101,8 +114,11 @@ int64_t default_chunk_rays(int Nt, int CH) {
 
 size_t workspace_bytes_for(int64_t R, int N, int Ni, int CH) {
   if (R <= 0) return 0;
-  const Layout L = make_layout(N, Ni > 0 ? Ni : 0, CH, PNR_MAX_HITS, true, nullptr);
-  int64_t Rc = default_chunk_rays(L.Nt, CH);
+  Layout L = make_layout(N, Ni > 0 ? Ni : 0, CH, PNR_MAX_HITS, true, nullptr);
+  // sized for the worst case (a caller may ask for softmax compositing, which needs raw) when raw is small, for the
+  // one-kernel path otherwise: with both heads raw is 456 B per sample against ~20 B of everything else
+  if (L.raw == 0 && CH <= 8) L.raw = (size_t)L.Nt * CH * 4;
+  int64_t Rc = L.raw ? default_chunk_rays(L.Nt, CH) : R;
   if (Rc > R) Rc = R;
   return chunk_bytes(L, Rc);
 }
@@ -161,6 +177,7 @@ extern "C" int pnr_render_fused(pnr_ctx* ctx, pnr_ctx* ctx_fine, const pnr_rende
     float* z0_s = cv.take<float>(L.z0, Rc);
     float* zall_s = cv.take<float>(L.zall, Rc);
     float* w0_s = cv.take<float>(L.w0, Rc);
+    float* w1_s = cv.take<float>(L.w1, Rc);
     int32_t* sb_s = cv.take<int32_t>(L.sb, Rc);
     float* near_s = cv.take<float>(L.near, Rc);
     float* far_s = cv.take<float>(L.far, Rc);
@@ -202,21 +219,32 @@ extern "C" int pnr_render_fused(pnr_ctx* ctx, pnr_ctx* ctx_fine, const pnr_rende
     else
       PNR_TRY(pnr_sample_stratified(near, far, a->t_vals, u, n, N, a->perturb, bid, tin, tout, boxes ? M : 0, z0, sb,
                                     stream));
-    // ---- a8 + a9 (coarse pass, or the only pass)
-    PNR_TRY(pnr_mlp_forward(ctx, nullptr, nullptr, rays, z0, n, N, raw, stream));
+    // ---- a8 + a9 (coarse pass, or the only pass): one kernel when the compositing epilogue applies
     pnr_composite_out o0 = offset_out(fine ? a->out0 : a->out, r0, N, C, K);
-    if (fine && !o0.weights) o0.weights = w0_s;
-    PNR_TRY(pnr_composite(raw, z0, rays, n, N, C, K, a->white_bkgd, a->sem_softmax, a->mask_outside, sb, a->box_sem,
-                          a->box_inst, a->B, &o0, stream));
+    if (!o0.weights) o0.weights = w0_s;
+    if (L.comp0) {
+      PNR_TRY(pnr_mlp_composite(ctx, rays, z0, n, N, a->white_bkgd, a->mask_outside, sb, a->box_sem, a->box_inst, a->B,
+                                &o0, stream));
+    } else {
+      PNR_TRY(pnr_mlp_forward(ctx, nullptr, nullptr, rays, z0, n, N, raw, stream));
+      PNR_TRY(pnr_composite(raw, z0, rays, n, N, C, K, a->white_bkgd, a->sem_softmax, a->mask_outside, sb, a->box_sem,
+                            a->box_inst, a->B, &o0, stream));
+    }
     if (!fine) continue;
     // ---- a10 + fine pass
     const float* uf = a->u_fine + (a->u_fine_stride ? r0 * a->u_fine_stride : 0);
     PNR_TRY(sample_pdf_strided(z0, o0.weights, n, N, Ni, uf, a->u_fine_stride, nullptr, nullptr, zall, stream));
     if (boxes) PNR_TRY(pnr_tag_samples(zall, n, Nt, bid, tin, tout, M, sb, stream));
-    PNR_TRY(pnr_mlp_forward(ctx_fine, nullptr, nullptr, rays, zall, n, Nt, raw, stream));
-    const pnr_composite_out o1 = offset_out(a->out, r0, Nt, C, K);
-    PNR_TRY(pnr_composite(raw, zall, rays, n, Nt, C, K, a->white_bkgd, a->sem_softmax, a->mask_outside, sb, a->box_sem,
-                          a->box_inst, a->B, &o1, stream));
+    pnr_composite_out o1 = offset_out(a->out, r0, Nt, C, K);
+    if (!o1.weights) o1.weights = w1_s;
+    if (L.comp1) {
+      PNR_TRY(pnr_mlp_composite(ctx_fine, rays, zall, n, Nt, a->white_bkgd, a->mask_outside, sb, a->box_sem, a->box_inst,
+                                a->B, &o1, stream));
+    } else {
+      PNR_TRY(pnr_mlp_forward(ctx_fine, nullptr, nullptr, rays, zall, n, Nt, raw, stream));
+      PNR_TRY(pnr_composite(raw, zall, rays, n, Nt, C, K, a->white_bkgd, a->sem_softmax, a->mask_outside, sb, a->box_sem,
+                            a->box_inst, a->B, &o1, stream));
+    }
   }
   return PNR_OK;
 }

@@ -7,6 +7,7 @@
 //               striding the (contiguous) channel axis so every raw row is read once, coalesced.
 #include <mutex>
 #include "common.cuh"
+#include "composite_math.cuh"
 
 namespace pnr {
 
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(kCompWarps * 32) composite_kernel(CompositeArg
   const float* raw = a.raw + r * N * CH;
   const float* z = a.z + r * N;
   const float dx = a.rays[r * 6 + 3], dy = a.rays[r * 6 + 4], dz = a.rays[r * 6 + 5];
-  const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+  const float dnorm = comp_dnorm(dx, dy, dz);
 
   float w[kCompMaxPerLane];
   float carry = 1.0f;  // product of (1 - alpha + 1e-10) over all earlier groups of 32 samples
@@ -116,27 +117,20 @@ __global__ void __launch_bounds__(kCompWarps * 32) composite_kernel(CompositeArg
     float alpha = 0.f, zi = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
     if (i < N) {
       zi = z[i];
-      const float dist = ((i + 1 < N) ? (z[i + 1] - zi) : 1e10f) * dnorm;
+      const float dist = comp_dist(zi, (i + 1 < N) ? z[i + 1] : 0.f, i + 1 < N, dnorm);
       const float* q = raw + (int64_t)i * CH;
-      float sig = fmaxf(q[3], 0.f);
-      if (a.mask_outside && a.sample_box != nullptr && a.sample_box[r * N + i] < 0) sig = 0.f;
-      alpha = 1.0f - expf(-sig * dist);
-      cr = 1.0f / (1.0f + expf(-q[0]));
-      cg = 1.0f / (1.0f + expf(-q[1]));
-      cb = 1.0f / (1.0f + expf(-q[2]));
+      const bool masked = a.mask_outside && a.sample_box != nullptr && a.sample_box[r * N + i] < 0;
+      alpha = comp_alpha(q[3], dist, masked);
+      cr = comp_sigmoid(q[0]);
+      cg = comp_sigmoid(q[1]);
+      cb = comp_sigmoid(q[2]);
     }
     // exclusive product scan of t = 1 - alpha + 1e-10 across the warp
     const float t = (i < N) ? (1.0f - alpha + 1e-10f) : 1.0f;
-    float incl = t;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const float o = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl *= o;
-    }
-    float excl = __shfl_up_sync(0xffffffffu, incl, 1);
-    if (lane == 0) excl = 1.0f;
+    float total;
+    const float excl = comp_scan32(t, lane, &total);
     const float T = carry * excl;
-    carry *= __shfl_sync(0xffffffffu, incl, 31);
+    carry *= total;
     const float wi = alpha * T;
     w[j] = wi;
     if (i < N) {
@@ -155,10 +149,7 @@ __global__ void __launch_bounds__(kCompWarps * 32) composite_kernel(CompositeArg
     }
     if (a.o.depth_map) a.o.depth_map[r] = acc_d;
     if (a.o.acc_map) a.o.acc_map[r] = acc_a;
-    if (a.o.disp_map) {
-      const float q = acc_d / acc_a;  // NaN when acc == 0, as in the oracle
-      a.o.disp_map[r] = 1.0f / ((q != q) ? q : fmaxf(1e-10f, q));
-    }
+    if (a.o.disp_map) a.o.disp_map[r] = comp_disp(acc_d, acc_a);
   }
 
   const int C = a.C, K = a.K;
@@ -386,6 +377,56 @@ __global__ void __launch_bounds__(kCompWarps * 32) composite_backward_kernel(Com
 }  // namespace pnr
 
 using namespace pnr;
+
+// ------------------------------------------------------------------------------------ fixed (bounding-box) maps
+// fixed_semantic_map[r,c] = sum_i w_i [box_sem[sample_box_i] == c] (likewise instances) from the per-sample weights
+// alone - the companion of the MLP kernel's compositing epilogue, which never sees the id tables.  One warp per ray,
+// samples in order (the sum order is the sample order), lanes own channels lane, lane+32, ...
+__global__ void __launch_bounds__(kCompWarps * 32) fixed_maps_kernel(
+    const float* __restrict__ weights, const int32_t* __restrict__ sample_box, const int32_t* __restrict__ box_sem,
+    const int32_t* __restrict__ box_inst, int64_t R, int N, int C, int K, int B, float* __restrict__ fsem,
+    float* __restrict__ finst) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * kCompWarps + (threadIdx.x >> 5);
+  if (r >= R) return;
+  float a[kCompMaxChan], b[kCompMaxChan];
+#pragma unroll
+  for (int q = 0; q < kCompMaxChan; ++q) a[q] = b[q] = 0.f;
+  for (int i0 = 0; i0 < N; i0 += 32) {
+    const int i = i0 + lane;
+    const float wl = i < N ? weights[r * N + i] : 0.f;
+    const int32_t sl = i < N ? sample_box[r * N + i] : -1;
+    const int32_t id_s = (fsem != nullptr && sl >= 0 && sl < B) ? box_sem[sl] : -1;
+    const int32_t id_i = (finst != nullptr && sl >= 0 && sl < B) ? box_inst[sl] : -1;
+    const int n = N - i0 < 32 ? N - i0 : 32;
+    for (int j = 0; j < n; ++j) {
+      const float wj = __shfl_sync(0xffffffffu, wl, j);
+      const int32_t cs = __shfl_sync(0xffffffffu, id_s, j), ci = __shfl_sync(0xffffffffu, id_i, j);
+#pragma unroll
+      for (int q = 0; q < kCompMaxChan; ++q) {
+        if (lane + 32 * q == cs) a[q] += wj;
+        if (lane + 32 * q == ci) b[q] += wj;
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < kCompMaxChan; ++q) {
+    const int c = lane + 32 * q;
+    if (fsem != nullptr && c < C) fsem[r * C + c] = a[q];
+    if (finst != nullptr && c < K) finst[r * K + c] = b[q];
+  }
+}
+
+int pnr::launch_fixed_maps(const float* weights, const int32_t* sample_box, const int32_t* box_sem,
+                           const int32_t* box_inst, int64_t R, int N, int C, int K, int B, float* fsem, float* finst,
+                           cudaStream_t stream) {
+  if (R == 0 || (!fsem && !finst)) return PNR_OK;
+  PNR_CHECK_ARG(C <= 32 * kCompMaxChan && K <= 32 * kCompMaxChan, "fixed maps: C=%d or K=%d > %d", C, K, 32 * kCompMaxChan);
+  fixed_maps_kernel<<<(unsigned)((R + kCompWarps - 1) / kCompWarps), kCompWarps * 32, 0, stream>>>(
+      weights, sample_box, box_sem, box_inst, R, N, C, K, B, fsem, finst);
+  PNR_LAUNCH_CHECK("fixed_maps_kernel");
+  return PNR_OK;
+}
 
 // ------------------------------------------------------------------------------------ label tiles
 // 8(e) / 8(f) rank 4: the per-ray tile a rank contributes to the all-gather when labels, not logits, are wanted:

@@ -156,6 +156,37 @@ class Network(nn.Module):
                                                     _capi.stream_ptr()), "pnr_mlp_forward")
         return raw
 
+    def forward_composite(self, rays: torch.Tensor, z: torch.Tensor, white_bkgd: bool = False,
+                          mask_outside: bool = False, sample_box: Optional[torch.Tensor] = None,
+                          box_sem: Optional[torch.Tensor] = None, box_inst: Optional[torch.Tensor] = None):
+        """Network.forward + raw2outputs in ONE kernel (pnr_mlp_composite): the compositing runs in the MLP's epilogue
+        and `raw` is never written.  Returns the dict raw2outputs returns.  Needs N % 32 == 0."""
+        R, N = z.shape
+        dev = rays.device
+        ctx = self.pack(dev if rays.is_cuda else None)
+        rp, zp = _capi.ptr(rays, torch.float32, "rays"), _capi.ptr(z, torch.float32, "z")
+        e = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
+        out = {"rgb_map": e(R, 3), "depth_map": e(R), "acc_map": e(R), "disp_map": e(R), "weights": e(R, N)}
+        if self.C > 0:
+            out["semantic_map"] = e(R, self.C)
+        if self.K > 0:
+            out["instance_map"] = e(R, self.K)
+        sb = sample_box.to(dev, torch.int32).contiguous() if sample_box is not None else None
+        bs = box_sem.to(dev, torch.int32).contiguous() if box_sem is not None else None
+        bi = box_inst.to(dev, torch.int32).contiguous() if box_inst is not None else None
+        B = 0
+        if sb is not None and bs is not None and self.C > 0:
+            out["fixed_semantic_map"], B = e(R, self.C), bs.shape[0]
+        if sb is not None and bi is not None and self.K > 0:
+            out["fixed_instance_map"], B = e(R, self.K), bi.shape[0]
+        co = _capi.PnrCompositeOut(**{k: _capi.ptr(out[k]) if k in out else None
+                                      for k, _ in _capi.PnrCompositeOut._fields_})
+        with torch.cuda.device(dev):
+            _capi.check(_capi.lib().pnr_mlp_composite(ctx, rp, zp, R, N, int(bool(white_bkgd)), int(bool(mask_outside)),
+                                                      _capi.ptr(sb), _capi.ptr(bs), _capi.ptr(bi), B, C.byref(co),
+                                                      _capi.stream_ptr()), "pnr_mlp_composite")
+        return out
+
     def range_status(self, reset: bool = True) -> int:
         """Sticky range-check word of this network's fused-MLP launches (synchronises the current stream).
         Bit 0 set: an activation left the range of the 16-bit operand format (fp16 modes: |x| > 65504) or was not
