@@ -505,7 +505,8 @@ def main():
                           "alg_tflop_per_frame": flop3 / 1e12, "frac_of_tensor_roofline": flop3 / (ms3 / 1e3) / 1e12 / peak,
                           "outputs": sorted(k for k in o3 if k.endswith("_map")),
                           "note": "both passes run the full network (heads included), so the algorithmic FLOPs are "
-                                  "256 evaluations x 1 345 792 per ray; one pnr_render_fused call, default workspace"}}
+                                  "256 evaluations x 1 345 792 per ray; one pnr_render_fused call, default workspace; "
+                                  "compositing runs in the MLP kernel's epilogue (raw is never written)"}}
         del r3, n3, b3, o3
 
     # ---------------- CPU baseline (rank 0, N=1): oracle port on the host cores, bounded strip + measured parity

@@ -313,7 +313,6 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
         const float* bias = consts + ed.bias_off;
         const float* aux = consts + ed.aux_off;
         const bool to_a = ed.kind == EPI_RELU_TO_A;
-        float* raw_row = p.raw + (valid ? s : 0) * p.CH;
         float c0 = 0.f, c1 = 0.f, c2 = 0.f;
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
@@ -343,11 +342,6 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
           if (rec) p.dbg[4096 + (st * 2 + h) * 3 + 1] = clock64();
 #endif
           const uint32_t acc = tmem_lane + ed.acc_col;
-          // EPI_LOGITS: where this half's columns go (the second half may be a logit layer of its own)
-          const bool own_half = h == 1 && ed.n_valid1 > 0;
-          float* out_row = raw_row + (own_half ? ed.out_off1 : ed.out_off);
-          const int out_c0 = own_half ? (int)ed.n0 : 0, out_valid = own_half ? (int)ed.n_valid1 : (int)ed.n_valid;
-          const int out_ch = (own_half ? (int)ed.out_off1 : (int)ed.out_off) + 1;   // composited channel of column out_c0
           // software pipeline: the load of the next group is in flight while a group is processed - also across
           // the part boundary, so signalling part a does not restart the load pipeline
           uint32_t ra[16], rb[16];
@@ -386,6 +380,11 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
                 if (two) epi_group_store<PASSES>(g + 1, ed, tmem_lane, hb, lb);
               }
             } else {
+              // EPI_LOGITS: where this half's columns go (the second half may be a logit layer of its own)
+              const bool own_half = h == 1 && ed.n_valid1 > 0;
+              float* out_row = p.raw + (valid ? s : 0) * p.CH + (own_half ? ed.out_off1 : ed.out_off);
+              const int out_c0 = own_half ? (int)ed.n0 : 0, out_valid = own_half ? (int)ed.n_valid1 : (int)ed.n_valid;
+              const int out_ch = (own_half ? (int)ed.out_off1 : (int)ed.out_off) + 1;   // composited channel of column out_c0
 #pragma unroll 1
               for (int g = lo; g < hi; g += 2) {
                 const bool two = g + 1 < hi;

@@ -2,7 +2,6 @@
 // C-ABI call.  The host side only sequences the stage kernels of this library over ray chunks; the chunk size
 // follows from the caller's workspace, so the one large intermediate - raw [chunk, N+Ni, 4+C+K] - is bounded
 // (~1.5 GB at the default workspace) instead of being materialised for the whole frame (46 GB at config 3).
-#include <cstdlib>
 #include <cstring>
 #include "common.cuh"
 #include "ray_math.h"   // PNR_MAX_HITS
@@ -28,18 +27,20 @@ struct Layout {
   size_t per_ray() const { return raw + z0 + zall + w0 + w1 + sb + near + far + hit + bid + tin + tout; }
 };
 
-// the compositing epilogue needs aligned groups of 32 samples per ray and composites logits, not softmax(logits)
-inline bool comp_ok(int n_samples, const pnr_render_args* a) {
-  static const bool off = getenv("PNR_NO_COMP") != nullptr;   // tuning aid: force the two-kernel path
-  return !off && n_samples % 32 == 0 && (!a || !a->sem_softmax);
+// The compositing epilogue needs aligned groups of 32 samples per ray and composites logits, not softmax(logits).
+// It is used when the network has heads: raw then is 456 B per sample (cfg3 frame: 470 -> 407 ms).  Without heads raw
+// is 16 B per sample and the epilogue's extra barriers at the tile boundary cost more than the second kernel saves
+// (cfg2 frame: 79.8 ms two kernels, 82.7 ms one), so the rgb + sigma configuration keeps the two-kernel path.
+inline bool comp_ok(int n_samples, int CH, const pnr_render_args* a) {
+  return CH > 4 && n_samples % 32 == 0 && (!a || !a->sem_softmax);
 }
 
 Layout make_layout(int N, int Ni, int CH, int M, bool boxes, const pnr_render_args* a) {
   Layout L{};
   L.N = N; L.Ni = Ni; L.Nt = N + Ni; L.CH = CH; L.M = M; L.boxes = boxes;
   const bool fine = Ni > 0;
-  L.comp0 = comp_ok(N, a);
-  L.comp1 = fine ? comp_ok(N + Ni, a) : L.comp0;
+  L.comp0 = comp_ok(N, CH, a);
+  L.comp1 = fine ? comp_ok(N + Ni, CH, a) : L.comp0;
   L.have_w1 = a && a->out.weights;
   L.have_z = a && a->z_vals;
   L.have_z0 = a && a->z_vals0;
