@@ -13,6 +13,13 @@
 // Epilogue -> MMA hand-offs are three monotonic shared-memory counters (E0 done, E1 part a done, E1 done), bumped
 // once per epilogue warp and watched by the scout thread: every stage carries the counts it needs.
 //
+// ACCUMULATOR FLIP.  A tile's last step (view or logits, N <= 128) accumulates in the lower 128 accumulator columns, and
+// so does the first half of the next tile's first layer - which therefore had to wait until the last step's epilogue
+// had drained them, at the one place where the epilogue warps have more work than the tensor pipe.  With acc_flip set,
+// odd tiles address every accumulator column XOR 128 (MMA destinations and epilogue loads alike; no accumulator
+// range straddles column 128): the first half of layer 0 then lands in the half the previous tile's last step does
+// not use and is issued right behind it.  Everything else (K order, activation columns) is unchanged.
+//
 // The program travels as a __grid_constant__ kernel parameter (constant bank, uniform datapath for the issuing
 // thread; nothing shared between contexts, streams, devices or graph replays).
 #pragma once
@@ -107,6 +114,8 @@ struct MlpProgram {
   int32_t sigma_bias_off, rgb_bias_off;   // float offsets into consts
   int32_t Lx, Ld;
   int32_t passes;                          // 1 or 3
+  int32_t acc_flip;                        // 1: odd tiles use the accumulator columns XOR 128 (see below)
+  int32_t reserved_;
   StageDesc st[kMaxStages];
   IssueDesc is[kMaxStages];
   EpiDesc ep[kMaxSteps];

@@ -132,13 +132,22 @@ __device__ __forceinline__ void epi_group_store(int g, const EpiDesc& ed, uint32
 
 __device__ __forceinline__ void epi_group_rgb(const uint32_t (&r)[16], int g, const EpiDesc& ed, const float* bias,
                                               const float* wr, float& c0, float& c1, float& c2) {
+  // bias and the three weight rows come as 16-byte shared-memory loads (every offset is a multiple of 4 floats)
+  const float4* b4 = reinterpret_cast<const float4*>(bias + g * 16);
+  const float4* w0 = reinterpret_cast<const float4*>(wr + g * 16);
+  const float4* w1 = reinterpret_cast<const float4*>(wr + ed.n + g * 16);
+  const float4* w2 = reinterpret_cast<const float4*>(wr + 2 * ed.n + g * 16);
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const int c = g * 16 + j;
-    const float v = fmaxf(__uint_as_float(r[j]) + bias[c], 0.f);
-    c0 += v * wr[c];
-    c1 += v * wr[ed.n + c];
-    c2 += v * wr[2 * ed.n + c];
+  for (int q = 0; q < 4; ++q) {
+    const float4 b = b4[q], a0 = w0[q], a1 = w1[q], a2 = w2[q];
+    const float v0 = fmaxf(__uint_as_float(r[4 * q + 0]) + b.x, 0.f);
+    const float v1 = fmaxf(__uint_as_float(r[4 * q + 1]) + b.y, 0.f);
+    const float v2 = fmaxf(__uint_as_float(r[4 * q + 2]) + b.z, 0.f);
+    const float v3 = fmaxf(__uint_as_float(r[4 * q + 3]) + b.w, 0.f);
+    c0 += v0 * a0.x; c1 += v0 * a1.x; c2 += v0 * a2.x;
+    c0 += v1 * a0.y; c1 += v1 * a1.y; c2 += v1 * a2.y;
+    c0 += v2 * a0.z; c1 += v2 * a1.z; c2 += v2 * a2.z;
+    c0 += v3 * a0.w; c1 += v3 * a1.w; c2 += v3 * a2.w;
   }
 }
 
@@ -341,12 +350,14 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
 #ifdef PNR_TIMELINE
           if (rec) p.dbg[4096 + (st * 2 + h) * 3 + 1] = clock64();
 #endif
-          const uint32_t acc = tmem_lane + ed.acc_col;
+          // accumulator address of 16-column group g (odd tiles: columns XOR 128 when the program says so)
+          const int flip = (prog.acc_flip && (it & 1)) ? 128 : 0;
+          auto acc_of = [&](int g) { return tmem_lane + (uint32_t)(((int)ed.acc_col + g * 16) ^ flip); };
           // software pipeline: the load of the next group is in flight while a group is processed - also across
           // the part boundary, so signalling part a does not restart the load pipeline
           uint32_t ra[16], rb[16];
-          if (na > 0) tmem_ld16(acc + a_lo * 16, ra);
-          else if (nb > 0) tmem_ld16(acc + b_lo * 16, ra);
+          if (na > 0) tmem_ld16(acc_of(a_lo), ra);
+          else if (nb > 0) tmem_ld16(acc_of(b_lo), ra);
 #pragma unroll
           for (int pi = 0; pi < 2; ++pi) {
             const int lo = pi == 0 ? a_lo : b_lo, hi = pi == 0 ? a_hi : b_hi;
@@ -362,14 +373,14 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
                 const bool two = g + 1 < hi;
                 const int after = (g + 2 < hi) ? g + 2 : nxt;
                 tc_wait_ld();
-                if (two) tmem_ld16(acc + (g + 1) * 16, rb);
+                if (two) tmem_ld16(acc_of(g + 1), rb);
                 epi_group_act<PASSES, FMT>(ra, g, ed, bias, aux, sig, vmax, ha, la);
                 if (two) {
                   tc_wait_ld();
-                  if (after >= 0) tmem_ld16(acc + after * 16, ra);
+                  if (after >= 0) tmem_ld16(acc_of(after), ra);
                   epi_group_act<PASSES, FMT>(rb, g + 1, ed, bias, aux, sig, vmax, hb, lb);
                 } else if (after >= 0) {
-                  tmem_ld16(acc + after * 16, ra);
+                  tmem_ld16(acc_of(after), ra);
                 }
                 if (war_pending) {  // the columns we are about to overwrite must have been consumed by the MMAs
                   mbar_wait_backoff(bar_war, parity);
@@ -390,7 +401,7 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
                 const bool two = g + 1 < hi;
                 const int after = (g + 2 < hi) ? g + 2 : nxt;
                 tc_wait_ld();
-                if (two) tmem_ld16(acc + (g + 1) * 16, rb);
+                if (two) tmem_ld16(acc_of(g + 1), rb);
                 if (ed.kind == EPI_VIEW_RGB) {
                   epi_group_rgb(ra, g, ed, bias, aux, c0, c1, c2);
                 } else if (COMP) {
@@ -400,7 +411,7 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
                 }
                 if (two) {
                   tc_wait_ld();
-                  if (after >= 0) tmem_ld16(acc + after * 16, ra);
+                  if (after >= 0) tmem_ld16(acc_of(after), ra);
                   if (ed.kind == EPI_VIEW_RGB) {
                     epi_group_rgb(rb, g + 1, ed, bias, aux, c0, c1, c2);
                   } else if (COMP) {
@@ -409,7 +420,7 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
                     epi_group_logits(rb, g + 1, out_c0, out_valid, bias, out_row);
                   }
                 } else if (after >= 0) {
-                  tmem_ld16(acc + after * 16, ra);
+                  tmem_ld16(acc_of(after), ra);
                 }
               }
             }
@@ -670,6 +681,7 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
     constexpr uint32_t kFullK = PASSES == 3 ? 4u : 8u;   // K16 steps of a full stage
     for (int it = 0; it < n_iter; ++it) {
       const int b = it & 1;
+      const uint32_t acc_flip = (prog.acc_flip && (it & 1)) ? 128u : 0u;
       const uint32_t dir_hi = smem_u32(smem + kSmemDir + b * 2 * kDirPartBytes);
 #pragma unroll 1
       for (int si = 0; si < n_stages; ++si, ++gs, slot = (slot + 1 == (uint32_t)kRing) ? 0u : slot + 1) {
@@ -702,7 +714,7 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
         // the high word is the same for every operand: SBO = 128 B, descriptor version 1
         const uint32_t b_hi0 = b_lo_base | (ring16 + slot * (uint32_t)(kStageBytes >> 4));
         const uint32_t b_lo0 = b_hi0 + lo_off16;
-        const uint32_t d_tmem = tmem + acc_col;
+        const uint32_t d_tmem = tmem + (acc_col ^ acc_flip);
         const uint32_t acc0 = (flags & F_FIRST) ? 0u : 1u;
         const uint32_t a_hi = tmem + a_off, a_lo = tmem + a_lo_off;
         const bool fast = a_kind == A_TMEM && ksteps == kFullK;

@@ -89,12 +89,14 @@ struct Builder {
   // E1 in two blocks signalled separately (mlp_program.h).  Pays off when a half spans several weight stages
   // (the x3 modes, K = 64 per stage: 75.4 k -> 71.5 k cycles per tile); the 1-pass modes keep one block.
   bool split_e1;
+  bool acc_flip = true;             // odd tiles use the accumulator columns XOR 128 when the program allows it
   bool out_of_fp16_range = false;   // a weight (after the feature_linear fold) exceeds 65504 or is not finite
   std::string err;
 
   Builder(int passes_, int fmt_) : passes(passes_), fmt(fmt_) {
     memset(&prog, 0, sizeof(prog));
     split_e1 = passes == 3;
+    if (const char* v = getenv("PNR_ACC_FLIP")) acc_flip = *v != '0';   // tuning aid (A/B on the GPU)
   }
 
   int add_consts(const float* src, int n_valid, int n_pad) {
@@ -231,13 +233,25 @@ struct Builder {
   // of the issue table.
   void finalize() {
     const int S = prog.n_steps;
+    // accumulator flip (mlp_program.h): allowed when no activation lives inside the accumulator region (the head
+    // columns of single-head programs do) and no accumulator range straddles column 128
+    bool flip = acc_flip;
+    for (int s = 0; s < S; ++s) flip = flip && !(prog.ep[s].kind == EPI_RELU_TO_A && prog.ep[s].dst_col < kColAHi);
+    for (int i = 0; i < prog.n_stages; ++i)
+      flip = flip && prog.st[i].acc_col / 128 == (prog.st[i].acc_col + prog.st[i].n - 1) / 128;
+    prog.acc_flip = flip ? 1 : 0;
     std::vector<int> at_a(S), at_b(S);
     for (int s = 0; s < S; ++s) {
       const StepInfo& in = steps[s];
       const int end = in.first_stage + in.n_stages;
       const EpiDesc& pe = prog.ep[(s + S - 1) % S];
       const bool split = in.n0_stage < end;
-      auto first_touch = [&](const Foot& f) {
+      auto first_touch = [&](Foot f) {
+        if (s == 0 && prog.acc_flip) {   // the previous step ran in the other tile parity: its accumulator columns
+          const int w = f.acc1 - f.acc0; //   are the XOR-128 image of what the program says
+          f.acc0 ^= 128;
+          f.acc1 = f.acc0 + w;
+        }
         int at = -1;
         for (int i = in.first_stage; i < end && at < 0; ++i)
           if (stage_touches(prog.st[i], f)) at = i;

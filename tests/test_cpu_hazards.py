@@ -21,7 +21,7 @@ def overlap(a, b):
     return a[0] < a[1] and b[0] < b[1] and a[0] < b[1] and b[0] < a[1]
 
 
-def events_and_edges(prog, tiles=2):
+def events_and_edges(prog, tiles=3):
     """Events of step s of tile t (aggregated over the epilogue warps):
       ('S', t, i)    MMA stage i
       ('L0', t, s)   E0's accumulator loads            (after acc_full[0])
@@ -40,9 +40,16 @@ def events_and_edges(prog, tiles=2):
     order = [(t, s) for t in range(tiles) for s in range(n_steps)]
     gidx = {ts: k for k, ts in enumerate(order)}
 
-    def cols(ed, c0, c1, to_a):
-        """(accumulator interval read, activation intervals written) of epilogue columns [c0, c1)."""
-        r = [(ed.acc_col + c0, ed.acc_col + c1)] if c0 < c1 else []
+    def fl(t, a0, a1):
+        """accumulator interval of tile t: odd tiles use the columns XOR 128 when the program flips (no range straddles 128)"""
+        if prog.acc_flip and (t & 1) and a0 < a1:
+            assert a0 // 128 == (a1 - 1) // 128
+            return (a0 ^ 128, (a0 ^ 128) + (a1 - a0))
+        return (a0, a1)
+
+    def cols(t, ed, c0, c1, to_a):
+        """(accumulator interval read, activation intervals written) of epilogue columns [c0, c1) in tile t."""
+        r = [fl(t, ed.acc_col + c0, ed.acc_col + c1)] if c0 < c1 else []
         w = []
         if to_a and c0 < c1:
             w = [(ed.dst_col + c0 // 2, ed.dst_col + c1 // 2)] + (
@@ -56,12 +63,12 @@ def events_and_edges(prog, tiles=2):
         for i in steps[s]:
             sd = prog.st[i]
             ev = ("S", t, i)
-            r = [(sd.acc_col, sd.acc_col + sd.n)]
+            r = [fl(t, sd.acc_col, sd.acc_col + sd.n)]
             if sd.a_kind == A_TMEM:
                 r.append((sd.a_off, sd.a_off + 8 * sd.ksteps))
                 if x3:
                     r.append((sd.a_lo_off, sd.a_lo_off + 8 * sd.ksteps))
-            reads[ev], writes[ev] = r, [(sd.acc_col, sd.acc_col + sd.n)]
+            reads[ev], writes[ev] = r, [fl(t, sd.acc_col, sd.acc_col + sd.n)]
             if prev_stage is not None:
                 edges.append((prev_stage, ev))        # the tensor pipe retires MMAs in issue order
             prev_stage = ev
@@ -80,10 +87,10 @@ def events_and_edges(prog, tiles=2):
         # a step issued as one half signals acc_full[0] and [1] from its last stage
         if not any(prog.st[i].flags & F_COMMIT_ACC0 for i in steps[s]):
             edges += [(("S", t, steps[s][-1]), (e, t, s)) for e in ("L0", "W0")]
-        reads[("L0", t, s)], writes[("L0", t, s)] = cols(ed, 0, ed.n0, False)[0], []
-        reads[("W0", t, s)], writes[("W0", t, s)] = [], cols(ed, 0, ed.n0, to_a)[1]
-        reads[("E1a", t, s)], writes[("E1a", t, s)] = cols(ed, ed.n0, ed.n1a, to_a)
-        reads[("E1b", t, s)], writes[("E1b", t, s)] = cols(ed, ed.n1a, ed.n, to_a)
+        reads[("L0", t, s)], writes[("L0", t, s)] = cols(t, ed, 0, ed.n0, False)[0], []
+        reads[("W0", t, s)], writes[("W0", t, s)] = [], cols(t, ed, 0, ed.n0, to_a)[1]
+        reads[("E1a", t, s)], writes[("E1a", t, s)] = cols(t, ed, ed.n0, ed.n1a, to_a)
+        reads[("E1b", t, s)], writes[("E1b", t, s)] = cols(t, ed, ed.n1a, ed.n, to_a)
         for d in ("D0", "D1a", "D1"):
             reads[(d, t, s)], writes[(d, t, s)] = [], []
         edges += [(("L0", t, s), ("D0", t, s)), (("W0", t, s), ("D0", t, s)),

@@ -42,7 +42,7 @@ class EpiDesc(C.Structure):
 class MlpProgram(C.Structure):
     _fields_ = [("n_stages", C.c_int32), ("n_steps", C.c_int32), ("n_consts", C.c_int32),
                 ("sigma_bias_off", C.c_int32), ("rgb_bias_off", C.c_int32), ("Lx", C.c_int32), ("Ld", C.c_int32),
-                ("passes", C.c_int32), ("st", StageDesc * K_MAX_STAGES), ("is_", IssueDesc * K_MAX_STAGES),
+                ("passes", C.c_int32), ("acc_flip", C.c_int32), ("reserved_", C.c_int32), ("st", StageDesc * K_MAX_STAGES), ("is_", IssueDesc * K_MAX_STAGES),
                 ("ep", EpiDesc * K_MAX_STEPS)]
 
 
