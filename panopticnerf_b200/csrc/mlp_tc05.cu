@@ -239,7 +239,11 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
   };
 
   float* consts = reinterpret_cast<float*>(smem + kSmemConsts);
-  float* part = reinterpret_cast<float*>(smem + kSmemPart);  // [2][128][4]
+  // [2 column shares][128][4]: partial sigma / rgb sums.  Single-buffered across tiles: a share-1 warp writes the next
+  // tile's sigma only in that tile's sigma step, whose MMAs waited for the previous step's counter, which every
+  // share-0 warp bumped AFTER its reads of this tile's sums (program order + the fence in signal()).  racecheck does
+  // not see that chain and reports a write-after-read here; double-buffering it costs registers for nothing.
+  float* part = reinterpret_cast<float*>(smem + kSmemPart);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBars);
 
   const uint32_t bar_full = smem_u32(&bars[0]);                 // [kRing]

@@ -106,3 +106,37 @@ def test_sample_pdf_order(emu, N, Ni, det):
     emu.emu_sample_pdf(_p(z), _p(w), C.c_int64(R), N, Ni, _p(u), _p(z_f), _p(idx))
     assert torch.equal(idx, idx_ref), int((idx != idx_ref).sum())
     assert torch.equal(z_f, z_f_ref)
+
+
+def test_interval_plan_properties(emu):
+    """Property test (hypothesis) of the a6 interval rule through the host build of csrc/ray_math.h: for arbitrary
+    interval tables the N depths are sorted, lie inside [near, far], and - when a hit interval survives the clipping -
+    every one of them lies inside some kept interval; rays without one get exactly the uniform depths."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(1, 8), st.integers(1, 96), st.floats(0.05, 5.0), st.floats(6.0, 60.0),
+           st.lists(st.tuples(st.floats(-5.0, 70.0), st.floats(0.0, 30.0), st.booleans()), min_size=8, max_size=8))
+    def run(M, N, near, far, raw):
+        tin = torch.tensor([[a for a, _, _ in raw[:M]]], dtype=torch.float32)
+        tout = tin + torch.tensor([[b for _, b, _ in raw[:M]]], dtype=torch.float32)
+        order = torch.argsort(tin, 1)
+        tin, tout = torch.gather(tin, 1, order), torch.gather(tout, 1, order)
+        bid = torch.tensor([[i if v else -1 for i, (_, _, v) in enumerate(raw[:M])]], dtype=torch.int32)
+        nr, fr = torch.tensor([near], dtype=torch.float32), torch.tensor([far], dtype=torch.float32)
+        t = torch.linspace(0, 1, N)
+        u = torch.zeros(1, N)
+        z = torch.zeros(1, N)
+        sb = torch.zeros(1, N, dtype=torch.int32)
+        emu.emu_intervals(_p(nr), _p(fr), _p(t), _p(u), C.c_int64(1), N, C.c_float(0.0), _p(bid), _p(tin), _p(tout),
+                          M, _p(z), _p(sb))
+        assert torch.equal(z, O.interval_z(nr, fr, t, bid, tin, tout))             # and the oracle agrees bit for bit
+        assert bool((z[:, 1:] >= z[:, :-1]).all()) and float(z.min()) >= nr.item() - 1e-4 and float(z.max()) <= fr.item() + 1e-4
+        a, b = torch.maximum(tin, nr[:, None]), torch.minimum(tout, fr[:, None])
+        kept = (bid >= 0) & (b - a > 0)
+        if kept.any():
+            inside = ((z[0, :, None] >= a[0][None] - 1e-4) & (z[0, :, None] <= b[0][None] + 1e-4) & kept[0][None]).any(1)
+            assert bool(inside.all())
+        else:
+            assert torch.equal(z, O.stratified_z(nr, fr, t))
+    run()

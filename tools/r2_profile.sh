@@ -37,3 +37,4 @@ for tool in memcheck racecheck synccheck; do
       -k "compositing_epilogue_matches and (cfg1 or cfg3-over3)" > gpurun_out/sanitizer_$tool.log 2>&1
   echo "== $tool: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|passed|failed' gpurun_out/sanitizer_$tool.log | tr '\n' ' ')"
 done
+bash tools/r2_scaling.sh 1
