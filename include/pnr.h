@@ -136,6 +136,9 @@ int pnr_mlp_forward(pnr_ctx* ctx, const float* pts, const float* viewdirs, const
  * [4096 + 3*(2*step+half)+{0,1,2}] epilogue (wait / accumulator ready / done), [6144 + stage] TMA issue. */
 int pnr_mlp_forward_timeline(pnr_ctx* ctx, const float* rays, const float* z, int64_t R, int32_t N,
                              float* raw, int64_t* timeline, void* stream);
+/* Development aid: the backward-trunk launches of `ctx` record the same timeline into timeline[8192] (device i64)
+ * until this is called again with NULL (-DPNR_TIMELINE builds only; ignored otherwise). */
+int pnr_debug_timeline(pnr_ctx* ctx, int64_t* timeline);
 
 /* a9: raw2outputs.  raw [R,N,4+C+K], z [R,N], rays [R,6].  Any output pointer may be NULL.
  * sem_softmax: composite softmax(logits) instead of logits.  sample_box/box_sem/box_inst nullable. */
@@ -193,6 +196,16 @@ int pnr_composite_backward(const float* raw, const float* z, const float* rays, 
                            const int32_t* sample_box, const int32_t* box_sem, const int32_t* box_inst,
                            int32_t B, const pnr_composite_grads* g, float* d_raw, void* stream);
 
+/* a8 backward, first slice (replaces autograd through Network.forward's trunk - the D
+ * `pts_linears` with their ReLUs and the skip concatenation): dL/d(embedded xyz) [R*N, 3 + 6*xyz_res] from
+ * grad_h = dL/dh of the trunk output [R*N, W].  One kernel on the same 128-sample tiles as pnr_mlp_forward: the
+ * forward trunk is recomputed (ReLU sign patterns stay in shared memory), then the layers run in reverse with the
+ * transposed weight stream on the tensor cores, gradients split hi/lo like activations.  Samples are given as pts
+ * [R*N,3] or as (rays [R,6], z [R,N]).  x3 precisions only; D <= 9.  The weight gradients and the head / view
+ * branches are not part of this slice. */
+int pnr_mlp_backward_trunk(pnr_ctx* ctx, const float* pts, const float* rays, const float* z, int64_t R, int32_t N,
+                           const float* grad_h, float* grad_emb, void* stream);
+
 /* a10: sample_pdf + merge.  z [R,N] coarse depths, weights [R,N] coarse weights; bins are the mid
  * points, the pdf is weights[1:-1]+1e-5.  u [R,Ni] is required (deterministic sampler: the host's
  * linspace(0,1,Ni) broadcast over rays, so the values are the caller's, bit for bit).
@@ -207,6 +220,7 @@ int pnr_sample_pdf(const float* z, const float* weights, int64_t R, int32_t N, i
  * the oracle's Network.forward. */
 #define PNR_PROGRAM_SPLIT_E1 4  /* flags: E1 signalled in two blocks */
 #define PNR_PROGRAM_NO_SPLIT 8  /* flags: start from one-block epilogues instead of the precision's default */
+#define PNR_PROGRAM_BACKWARD 16 /* flags: the backward program of the trunk (pnr_mlp_backward_trunk) instead */
 int pnr_program_host(const pnr_config* cfg, const float* const* tensors_host, const int64_t* shapes, int32_t n,
                      int32_t flags, void* program, size_t program_cap, size_t* program_bytes,
                      void* wpacked, size_t wpacked_cap, size_t* wpacked_bytes,

@@ -20,6 +20,16 @@
 // range straddles column 128): the first half of layer 0 then lands in the half the previous tile's last step does
 // not use and is issued right behind it.  Everything else (K order, activation columns) is unchanged.
 //
+// BACKWARD (first slice of the training path: dL/d(embedded input) through the trunk, on the same tiles).  A backward
+// program is the trunk's forward steps - whose EPI_RELU_TO_A epilogues also save the 16-column sign patterns of their
+// activations in shared memory (slot n_valid-1; the view-direction embedding's region, unused here) - followed by one
+// step per layer in reverse order with the TRANSPOSED weights streamed the same way: the A operand is the gradient
+// w.r.t. the layer's pre-activation (tensor-memory activation columns, hi/lo split like any activation), the
+// accumulator receives the gradient w.r.t. the layer's input, and the epilogue gates it with the saved pattern of the
+// layer below.  The last forward layer's epilogue does not keep its activation: it loads the incoming gradient from
+// global memory and gates it with its own sign pattern.  The embedded-input columns (layer 0, and the skip layer's
+// first columns) are written / accumulated to the output rows by EPI_GRAD_OUT steps.
+//
 // The program travels as a __grid_constant__ kernel parameter (constant bank, uniform datapath for the issuing
 // thread; nothing shared between contexts, streams, devices or graph replays).
 #pragma once
@@ -64,7 +74,12 @@ enum : uint16_t {
   F_WAIT_EMB = 64, F_RELEASE_EMB = 128, F_WAIT_DIR = 256, F_RELEASE_DIR = 512,
   F_WAIT_E1A = 1024     // first stage that touches anything E1 part a of the previous step reads or writes
 };
-enum : uint8_t { EPI_RELU_TO_A = 0, EPI_VIEW_RGB = 2, EPI_LOGITS = 3 };   // (1 was a linear hand-over: feature_linear is folded now)
+enum : uint8_t { EPI_RELU_TO_A = 0, EPI_VIEW_RGB = 2, EPI_LOGITS = 3,   // (1 was a linear hand-over: feature_linear is folded now)
+                 // backward programs (BWD kernels, see "BACKWARD" below):
+                 EPI_MASK_TO_A = 4,     // v = acc where the saved ReLU sign pattern (slot n_valid-1) is set, else 0 -> A operand
+                 EPI_LOADG_TO_A = 5,    // last forward layer: v = grad_in where acc + bias > 0, else 0 -> A operand
+                 EPI_GRAD_OUT = 6 };    // acc columns [0, n_valid) -> grad row + out_off (added to it when n_valid1 != 0)
+constexpr bool epi_writes_a(uint8_t kind) { return kind == EPI_RELU_TO_A || kind == EPI_MASK_TO_A || kind == EPI_LOADG_TO_A; }
 
 struct StageDesc {     // one weight stage = one bulk copy + its MMAs
   uint32_t gofs;       // byte offset into the packed weight stream
@@ -121,6 +136,8 @@ struct MlpProgram {
   EpiDesc ep[kMaxSteps];
 };
 
+enum { kMlpForward = 0, kMlpComposite = 1, kMlpBackward = 2 };   // launch_mlp's `mode`
+
 // Launch arguments of the fused kernel (device pointers).
 struct MlpParams {
   const uint8_t* wpacked;
@@ -148,6 +165,8 @@ struct MlpParams {
   float* disp_map;        // [R]
   float* sem_map;         // [R,C]
   float* inst_map;        // [R,K]
+  // ---- backward kernels only: dL/dh of the trunk output, [S, W]; `raw` receives dL/d(embedded input), row stride CH
+  const float* grad_in;
 };
 
 // What a launch carries: arguments + the context's program, as ONE __grid_constant__ kernel parameter.
@@ -157,6 +176,10 @@ struct MlpLaunch {
 };
 static_assert(sizeof(MlpLaunch) <= 32764, "kernel parameter space is 32764 bytes");
 
+// backward kernels: ReLU sign patterns, uint16 [slot][16-column group][row], in the view-direction region
+constexpr int kSmemMask = kSmemDir;
+constexpr int kMaskSlotU16 = 16 * kTileM;                     // one layer of up to 256 columns
+constexpr int kMaxMaskSlots = 4 * kDirPartBytes / (kMaskSlotU16 * 2);   // 8
 constexpr int kSmemConsts = kSmemProg;   // (the program itself is in the kernel's parameter bank)
 constexpr int kSmemPart = kSmemConsts + kMaxConsts * 4;      // [kEpiWarps/4][128][4] floats
 constexpr int kSmemBars = kSmemPart + (kEpiWarps / 4) * kTileM * 4 * 4;

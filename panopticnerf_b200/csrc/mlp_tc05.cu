@@ -163,6 +163,67 @@ __device__ __forceinline__ void epi_group_logits(const uint32_t (&r)[16], int g,
 }
 
 // ------------------------------------------------------------------------------------------------
+// Backward programs (BWD kernels): the three hand-overs that write an A operand, and the gradient output.
+//   EPI_RELU_TO_A   forward layer: v = relu(acc + bias); its sign pattern is saved (slot n_valid-1) for the way back
+//   EPI_LOADG_TO_A  last forward layer: v = incoming gradient where acc + bias > 0 (relu' = 0 at 0, like autograd)
+//   EPI_MASK_TO_A   backward layer: v = acc where the saved pattern of the layer below is set
+// `mask_row` = this thread's row in slot 0 / group 0 of the pattern array; `gin` = this row of the incoming gradient.
+// ------------------------------------------------------------------------------------------------
+template <int PASSES, int FMT>
+__device__ __forceinline__ void epi_group_bwd(const uint32_t (&r)[16], int g, const EpiDesc& ed, const float* bias,
+                                              uint16_t* mask_row, const float* gin, uint32_t& vmax,
+                                              uint32_t (&hi)[8], uint32_t (&lo)[8]) {
+  float v[16];
+  if (ed.kind == EPI_MASK_TO_A) {
+    const uint32_t m = ed.n_valid ? mask_row[((ed.n_valid - 1) * 16 + g) * kTileM] : 0xFFFFu;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = ((m >> j) & 1u) ? __uint_as_float(r[j]) : 0.f;
+  } else {
+    const float4* b4 = reinterpret_cast<const float4*>(bias + g * 16);
+    uint32_t m = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 b = b4[q];
+      v[4 * q + 0] = fmaxf(__uint_as_float(r[4 * q + 0]) + b.x, 0.f);
+      v[4 * q + 1] = fmaxf(__uint_as_float(r[4 * q + 1]) + b.y, 0.f);
+      v[4 * q + 2] = fmaxf(__uint_as_float(r[4 * q + 2]) + b.z, 0.f);
+      v[4 * q + 3] = fmaxf(__uint_as_float(r[4 * q + 3]) + b.w, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) m |= (v[j] > 0.f ? 1u : 0u) << j;
+    if (ed.kind == EPI_LOADG_TO_A) {
+      const float4* g4 = reinterpret_cast<const float4*>(gin + g * 16);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 x = g4[q];
+        v[4 * q + 0] = ((m >> (4 * q + 0)) & 1u) ? x.x : 0.f;
+        v[4 * q + 1] = ((m >> (4 * q + 1)) & 1u) ? x.y : 0.f;
+        v[4 * q + 2] = ((m >> (4 * q + 2)) & 1u) ? x.z : 0.f;
+        v[4 * q + 3] = ((m >> (4 * q + 3)) & 1u) ? x.w : 0.f;
+      }
+    } else if (ed.n_valid) {
+      mask_row[((ed.n_valid - 1) * 16 + g) * kTileM] = (uint16_t)m;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    split_x2<FMT>(v[4 * q + 0], v[4 * q + 1], hi[2 * q], lo[2 * q]);
+    split_x2<FMT>(v[4 * q + 2], v[4 * q + 3], hi[2 * q + 1], lo[2 * q + 1]);
+    // gradients carry a sign: the range check compares magnitudes
+    vmax = __vimax3_u16x2(vmax, hi[2 * q] & 0x7FFF7FFFu, hi[2 * q + 1] & 0x7FFF7FFFu);
+  }
+}
+
+// gradient w.r.t. the embedded input: accumulator columns [0, n_valid) of this group -> the sample's output row
+__device__ __forceinline__ void epi_group_gradout(const uint32_t (&r)[16], int g, int n_valid, bool accumulate, float* dst) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int ch = g * 16 + j;
+    if (ch < n_valid) dst[ch] = accumulate ? dst[ch] + __uint_as_float(r[j]) : __uint_as_float(r[j]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Compositing epilogue building blocks (COMP kernels).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum32(float v) {
@@ -214,9 +275,13 @@ __device__ __forceinline__ constexpr uint32_t inf_bits16() {
 // over aligned groups of 32 samples, carried across groups, tiles and warps through shared memory), logits and
 // colours reduced per group with a fixed shuffle tree and accumulated per ray in ray order - and only weights and
 // the per-ray maps leave the SM: `raw` (456 B per sample with both heads) is never written.
-template <int PASSES, int FMT, bool COMP>
+//
+// BWD = true  : the program is a backward program (mlp_program.h): the forward trunk with its ReLU sign patterns kept
+// in shared memory, then the layers in reverse with transposed weights; input `grad_in`, output `raw`.
+template <int PASSES, int FMT, bool COMP, bool BWD = false>
 __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kMlpThreads, 1)
 mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
+  static_assert(!(COMP && BWD), "the compositing epilogue belongs to forward programs");
   extern __shared__ __align__(1024) uint8_t smem[];
   const MlpParams& p = L.p;
   const MlpProgram& prog = L.prog;
@@ -325,8 +390,11 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
         const uint32_t parity = gstep & 1u;
         const float* bias = consts + ed.bias_off;
         const float* aux = consts + ed.aux_off;
-        const bool to_a = ed.kind == EPI_RELU_TO_A;
+        const bool to_a = BWD ? ed.kind != EPI_GRAD_OUT : ed.kind == EPI_RELU_TO_A;
         float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+        // backward programs: this row's sign patterns and its row of the incoming gradient (tail rows read row S-1)
+        uint16_t* mask_row = reinterpret_cast<uint16_t*>(smem + kSmemMask) + row;
+        const float* gin = BWD ? p.grad_in + (valid ? s : p.S - 1) * (int64_t)ed.n : nullptr;
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
 #ifdef PNR_TIMELINE
@@ -378,11 +446,13 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
                 const int after = (g + 2 < hi) ? g + 2 : nxt;
                 tc_wait_ld();
                 if (two) tmem_ld16(acc_of(g + 1), rb);
-                epi_group_act<PASSES, FMT>(ra, g, ed, bias, aux, sig, vmax, ha, la);
+                if (BWD) epi_group_bwd<PASSES, FMT>(ra, g, ed, bias, mask_row, gin, vmax, ha, la);
+                else epi_group_act<PASSES, FMT>(ra, g, ed, bias, aux, sig, vmax, ha, la);
                 if (two) {
                   tc_wait_ld();
                   if (after >= 0) tmem_ld16(acc_of(after), ra);
-                  epi_group_act<PASSES, FMT>(rb, g + 1, ed, bias, aux, sig, vmax, hb, lb);
+                  if (BWD) epi_group_bwd<PASSES, FMT>(rb, g + 1, ed, bias, mask_row, gin, vmax, hb, lb);
+                  else epi_group_act<PASSES, FMT>(rb, g + 1, ed, bias, aux, sig, vmax, hb, lb);
                 } else if (after >= 0) {
                   tmem_ld16(acc_of(after), ra);
                 }
@@ -396,7 +466,7 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
               }
             } else {
               // EPI_LOGITS: where this half's columns go (the second half may be a logit layer of its own)
-              const bool own_half = h == 1 && ed.n_valid1 > 0;
+              const bool own_half = !BWD && h == 1 && ed.n_valid1 > 0;
               float* out_row = p.raw + (valid ? s : 0) * p.CH + (own_half ? ed.out_off1 : ed.out_off);
               const int out_c0 = own_half ? (int)ed.n0 : 0, out_valid = own_half ? (int)ed.n_valid1 : (int)ed.n_valid;
               const int out_ch = (own_half ? (int)ed.out_off1 : (int)ed.out_off) + 1;   // composited channel of column out_c0
@@ -406,7 +476,9 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
                 const int after = (g + 2 < hi) ? g + 2 : nxt;
                 tc_wait_ld();
                 if (two) tmem_ld16(acc_of(g + 1), rb);
-                if (ed.kind == EPI_VIEW_RGB) {
+                if (BWD) {
+                  if (valid) epi_group_gradout(ra, g, ed.n_valid, ed.n_valid1 != 0, out_row);
+                } else if (ed.kind == EPI_VIEW_RGB) {
                   epi_group_rgb(ra, g, ed, bias, aux, c0, c1, c2);
                 } else if (COMP) {
                   epi_group_logits_comp(ra, g, out_c0, out_valid, out_ch, bias, w_mine, lane, qsum_q);
@@ -416,7 +488,9 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
                 if (two) {
                   tc_wait_ld();
                   if (after >= 0) tmem_ld16(acc_of(after), ra);
-                  if (ed.kind == EPI_VIEW_RGB) {
+                  if (BWD) {
+                    if (valid) epi_group_gradout(rb, g + 1, ed.n_valid, ed.n_valid1 != 0, out_row);
+                  } else if (ed.kind == EPI_VIEW_RGB) {
                     epi_group_rgb(rb, g + 1, ed, bias, aux, c0, c1, c2);
                   } else if (COMP) {
                     epi_group_logits_comp(rb, g + 1, out_c0, out_valid, out_ch, bias, w_mine, lane, qsum_q);
@@ -430,7 +504,7 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
             }
             if (pi == 0 && h == 1) signal(cnt_e1a);   // hand-off after part a of E1
           }
-          if (h == 1) {
+          if (!BWD && h == 1) {
             if (ed.sigma) {
               part[(ch * kTileM + row) * 4 + 3] = sig;
               sig = 0.f;
@@ -570,7 +644,7 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
       float x[3], d[3];
       if (p.pts != nullptr) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) { x[c] = p.pts[s * 3 + c]; d[c] = p.viewdirs[s * 3 + c]; }
+        for (int c = 0; c < 3; ++c) { x[c] = p.pts[s * 3 + c]; d[c] = BWD ? 0.f : p.viewdirs[s * 3 + c]; }
       } else {
         const int64_t ray = s / p.N;
         const float zi = p.z[s];
@@ -591,12 +665,14 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
       encode_row<PASSES, FMT, 10, 64>(x, Lx, emb_hi, emb_lo, row);
       fence_proxy_async_smem();
       mbar_arrive(bar_emb_full);
-      const int b = it & 1;
-      uint8_t* dir_hi = smem + kSmemDir + b * 2 * kDirPartBytes;
-      mbar_wait_backoff(bar_dir_empty + 8 * b, (uint32_t)(((it >> 1) & 1) ^ 1));
-      encode_row<PASSES, FMT, 4, 32>(d, Ld, dir_hi, dir_hi + kDirPartBytes, row);
-      fence_proxy_async_smem();
-      mbar_arrive(bar_dir_full + 8 * b);
+      if (!BWD) {   // (backward programs stop at the trunk: the view-direction region holds their sign patterns)
+        const int b = it & 1;
+        uint8_t* dir_hi = smem + kSmemDir + b * 2 * kDirPartBytes;
+        mbar_wait_backoff(bar_dir_empty + 8 * b, (uint32_t)(((it >> 1) & 1) ^ 1));
+        encode_row<PASSES, FMT, 4, 32>(d, Ld, dir_hi, dir_hi + kDirPartBytes, row);
+        fence_proxy_async_smem();
+        mbar_arrive(bar_dir_full + 8 * b);
+      }
     }
   } else if (warp == kEpiWarps + kProWarps) {
     // =============================================================== TMA producer (one elected thread)
@@ -798,32 +874,34 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
 // Per-device launch state: the > 48 KB dynamic shared-memory opt-in is a per-device function attribute, and so
 // is the SM count the persistent grid is sized by.
 struct DeviceState {
-  bool attr_done[2][2][2] = {};
+  bool attr_done[2][2][3] = {};   // [x3][bf16][plain / compositing epilogue / backward program]
 };
 static DeviceState g_dev[kMaxDevices];
 static std::mutex g_dev_mutex;
 
-template <int PASSES, int FMT, bool COMP>
+template <int PASSES, int FMT, bool COMP, bool BWD = false>
 static int launch_one(const MlpLaunch& L, int dev, int grid, cudaStream_t stream) {
   constexpr int kSmem = COMP ? kSmemTotalComp : kSmemTotal;
   {
     std::lock_guard<std::mutex> lock(g_dev_mutex);
-    bool& done = g_dev[dev].attr_done[PASSES == 3][FMT == kFmtBF16][COMP];
+    bool& done = g_dev[dev].attr_done[PASSES == 3][FMT == kFmtBF16][BWD ? 2 : (COMP ? 1 : 0)];
     if (!done) {
-      PNR_CUDA(cudaFuncSetAttribute(mlp_fused_kernel<PASSES, FMT, COMP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      PNR_CUDA(cudaFuncSetAttribute(mlp_fused_kernel<PASSES, FMT, COMP, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     kSmem));
       done = true;
     }
   }
-  mlp_fused_kernel<PASSES, FMT, COMP><<<grid, kMlpThreads, kSmem, stream>>>(L);
+  mlp_fused_kernel<PASSES, FMT, COMP, BWD><<<grid, kMlpThreads, kSmem, stream>>>(L);
   PNR_LAUNCH_CHECK("mlp_fused_kernel");
   return PNR_OK;
 }
 
-// Launches on the CURRENT device (the caller has made the context's device current).  `composite`: the
+// Launches on the CURRENT device (the caller has made the context's device current).  mode 1: the
 // compositing-epilogue variant; the launch's rays_per_cta is set here (whole rays per CTA, a multiple of the
 // 128 / gcd(N, 128) rays that make whole tiles, so that every CTA's range starts on a 32-sample boundary).
-int launch_mlp(MlpLaunch& L, int passes, int fmt, bool composite, cudaStream_t stream) {
+// mode 2: L.prog is a backward program (x3 precisions only).
+int launch_mlp(MlpLaunch& L, int passes, int fmt, int mode, cudaStream_t stream) {
+  const bool composite = mode == kMlpComposite;
   int dev = 0;
   PNR_CUDA(cudaGetDevice(&dev));
   PNR_CHECK_ARG(dev >= 0 && dev < kMaxDevices, "launch_mlp: device ordinal %d >= %d", dev, kMaxDevices);
@@ -835,6 +913,11 @@ int launch_mlp(MlpLaunch& L, int passes, int fmt, bool composite, cudaStream_t s
   if (composite) {
     const int64_t R = L.p.S / L.p.N;
     L.p.rays_per_cta = (R + grid - 1) / grid;
+  }
+  if (mode == kMlpBackward) {
+    if (passes != 3) return set_error(PNR_ERR_UNSUPPORTED, "backward programs run in the x3 precisions only");
+    return fmt == kFmtF16 ? launch_one<3, kFmtF16, false, true>(L, dev, grid, stream)
+                          : launch_one<3, kFmtBF16, false, true>(L, dev, grid, stream);
   }
 #define PNR_LAUNCH(P, F) (composite ? launch_one<P, F, true>(L, dev, grid, stream) : launch_one<P, F, false>(L, dev, grid, stream))
   if (fmt == kFmtF16) return passes == 3 ? PNR_LAUNCH(3, kFmtF16) : PNR_LAUNCH(1, kFmtF16);

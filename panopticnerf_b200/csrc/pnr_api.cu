@@ -24,7 +24,7 @@ int set_error(int code, const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches += n; }
 
-int launch_mlp(MlpLaunch& L, int passes, int fmt, bool composite, cudaStream_t stream);  // mlp_tc05.cu
+int launch_mlp(MlpLaunch& L, int passes, int fmt, int mode, cudaStream_t stream);  // mlp_tc05.cu
 
 }  // namespace pnr
 
@@ -42,6 +42,14 @@ struct pnr_ctx {
   float* d_consts = nullptr;
   uint32_t* d_status = nullptr; // sticky range-check word of the fused MLP (bit 0: activation out of operand range)
   size_t wpacked_bytes = 0;
+  // backward program of the trunk (pnr_mlp_backward_trunk): built from a host copy of the trunk weights on first use
+  std::vector<std::vector<float>> host_trunk;   // weight, bias per trunk layer, as given to pnr_load_weights
+  std::vector<int64_t> host_trunk_shapes;
+  bool bwd_ready = false;
+  long long* dbg_timeline = nullptr;   // development aid (pnr_debug_timeline)
+  MlpLaunch bwd_launch;
+  uint8_t* d_wpacked_bwd = nullptr;
+  float* d_consts_bwd = nullptr;
 };
 
 // ---------------------------------------------------------------- host-side 16-bit split (RNE, = cvt.rn.*.f32)
@@ -208,7 +216,7 @@ struct Builder {
   Foot epi_foot(int s, int c0, int c1) const {
     const EpiDesc& e = prog.ep[s];
     Foot f{e.acc_col + c0, e.acc_col + c1, 0, 0, 0, 0};
-    if (e.kind == EPI_RELU_TO_A && c0 < c1) {
+    if (epi_writes_a(e.kind) && c0 < c1) {
       f.hi0 = e.dst_col + c0 / 2; f.hi1 = e.dst_col + c1 / 2;
       if (passes == 3) { f.lo0 = e.dst_lo_col + c0 / 2; f.lo1 = e.dst_lo_col + c1 / 2; }
     }
@@ -236,7 +244,7 @@ struct Builder {
     // accumulator flip (mlp_program.h): allowed when no activation lives inside the accumulator region (the head
     // columns of single-head programs do) and no accumulator range straddles column 128
     bool flip = acc_flip;
-    for (int s = 0; s < S; ++s) flip = flip && !(prog.ep[s].kind == EPI_RELU_TO_A && prog.ep[s].dst_col < kColAHi);
+    for (int s = 0; s < S; ++s) flip = flip && !(epi_writes_a(prog.ep[s].kind) && prog.ep[s].dst_col < kColAHi);
     for (int i = 0; i < prog.n_stages; ++i)
       flip = flip && prog.st[i].acc_col / 128 == (prog.st[i].acc_col + prog.st[i].n - 1) / 128;
     prog.acc_flip = flip ? 1 : 0;
@@ -268,7 +276,7 @@ struct Builder {
       // E0 of this step overwrites dst columns [dst, dst + n0/2) (hi and lo): last stage reading them
       const EpiDesc& e = prog.ep[s];
       int war = in.first_stage;
-      if (e.kind == EPI_RELU_TO_A) {
+      if (epi_writes_a(e.kind)) {
         Foot f = epi_foot(s, 0, e.n0);
         f.acc0 = f.acc1 = 0;   // stores only: the loads of E0 are ordered by acc_full
         for (int i = in.first_stage; i < end; ++i)
@@ -362,6 +370,8 @@ extern "C" int pnr_destroy(pnr_ctx* ctx) {
   DeviceGuard guard(ctx->cfg.device);
   cudaFree(ctx->d_wpacked);
   cudaFree(ctx->d_consts);
+  cudaFree(ctx->d_wpacked_bwd);
+  cudaFree(ctx->d_consts_bwd);
   cudaFree(ctx->d_status);
   delete ctx;
   return PNR_OK;
@@ -553,6 +563,93 @@ static int build_program(const pnr_config& c, const float* const* t, const int64
   return PNR_OK;
 }
 
+
+// Backward program of the trunk (mlp_program.h, "BACKWARD"): t / shapes = the trunk's weight, bias pairs (the first
+// 2*D tensors of pnr_load_weights' list).  Forward steps 0..D-1 (sign patterns kept, the last one loads the incoming
+// gradient), then for l = D-1..0 the gradient w.r.t. layer l's input: g_l [128, W] x W_l [W, in_l], i.e. a step whose
+// weight matrix is W_l transposed; the embedded-input columns of layer 0 and of the skip layer go to the output rows.
+static int build_backward_program(const pnr_config& c, const float* const* t, const int64_t* shapes, int32_t n,
+                                  Builder& bld) {
+  const int D = c.D, W = c.W, Ex = 3 + 6 * c.xyz_res, skip = D / 2;
+  PNR_CHECK_ARG(n >= 2 * D, "backward program: got %d tensors, the trunk has %d", n, 2 * D);
+  if (bld.passes != 3)
+    return set_error(PNR_ERR_UNSUPPORTED, "backward program: precision must be fp16x3 or bf16x3");
+  if (D - 1 > kMaxMaskSlots)
+    return set_error(PNR_ERR_UNSUPPORTED, "backward program: D=%d needs %d sign-pattern slots, %d fit", D, D - 1, kMaxMaskSlots);
+  std::vector<Mat> trunk(D);
+  std::vector<const float*> trunk_b(D);
+  for (int i = 0; i < D; ++i) {
+    const int in = i == 0 ? Ex : (i == skip + 1 ? W + Ex : W);
+    if (shapes[4 * i] != W || shapes[4 * i + 1] != in || shapes[4 * i + 2] != W || shapes[4 * i + 3] != 1 || !t[2 * i] || !t[2 * i + 1])
+      return set_error(PNR_ERR_ARG, "backward program: trunk layer %d: expected weight [%d,%d] + bias [%d,1]", i, W, in, W);
+    trunk[i] = Mat{t[2 * i], W, in};
+    trunk_b[i] = t[2 * i + 1];
+  }
+  bld.prog.Lx = c.xyz_res;
+  bld.prog.Ld = c.view_res;
+  bld.prog.passes = bld.passes;
+  auto seg_tmem = [&](const Mat& m, int col0, int k) {
+    return Seg{A_TMEM, m, col0, k, round_up(k, 16), kColAHi, kColALo, false};
+  };
+  bool ok = true;
+  for (int i = 0; i < D && ok; ++i) {   // forward, as in build_program (no sigma head)
+    EpiDesc ed{};
+    ed.kind = (i == D - 1) ? EPI_LOADG_TO_A : EPI_RELU_TO_A;
+    ed.n_valid = (i == D - 1) ? 0 : (uint16_t)(i + 1);      // sign-pattern slot + 1
+    ed.dst_col = kColAHi;
+    ed.dst_lo_col = kColALo;
+    ed.bias_off = (uint16_t)bld.add_consts(trunk_b[i], W, W);
+    std::vector<Seg> segs;
+    if (i == 0) {
+      segs.push_back(Seg{A_EMB, trunk[i], 0, Ex, 64, 0, 0, false});
+    } else if (i == skip + 1) {
+      segs.push_back(Seg{A_EMB, trunk[i], 0, Ex, 64, 0, 0, true});
+      segs.push_back(seg_tmem(trunk[i], Ex, W));
+    } else {
+      segs.push_back(seg_tmem(trunk[i], 0, W));
+    }
+    ok = bld.add_step(segs, W, kColAcc, ed, i == 0);
+  }
+  std::vector<float> wt;   // W_l transposed: [in_l, W] row-major (packed inside add_step, so one buffer serves all)
+  for (int l = D - 1; l >= 0 && ok; --l) {
+    const int in = trunk[l].in;
+    wt.assign((size_t)in * W, 0.f);
+    for (int o = 0; o < W; ++o)
+      for (int k = 0; k < in; ++k) wt[(size_t)k * W + o] = trunk[l].w[(size_t)o * in + k];
+    auto grad_out = [&](const float* rows, bool accumulate) {    // embedded-input columns -> output rows
+      EpiDesc eo{};
+      eo.kind = EPI_GRAD_OUT;
+      eo.n_valid = (uint16_t)Ex;
+      eo.n_valid1 = accumulate ? 1 : 0;
+      eo.out_off = 0;
+      return bld.add_step({seg_tmem(Mat{rows, Ex, W}, 0, W)}, 64, kColAcc, eo, false);
+    };
+    auto grad_h = [&](const float* rows) {                       // hidden columns, gated by layer l-1's sign pattern
+      EpiDesc em{};
+      em.kind = EPI_MASK_TO_A;
+      em.n_valid = (uint16_t)l;                                  // slot (l - 1) + 1
+      em.dst_col = kColAHi;
+      em.dst_lo_col = kColALo;
+      return bld.add_step({seg_tmem(Mat{rows, W, W}, 0, W)}, W, kColAcc, em, false);
+    };
+    if (l == 0) {
+      ok = grad_out(wt.data(), true);
+    } else if (l == skip + 1) {   // input = [embedded xyz ; h]: the embedded part first (the next step overwrites g_l)
+      ok = grad_out(wt.data(), false) && grad_h(wt.data() + (size_t)Ex * W);
+    } else {
+      ok = grad_h(wt.data());
+    }
+  }
+  if (!ok) return set_error(PNR_ERR_UNSUPPORTED, "backward program: build failed: %s", bld.err.c_str());
+  if ((int)bld.consts.size() > kMaxConsts)
+    return set_error(PNR_ERR_UNSUPPORTED, "backward program: %d constants > %d", (int)bld.consts.size(), kMaxConsts);
+  if (bld.out_of_fp16_range && bld.fmt == kFmtF16)
+    return set_error(PNR_ERR_UNSUPPORTED, "backward program: a weight is outside the fp16 range: use precision bf16x3");
+  bld.prog.n_consts = (int)bld.consts.size();
+  bld.finalize();
+  return PNR_OK;
+}
+
 extern "C" int pnr_load_weights(pnr_ctx* ctx, const float* const* t, const int64_t* shapes, int32_t n) {
   PNR_CHECK_ARG(ctx && t && shapes, "pnr_load_weights: null pointer");
   const pnr_config& c = ctx->cfg;
@@ -569,6 +666,12 @@ extern "C" int pnr_load_weights(pnr_ctx* ctx, const float* const* t, const int64
   PNR_CUDA(cudaMalloc(&ctx->d_wpacked, ctx->wpacked_bytes));
   PNR_CUDA(cudaMalloc(&ctx->d_consts, bld.consts.size() * 4));
   ctx->launch.prog = bld.prog;
+  // host copy of the trunk for the backward program (built on the first pnr_mlp_backward_trunk after this load)
+  ctx->bwd_ready = false;
+  ctx->host_trunk.clear();
+  ctx->host_trunk_shapes.assign(shapes, shapes + 4 * c.D);
+  for (int i = 0; i < 2 * c.D; ++i)
+    ctx->host_trunk.emplace_back(t[i], t[i] + (size_t)shapes[2 * i] * (size_t)shapes[2 * i + 1]);
   PNR_CUDA(cudaMemcpy(ctx->d_wpacked, bld.wbuf.data(), ctx->wpacked_bytes, cudaMemcpyHostToDevice));
   PNR_CUDA(cudaMemcpy(ctx->d_consts, bld.consts.data(), bld.consts.size() * 4, cudaMemcpyHostToDevice));
   ctx->loaded = true;
@@ -581,12 +684,13 @@ extern "C" int pnr_program_host(const pnr_config* cfg, const float* const* t, co
                                 size_t* n_consts) {
   PNR_CHECK_ARG(cfg && t && shapes && program_bytes && wpacked_bytes && n_consts, "pnr_program_host: null pointer");
   if (const int rc = check_config(cfg)) return rc;
-  PNR_CHECK_ARG((flags & ~(PNR_PROGRAM_SPLIT_E1 | PNR_PROGRAM_NO_SPLIT)) == 0,
+  PNR_CHECK_ARG((flags & ~(PNR_PROGRAM_SPLIT_E1 | PNR_PROGRAM_NO_SPLIT | PNR_PROGRAM_BACKWARD)) == 0,
                 "pnr_program_host: unknown flags 0x%x", flags);
   Builder bld(precision_passes(cfg->precision), precision_fmt(cfg->precision));
   if (flags & PNR_PROGRAM_NO_SPLIT) bld.split_e1 = false;
   if (flags & PNR_PROGRAM_SPLIT_E1) bld.split_e1 = true;
-  const int rc = build_program(*cfg, t, shapes, n, bld);
+  const int rc = (flags & PNR_PROGRAM_BACKWARD) ? build_backward_program(*cfg, t, shapes, n, bld)
+                                                : build_program(*cfg, t, shapes, n, bld);
   if (rc != PNR_OK) return rc;
   *program_bytes = sizeof(MlpProgram);
   *wpacked_bytes = bld.wbuf.size() * 2;
@@ -608,6 +712,12 @@ extern "C" int pnr_program_host(const pnr_config* cfg, const float* const* t, co
 
 static int mlp_forward_impl(pnr_ctx* ctx, const float* pts, const float* viewdirs, const float* rays,
                             const float* z, int64_t R, int32_t N, float* raw, void* stream, long long* dbg);
+
+extern "C" int pnr_debug_timeline(pnr_ctx* ctx, int64_t* timeline) {
+  PNR_CHECK_ARG(ctx, "pnr_debug_timeline: null context");
+  ctx->dbg_timeline = (long long*)timeline;
+  return PNR_OK;
+}
 
 extern "C" int pnr_mlp_forward(pnr_ctx* ctx, const float* pts, const float* viewdirs, const float* rays,
                                const float* z, int64_t R, int32_t N, float* raw, void* stream) {
@@ -637,7 +747,7 @@ static int mlp_forward_impl(pnr_ctx* ctx, const float* pts, const float* viewdir
   p.status = ctx->d_status;
   p.dbg = dbg;
   DeviceGuard guard(ctx->cfg.device);   // launch on the context's device whatever the caller's current one is
-  return launch_mlp(ctx->launch, ctx->passes, ctx->fmt, false, (cudaStream_t)stream);
+  return launch_mlp(ctx->launch, ctx->passes, ctx->fmt, kMlpForward, (cudaStream_t)stream);
 }
 
 extern "C" int pnr_mlp_composite(pnr_ctx* ctx, const float* rays, const float* z, int64_t R, int32_t N,
@@ -667,7 +777,7 @@ extern "C" int pnr_mlp_composite(pnr_ctx* ctx, const float* rays, const float* z
   p.weights = out->weights; p.rgb_map = out->rgb_map; p.depth_map = out->depth_map; p.acc_map = out->acc_map;
   p.disp_map = out->disp_map; p.sem_map = C > 0 ? out->semantic_map : nullptr; p.inst_map = K > 0 ? out->instance_map : nullptr;
   DeviceGuard guard(ctx->cfg.device);
-  if (const int rc = launch_mlp(ctx->launch, ctx->passes, ctx->fmt, true, (cudaStream_t)stream)) return rc;
+  if (const int rc = launch_mlp(ctx->launch, ctx->passes, ctx->fmt, kMlpComposite, (cudaStream_t)stream)) return rc;
   const bool fs = C > 0 && out->fixed_semantic_map && sample_box && box_sem;
   const bool fi = K > 0 && out->fixed_instance_map && sample_box && box_inst;
   if (fs || fi)
@@ -675,6 +785,47 @@ extern "C" int pnr_mlp_composite(pnr_ctx* ctx, const float* rays, const float* z
                              fs ? out->fixed_semantic_map : nullptr, fi ? out->fixed_instance_map : nullptr,
                              (cudaStream_t)stream);
   return PNR_OK;
+}
+
+
+// dL/d(embedded xyz) through the trunk (first slice of the MLP backward): the forward trunk is
+// recomputed per tile (sign patterns stay in shared memory), then the layers run in reverse on the same tiles with
+// the transposed weight stream.  grad_h = dL/dh of the trunk output [R*N, W]; grad_emb [R*N, 3 + 6*xyz_res].
+extern "C" int pnr_mlp_backward_trunk(pnr_ctx* ctx, const float* pts, const float* rays, const float* z, int64_t R,
+                                      int32_t N, const float* grad_h, float* grad_emb, void* stream) {
+  if (R == 0) return PNR_OK;
+  PNR_CHECK_ARG(ctx && grad_h && grad_emb, "pnr_mlp_backward_trunk: null pointer");
+  if (!ctx->loaded) return set_error(PNR_ERR_STATE, "pnr_mlp_backward_trunk: pnr_load_weights has not been called");
+  PNR_CHECK_ARG(R > 0 && N >= 1, "pnr_mlp_backward_trunk: bad sizes R=%lld N=%d", (long long)R, N);
+  PNR_CHECK_ARG(pts || (rays && z), "pnr_mlp_backward_trunk: need pts or (rays, z)");
+  const int64_t S = R * (int64_t)N;
+  PNR_CHECK_ARG((S + kTileM - 1) / kTileM < (int64_t)1 << 31, "pnr_mlp_backward_trunk: too many samples");
+  DeviceGuard guard(ctx->cfg.device);
+  if (!ctx->bwd_ready) {
+    Builder bld(ctx->passes, ctx->fmt);
+    std::vector<const float*> tp;
+    for (const auto& v : ctx->host_trunk) tp.push_back(v.data());
+    if (const int rc = build_backward_program(ctx->cfg, tp.data(), ctx->host_trunk_shapes.data(), (int32_t)tp.size(), bld))
+      return rc;
+    cudaFree(ctx->d_wpacked_bwd); cudaFree(ctx->d_consts_bwd);
+    ctx->d_wpacked_bwd = nullptr; ctx->d_consts_bwd = nullptr;
+    PNR_CUDA(cudaMalloc(&ctx->d_wpacked_bwd, bld.wbuf.size() * 2));
+    PNR_CUDA(cudaMalloc(&ctx->d_consts_bwd, bld.consts.size() * 4));
+    PNR_CUDA(cudaMemcpy(ctx->d_wpacked_bwd, bld.wbuf.data(), bld.wbuf.size() * 2, cudaMemcpyHostToDevice));
+    PNR_CUDA(cudaMemcpy(ctx->d_consts_bwd, bld.consts.data(), bld.consts.size() * 4, cudaMemcpyHostToDevice));
+    memset(&ctx->bwd_launch.p, 0, sizeof(MlpParams));
+    ctx->bwd_launch.prog = bld.prog;
+    ctx->bwd_ready = true;
+  }
+  MlpParams& p = ctx->bwd_launch.p;
+  p.wpacked = ctx->d_wpacked_bwd; p.consts = ctx->d_consts_bwd;
+  p.pts = pts; p.viewdirs = nullptr; p.rays = rays; p.z = z;
+  p.S = S; p.N = N; p.CH = 3 + 6 * ctx->cfg.xyz_res; p.raw = grad_emb;
+  p.num_tiles = (int32_t)((S + kTileM - 1) / kTileM);
+  p.status = ctx->d_status;
+  p.dbg = ctx->dbg_timeline;
+  p.grad_in = grad_h;
+  return launch_mlp(ctx->bwd_launch, ctx->passes, ctx->fmt, kMlpBackward, (cudaStream_t)stream);
 }
 
 namespace pnr {

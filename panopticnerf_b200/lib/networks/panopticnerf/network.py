@@ -187,6 +187,29 @@ class Network(nn.Module):
                                                       _capi.stream_ptr()), "pnr_mlp_composite")
         return out
 
+    def backward_trunk(self, grad_h: torch.Tensor, pts: Optional[torch.Tensor] = None,
+                       rays: Optional[torch.Tensor] = None, z: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """First slice of the MLP backward (pnr_mlp_backward_trunk): dL/d(embedded xyz) [S, 3 + 6*xyz_res] from
+        grad_h = dL/dh of the trunk output [S, W], for the samples given as pts [S,3] or as (rays [R,6], z [R,N]).
+        What autograd computes through `pts_linears` (ReLUs, skip concatenation) of the reference Network."""
+        if pts is not None:
+            S_, N = pts.shape[0], 1
+            R = S_
+            dev = pts.device
+        else:
+            R, N = z.shape
+            S_ = R * N
+            dev = rays.device
+        assert grad_h.shape == (S_, self.W), f"grad_h must be [{S_}, {self.W}]"
+        ctx = self.pack(dev if grad_h.is_cuda else None)
+        out = torch.empty(S_, 3 + 6 * self.Lx, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _capi.check(_capi.lib().pnr_mlp_backward_trunk(
+                ctx, _capi.ptr(pts, torch.float32, "pts"), _capi.ptr(rays, torch.float32, "rays"),
+                _capi.ptr(z, torch.float32, "z"), R, N, _capi.ptr(grad_h, torch.float32, "grad_h"), _capi.ptr(out),
+                _capi.stream_ptr()), "pnr_mlp_backward_trunk")
+        return out
+
     def range_status(self, reset: bool = True) -> int:
         """Sticky range-check word of this network's fused-MLP launches (synchronises the current stream).
         Bit 0 set: an activation left the range of the 16-bit operand format (fp16 modes: |x| > 65504) or was not

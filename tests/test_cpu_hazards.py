@@ -13,8 +13,9 @@ import itertools
 import pytest
 
 from panopticnerf_b200 import make_cfg, make_network, synthetic as S
-from test_cpu_program import (A_TMEM, EPI_RELU_TO_A, F_COMMIT_ACC0, F_COMMIT_ACC1, F_COMMIT_WAR,
-                              F_WAIT_E0, F_WAIT_E1, F_WAIT_E1A, PROGRAM_NO_SPLIT, PROGRAM_SPLIT_E1, build)
+from test_cpu_program import (A_TMEM, EPI_LOADG_TO_A, EPI_MASK_TO_A, EPI_RELU_TO_A, F_COMMIT_ACC0, F_COMMIT_ACC1,
+                              F_COMMIT_WAR, F_WAIT_E0, F_WAIT_E1, F_WAIT_E1A, PROGRAM_BACKWARD, PROGRAM_NO_SPLIT,
+                              PROGRAM_SPLIT_E1, build)
 
 
 def overlap(a, b):
@@ -59,7 +60,7 @@ def events_and_edges(prog, tiles=3):
     prev_stage = None
     for t, s in order:
         ed = prog.ep[s]
-        to_a = ed.kind == EPI_RELU_TO_A
+        to_a = ed.kind in (EPI_RELU_TO_A, EPI_MASK_TO_A, EPI_LOADG_TO_A)
         for i in steps[s]:
             sd = prog.st[i]
             ev = ("S", t, i)
@@ -149,6 +150,17 @@ def test_every_tensor_memory_conflict_is_ordered(preset, over, flags):
     """Default program of the precision, one-block E1, two-block E1."""
     cfg = make_cfg(preset, **over)
     prog, _, _ = build(cfg, S.init_network_weights(make_network(cfg), seed=0), flags=flags)
+    checked, bad = unordered_conflicts(prog)
+    assert checked > 20
+    assert not bad, f"{preset} {over} flags={flags}: unordered tensor-memory conflicts, e.g. {bad[:3]}"
+
+
+@pytest.mark.parametrize("preset,over", [("cfg2", {}), ("cfg2", dict(precision="bf16x3", D=5, W=128)), ("cfg1", dict(D=3, W=64))])
+@pytest.mark.parametrize("flags", [0, PROGRAM_NO_SPLIT])
+def test_backward_program_conflicts_are_ordered(preset, over, flags):
+    """The backward program of the trunk (forward steps + the layers in reverse) under the same analysis."""
+    cfg = make_cfg(preset, **over)
+    prog, _, _ = build(cfg, S.init_network_weights(make_network(cfg), seed=0), flags=flags | PROGRAM_BACKWARD)
     checked, bad = unordered_conflicts(prog)
     assert checked > 20
     assert not bad, f"{preset} {over} flags={flags}: unordered tensor-memory conflicts, e.g. {bad[:3]}"

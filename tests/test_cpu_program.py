@@ -20,6 +20,8 @@ F_FIRST, F_WAIT_E0, F_WAIT_E1, F_COMMIT_ACC0, F_COMMIT_ACC1, F_COMMIT_WAR = 1, 2
 F_WAIT_E1A = 1024
 PROGRAM_SPLIT_E1, PROGRAM_NO_SPLIT = 4, 8
 EPI_RELU_TO_A, EPI_VIEW_RGB, EPI_LOGITS = 0, 2, 3
+EPI_MASK_TO_A, EPI_LOADG_TO_A, EPI_GRAD_OUT = 4, 5, 6          # backward programs
+PROGRAM_BACKWARD = 16
 COL_A_HI, COL_HEAD_HI = 256, 128
 
 
@@ -85,7 +87,7 @@ def split16(x: np.ndarray, bf16: bool):
     return hi.double().numpy(), lo.double().numpy()
 
 
-def replay(prog, w16, consts, cfg, pts, viewdirs, operand_precision: bool = False):
+def replay(prog, w16, consts, cfg, pts, viewdirs, operand_precision: bool = False, grad_in=None):
     """What the kernel computes for these samples, from the packed program.  Default: exact activations, float64
     (tests the program).  operand_precision=True also rounds the A operands like the tensor cores see them:
     fp32 activations split into 16-bit hi (+ lo in the x3 modes), products hi*Whi (+ lo*Whi + hi*Wlo)."""
@@ -96,8 +98,9 @@ def replay(prog, w16, consts, cfg, pts, viewdirs, operand_precision: bool = Fals
     act = {COL_A_HI: np.zeros((S_, 256)), COL_HEAD_HI: np.zeros((S_, 128))}
     acc = np.zeros((S_, 256))
     CH = 4 + cfg.num_classes + cfg.num_instances
-    out = np.zeros((S_, CH))
+    out = np.zeros((S_, CH if grad_in is None else 3 + 6 * cfg.xyz_res))
     sig = np.zeros(S_)
+    masks = {}                       # backward programs: ReLU sign pattern per slot
     step = -1
     stages_of = []
     for i in range(prog.n_stages):
@@ -152,10 +155,20 @@ def replay(prog, w16, consts, cfg, pts, viewdirs, operand_precision: bool = Fals
             assert (d.idesc >> 7) & 7 == int(bf16)
         n = ed.n
         v = acc[:, ed.acc_col:ed.acc_col + n] + consts[ed.bias_off:ed.bias_off + n][None]
-        if ed.kind == EPI_RELU_TO_A:
+        if ed.kind == EPI_MASK_TO_A:         # gradient w.r.t. a hidden layer's output, gated by its sign pattern
+            v = acc[:, ed.acc_col:ed.acc_col + n]
+            act[ed.dst_col][:, :n] = np.where(masks[ed.n_valid - 1][:, :n], v, 0.0) if ed.n_valid else v
+        elif ed.kind == EPI_LOADG_TO_A:      # last forward layer: the incoming gradient gated by its own pattern
+            act[ed.dst_col][:, :n] = np.where(v > 0.0, grad_in[:, :n], 0.0)
+        elif ed.kind == EPI_GRAD_OUT:
+            v = acc[:, ed.acc_col:ed.acc_col + ed.n_valid]
+            out[:, ed.out_off:ed.out_off + ed.n_valid] = v + (out[:, ed.out_off:ed.out_off + ed.n_valid] if ed.n_valid1 else 0.0)
+        elif ed.kind == EPI_RELU_TO_A:
             v = np.maximum(v, 0.0)
             if ed.sigma:
                 sig = v @ consts[ed.aux_off:ed.aux_off + n].astype(np.float64)
+            if grad_in is not None and ed.n_valid:
+                masks[ed.n_valid - 1] = v > 0.0
             act[ed.dst_col][:, :n] = v
         elif ed.kind == EPI_VIEW_RGB:
             v = np.maximum(v, 0.0)
@@ -246,6 +259,68 @@ def test_operand_precision_of_each_mode(precision, bound):
     assert worst <= bound, f"{precision}: {worst:.3e} > {bound:.1e}"
     if precision in ("fp16", "bf16"):
         assert worst > 1e-4          # and really outside the tolerance: the mode must stay labelled "fast"
+
+
+def trunk_grad_oracle(cfg, net, pts, grad_h):
+    """dL/d(embedded xyz) by autograd through the oracle network's trunk (float64)."""
+    onet = O.Network(cfg).double()
+    onet.load_state_dict({k: v.double() for k, v in net.state_dict().items()})
+    ex = O.embed(pts, cfg.xyz_res).double().requires_grad_(True)
+    h = ex
+    min_z = torch.full((pts.shape[0],), float("inf"), dtype=torch.float64)
+    for i, lin in enumerate(onet.pts_linears):
+        pre = lin(h)
+        min_z = torch.minimum(min_z, pre.detach().abs().min(dim=1).values)
+        h = torch.relu(pre)
+        if i == onet.skip:
+            h = torch.cat([ex, h], -1)
+    h.backward(grad_h.double())
+    return ex.grad, min_z
+
+
+def assert_grad_close(got, ref, min_z, what, rel, kink=1e-6):
+    """relu' is discontinuous: a sample with a pre-activation within rounding distance of zero may take the other
+    branch (one gated unit = an O(1e-3) step in its gradient).  Those rows (|z| < kink somewhere in the trunk's
+    2048 units; kink ~ 10x the rounding error of z in the mode under test) only have to be sane; every other row is
+    held to `rel` of the gradient's RMS."""
+    strict = min_z >= kink
+    assert strict.float().mean() > 0.4, f"{what}: {int((~strict).sum())} of {len(strict)} rows sit on a ReLU kink"
+    assert_close(got[strict], ref[strict], rms(ref), what, rel=rel)
+    if (~strict).any():
+        assert_close(got[~strict], ref[~strict], rms(ref), what + " (rows on a ReLU kink)", rel=1.0)
+
+
+@pytest.mark.parametrize("preset,over", [("cfg2", {}), ("cfg3", dict(precision="bf16x3")), ("cfg1", dict(D=5, W=128)),
+                                         ("cfg1", dict(xyz_res=4, D=3, W=64))])
+def test_backward_program_replay_matches_autograd(preset, over):
+    """The backward program of the trunk (forward steps that keep their ReLU sign patterns, then the layers in reverse
+    with transposed weights) replayed on the CPU = autograd through the oracle's trunk."""
+    cfg = make_cfg(preset, **over)
+    net = S.init_network_weights(make_network(cfg), seed=4)
+    prog, w16, consts = build(cfg, net, flags=PROGRAM_BACKWARD)
+    assert prog.n_steps == 2 * cfg.D + 1
+    g = torch.Generator().manual_seed(6)
+    pts = (torch.rand(200, 3, generator=g) * 2 - 1) * 4
+    grad_h = torch.randn(200, cfg.W, generator=g)
+    got, stages_of = replay(prog, w16, consts, cfg, pts, torch.zeros_like(pts), grad_in=grad_h.double().numpy())
+    check_invariants(prog, stages_of)
+    ref, min_z = trunk_grad_oracle(cfg, net, pts, grad_h)
+    tol = {"fp16x3": 2e-5, "bf16x3": 1e-4}[cfg.precision]
+    kink = {"fp16x3": 1e-6, "bf16x3": 2e-5}[cfg.precision]
+    assert_grad_close(torch.from_numpy(got), ref, min_z, f"{preset} {over} d_emb", tol, kink)
+    # with the operands rounded like the tensor cores see them (gradients split hi/lo as activations are)
+    got_op, _ = replay(prog, w16, consts, cfg, pts, torch.zeros_like(pts), operand_precision=True, grad_in=grad_h.double().numpy())
+    assert_grad_close(torch.from_numpy(got_op), ref, min_z, f"{preset} {over} d_emb (operand precision)", 1e-4, kink)
+
+
+def test_backward_program_limits():
+    cfg = make_cfg("cfg2", precision="fp16")
+    net = S.init_network_weights(make_network(cfg), seed=0)
+    with pytest.raises(_capi.PnrError, match="x3"):
+        build(cfg, net, flags=PROGRAM_BACKWARD)
+    cfg = make_cfg("cfg2", D=12)
+    with pytest.raises(_capi.PnrError, match="slots"):
+        build(cfg, S.init_network_weights(make_network(cfg), seed=0), flags=PROGRAM_BACKWARD)
 
 
 def test_program_host_rejects_bad_input():

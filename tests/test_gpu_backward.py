@@ -123,3 +123,60 @@ def test_composite_backward_rejects_what_it_does_not_implement():
         P.raw2outputs_backward(raw.to(DEV), z.to(DEV), d.to(DEV), {}, num_classes=3, sem_activation="softmax")
     with pytest.raises(ValueError, match="disp_map"):
         P.raw2outputs_backward(raw.to(DEV), z.to(DEV), d.to(DEV), {"disp_map": torch.zeros(4, device=DEV)}, num_classes=3)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# MLP backward, first slice: dL/d(embedded xyz) through the trunk (pnr_mlp_backward_trunk) vs autograd through the
+# oracle network's pts_linears (float64), 1e-4 of the gradient's RMS.  relu' is discontinuous, so rows with a
+# pre-activation within rounding distance of zero are only checked for sanity (test_cpu_program.assert_grad_close).
+# ------------------------------------------------------------------------------------------------------------------
+from panopticnerf_b200 import make_cfg, make_network, synthetic as S       # noqa: E402
+from test_cpu_program import assert_grad_close, trunk_grad_oracle          # noqa: E402
+
+
+@pytest.mark.parametrize("preset,over,n", [("cfg2", {}, 1000), ("cfg2", dict(precision="bf16x3"), 517),
+                                           ("cfg1", dict(D=5, W=128), 128 * 3), ("cfg1", dict(D=3, W=64, xyz_res=4), 77),
+                                           ("cfg3", {}, 40000)])
+def test_mlp_backward_trunk_matches_autograd(preset, over, n):
+    cfg = make_cfg(preset, **over)
+    net = S.init_network_weights(make_network(cfg), seed=2).to(DEV)
+    g = torch.Generator().manual_seed(n)
+    pts = (torch.rand(n, 3, generator=g) * 2 - 1) * 4
+    grad_h = torch.randn(n, cfg.W, generator=g)
+    got = net.backward_trunk(grad_h.to(DEV), pts=pts.to(DEV)).cpu()
+    assert net.range_status() == 0
+    ref, min_z = trunk_grad_oracle(cfg, net.cpu(), pts, grad_h)
+    kink = {"fp16x3": 1e-5, "bf16x3": 3e-5}[cfg.precision]
+    assert_grad_close(got.double(), ref, min_z, f"{preset} {over} d_emb", 1e-4, kink)
+
+
+def test_mlp_backward_trunk_rays_mode_is_deterministic_and_chunk_invariant():
+    """(rays, z) addressing forms the same points as the forward kernel does; two runs agree bit for bit and a
+    sample's gradient does not depend on which tile or launch it was in."""
+    cfg = make_cfg("cfg2")
+    net = S.init_network_weights(make_network(cfg), seed=5).to(DEV)
+    g = torch.Generator().manual_seed(1)
+    R, N = 301, 64
+    rays = torch.cat([torch.randn(R, 3, generator=g), torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1)], -1).to(DEV)
+    z = torch.sort(torch.rand(R, N, generator=g) * 20 + 1, -1).values.to(DEV)
+    grad_h = torch.randn(R * N, cfg.W, generator=g).to(DEV)
+    a = net.backward_trunk(grad_h, rays=rays, z=z)
+    b = net.backward_trunk(grad_h, rays=rays, z=z)
+    assert torch.equal(a, b)
+    pts = (rays[:, None, :3] + rays[:, None, 3:] * z[..., None]).reshape(-1, 3)
+    c = net.backward_trunk(grad_h, pts=pts)
+    assert torch.equal(a, c)
+    lo, hi = 100 * N, 187 * N                      # a chunk that starts and ends inside tiles
+    d = net.backward_trunk(grad_h[lo:hi].contiguous(), rays=rays[100:187].contiguous(), z=z[100:187].contiguous())
+    assert torch.equal(a[lo:hi], d)
+
+
+def test_mlp_backward_trunk_rejects_what_it_does_not_implement():
+    from panopticnerf_b200 import _capi
+    cfg = make_cfg("cfg2", precision="fp16")
+    net = S.init_network_weights(make_network(cfg), seed=0).to(DEV)
+    with pytest.raises(_capi.PnrError, match="x3"):
+        net.backward_trunk(torch.zeros(128, cfg.W, device=DEV), pts=torch.zeros(128, 3, device=DEV))
+    net = S.init_network_weights(make_network(make_cfg("cfg2")), seed=0).to(DEV)
+    with pytest.raises(_capi.PnrError, match="CUDA tensor"):
+        net.backward_trunk(torch.zeros(128, 256), pts=torch.zeros(128, 3, device=DEV))

@@ -8,6 +8,8 @@ sys.path.insert(0, str(ROOT))
 import panopticnerf_b200 as PN
 from panopticnerf_b200 import _capi, synthetic as S
 from panopticnerf_b200.lib.networks.renderer import panopticnerf_renderer as P
+backward = "--backward" in sys.argv          # the trunk-backward kernel instead of the forward one
+sys.argv = [a for a in sys.argv if a != "--backward"]
 prec = sys.argv[1] if len(sys.argv) > 1 else "fp16x3"
 preset = sys.argv[2] if len(sys.argv) > 2 else "cfg2"
 cfg = PN.make_cfg(preset, precision=prec)
@@ -20,7 +22,13 @@ z = P.stratified_z(near, far, torch.linspace(0, 1, cfg.N_samples).to(dev))
 ctx = net.pack(dev)
 raw = torch.empty(rays.shape[0], cfg.N_samples, net.out_channels, device=dev)
 tl = torch.zeros(8192, dtype=torch.int64, device=dev)
-for _ in range(2):
+if backward:
+    grad_h = torch.randn(z.numel(), cfg.W, device=dev)
+    _capi.check(_capi.lib().pnr_debug_timeline(ctx, tl.data_ptr()))
+    for _ in range(2):
+        net.backward_trunk(grad_h, rays=rays, z=z)
+    _capi.check(_capi.lib().pnr_debug_timeline(ctx, None))
+for _ in range(0 if backward else 2):
     _capi.check(_capi.lib().pnr_mlp_forward_timeline(ctx, rays.data_ptr(), z.data_ptr(), rays.shape[0], cfg.N_samples,
                                                      raw.data_ptr(), tl.data_ptr(), _capi.stream_ptr()))
 torch.cuda.synchronize()
@@ -32,7 +40,7 @@ print("stage: arrive  ready  issued   (waits=ready-arrive, issue=issued-ready) |
 for i, (a, r, m, c, d) in enumerate(mma):
     print(f"{i:4d} {a - t0:8d}  wait {r - a:5d} mma {m - r:5d} commit {c - m:5d} sync {d - c:5d} | next-gap {(mma[i + 1][0] - d) if i + 1 < len(mma) else 0:5d} | tma {t[6144 + i] - t0:8d}")
 print("step half: wait_start acc_ready done  (wait, work)")
-for k in range(48):
+for k in range(2 * 24):
     w, a, d = t[4096 + k * 3:4096 + k * 3 + 3]
     if w > 0:
         print(f"{k // 2:3d} h{k % 2} {w - t0:8d} {a - t0:8d} {d - t0:8d}   wait {a - w:6d} work {d - a:6d}")
