@@ -197,14 +197,15 @@ int pnr_composite_backward(const float* raw, const float* z, const float* rays, 
                            int32_t B, const pnr_composite_grads* g, float* d_raw, void* stream);
 
 /* a8 backward, first slice (replaces autograd through Network.forward's trunk - the D
- * `pts_linears` with their ReLUs and the skip concatenation): dL/d(embedded xyz) [R*N, 3 + 6*xyz_res] from
+ * `pts_linears` with their ReLUs and the skip concatenation): dL/d(embedded xyz) (the first 3 + 6*xyz_res columns
+ * of grad_emb [R*N, ld_emb]; ld_emb = 64 on a 16-byte aligned base lets the kernel use 16-byte stores) from
  * grad_h = dL/dh of the trunk output [R*N, W].  One kernel on the same 128-sample tiles as pnr_mlp_forward: the
  * forward trunk is recomputed (ReLU sign patterns stay in shared memory), then the layers run in reverse with the
  * transposed weight stream on the tensor cores, gradients split hi/lo like activations.  Samples are given as pts
  * [R*N,3] or as (rays [R,6], z [R,N]).  x3 precisions only; D <= 9.  The weight gradients and the head / view
  * branches are not part of this slice. */
 int pnr_mlp_backward_trunk(pnr_ctx* ctx, const float* pts, const float* rays, const float* z, int64_t R, int32_t N,
-                           const float* grad_h, float* grad_emb, void* stream);
+                           const float* grad_h, float* grad_emb, int32_t ld_emb, void* stream);
 
 /* a10: sample_pdf + merge.  z [R,N] coarse depths, weights [R,N] coarse weights; bins are the mid
  * points, the pdf is weights[1:-1]+1e-5.  u [R,Ni] is required (deterministic sampler: the host's

@@ -215,12 +215,29 @@ __device__ __forceinline__ void epi_group_bwd(const uint32_t (&r)[16], int g, co
 }
 
 // gradient w.r.t. the embedded input: accumulator columns [0, n_valid) of this group -> the sample's output row
-__device__ __forceinline__ void epi_group_gradout(const uint32_t (&r)[16], int g, int n_valid, bool accumulate, float* dst) {
+// (accumulating: all loads first - one memory latency per group, not one per column).  `vec`: the output rows are
+// 16-byte aligned and padded to whole groups (row stride a multiple of 4 floats >= the step's width; the padding
+// columns receive the zero-padded weights' zeros): four 16-byte accesses per group instead of sixteen 4-byte ones
+// whose 32 lanes each touch a different sector.
+__device__ __forceinline__ void epi_group_gradout(const uint32_t (&r)[16], int g, int n_valid, bool accumulate, bool vec,
+                                                  float* dst) {
+  if (vec) {
+    float4* d4 = reinterpret_cast<float4*>(dst + g * 16);
+    float4 prev[4];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const int ch = g * 16 + j;
-    if (ch < n_valid) dst[ch] = accumulate ? dst[ch] + __uint_as_float(r[j]) : __uint_as_float(r[j]);
+    for (int q = 0; q < 4; ++q) prev[q] = accumulate ? d4[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      d4[q] = make_float4(prev[q].x + __uint_as_float(r[4 * q + 0]), prev[q].y + __uint_as_float(r[4 * q + 1]),
+                          prev[q].z + __uint_as_float(r[4 * q + 2]), prev[q].w + __uint_as_float(r[4 * q + 3]));
+    return;
   }
+  float prev[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) prev[j] = (accumulate && g * 16 + j < n_valid) ? dst[g * 16 + j] : 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    if (g * 16 + j < n_valid) dst[g * 16 + j] = prev[j] + __uint_as_float(r[j]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -395,6 +412,10 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
         // backward programs: this row's sign patterns and its row of the incoming gradient (tail rows read row S-1)
         uint16_t* mask_row = reinterpret_cast<uint16_t*>(smem + kSmemMask) + row;
         const float* gin = BWD ? p.grad_in + (valid ? s : p.S - 1) * (int64_t)ed.n : nullptr;
+        if (BWD && st == 0) {   // this row of the incoming gradient is needed D-1 steps from now: bring it into L2
+          const float* g0 = p.grad_in + (valid ? s : p.S - 1) * (int64_t)prog.ep[0].n;
+          for (int c = ch * 32; c < (int)prog.ep[0].n; c += kCh * 32) prefetch_l2(g0 + c);
+        }
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
 #ifdef PNR_TIMELINE
@@ -470,6 +491,8 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
               float* out_row = p.raw + (valid ? s : 0) * p.CH + (own_half ? ed.out_off1 : ed.out_off);
               const int out_c0 = own_half ? (int)ed.n0 : 0, out_valid = own_half ? (int)ed.n_valid1 : (int)ed.n_valid;
               const int out_ch = (own_half ? (int)ed.out_off1 : (int)ed.out_off) + 1;   // composited channel of column out_c0
+              const bool out_vec = BWD && (p.CH & 3) == 0 && (int)ed.n <= p.CH && (reinterpret_cast<uintptr_t>(p.raw) & 15) == 0 &&
+                                   (ed.out_off & 3) == 0;
 #pragma unroll 1
               for (int g = lo; g < hi; g += 2) {
                 const bool two = g + 1 < hi;
@@ -477,7 +500,7 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
                 tc_wait_ld();
                 if (two) tmem_ld16(acc_of(g + 1), rb);
                 if (BWD) {
-                  if (valid) epi_group_gradout(ra, g, ed.n_valid, ed.n_valid1 != 0, out_row);
+                  if (valid) epi_group_gradout(ra, g, ed.n_valid, ed.n_valid1 != 0, out_vec, out_row);
                 } else if (ed.kind == EPI_VIEW_RGB) {
                   epi_group_rgb(ra, g, ed, bias, aux, c0, c1, c2);
                 } else if (COMP) {
@@ -489,7 +512,7 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
                   tc_wait_ld();
                   if (after >= 0) tmem_ld16(acc_of(after), ra);
                   if (BWD) {
-                    if (valid) epi_group_gradout(rb, g + 1, ed.n_valid, ed.n_valid1 != 0, out_row);
+                    if (valid) epi_group_gradout(rb, g + 1, ed.n_valid, ed.n_valid1 != 0, out_vec, out_row);
                   } else if (ed.kind == EPI_VIEW_RGB) {
                     epi_group_rgb(rb, g + 1, ed, bias, aux, c0, c1, c2);
                   } else if (COMP) {

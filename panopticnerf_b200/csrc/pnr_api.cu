@@ -622,7 +622,8 @@ static int build_backward_program(const pnr_config& c, const float* const* t, co
       eo.n_valid = (uint16_t)Ex;
       eo.n_valid1 = accumulate ? 1 : 0;
       eo.out_off = 0;
-      return bld.add_step({seg_tmem(Mat{rows, Ex, W}, 0, W)}, 64, kColAcc, eo, false);
+      // one N = 64 half: two N = 32 halves would double the MMA count for the same tensor time per MMA
+      return bld.add_step({seg_tmem(Mat{rows, Ex, W}, 0, W)}, 64, kColAcc, eo, false, nullptr, 64);
     };
     auto grad_h = [&](const float* rows) {                       // hidden columns, gated by layer l-1's sign pattern
       EpiDesc em{};
@@ -790,14 +791,17 @@ extern "C" int pnr_mlp_composite(pnr_ctx* ctx, const float* rays, const float* z
 
 // dL/d(embedded xyz) through the trunk (first slice of the MLP backward): the forward trunk is
 // recomputed per tile (sign patterns stay in shared memory), then the layers run in reverse on the same tiles with
-// the transposed weight stream.  grad_h = dL/dh of the trunk output [R*N, W]; grad_emb [R*N, 3 + 6*xyz_res].
+// the transposed weight stream.  grad_h = dL/dh of the trunk output [R*N, W]; grad_emb [R*N, ld_emb], the first
+// 3 + 6*xyz_res columns of a row are the gradient (ld_emb = 64 with a 16-byte aligned base: vector stores).
 extern "C" int pnr_mlp_backward_trunk(pnr_ctx* ctx, const float* pts, const float* rays, const float* z, int64_t R,
-                                      int32_t N, const float* grad_h, float* grad_emb, void* stream) {
+                                      int32_t N, const float* grad_h, float* grad_emb, int32_t ld_emb, void* stream) {
   if (R == 0) return PNR_OK;
   PNR_CHECK_ARG(ctx && grad_h && grad_emb, "pnr_mlp_backward_trunk: null pointer");
   if (!ctx->loaded) return set_error(PNR_ERR_STATE, "pnr_mlp_backward_trunk: pnr_load_weights has not been called");
   PNR_CHECK_ARG(R > 0 && N >= 1, "pnr_mlp_backward_trunk: bad sizes R=%lld N=%d", (long long)R, N);
   PNR_CHECK_ARG(pts || (rays && z), "pnr_mlp_backward_trunk: need pts or (rays, z)");
+  PNR_CHECK_ARG(ld_emb >= 3 + 6 * ctx->cfg.xyz_res, "pnr_mlp_backward_trunk: ld_emb=%d < %d columns", ld_emb,
+                3 + 6 * ctx->cfg.xyz_res);
   const int64_t S = R * (int64_t)N;
   PNR_CHECK_ARG((S + kTileM - 1) / kTileM < (int64_t)1 << 31, "pnr_mlp_backward_trunk: too many samples");
   DeviceGuard guard(ctx->cfg.device);
@@ -820,7 +824,7 @@ extern "C" int pnr_mlp_backward_trunk(pnr_ctx* ctx, const float* pts, const floa
   MlpParams& p = ctx->bwd_launch.p;
   p.wpacked = ctx->d_wpacked_bwd; p.consts = ctx->d_consts_bwd;
   p.pts = pts; p.viewdirs = nullptr; p.rays = rays; p.z = z;
-  p.S = S; p.N = N; p.CH = 3 + 6 * ctx->cfg.xyz_res; p.raw = grad_emb;
+  p.S = S; p.N = N; p.CH = ld_emb; p.raw = grad_emb;
   p.num_tiles = (int32_t)((S + kTileM - 1) / kTileM);
   p.status = ctx->d_status;
   p.dbg = ctx->dbg_timeline;

@@ -94,6 +94,9 @@ __device__ __forceinline__ uint32_t ld_acquire_smem(uint32_t addr) {
 __device__ __forceinline__ void red_add_smem(uint32_t addr, uint32_t v) {
   asm volatile("red.relaxed.cta.shared::cta.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 __device__ __forceinline__ uint32_t ld_volatile_smem(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.volatile.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");

@@ -202,13 +202,15 @@ class Network(nn.Module):
             dev = rays.device
         assert grad_h.shape == (S_, self.W), f"grad_h must be [{S_}, {self.W}]"
         ctx = self.pack(dev if grad_h.is_cuda else None)
-        out = torch.empty(S_, 3 + 6 * self.Lx, dtype=torch.float32, device=dev)
+        Ex = 3 + 6 * self.Lx
+        ld = (Ex + 15) // 16 * 16                  # rows padded to whole 16-column groups: 16-byte stores in the kernel
+        out = torch.empty(S_, ld, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             _capi.check(_capi.lib().pnr_mlp_backward_trunk(
                 ctx, _capi.ptr(pts, torch.float32, "pts"), _capi.ptr(rays, torch.float32, "rays"),
-                _capi.ptr(z, torch.float32, "z"), R, N, _capi.ptr(grad_h, torch.float32, "grad_h"), _capi.ptr(out),
+                _capi.ptr(z, torch.float32, "z"), R, N, _capi.ptr(grad_h, torch.float32, "grad_h"), _capi.ptr(out), ld,
                 _capi.stream_ptr()), "pnr_mlp_backward_trunk")
-        return out
+        return out[:, :Ex]
 
     def range_status(self, reset: bool = True) -> int:
         """Sticky range-check word of this network's fused-MLP launches (synchronises the current stream).

@@ -180,3 +180,19 @@ def test_mlp_backward_trunk_rejects_what_it_does_not_implement():
     net = S.init_network_weights(make_network(make_cfg("cfg2")), seed=0).to(DEV)
     with pytest.raises(_capi.PnrError, match="CUDA tensor"):
         net.backward_trunk(torch.zeros(128, 256), pts=torch.zeros(128, 3, device=DEV))
+
+
+def test_mlp_backward_trunk_unpadded_rows_match_padded():
+    """ld_emb = 3 + 6*xyz_res (scalar stores) gives the same numbers as the padded rows the Python layer uses."""
+    from panopticnerf_b200 import _capi
+    cfg = make_cfg("cfg2")
+    net = S.init_network_weights(make_network(cfg), seed=8).to(DEV)
+    g = torch.Generator().manual_seed(3)
+    n, Ex = 700, 3 + 6 * cfg.xyz_res
+    pts = ((torch.rand(n, 3, generator=g) * 2 - 1) * 3).to(DEV)
+    grad_h = torch.randn(n, cfg.W, generator=g).to(DEV)
+    padded = net.backward_trunk(grad_h, pts=pts)
+    out = torch.full((n, Ex), float("nan"), device=DEV)
+    _capi.check(_capi.lib().pnr_mlp_backward_trunk(net.pack(torch.device(DEV)), pts.data_ptr(), None, None, n, 1,
+                                                   grad_h.data_ptr(), out.data_ptr(), Ex, _capi.stream_ptr()))
+    assert torch.equal(out, padded)
