@@ -119,7 +119,10 @@ int pnr_tag_samples(const float* z, int64_t R, int32_t N, const int32_t* box_id,
  * rays [rows*W, 6] = origin || unnormalised direction, row-major over (v, u).
  * camera 0 = pinhole: d_cam = ((u-cx)/fx, (v-cy)/fy, 1); camera 1 = equirectangular:
  * lon = (u/W-0.5)*2pi, lat = (0.5-v/H)*pi, d_cam = (cos lat sin lon, -sin lat, cos lat cos lon).
- * intr_host = {fx, fy, cx, cy}; c2w_host = row-major 3x4 [R|t]: d = R d_cam, o = t. */
+ * camera 2 = KITTI-360 fisheye (unified / MEI model), intr_host = {gamma1, gamma2, u0, v0, xi, k1, k2}: the pixel's
+ * distorted normalised point is undistorted radially (rd = ro (1 + k1 ro^2 + k2 ro^4), 8 Newton steps from ro = rd)
+ * and lifted to the unit sphere, d_cam = (f x, f y, f - xi), f = (xi + sqrt(1 + (1 - xi^2) r^2)) / (1 + r^2).
+ * intr_host = {fx, fy, cx, cy} otherwise; c2w_host = row-major 3x4 [R|t]: d = R d_cam, o = t. */
 int pnr_generate_rays(int32_t H, int32_t W, int32_t row0, int32_t rows, int32_t camera, const float* intr_host,
                       const float* c2w_host, float* rays, void* stream);
 
@@ -165,6 +168,51 @@ int pnr_composite(const float* raw, const float* z, const float* rays, int64_t R
 int pnr_label_tiles(const float* rgb_map, const float* depth_map, const float* semantic_map,
                     const float* instance_map, int64_t R, int32_t C, int32_t K, uint8_t* rgb8,
                     float* depth_out, int16_t* sem_label, int16_t* inst_label, void* stream);
+
+/* 8(f) rank 2, the loss side: the per-ray terms of the training objective on the rendered maps and their gradients
+ * w.r.t. those maps, in one pass (inputs any subset; NULL skips a term / an output):
+ *   photometric  sum_c (rgb_map - rgb_gt)^2  (+ the same for the coarse map rgb_map0)
+ *   depth        |depth_map - depth_gt| where depth_gt > 0
+ *   semantic     label >= 0: cross-entropy of semantic_map [R,C] against label - softmax CE when the map holds rendered
+ *                logits (sem_is_prob = 0), -log(max(p_label, eps)) when it holds rendered probabilities - times
+ *                label_weight[r] (optional confidence)
+ *   fixed        -log(max(fixed_semantic_map[label], eps)) * label_weight
+ * per_ray [R,4] receives the four unweighted values; the caller sums them.  Every gradient is already multiplied by
+ * the term's weight w_* and normaliser inv_n_* (1 / number of elements or valid rays, which the caller knows), i.e.
+ * it is dL/dmap of L = w_rgb*mean_rgb + w_depth*mean_depth + w_sem*mean_sem + w_fix*mean_fix, ready for
+ * pnr_composite_backward.  (Terms as in the paper; the reference's NetworkWrapper is not in the mount.) */
+typedef struct pnr_loss_args {
+  int64_t R; int32_t C; int32_t sem_is_prob;
+  const float* rgb_map; const float* rgb_map0; const float* rgb_gt;
+  const float* depth_map; const float* depth_gt;
+  const float* semantic_map; const float* fixed_semantic_map; const int32_t* label; const float* label_weight;
+  float w_rgb, w_depth, w_sem, w_fix;
+  float inv_n_rgb, inv_n_depth, inv_n_sem;
+  float eps;
+  float* per_ray;
+  float* d_rgb_map; float* d_rgb_map0; float* d_depth_map; float* d_semantic_map; float* d_fixed_semantic_map;
+} pnr_loss_args;
+int pnr_losses(const pnr_loss_args* args, void* stream);
+
+/* 8(f) rank 4: panoptic label fusion + colour mapping of the composited maps (the step after the path).
+ * s = argmax semantic_map [R,C] (ties -> lowest index, NaN = -inf).  A stuff class (is_thing[s] == 0, or no instance
+ * map) gives id(s)*1000 with id(s) = class_id[s] (or s when class_id is NULL).  A thing class takes the best instance
+ * slot among the slots k with inst_class[k] == s: panoptic = inst_id[k] (or id(s)*1000 + k + 1 when inst_id is NULL);
+ * without such a slot it falls back to id(s)*1000.  color [R,3] u8: palette[s], for instances averaged with a colour
+ * hashed from the panoptic id.  Outputs are optional.  (Rule chosen here; the reference's is not in the mount.) */
+int pnr_panoptic_fuse(const float* semantic_map, const float* instance_map, int64_t R, int32_t C, int32_t K,
+                      const uint8_t* is_thing, const int32_t* inst_class, const int32_t* inst_id,
+                      const int32_t* class_id, const uint8_t* palette, int32_t* panoptic, int16_t* sem_label,
+                      int16_t* inst_slot, uint8_t* color, void* stream);
+
+/* 8(f) rank 4: multi-resolution hash-grid features (the 360 model's extra encoder; published algorithm of
+ * Mueller et al. 2022): level l has resolution floor(base_resolution * per_level_scale^l) (double, on the host);
+ * x [n,3] is mapped to [0,1]^3 by aabb (DEVICE {lo.xyz, hi.xyz}; NULL: already normalised) and clamped; the 8 corners
+ * of its cell are read from table [L, 2^T_log2, F] fp32 - dense index x + y*(res+1) + z*(res+1)^2 while the level fits,
+ * else (x*1) ^ (y*2654435761) ^ (z*805459861) mod 2^T_log2 - and blended trilinearly (corner order x fastest).
+ * out [n, L*F], level-major.  F in {1,2,4,8}. */
+int pnr_hashgrid_encode(const float* x, int64_t n, const float* aabb, const float* table, int32_t L, int32_t F,
+                        int32_t T_log2, float base_resolution, float per_level_scale, float* out, void* stream);
 
 /* a8 + a9 in ONE kernel: Network.forward with the compositing done in the MLP's epilogue - per-sample alpha /
  * transmittance / weight right after the sigma-producing layer, colours and logits reduced on chip per ray - so the

@@ -23,6 +23,7 @@ import math
 from types import SimpleNamespace
 from typing import Dict, Optional
 
+import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -496,17 +497,43 @@ def make_renderer(cfg, net, net_fine=None) -> Renderer:
     return Renderer(cfg, net, net_fine)
 
 
+def _sqrt_rn(x: torch.Tensor) -> torch.Tensor:
+    """Correctly rounded fp32 square root (torch.sqrt on CPU goes through a vector math library that is not: about
+    0.5 % of its results are one ulp off; numpy's float32 sqrt is the hardware instruction)."""
+    return torch.from_numpy(np.sqrt(x.detach().to(torch.float32).contiguous().numpy()))
+
+
 def generate_rays(H: int, W: int, intr, c2w: torch.Tensor, camera: str = "pinhole", row0: int = 0,
                   rows: Optional[int] = None) -> torch.Tensor:
     """SURVEY 8(f) rank 3 (the step before the path; reference: ray generation in the KITTI-360 dataset
     loader, not in the mount).  rays [rows*W, 6] = origin || unnormalised direction for a pinhole or an
     equirectangular camera with camera-to-world [R|t] (3x4).  Elementwise fp32, fixed association order."""
     rows = H - row0 if rows is None else rows
-    fx, fy, cx, cy = [float(x) for x in intr]
+    fx, fy, cx, cy = [float(x) for x in intr[:4]]
     v, u = torch.meshgrid(torch.arange(row0, row0 + rows, dtype=torch.float32),
                           torch.arange(W, dtype=torch.float32), indexing="ij")
     if camera == "pinhole":
         x, y, z = (u - cx) / fx, (v - cy) / fy, torch.ones_like(u)
+    elif camera == "fisheye":
+        # KITTI-360 fisheye, unified (MEI) model; intr = (gamma1, gamma2, u0, v0, xi, k1, k2).  Published model
+        # (kitti360scripts CameraFisheye.cam2image is the projection); the inverse below is this repo's: radial
+        # undistortion by 8 Newton steps from ro = rd, then the lift to the unit sphere.  Every op fp32, in this order.
+        xi, k1, k2 = [torch.tensor(float(t), dtype=torch.float32) for t in intr[4:7]]
+        mx, my = (u - cx) / fx, (v - cy) / fy
+        rd = _sqrt_rn(mx * mx + my * my)
+        k1x3, k2x5 = 3.0 * k1, 5.0 * k2
+        ro = rd
+        for _ in range(8):
+            ro2 = ro * ro
+            f = ro * (1.0 + ro2 * (k1 + k2 * ro2)) - rd
+            fp = 1.0 + ro2 * (k1x3 + k2x5 * ro2)
+            ro = ro - f / fp
+        scale = torch.where(rd > 0, ro / rd, torch.ones_like(rd))
+        px, py = mx * scale, my * scale
+        r2 = px * px + py * py
+        # (xi > 1: pixels beyond the mirror's field of view have a negative radicand; it is clamped, the caller masks them)
+        fac = (xi + _sqrt_rn(torch.clamp_min(1.0 + (1.0 - xi * xi) * r2, 0.0))) / (1.0 + r2)
+        x, y, z = fac * px, fac * py, fac - xi
     else:
         lon = (u / float(W) - 0.5) * 6.2831853071795864769
         lat = (0.5 - v / float(H)) * 3.14159265358979323846

@@ -35,6 +35,15 @@ class PnrCompositeOut(C.Structure):
                  "instance_map", "fixed_semantic_map", "fixed_instance_map")]
 
 
+class PnrLossArgs(C.Structure):
+    _fields_ = [("R", C.c_int64), ("C", C.c_int32), ("sem_is_prob", C.c_int32)] + \
+               [(k, C.c_void_p) for k in ("rgb_map", "rgb_map0", "rgb_gt", "depth_map", "depth_gt", "semantic_map",
+                                          "fixed_semantic_map", "label", "label_weight")] + \
+               [(k, C.c_float) for k in ("w_rgb", "w_depth", "w_sem", "w_fix", "inv_n_rgb", "inv_n_depth", "inv_n_sem", "eps")] + \
+               [(k, C.c_void_p) for k in ("per_ray", "d_rgb_map", "d_rgb_map0", "d_depth_map", "d_semantic_map",
+                                          "d_fixed_semantic_map")]
+
+
 class PnrCompositeGrads(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in
                 ("rgb_map", "depth_map", "acc_map", "weights", "semantic_map",
@@ -85,6 +94,9 @@ SIGNATURES = {
     "pnr_mlp_backward_trunk": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _i32, _vp]),
     "pnr_composite": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32,
                                 C.POINTER(PnrCompositeOut), _vp]),
+    "pnr_losses": (C.c_int, [C.POINTER(PnrLossArgs), _vp]),
+    "pnr_panoptic_fuse": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pnr_hashgrid_encode": (C.c_int, [_vp, _i64, _vp, _vp, _i32, _i32, _i32, C.c_float, C.c_float, _vp, _vp]),
     "pnr_label_tiles": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "pnr_composite_backward": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp,
                                          _i32, C.POINTER(PnrCompositeGrads), _vp, _vp]),

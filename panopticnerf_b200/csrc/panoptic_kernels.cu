@@ -1,0 +1,323 @@
+// panoptic_kernels.cu — SURVEY 8(f) rank 4: what follows / feeds the render path in the 360 model.
+//   * panoptic label fusion + colour mapping of the composited maps (per ray; one warp per ray),
+//   * the multi-resolution hash-grid feature encoder (per point and level; gather-bound, L2 / HBM).
+// The reference's versions are not in the mount: both rules are stated here and in oracle/reference_panoptic.py
+// ("chosen, unverified"), and the kernels are held to that oracle.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include "../../include/pnr.h"
+#include "common.cuh"
+
+namespace pnr {
+namespace {
+
+// argmax over the channels c < n with keep(c); lanes stride the channels; NaN counts as -inf; ties -> lowest index;
+// -1 when no channel is kept
+template <class Keep>
+__device__ __forceinline__ int warp_argmax_if(const float* __restrict__ v, int n, int lane, Keep keep) {
+  float best = -INFINITY;
+  int arg = 0x7fffffff;
+  for (int c = lane; c < n; c += 32) {
+    if (!keep(c)) continue;
+    float x = v[c];
+    if (x != x) x = -INFINITY;
+    if (x > best || arg == 0x7fffffff) { best = x; arg = c; }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, d);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, d);
+    if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+  }
+  return arg == 0x7fffffff ? -1 : arg;
+}
+
+struct FuseArgs {
+  const float* sem; const float* inst; int64_t R; int C, K;
+  const uint8_t* is_thing;      // [C] 1 = the class has instances
+  const int32_t* inst_class;    // [K] class channel of instance slot k
+  const int32_t* inst_id;       // [K] global instance id of slot k (KITTI-360: semanticId*1000 + n), or null
+  const int32_t* class_id;      // [C] dataset id of class channel c (stuff id = class_id*1000), or null: the channel
+  const uint8_t* palette;       // [C,3] u8 colours, or null
+  int32_t* panoptic; int16_t* sem_label; int16_t* inst_slot; uint8_t* color;
+};
+
+// Fusion rule: s = argmax of the semantic map.  A stuff class gives id(s)*1000.  A thing class takes the best
+// instance slot AMONG THE SLOTS OF THAT CLASS (the instance head cannot contradict the semantic head); without such
+// a slot the pixel falls back to id(s)*1000.  Colour: the class colour, for instances averaged with a colour hashed
+// from the instance id (Knuth multiplicative hash, one byte per channel).
+__global__ void __launch_bounds__(256) panoptic_fuse_kernel(FuseArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= a.R) return;
+  const int s = warp_argmax_if(a.sem + r * a.C, a.C, lane, [](int) { return true; });
+  int k = -1;
+  if (s >= 0 && a.K > 0 && a.inst != nullptr && a.is_thing != nullptr && a.is_thing[s])
+    k = warp_argmax_if(a.inst + r * a.K, a.K, lane, [&](int c) { return a.inst_class[c] == s; });
+  if (lane != 0) return;
+  const int cid = s < 0 ? -1 : (a.class_id ? a.class_id[s] : s);
+  const int pan = s < 0 ? -1 : (k >= 0 ? (a.inst_id ? a.inst_id[k] : cid * 1000 + k + 1) : cid * 1000);
+  if (a.panoptic) a.panoptic[r] = pan;
+  if (a.sem_label) a.sem_label[r] = (int16_t)s;
+  if (a.inst_slot) a.inst_slot[r] = (int16_t)k;
+  if (a.color) {
+    uint32_t c0 = 0, c1 = 0, c2 = 0;
+    if (s >= 0 && a.palette) { c0 = a.palette[s * 3]; c1 = a.palette[s * 3 + 1]; c2 = a.palette[s * 3 + 2]; }
+    if (k >= 0) {
+      const uint32_t h = (uint32_t)pan * 2654435761u;
+      c0 = (c0 + ((h >> 8) & 0xFFu) + 1u) >> 1;
+      c1 = (c1 + ((h >> 16) & 0xFFu) + 1u) >> 1;
+      c2 = (c2 + ((h >> 24) & 0xFFu) + 1u) >> 1;
+    }
+    a.color[r * 3] = (uint8_t)c0; a.color[r * 3 + 1] = (uint8_t)c1; a.color[r * 3 + 2] = (uint8_t)c2;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ hash grid
+// Multi-resolution hash encoding (Mueller et al. 2022, the published algorithm): level l has resolution
+// res_l = floor(base * scale^l); a point x in [0,1]^3 is scaled by res_l, its cell's 8 corners are looked up in a
+// table of T entries x F features - by the dense index x + y*(res+1) + z*(res+1)^2 when (res+1)^3 <= T, else by
+// the spatial hash (x * 1) ^ (y * 2654435761) ^ (z * 805459861) mod T - and blended trilinearly.
+// out[n, L*F], level-major.  blockIdx.y = a group of consecutive levels, so a block's gathers stay inside a few
+// levels' tables (the coarse levels live in L1/L2, the fine ones stream from HBM at one 32-byte sector per corner).
+struct HashArgs {
+  const float* x; int64_t n; const float* table; float* out;
+  const float* aabb;   // device {lo.xyz, hi.xyz} or null (x already in [0,1]^3)
+  int L, F, T_log2;
+  uint32_t res[32];    // resolution of every level, floor(base * scale^l) evaluated in double on the host
+};
+
+__device__ __forceinline__ uint32_t hash_index(uint32_t x, uint32_t y, uint32_t z, uint32_t res1, bool dense, uint32_t mask) {
+  if (dense) return x + y * res1 + z * res1 * res1;
+  return (x ^ (y * 2654435761u) ^ (z * 805459861u)) & mask;
+}
+
+// One thread = one point x LPT consecutive levels with LPT * F = 8 features: its output is one whole 32-byte sector
+// (a thread per (point, level) writes 8 bytes into every 128-byte row - four partial writes per sector from four
+// different blocks, which the memory system turns into read-modify-writes: measured 4x the algorithmic write traffic
+// plus as much again in sector fills, profiles/r02_hashgrid_fuse_ncu.txt, first capture).
+template <int F>
+__global__ void __launch_bounds__(256) hashgrid_kernel(HashArgs a) {
+  constexpr int LPT = 8 / F;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int l0 = blockIdx.y * LPT;
+  if (i >= a.n) return;
+  const uint32_t T = 1u << a.T_log2, mask = T - 1u;
+  float v[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    float t = a.x[i * 3 + d];
+    if (a.aabb) t = __fdiv_rn(__fsub_rn(t, a.aabb[d]), __fsub_rn(a.aabb[3 + d], a.aabb[d]));
+    v[d] = fminf(fmaxf(t, 0.0f), 1.0f);                  // outside points take the border cell
+  }
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+  for (int ll = 0; ll < LPT; ++ll) {
+    const int l = l0 + ll;
+    if (l >= a.L) break;
+    const uint32_t res = a.res[l], res1 = res + 1u;
+    const float res_f = (float)res;
+    const bool dense = (uint64_t)res1 * res1 * res1 <= (uint64_t)T;
+    float w[3];
+    uint32_t c[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float p = __fmul_rn(v[d], res_f);
+      float fl = floorf(p);
+      if (fl >= res_f) fl = res_f - 1.0f;                // v == 1 belongs to the last cell (weight 1 on its far corner)
+      c[d] = (uint32_t)fl;
+      w[d] = __fsub_rn(p, fl);
+    }
+    const float* tab = a.table + (size_t)l * T * F;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {   // corner order: x fastest; the sum runs in this order (fixed for the oracle)
+      const uint32_t dx = k & 1, dy = (k >> 1) & 1, dz = k >> 2;
+      const float wx = dx ? w[0] : __fsub_rn(1.0f, w[0]);
+      const float wy = dy ? w[1] : __fsub_rn(1.0f, w[1]);
+      const float wz = dz ? w[2] : __fsub_rn(1.0f, w[2]);
+      const float wk = __fmul_rn(__fmul_rn(wx, wy), wz);
+      const uint32_t idx = hash_index(c[0] + dx, c[1] + dy, c[2] + dz, res1, dense, mask);
+      if (F == 2) {
+        const float2 t = __ldg(reinterpret_cast<const float2*>(tab) + idx);
+        acc[ll * 2] = __fadd_rn(acc[ll * 2], __fmul_rn(wk, t.x));
+        acc[ll * 2 + 1] = __fadd_rn(acc[ll * 2 + 1], __fmul_rn(wk, t.y));
+      } else if (F == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(tab) + idx);
+        acc[ll * 4] = __fadd_rn(acc[ll * 4], __fmul_rn(wk, t.x));
+        acc[ll * 4 + 1] = __fadd_rn(acc[ll * 4 + 1], __fmul_rn(wk, t.y));
+        acc[ll * 4 + 2] = __fadd_rn(acc[ll * 4 + 2], __fmul_rn(wk, t.z));
+        acc[ll * 4 + 3] = __fadd_rn(acc[ll * 4 + 3], __fmul_rn(wk, t.w));
+      } else {
+#pragma unroll
+        for (int f = 0; f < F; ++f)
+          acc[ll * F + f] = __fadd_rn(acc[ll * F + f], __fmul_rn(wk, __ldg(tab + (size_t)idx * F + f)));
+      }
+    }
+  }
+  const int width = a.L * F;
+  float* o = a.out + i * (int64_t)width + l0 * F;
+  const int n_out = min(8, width - l0 * F);
+  if (n_out == 8 && (width & 7) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 31) == 0) {
+    reinterpret_cast<float4*>(o)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    reinterpret_cast<float4*>(o)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < n_out) o[j] = acc[j];
+  }
+}
+
+}  // namespace
+}  // namespace pnr
+
+using namespace pnr;
+
+extern "C" int pnr_panoptic_fuse(const float* semantic_map, const float* instance_map, int64_t R, int32_t C, int32_t K,
+                                 const uint8_t* is_thing, const int32_t* inst_class, const int32_t* inst_id,
+                                 const int32_t* class_id, const uint8_t* palette, int32_t* panoptic, int16_t* sem_label,
+                                 int16_t* inst_slot, uint8_t* color, void* stream) {
+  if (R == 0) return PNR_OK;
+  PNR_CHECK_ARG(R > 0 && semantic_map && C > 0 && C < 32768 && K >= 0 && K < 32768, "pnr_panoptic_fuse: bad sizes / null semantic_map");
+  PNR_CHECK_ARG(!(instance_map && K > 0) || (is_thing && inst_class),
+                "pnr_panoptic_fuse: instance_map needs is_thing [C] and inst_class [K]");
+  FuseArgs a{semantic_map, K > 0 ? instance_map : nullptr, R, C, K, is_thing, inst_class, inst_id, class_id, palette,
+             panoptic, sem_label, inst_slot, color};
+  panoptic_fuse_kernel<<<(unsigned)((R + 7) / 8), 256, 0, (cudaStream_t)stream>>>(a);
+  PNR_LAUNCH_CHECK("panoptic_fuse_kernel");
+  return PNR_OK;
+}
+
+extern "C" int pnr_hashgrid_encode(const float* x, int64_t n, const float* aabb, const float* table, int32_t L, int32_t F,
+                                   int32_t T_log2, float base_resolution, float per_level_scale, float* out, void* stream) {
+  if (n == 0) return PNR_OK;
+  PNR_CHECK_ARG(x && table && out && n > 0, "pnr_hashgrid_encode: null pointer");
+  PNR_CHECK_ARG(L >= 1 && L <= 32 && (F == 1 || F == 2 || F == 4 || F == 8), "pnr_hashgrid_encode: L=%d F=%d (L in [1,32], F in {1,2,4,8})", L, F);
+  PNR_CHECK_ARG(T_log2 >= 4 && T_log2 <= 28, "pnr_hashgrid_encode: T_log2=%d outside [4,28]", T_log2);
+  PNR_CHECK_ARG(base_resolution >= 1.0f && per_level_scale >= 1.0f, "pnr_hashgrid_encode: base_resolution / per_level_scale < 1");
+  PNR_CHECK_ARG((double)base_resolution * pow((double)per_level_scale, (double)(L - 1)) < 1048576.0, "pnr_hashgrid_encode: finest resolution >= 2^20");
+  HashArgs a{x, n, table, out, aabb, L, F, T_log2, {}};
+  for (int l = 0; l < L; ++l) a.res[l] = (uint32_t)floor((double)base_resolution * pow((double)per_level_scale, (double)l));
+  const int lpt = 8 / F;   // levels per thread: 8 output features = one 32-byte sector
+  const dim3 grid((unsigned)((n + 255) / 256), (unsigned)((L + lpt - 1) / lpt));
+  switch (F) {
+    case 1: hashgrid_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(a); break;
+    case 2: hashgrid_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(a); break;
+    case 4: hashgrid_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(a); break;
+    default: hashgrid_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(a); break;
+  }
+  PNR_LAUNCH_CHECK("hashgrid_kernel");
+  return PNR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ losses
+// SURVEY 8(f) rank 2, the loss side (the reference's NetworkWrapper computes these with torch ops on the rendered
+// maps; its exact terms are not in the mount - the four below are the paper's: photometric, depth, 2D pseudo-label
+// cross-entropy on the rendered semantics, and the cross-entropy of the fixed (bounding-primitive) semantics).
+// One pass per ray: the per-ray value of every term and the gradient w.r.t. every map it reads, already scaled by
+// the term's weight and normaliser, so that `pnr_composite_backward` can consume them directly.
+namespace pnr {
+namespace {
+
+struct LossArgs {
+  pnr_loss_args a;
+};
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, d));
+  return v;
+}
+__device__ __forceinline__ float warp_add(float v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+
+__global__ void __launch_bounds__(256) losses_kernel(LossArgs L) {
+  const pnr_loss_args& a = L.a;
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= a.R) return;
+  float l_rgb = 0.f, l_depth = 0.f, l_sem = 0.f, l_fix = 0.f;
+  // photometric: sum over the 3 channels of (rgb - gt)^2, fine and (optionally) coarse
+  if (a.rgb_gt != nullptr && lane < 3) {
+    const float gt = a.rgb_gt[r * 3 + lane];
+    if (a.rgb_map != nullptr) {
+      const float d = a.rgb_map[r * 3 + lane] - gt;
+      l_rgb += d * d;
+      if (a.d_rgb_map) a.d_rgb_map[r * 3 + lane] = 2.0f * d * a.w_rgb * a.inv_n_rgb;
+    }
+    if (a.rgb_map0 != nullptr) {
+      const float d = a.rgb_map0[r * 3 + lane] - gt;
+      l_rgb += d * d;
+      if (a.d_rgb_map0) a.d_rgb_map0[r * 3 + lane] = 2.0f * d * a.w_rgb * a.inv_n_rgb;
+    }
+  }
+  l_rgb = warp_add(l_rgb);
+  // depth: |depth - gt| where gt > 0
+  if (a.depth_map != nullptr && a.depth_gt != nullptr) {
+    const float gt = a.depth_gt[r];
+    const bool ok = gt > 0.f;
+    const float d = a.depth_map[r] - gt;
+    l_depth = ok ? fabsf(d) : 0.f;
+    if (a.d_depth_map && lane == 0) a.d_depth_map[r] = ok ? (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * a.w_depth * a.inv_n_depth : 0.f;
+  }
+  const int label = a.label ? a.label[r] : -1;
+  const bool has = label >= 0 && label < a.C;
+  const float conf = (has && a.label_weight) ? a.label_weight[r] : 1.0f;
+  // 2D pseudo-label cross-entropy on the rendered semantics
+  if (a.semantic_map != nullptr && a.C > 0) {
+    const float* s = a.semantic_map + r * a.C;
+    if (a.sem_is_prob) {     // the map is a rendered probability: -log(max(p_label, eps))
+      const float p = has ? s[label] : 1.0f;
+      const float pc = fmaxf(p, a.eps);
+      l_sem = has ? -logf(pc) * conf : 0.f;
+      if (a.d_semantic_map)
+        for (int c = lane; c < a.C; c += 32)
+          a.d_semantic_map[r * a.C + c] = (has && c == label && p > a.eps) ? -conf * a.w_sem * a.inv_n_sem / pc : 0.f;
+    } else {                 // the map is rendered logits: softmax cross-entropy
+      float m = -INFINITY;
+      for (int c = lane; c < a.C; c += 32) m = fmaxf(m, s[c]);
+      m = warp_max(m);
+      float z = 0.f;
+      for (int c = lane; c < a.C; c += 32) z += expf(s[c] - m);
+      z = warp_add(z);
+      const float lse = m + logf(z);
+      l_sem = has ? (lse - s[label]) * conf : 0.f;
+      if (a.d_semantic_map)
+        for (int c = lane; c < a.C; c += 32)
+          a.d_semantic_map[r * a.C + c] = has ? (expf(s[c] - lse) - (c == label ? 1.f : 0.f)) * conf * a.w_sem * a.inv_n_sem : 0.f;
+    }
+  }
+  // fixed (bounding-primitive) semantics: a rendered probability by construction
+  if (a.fixed_semantic_map != nullptr && a.C > 0) {
+    const float p = has ? a.fixed_semantic_map[r * a.C + label] : 1.0f;
+    const float pc = fmaxf(p, a.eps);
+    l_fix = has ? -logf(pc) * conf : 0.f;
+    if (a.d_fixed_semantic_map)
+      for (int c = lane; c < a.C; c += 32)
+        a.d_fixed_semantic_map[r * a.C + c] = (has && c == label && p > a.eps) ? -conf * a.w_fix * a.inv_n_sem / pc : 0.f;
+  }
+  if (a.per_ray != nullptr && lane == 0)
+    *reinterpret_cast<float4*>(a.per_ray + r * 4) = make_float4(l_rgb, l_depth, l_sem, l_fix);
+}
+
+}  // namespace
+}  // namespace pnr
+
+extern "C" int pnr_losses(const pnr_loss_args* args, void* stream) {
+  PNR_CHECK_ARG(args, "pnr_losses: null pointer");
+  if (args->R == 0) return PNR_OK;
+  PNR_CHECK_ARG(args->R > 0 && args->C >= 0 && args->C < 32768, "pnr_losses: bad sizes");
+  PNR_CHECK_ARG(!(args->rgb_map || args->rgb_map0) || args->rgb_gt, "pnr_losses: rgb maps without rgb_gt");
+  PNR_CHECK_ARG(!(args->semantic_map || args->fixed_semantic_map) || (args->label && args->C > 0),
+                "pnr_losses: semantic maps need label [R] and C > 0");
+  PNR_CHECK_ARG(args->eps > 0.f, "pnr_losses: eps must be > 0");
+  LossArgs L{*args};
+  losses_kernel<<<(unsigned)((args->R + 7) / 8), 256, 0, (cudaStream_t)stream>>>(L);
+  PNR_LAUNCH_CHECK("losses_kernel");
+  return PNR_OK;
+}

@@ -21,15 +21,18 @@
 #define PNR_SUB(a, b) __fsub_rn((a), (b))
 #define PNR_DIV(a, b) __fdiv_rn((a), (b))
 #define PNR_DADD(a, b) __dadd_rn((a), (b))
+#define PNR_SQRT(a) __fsqrt_rn((a))
 #else
 #define PNR_MUL(a, b) ((a) * (b))
 #define PNR_ADD(a, b) ((a) + (b))
 #define PNR_SUB(a, b) ((a) - (b))
 #define PNR_DIV(a, b) ((a) / (b))
 #define PNR_DADD(a, b) ((a) + (b))
+#define PNR_SQRT(a) sqrtf((a))
 #endif
 
 #define PNR_MAX_HITS 8
+#define PNR_FISHEYE_NEWTON 8   // fixed iteration count: the ray is a pure function of the pixel
 
 PNR_HD float pnr_min_nan(float a, float b) { return (a != a) ? a : ((b != b) ? b : (b < a ? b : a)); }
 PNR_HD float pnr_max_nan(float a, float b) { return (a != a) ? a : ((b != b) ? b : (b > a ? b : a)); }
@@ -211,4 +214,33 @@ PNR_HD float pnr_pdf_sample(const float* z, const float* cdf, int Nb, float u, i
   const float t = PNR_DIV(PNR_SUB(u, cb), denom);
   *idx_out = idx;
   return PNR_ADD(bb, PNR_MUL(t, PNR_SUB(ba, bb)));
+}
+
+// 8(f) rank 3: KITTI-360 fisheye (unified / MEI model; intr = gamma1, gamma2, u0, v0, xi, k1, k2).  Pixel (u, v) ->
+// direction on the unit sphere in the camera frame.  m = distorted normalised point; radial undistortion
+// rd = ro (1 + k1 ro^2 + k2 ro^4) solved for ro by PNR_FISHEYE_NEWTON Newton steps from ro = rd; lift:
+// X = (f x, f y, f - xi), f = (xi + sqrt(max(1 + (1 - xi^2) r^2, 0))) / (1 + r^2)  (xi > 1: beyond the mirror's
+// field of view the radicand is negative; it is clamped and the caller masks those pixels).
+PNR_HD void pnr_fisheye_dir(float u, float v, float g1, float g2, float u0, float v0, float xi, float k1, float k2,
+                            float* x, float* y, float* z) {
+  const float mx = PNR_DIV(PNR_SUB(u, u0), g1);
+  const float my = PNR_DIV(PNR_SUB(v, v0), g2);
+  const float rd = PNR_SQRT(PNR_ADD(PNR_MUL(mx, mx), PNR_MUL(my, my)));
+  const float k1x3 = PNR_MUL(3.0f, k1), k2x5 = PNR_MUL(5.0f, k2);
+  float ro = rd;
+  for (int it = 0; it < PNR_FISHEYE_NEWTON; ++it) {
+    const float ro2 = PNR_MUL(ro, ro);
+    const float f = PNR_SUB(PNR_MUL(ro, PNR_ADD(1.0f, PNR_MUL(ro2, PNR_ADD(k1, PNR_MUL(k2, ro2))))), rd);
+    const float fp = PNR_ADD(1.0f, PNR_MUL(ro2, PNR_ADD(k1x3, PNR_MUL(k2x5, ro2))));
+    ro = PNR_SUB(ro, PNR_DIV(f, fp));
+  }
+  const float scale = rd > 0.f ? PNR_DIV(ro, rd) : 1.0f;
+  const float px = PNR_MUL(mx, scale), py = PNR_MUL(my, scale);
+  const float r2 = PNR_ADD(PNR_MUL(px, px), PNR_MUL(py, py));
+  float rad = PNR_ADD(1.0f, PNR_MUL(PNR_SUB(1.0f, PNR_MUL(xi, xi)), r2));
+  if (rad < 0.f) rad = 0.f;
+  const float fac = PNR_DIV(PNR_ADD(xi, PNR_SQRT(rad)), PNR_ADD(1.0f, r2));
+  *x = PNR_MUL(fac, px);
+  *y = PNR_MUL(fac, py);
+  *z = PNR_SUB(fac, xi);
 }

@@ -8,6 +8,7 @@
 #include <mutex>
 #include "common.cuh"
 #include "composite_math.cuh"
+#include "ray_math.h"
 
 namespace pnr {
 
@@ -43,7 +44,7 @@ __global__ void __launch_bounds__(kEncTile) encode_kernel(const float* __restric
 }
 
 // ------------------------------------------------------------------------------------ ray generation
-struct CamArgs { float fx, fy, cx, cy; float c2w[12]; int H, W, row0, rows, camera; };
+struct CamArgs { float fx, fy, cx, cy; float xi, k1, k2; float c2w[12]; int H, W, row0, rows, camera; };
 
 __global__ void __launch_bounds__(256) rays_kernel(CamArgs a, float* __restrict__ rays) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -54,6 +55,8 @@ __global__ void __launch_bounds__(256) rays_kernel(CamArgs a, float* __restrict_
     x = __fdiv_rn(__fsub_rn((float)u, a.cx), a.fx);
     y = __fdiv_rn(__fsub_rn((float)v, a.cy), a.fy);
     z = 1.0f;
+  } else if (a.camera == 2) {   // KITTI-360 fisheye (MEI): ray_math.h, also compiled for the host by the CPU tests
+    pnr_fisheye_dir((float)u, (float)v, a.fx, a.fy, a.cx, a.cy, a.xi, a.k1, a.k2, &x, &y, &z);
   } else {
     const float lon = __fmul_rn(__fsub_rn(__fdiv_rn((float)u, (float)a.W), 0.5f), 6.2831853071795864769f);
     const float lat = __fmul_rn(__fsub_rn(0.5f, __fdiv_rn((float)v, (float)a.H)), 3.14159265358979323846f);
@@ -518,9 +521,11 @@ extern "C" int pnr_generate_rays(int32_t H, int32_t W, int32_t row0, int32_t row
   if (rows == 0 || W == 0) return PNR_OK;
   PNR_CHECK_ARG(intr_host && c2w_host && rays, "pnr_generate_rays: null pointer");
   PNR_CHECK_ARG(H > 0 && W > 0 && rows > 0 && row0 >= 0 && row0 + rows <= H, "pnr_generate_rays: bad image window");
-  PNR_CHECK_ARG(camera == 0 || camera == 1, "pnr_generate_rays: camera %d (0 pinhole, 1 equirect)", camera);
+  PNR_CHECK_ARG(camera >= 0 && camera <= 2, "pnr_generate_rays: camera %d (0 pinhole, 1 equirect, 2 fisheye)", camera);
   CamArgs a;
   a.fx = intr_host[0]; a.fy = intr_host[1]; a.cx = intr_host[2]; a.cy = intr_host[3];
+  a.xi = a.k1 = a.k2 = 0.f;
+  if (camera == 2) { a.xi = intr_host[4]; a.k1 = intr_host[5]; a.k2 = intr_host[6]; }
   for (int i = 0; i < 12; ++i) a.c2w[i] = c2w_host[i];
   a.H = H; a.W = W; a.row0 = row0; a.rows = rows; a.camera = camera;
   const int64_t n = (int64_t)rows * W;

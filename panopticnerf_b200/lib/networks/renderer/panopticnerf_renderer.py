@@ -142,10 +142,14 @@ def generate_rays(H: int, W: int, intr, c2w: torch.Tensor, camera: str = "pinhol
     """Camera rays on the device: only 16 floats cross the host/device boundary."""
     rows = H - row0 if rows is None else rows
     rays = torch.empty(rows * W, 6, dtype=_F32, device=device)
-    k = (C.c_float * 4)(*[float(x) for x in intr])
+    cam = {"pinhole": 0, "equirect": 1, "fisheye": 2}[camera]
+    vals = [float(x) for x in intr]
+    if len(vals) != (7 if cam == 2 else 4):
+        raise ValueError(f"generate_rays: camera '{camera}' takes {7 if cam == 2 else 4} intrinsics, got {len(vals)}")
+    k = (C.c_float * len(vals))(*vals)
     m = (C.c_float * 12)(*[float(x) for x in c2w.detach().to("cpu", _F32).reshape(-1)[:12].tolist()])
     with torch.cuda.device(rays.device):
-        _capi.check(_capi.lib().pnr_generate_rays(int(H), int(W), int(row0), int(rows), 0 if camera == "pinhole" else 1,
+        _capi.check(_capi.lib().pnr_generate_rays(int(H), int(W), int(row0), int(rows), cam,
                                                   k, m, _capi.ptr(rays), _capi.stream_ptr()), "pnr_generate_rays")
     return rays
 

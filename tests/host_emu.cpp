@@ -77,4 +77,12 @@ void emu_sample_pdf(const float* z, const float* w, int64_t R, int N, int Ni, co
     }
   }
 }
+
+void emu_fisheye(int H, int W, const float* k, float* dirs) {
+  for (int v = 0; v < H; ++v)
+    for (int u = 0; u < W; ++u) {
+      float* o = dirs + ((size_t)v * W + u) * 3;
+      pnr_fisheye_dir((float)u, (float)v, k[0], k[1], k[2], k[3], k[4], k[5], k[6], o, o + 1, o + 2);
+    }
+}
 }

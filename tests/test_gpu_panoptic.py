@@ -1,0 +1,63 @@
+"""GPU parity of the steps beside the render path through the C ABI vs oracle/reference_panoptic.py:
+panoptic fusion + colour mapping (exact) and the hash-grid encoder (bit-exact: same fp32 operation order)."""
+import pytest
+import torch
+
+from oracle import reference_panoptic as OP
+from panopticnerf_b200.lib.networks.encoding import HashGrid
+from panopticnerf_b200.lib.visualizers import fuse_panoptic
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("R,C,K", [(1000, 45, 64), (77, 3, 0), (513, 19, 5), (4, 100, 128)])
+def test_panoptic_fuse_matches_oracle(R, C, K):
+    g = torch.Generator().manual_seed(R + C)
+    sem = torch.rand(R, C, generator=g)
+    sem[::7, :] = sem[::7, :].round(decimals=1)            # ties
+    sem[5 % R, 0] = float("nan")
+    inst = torch.rand(R, K, generator=g) if K else None
+    is_thing = (torch.rand(C, generator=g) > 0.5).to(torch.uint8)
+    inst_class = torch.randint(0, C, (K,), generator=g) if K else None
+    inst_id = (inst_class * 1000 + torch.arange(K) + 1) if K else None
+    class_id = torch.randperm(C, generator=g) + 3
+    pal = torch.randint(0, 256, (C, 3), generator=g, dtype=torch.uint8)
+    out = {"semantic_map": sem.to(DEV)}
+    if K:
+        out["instance_map"] = inst.to(DEV)
+    got = fuse_panoptic(out, is_thing, inst_class, inst_id, class_id, pal)
+    pan, s, k, col = OP.panoptic_fuse(sem, inst, is_thing, inst_class, inst_id, class_id, pal)
+    assert torch.equal(got["semantic"].cpu(), s) and torch.equal(got["instance_slot"].cpu(), k)
+    assert torch.equal(got["panoptic"].cpu(), pan) and torch.equal(got["color"].cpu(), col)
+    if K:     # without id tables
+        got2 = fuse_panoptic(out, is_thing, inst_class)
+        assert torch.equal(got2["panoptic"].cpu(), OP.panoptic_fuse(sem, inst, is_thing, inst_class)[0]) and "color" not in got2
+
+
+@pytest.mark.parametrize("L,F,T_log2,base,scale,n", [(16, 2, 19, 16.0, 1.3819, 20000), (8, 4, 14, 4.0, 2.0, 3001),
+                                                     (4, 1, 10, 2.0, 1.5, 257), (6, 8, 12, 8.0, 1.7, 999)])
+def test_hashgrid_encode_bit_exact(L, F, T_log2, base, scale, n):
+    aabb = torch.tensor([[-40.0, -3.0, -40.0], [40.0, 12.0, 40.0]])
+    enc = HashGrid(L, F, T_log2, base, scale, aabb=aabb, seed=L)
+    with torch.no_grad():
+        enc.table.mul_(1e4)                         # O(1) features
+    g = torch.Generator().manual_seed(n)
+    x = (torch.rand(n, 3, generator=g) * 2 - 1) * torch.tensor([44.0, 9.0, 44.0]) + torch.tensor([0.0, 4.5, 0.0])   # some outside
+    x[0] = aabb[1]                                  # exactly on the far corner
+    x[1] = aabb[0]
+    ref = OP.hashgrid_encode(x, aabb, enc.table.detach(), base, scale)
+    got = enc.to(DEV)(x.to(DEV)).cpu()
+    assert got.shape == (n, L * F)
+    assert torch.equal(got, ref)
+    assert torch.equal(enc(x.to(DEV).reshape(n, 1, 3)).cpu().reshape(n, -1), ref)      # leading shape is kept
+
+
+def test_hashgrid_rejects_bad_arguments():
+    from panopticnerf_b200 import _capi
+    enc = HashGrid(4, 2, 10)
+    with pytest.raises(_capi.PnrError, match="CUDA tensor"):
+        enc(torch.zeros(5, 3))
+    bad = HashGrid(4, 3, 10).to(DEV)
+    with pytest.raises(_capi.PnrError, match="F=3"):
+        bad(torch.zeros(5, 3, device=DEV))

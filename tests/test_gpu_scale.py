@@ -34,6 +34,20 @@ def test_generate_rays_pinhole_bit_exact_and_equirect():
     assert P.generate_rays(cfg.H, cfg.W_img, k, _pose(), rows=0, device=DEV).shape == (0, 6)
 
 
+def test_generate_rays_fisheye_bit_exact():
+    """KITTI-360 fisheye (MEI) camera: every operation of the unprojection is a separately rounded fp32 op in a fixed
+    order (8 Newton steps), so the device rays equal the oracle's bit for bit - also beyond the field of view."""
+    k = (1336.3220825849971, 1335.7883350012958, 716.94323510126321, 705.76498308221585, 2.2134047507854890,
+         1.6798235660113681e-02, 1.6548773243373522)
+    ref = O.generate_rays(1400, 1400, k, _pose(), "fisheye", row0=0, rows=1400)
+    got = P.generate_rays(1400, 1400, k, _pose(), "fisheye", row0=0, rows=1400, device=DEV)
+    assert torch.equal(got.cpu(), ref)
+    sub = P.generate_rays(1400, 1400, k, _pose(), "fisheye", row0=650, rows=9, device=DEV)
+    assert torch.equal(sub.cpu(), ref[650 * 1400:659 * 1400])
+    with pytest.raises(ValueError, match="7 intrinsics"):
+        P.generate_rays(1400, 1400, k[:4], _pose(), "fisheye", device=DEV)
+
+
 def test_render_from_camera_equals_render_from_rays():
     cfg = PN.make_cfg("cfg1")
     net = S.init_network_weights(PN.make_network(cfg)).to(DEV)
