@@ -139,7 +139,7 @@ int pnr_mlp_forward(pnr_ctx* ctx, const float* pts, const float* viewdirs, const
  * [4096 + 3*(2*step+half)+{0,1,2}] epilogue (wait / accumulator ready / done), [6144 + stage] TMA issue. */
 int pnr_mlp_forward_timeline(pnr_ctx* ctx, const float* rays, const float* z, int64_t R, int32_t N,
                              float* raw, int64_t* timeline, void* stream);
-/* Development aid: the backward-trunk launches of `ctx` record the same timeline into timeline[8192] (device i64)
+/* Development aid: the pnr_mlp_composite and pnr_mlp_backward_trunk launches of `ctx` record the same timeline into timeline[8192] (device i64)
  * until this is called again with NULL (-DPNR_TIMELINE builds only; ignored otherwise). */
 int pnr_debug_timeline(pnr_ctx* ctx, int64_t* timeline);
 

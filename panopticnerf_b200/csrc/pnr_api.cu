@@ -772,7 +772,7 @@ extern "C" int pnr_mlp_composite(pnr_ctx* ctx, const float* rays, const float* z
   p.S = S; p.N = N; p.CH = 4 + C + K; p.raw = nullptr;
   p.num_tiles = (int32_t)((S + kTileM - 1) / kTileM);
   p.status = ctx->d_status;
-  p.dbg = nullptr;
+  p.dbg = ctx->dbg_timeline;
   p.sample_box = sample_box; p.mask_outside = mask_outside; p.white_bkgd = white_bkgd;
   p.C = C; p.K = K;
   p.weights = out->weights; p.rgb_map = out->rgb_map; p.depth_map = out->depth_map; p.acc_map = out->acc_map;

@@ -9,7 +9,8 @@ import panopticnerf_b200 as PN
 from panopticnerf_b200 import _capi, synthetic as S
 from panopticnerf_b200.lib.networks.renderer import panopticnerf_renderer as P
 backward = "--backward" in sys.argv          # the trunk-backward kernel instead of the forward one
-sys.argv = [a for a in sys.argv if a != "--backward"]
+composite = "--composite" in sys.argv        # the forward kernel with the compositing epilogue
+sys.argv = [a for a in sys.argv if a not in ("--backward", "--composite")]
 prec = sys.argv[1] if len(sys.argv) > 1 else "fp16x3"
 preset = sys.argv[2] if len(sys.argv) > 2 else "cfg2"
 cfg = PN.make_cfg(preset, precision=prec)
@@ -28,7 +29,12 @@ if backward:
     for _ in range(2):
         net.backward_trunk(grad_h, rays=rays, z=z)
     _capi.check(_capi.lib().pnr_debug_timeline(ctx, None))
-for _ in range(0 if backward else 2):
+if composite:
+    _capi.check(_capi.lib().pnr_debug_timeline(ctx, tl.data_ptr()))
+    for _ in range(2):
+        net.forward_composite(rays, z)
+    _capi.check(_capi.lib().pnr_debug_timeline(ctx, None))
+for _ in range(0 if (backward or composite) else 2):
     _capi.check(_capi.lib().pnr_mlp_forward_timeline(ctx, rays.data_ptr(), z.data_ptr(), rays.shape[0], cfg.N_samples,
                                                      raw.data_ptr(), tl.data_ptr(), _capi.stream_ptr()))
 torch.cuda.synchronize()
