@@ -250,10 +250,20 @@ int pnr_composite_backward(const float* raw, const float* z, const float* rays, 
  * grad_h = dL/dh of the trunk output [R*N, W].  One kernel on the same 128-sample tiles as pnr_mlp_forward: the
  * forward trunk is recomputed (ReLU sign patterns stay in shared memory), then the layers run in reverse with the
  * transposed weight stream on the tensor cores, gradients split hi/lo like activations.  Samples are given as pts
- * [R*N,3] or as (rays [R,6], z [R,N]).  x3 precisions only; D <= 9.  The weight gradients and the head / view
- * branches are not part of this slice. */
+ * [R*N,3] or as (rays [R,6], z [R,N]).  x3 precisions only; D <= 9.  grad_scale: a power of two applied to grad_h on
+ * load and removed from everything the kernel writes (exact): pick it so that max |grad_h| * grad_scale is a few
+ * hundred, or the fp16 operand parts of small gradients go subnormal (1.0 when grad_h is already O(1)). */
 int pnr_mlp_backward_trunk(pnr_ctx* ctx, const float* pts, const float* rays, const float* z, int64_t R, int32_t N,
-                           const float* grad_h, float* grad_emb, int32_t ld_emb, void* stream);
+                           const float* grad_h, float grad_scale, float* grad_emb, int32_t ld_emb, float* stash,
+                           void* stream);
+/* The weight gradients of the trunk come from `stash` [2D-1, R*N, W] fp32 (NULL: not kept): every A operand the
+ * kernel produces on the way - slot i < D-1: H_i, the activations of forward layer i; slot 2D-2-j: dZ_j, the gradient
+ * w.r.t. layer j's pre-activation - so that dW_j = dZ_j^T [H_{j-1} (, gamma(x))], db_j = sum_s dZ_j are plain GEMMs
+ * / reductions for the caller's BLAS.  pnr_mlp_trunk_forward returns the trunk's output h [R*N, W] (16-byte
+ * aligned), the input of the layers after the trunk (alpha / feature / view / rgb / heads), which the caller
+ * differentiates itself to obtain grad_h. */
+int pnr_mlp_trunk_forward(pnr_ctx* ctx, const float* pts, const float* rays, const float* z, int64_t R, int32_t N,
+                          float* h_out, void* stream);
 
 /* a10: sample_pdf + merge.  z [R,N] coarse depths, weights [R,N] coarse weights; bins are the mid
  * points, the pdf is weights[1:-1]+1e-5.  u [R,Ni] is required (deterministic sampler: the host's

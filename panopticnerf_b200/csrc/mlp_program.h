@@ -78,7 +78,11 @@ enum : uint8_t { EPI_RELU_TO_A = 0, EPI_VIEW_RGB = 2, EPI_LOGITS = 3,   // (1 wa
                  // backward programs (BWD kernels, see "BACKWARD" below):
                  EPI_MASK_TO_A = 4,     // v = acc where the saved ReLU sign pattern (slot n_valid-1) is set, else 0 -> A operand
                  EPI_LOADG_TO_A = 5,    // last forward layer: v = grad_in where acc + bias > 0, else 0 -> A operand
-                 EPI_GRAD_OUT = 6 };    // acc columns [0, n_valid) -> grad row + out_off (added to it when n_valid1 != 0)
+                 EPI_GRAD_OUT = 6,      // acc columns [0, n_valid) -> grad row + out_off (added to it when n_valid1 != 0)
+                 EPI_ACT_OUT = 7 };     // relu(acc + bias) -> output row (the trunk's output h, for the layers torch differentiates)
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
 constexpr bool epi_writes_a(uint8_t kind) { return kind == EPI_RELU_TO_A || kind == EPI_MASK_TO_A || kind == EPI_LOADG_TO_A; }
 
 struct StageDesc {     // one weight stage = one bulk copy + its MMAs
@@ -120,6 +124,7 @@ struct EpiDesc {
   uint16_t aux_off;    // sigma weights (EPI_*_TO_A with sigma) or rgb weights [3][n] (EPI_VIEW_RGB)
   uint16_t out_off;    // EPI_LOGITS: channel offset in the raw row of column 0 (columns [0, n0), n_valid real ones)
   uint16_t out_off1;   //             and of column n0 (columns [n0, n), n_valid1 real ones) when the second half is a
+                       // (backward programs: stash slot + 1 of the A operand this epilogue produces, 0 = not kept)
   uint16_t n_valid1;   //             layer of its own (two logit layers issued as the two halves of one step)
   uint16_t n1a;        // E1 part a = columns [n0, n1a), part b = [n1a, n)   (multiple of 16; n1a = n: one block)
 };
@@ -167,6 +172,13 @@ struct MlpParams {
   float* inst_map;        // [R,K]
   // ---- backward kernels only: dL/dh of the trunk output, [S, W]; `raw` receives dL/d(embedded input), row stride CH
   const float* grad_in;
+  // optional fp32 copies of every A operand the epilogues produce (hidden activations on the way up, pre-activation
+  // gradients on the way down): slot k = stash + k * S * W, rows of W floats.  What the weight-gradient GEMMs read.
+  float* stash;
+  // the incoming gradient is multiplied by grad_scale as it is loaded and every gradient that leaves the kernel
+  // (output rows, stashed dZ) by grad_unscale = 1 / grad_scale: a power of two chosen by the caller so that the
+  // 16-bit operand parts of small gradients stay in the normal range (the backward pass is linear in grad_in)
+  float grad_scale, grad_unscale;
 };
 
 // What a launch carries: arguments + the context's program, as ONE __grid_constant__ kernel parameter.

@@ -171,9 +171,10 @@ __device__ __forceinline__ void epi_group_logits(const uint32_t (&r)[16], int g,
 // ------------------------------------------------------------------------------------------------
 template <int PASSES, int FMT>
 __device__ __forceinline__ void epi_group_bwd(const uint32_t (&r)[16], int g, const EpiDesc& ed, const float* bias,
-                                              uint16_t* mask_row, const float* gin, uint32_t& vmax,
-                                              uint32_t (&hi)[8], uint32_t (&lo)[8]) {
+                                              uint16_t* mask_row, const float* gin, float* stash_row, float gscale,
+                                              float gunscale, uint32_t& vmax, uint32_t (&hi)[8], uint32_t (&lo)[8]) {
   float v[16];
+  float sscale = gunscale;     // what the stash receives: gradients unscaled, forward activations as they are
   if (ed.kind == EPI_MASK_TO_A) {
     const uint32_t m = ed.n_valid ? mask_row[((ed.n_valid - 1) * 16 + g) * kTileM] : 0xFFFFu;
 #pragma unroll
@@ -196,14 +197,21 @@ __device__ __forceinline__ void epi_group_bwd(const uint32_t (&r)[16], int g, co
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float4 x = g4[q];
-        v[4 * q + 0] = ((m >> (4 * q + 0)) & 1u) ? x.x : 0.f;
-        v[4 * q + 1] = ((m >> (4 * q + 1)) & 1u) ? x.y : 0.f;
-        v[4 * q + 2] = ((m >> (4 * q + 2)) & 1u) ? x.z : 0.f;
-        v[4 * q + 3] = ((m >> (4 * q + 3)) & 1u) ? x.w : 0.f;
+        v[4 * q + 0] = ((m >> (4 * q + 0)) & 1u) ? x.x * gscale : 0.f;
+        v[4 * q + 1] = ((m >> (4 * q + 1)) & 1u) ? x.y * gscale : 0.f;
+        v[4 * q + 2] = ((m >> (4 * q + 2)) & 1u) ? x.z * gscale : 0.f;
+        v[4 * q + 3] = ((m >> (4 * q + 3)) & 1u) ? x.w * gscale : 0.f;
       }
-    } else if (ed.n_valid) {
-      mask_row[((ed.n_valid - 1) * 16 + g) * kTileM] = (uint16_t)m;
+    } else {
+      sscale = 1.0f;
+      if (ed.n_valid) mask_row[((ed.n_valid - 1) * 16 + g) * kTileM] = (uint16_t)m;
     }
+  }
+  if (stash_row != nullptr) {   // fp32 copy of the operand for the weight-gradient GEMMs
+    float4* s4 = reinterpret_cast<float4*>(stash_row + g * 16);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      s4[q] = make_float4(v[4 * q] * sscale, v[4 * q + 1] * sscale, v[4 * q + 2] * sscale, v[4 * q + 3] * sscale);
   }
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -214,13 +222,25 @@ __device__ __forceinline__ void epi_group_bwd(const uint32_t (&r)[16], int g, co
   }
 }
 
+// the trunk's output activations: relu(acc + bias) of this group -> the sample's output row (16-byte stores)
+__device__ __forceinline__ void epi_group_actout(const uint32_t (&r)[16], int g, const float* bias, float* dst) {
+  const float4* b4 = reinterpret_cast<const float4*>(bias + g * 16);
+  float4* d4 = reinterpret_cast<float4*>(dst + g * 16);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 b = b4[q];
+    d4[q] = make_float4(fmaxf(__uint_as_float(r[4 * q + 0]) + b.x, 0.f), fmaxf(__uint_as_float(r[4 * q + 1]) + b.y, 0.f),
+                        fmaxf(__uint_as_float(r[4 * q + 2]) + b.z, 0.f), fmaxf(__uint_as_float(r[4 * q + 3]) + b.w, 0.f));
+  }
+}
+
 // gradient w.r.t. the embedded input: accumulator columns [0, n_valid) of this group -> the sample's output row
 // (accumulating: all loads first - one memory latency per group, not one per column).  `vec`: the output rows are
 // 16-byte aligned and padded to whole groups (row stride a multiple of 4 floats >= the step's width; the padding
 // columns receive the zero-padded weights' zeros): four 16-byte accesses per group instead of sixteen 4-byte ones
 // whose 32 lanes each touch a different sector.
 __device__ __forceinline__ void epi_group_gradout(const uint32_t (&r)[16], int g, int n_valid, bool accumulate, bool vec,
-                                                  float* dst) {
+                                                  float us, float* dst) {
   if (vec) {
     float4* d4 = reinterpret_cast<float4*>(dst + g * 16);
     float4 prev[4];
@@ -228,8 +248,8 @@ __device__ __forceinline__ void epi_group_gradout(const uint32_t (&r)[16], int g
     for (int q = 0; q < 4; ++q) prev[q] = accumulate ? d4[q] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int q = 0; q < 4; ++q)
-      d4[q] = make_float4(prev[q].x + __uint_as_float(r[4 * q + 0]), prev[q].y + __uint_as_float(r[4 * q + 1]),
-                          prev[q].z + __uint_as_float(r[4 * q + 2]), prev[q].w + __uint_as_float(r[4 * q + 3]));
+      d4[q] = make_float4(prev[q].x + __uint_as_float(r[4 * q + 0]) * us, prev[q].y + __uint_as_float(r[4 * q + 1]) * us,
+                          prev[q].z + __uint_as_float(r[4 * q + 2]) * us, prev[q].w + __uint_as_float(r[4 * q + 3]) * us);
     return;
   }
   float prev[16];
@@ -237,7 +257,7 @@ __device__ __forceinline__ void epi_group_gradout(const uint32_t (&r)[16], int g
   for (int j = 0; j < 16; ++j) prev[j] = (accumulate && g * 16 + j < n_valid) ? dst[g * 16 + j] : 0.f;
 #pragma unroll
   for (int j = 0; j < 16; ++j)
-    if (g * 16 + j < n_valid) dst[g * 16 + j] = prev[j] + __uint_as_float(r[j]);
+    if (g * 16 + j < n_valid) dst[g * 16 + j] = prev[j] + __uint_as_float(r[j]) * us;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -407,12 +427,14 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
         const uint32_t parity = gstep & 1u;
         const float* bias = consts + ed.bias_off;
         const float* aux = consts + ed.aux_off;
-        const bool to_a = BWD ? ed.kind != EPI_GRAD_OUT : ed.kind == EPI_RELU_TO_A;
+        const bool to_a = BWD ? epi_writes_a(ed.kind) : ed.kind == EPI_RELU_TO_A;
         float c0 = 0.f, c1 = 0.f, c2 = 0.f;
         // backward programs: this row's sign patterns and its row of the incoming gradient (tail rows read row S-1)
         uint16_t* mask_row = reinterpret_cast<uint16_t*>(smem + kSmemMask) + row;
-        const float* gin = BWD ? p.grad_in + (valid ? s : p.S - 1) * (int64_t)ed.n : nullptr;
-        if (BWD && st == 0) {   // this row of the incoming gradient is needed D-1 steps from now: bring it into L2
+        const float* gin = (BWD && ed.kind == EPI_LOADG_TO_A) ? p.grad_in + (valid ? s : p.S - 1) * (int64_t)ed.n : nullptr;
+        float* stash_row = (BWD && p.stash != nullptr && ed.out_off1 != 0 && valid)
+                               ? p.stash + ((int64_t)(ed.out_off1 - 1) * p.S + s) * (int64_t)ed.n : nullptr;
+        if (BWD && st == 0 && p.grad_in != nullptr) {   // this row of the incoming gradient is needed D-1 steps from now: bring it into L2
           const float* g0 = p.grad_in + (valid ? s : p.S - 1) * (int64_t)prog.ep[0].n;
           for (int c = ch * 32; c < (int)prog.ep[0].n; c += kCh * 32) prefetch_l2(g0 + c);
         }
@@ -467,12 +489,12 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
                 const int after = (g + 2 < hi) ? g + 2 : nxt;
                 tc_wait_ld();
                 if (two) tmem_ld16(acc_of(g + 1), rb);
-                if (BWD) epi_group_bwd<PASSES, FMT>(ra, g, ed, bias, mask_row, gin, vmax, ha, la);
+                if (BWD) epi_group_bwd<PASSES, FMT>(ra, g, ed, bias, mask_row, gin, stash_row, p.grad_scale, p.grad_unscale, vmax, ha, la);
                 else epi_group_act<PASSES, FMT>(ra, g, ed, bias, aux, sig, vmax, ha, la);
                 if (two) {
                   tc_wait_ld();
                   if (after >= 0) tmem_ld16(acc_of(after), ra);
-                  if (BWD) epi_group_bwd<PASSES, FMT>(rb, g + 1, ed, bias, mask_row, gin, vmax, hb, lb);
+                  if (BWD) epi_group_bwd<PASSES, FMT>(rb, g + 1, ed, bias, mask_row, gin, stash_row, p.grad_scale, p.grad_unscale, vmax, hb, lb);
                   else epi_group_act<PASSES, FMT>(rb, g + 1, ed, bias, aux, sig, vmax, hb, lb);
                 } else if (after >= 0) {
                   tmem_ld16(acc_of(after), ra);
@@ -500,7 +522,8 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
                 tc_wait_ld();
                 if (two) tmem_ld16(acc_of(g + 1), rb);
                 if (BWD) {
-                  if (valid) epi_group_gradout(ra, g, ed.n_valid, ed.n_valid1 != 0, out_vec, out_row);
+                  if (valid && ed.kind == EPI_ACT_OUT) epi_group_actout(ra, g, bias, out_row);
+                  else if (valid) epi_group_gradout(ra, g, ed.n_valid, ed.n_valid1 != 0, out_vec, p.grad_unscale, out_row);
                 } else if (ed.kind == EPI_VIEW_RGB) {
                   epi_group_rgb(ra, g, ed, bias, aux, c0, c1, c2);
                 } else if (COMP) {
@@ -512,7 +535,8 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
                   tc_wait_ld();
                   if (after >= 0) tmem_ld16(acc_of(after), ra);
                   if (BWD) {
-                    if (valid) epi_group_gradout(rb, g + 1, ed.n_valid, ed.n_valid1 != 0, out_vec, out_row);
+                    if (valid && ed.kind == EPI_ACT_OUT) epi_group_actout(rb, g + 1, bias, out_row);
+                    else if (valid) epi_group_gradout(rb, g + 1, ed.n_valid, ed.n_valid1 != 0, out_vec, p.grad_unscale, out_row);
                   } else if (ed.kind == EPI_VIEW_RGB) {
                     epi_group_rgb(rb, g + 1, ed, bias, aux, c0, c1, c2);
                   } else if (COMP) {

@@ -45,11 +45,15 @@ struct pnr_ctx {
   // backward program of the trunk (pnr_mlp_backward_trunk): built from a host copy of the trunk weights on first use
   std::vector<std::vector<float>> host_trunk;   // weight, bias per trunk layer, as given to pnr_load_weights
   std::vector<int64_t> host_trunk_shapes;
-  bool bwd_ready = false;
   long long* dbg_timeline = nullptr;   // development aid (pnr_debug_timeline)
-  MlpLaunch bwd_launch;
-  uint8_t* d_wpacked_bwd = nullptr;
-  float* d_consts_bwd = nullptr;
+  struct Aux {                         // a second program over the same weights, with its own packed stream
+    bool ready = false;
+    MlpLaunch launch;
+    uint8_t* d_wpacked = nullptr;
+    float* d_consts = nullptr;
+  };
+  Aux bwd;                             // forward trunk + the layers in reverse (pnr_mlp_backward_trunk)
+  Aux trunk_fwd;                       // forward trunk only, output = its activations (pnr_mlp_trunk_forward)
 };
 
 // ---------------------------------------------------------------- host-side 16-bit split (RNE, = cvt.rn.*.f32)
@@ -370,8 +374,10 @@ extern "C" int pnr_destroy(pnr_ctx* ctx) {
   DeviceGuard guard(ctx->cfg.device);
   cudaFree(ctx->d_wpacked);
   cudaFree(ctx->d_consts);
-  cudaFree(ctx->d_wpacked_bwd);
-  cudaFree(ctx->d_consts_bwd);
+  cudaFree(ctx->bwd.d_wpacked);
+  cudaFree(ctx->bwd.d_consts);
+  cudaFree(ctx->trunk_fwd.d_wpacked);
+  cudaFree(ctx->trunk_fwd.d_consts);
   cudaFree(ctx->d_status);
   delete ctx;
   return PNR_OK;
@@ -568,8 +574,11 @@ static int build_program(const pnr_config& c, const float* const* t, const int64
 // 2*D tensors of pnr_load_weights' list).  Forward steps 0..D-1 (sign patterns kept, the last one loads the incoming
 // gradient), then for l = D-1..0 the gradient w.r.t. layer l's input: g_l [128, W] x W_l [W, in_l], i.e. a step whose
 // weight matrix is W_l transposed; the embedded-input columns of layer 0 and of the skip layer go to the output rows.
+// forward_only: just the trunk, whose last layer writes its activations to the output rows (EPI_ACT_OUT).
+// Stash slots (MlpParams::stash): H_i of forward layer i < D-1 in slot i; the pre-activation gradient dZ_j in slot
+// 2D-2-j (the order they are produced in: dZ_{D-1} by the last forward layer's epilogue, then D-2 .. 0).
 static int build_backward_program(const pnr_config& c, const float* const* t, const int64_t* shapes, int32_t n,
-                                  Builder& bld) {
+                                  Builder& bld, bool forward_only = false) {
   const int D = c.D, W = c.W, Ex = 3 + 6 * c.xyz_res, skip = D / 2;
   PNR_CHECK_ARG(n >= 2 * D, "backward program: got %d tensors, the trunk has %d", n, 2 * D);
   if (bld.passes != 3)
@@ -594,8 +603,9 @@ static int build_backward_program(const pnr_config& c, const float* const* t, co
   bool ok = true;
   for (int i = 0; i < D && ok; ++i) {   // forward, as in build_program (no sigma head)
     EpiDesc ed{};
-    ed.kind = (i == D - 1) ? EPI_LOADG_TO_A : EPI_RELU_TO_A;
-    ed.n_valid = (i == D - 1) ? 0 : (uint16_t)(i + 1);      // sign-pattern slot + 1
+    ed.kind = (i == D - 1) ? (forward_only ? EPI_ACT_OUT : EPI_LOADG_TO_A) : EPI_RELU_TO_A;
+    ed.n_valid = (i == D - 1 || forward_only) ? 0 : (uint16_t)(i + 1);      // sign-pattern slot + 1
+    ed.out_off1 = forward_only ? 0 : (uint16_t)(i + 1);                       // stash slot + 1: H_i, or dZ_{D-1} for i = D-1
     ed.dst_col = kColAHi;
     ed.dst_lo_col = kColALo;
     ed.bias_off = (uint16_t)bld.add_consts(trunk_b[i], W, W);
@@ -611,7 +621,7 @@ static int build_backward_program(const pnr_config& c, const float* const* t, co
     ok = bld.add_step(segs, W, kColAcc, ed, i == 0);
   }
   std::vector<float> wt;   // W_l transposed: [in_l, W] row-major (packed inside add_step, so one buffer serves all)
-  for (int l = D - 1; l >= 0 && ok; --l) {
+  for (int l = forward_only ? -1 : D - 1; l >= 0 && ok; --l) {
     const int in = trunk[l].in;
     wt.assign((size_t)in * W, 0.f);
     for (int o = 0; o < W; ++o)
@@ -629,6 +639,7 @@ static int build_backward_program(const pnr_config& c, const float* const* t, co
       EpiDesc em{};
       em.kind = EPI_MASK_TO_A;
       em.n_valid = (uint16_t)l;                                  // slot (l - 1) + 1
+      em.out_off1 = (uint16_t)(2 * D - 2 - (l - 1) + 1);          // stash slot + 1 of dZ_{l-1}
       em.dst_col = kColAHi;
       em.dst_lo_col = kColALo;
       return bld.add_step({seg_tmem(Mat{rows, W, W}, 0, W)}, W, kColAcc, em, false);
@@ -668,7 +679,7 @@ extern "C" int pnr_load_weights(pnr_ctx* ctx, const float* const* t, const int64
   PNR_CUDA(cudaMalloc(&ctx->d_consts, bld.consts.size() * 4));
   ctx->launch.prog = bld.prog;
   // host copy of the trunk for the backward program (built on the first pnr_mlp_backward_trunk after this load)
-  ctx->bwd_ready = false;
+  ctx->bwd.ready = ctx->trunk_fwd.ready = false;
   ctx->host_trunk.clear();
   ctx->host_trunk_shapes.assign(shapes, shapes + 4 * c.D);
   for (int i = 0; i < 2 * c.D; ++i)
@@ -789,47 +800,84 @@ extern "C" int pnr_mlp_composite(pnr_ctx* ctx, const float* rays, const float* z
 }
 
 
-// dL/d(embedded xyz) through the trunk (first slice of the MLP backward): the forward trunk is
-// recomputed per tile (sign patterns stay in shared memory), then the layers run in reverse on the same tiles with
-// the transposed weight stream.  grad_h = dL/dh of the trunk output [R*N, W]; grad_emb [R*N, ld_emb], the first
-// 3 + 6*xyz_res columns of a row are the gradient (ld_emb = 64 with a 16-byte aligned base: vector stores).
-extern "C" int pnr_mlp_backward_trunk(pnr_ctx* ctx, const float* pts, const float* rays, const float* z, int64_t R,
-                                      int32_t N, const float* grad_h, float* grad_emb, int32_t ld_emb, void* stream) {
-  if (R == 0) return PNR_OK;
-  PNR_CHECK_ARG(ctx && grad_h && grad_emb, "pnr_mlp_backward_trunk: null pointer");
-  if (!ctx->loaded) return set_error(PNR_ERR_STATE, "pnr_mlp_backward_trunk: pnr_load_weights has not been called");
-  PNR_CHECK_ARG(R > 0 && N >= 1, "pnr_mlp_backward_trunk: bad sizes R=%lld N=%d", (long long)R, N);
-  PNR_CHECK_ARG(pts || (rays && z), "pnr_mlp_backward_trunk: need pts or (rays, z)");
-  PNR_CHECK_ARG(ld_emb >= 3 + 6 * ctx->cfg.xyz_res, "pnr_mlp_backward_trunk: ld_emb=%d < %d columns", ld_emb,
-                3 + 6 * ctx->cfg.xyz_res);
+// Build (once per weight load) the second program `aux` runs and upload its packed weights / constants.
+static int ensure_aux(pnr_ctx* ctx, pnr_ctx::Aux& aux, bool forward_only) {
+  if (aux.ready) return PNR_OK;
+  Builder bld(ctx->passes, ctx->fmt);
+  std::vector<const float*> tp;
+  for (const auto& v : ctx->host_trunk) tp.push_back(v.data());
+  if (const int rc = build_backward_program(ctx->cfg, tp.data(), ctx->host_trunk_shapes.data(), (int32_t)tp.size(), bld,
+                                            forward_only))
+    return rc;
+  cudaFree(aux.d_wpacked); cudaFree(aux.d_consts);
+  aux.d_wpacked = nullptr; aux.d_consts = nullptr;
+  PNR_CUDA(cudaMalloc(&aux.d_wpacked, bld.wbuf.size() * 2));
+  PNR_CUDA(cudaMalloc(&aux.d_consts, bld.consts.size() * 4));
+  PNR_CUDA(cudaMemcpy(aux.d_wpacked, bld.wbuf.data(), bld.wbuf.size() * 2, cudaMemcpyHostToDevice));
+  PNR_CUDA(cudaMemcpy(aux.d_consts, bld.consts.data(), bld.consts.size() * 4, cudaMemcpyHostToDevice));
+  memset(&aux.launch.p, 0, sizeof(MlpParams));
+  aux.launch.prog = bld.prog;
+  aux.ready = true;
+  return PNR_OK;
+}
+
+static int aux_launch(pnr_ctx* ctx, pnr_ctx::Aux& aux, const char* what, const float* pts, const float* rays, const float* z,
+                      int64_t R, int32_t N, const float* grad_h, float grad_scale, float* out, int32_t ld_out, float* stash,
+                      void* stream) {
+  if (!ctx->loaded) return set_error(PNR_ERR_STATE, "%s: pnr_load_weights has not been called", what);
+  PNR_CHECK_ARG(R > 0 && N >= 1, "%s: bad sizes R=%lld N=%d", what, (long long)R, N);
+  PNR_CHECK_ARG(pts || (rays && z), "%s: need pts or (rays, z)", what);
   const int64_t S = R * (int64_t)N;
-  PNR_CHECK_ARG((S + kTileM - 1) / kTileM < (int64_t)1 << 31, "pnr_mlp_backward_trunk: too many samples");
+  PNR_CHECK_ARG((S + kTileM - 1) / kTileM < (int64_t)1 << 31, "%s: too many samples", what);
+  PNR_CHECK_ARG(stash == nullptr || (reinterpret_cast<uintptr_t>(stash) & 15) == 0, "%s: stash must be 16-byte aligned", what);
   DeviceGuard guard(ctx->cfg.device);
-  if (!ctx->bwd_ready) {
-    Builder bld(ctx->passes, ctx->fmt);
-    std::vector<const float*> tp;
-    for (const auto& v : ctx->host_trunk) tp.push_back(v.data());
-    if (const int rc = build_backward_program(ctx->cfg, tp.data(), ctx->host_trunk_shapes.data(), (int32_t)tp.size(), bld))
-      return rc;
-    cudaFree(ctx->d_wpacked_bwd); cudaFree(ctx->d_consts_bwd);
-    ctx->d_wpacked_bwd = nullptr; ctx->d_consts_bwd = nullptr;
-    PNR_CUDA(cudaMalloc(&ctx->d_wpacked_bwd, bld.wbuf.size() * 2));
-    PNR_CUDA(cudaMalloc(&ctx->d_consts_bwd, bld.consts.size() * 4));
-    PNR_CUDA(cudaMemcpy(ctx->d_wpacked_bwd, bld.wbuf.data(), bld.wbuf.size() * 2, cudaMemcpyHostToDevice));
-    PNR_CUDA(cudaMemcpy(ctx->d_consts_bwd, bld.consts.data(), bld.consts.size() * 4, cudaMemcpyHostToDevice));
-    memset(&ctx->bwd_launch.p, 0, sizeof(MlpParams));
-    ctx->bwd_launch.prog = bld.prog;
-    ctx->bwd_ready = true;
-  }
-  MlpParams& p = ctx->bwd_launch.p;
-  p.wpacked = ctx->d_wpacked_bwd; p.consts = ctx->d_consts_bwd;
+  if (const int rc = ensure_aux(ctx, aux, grad_h == nullptr)) return rc;
+  MlpParams& p = aux.launch.p;
+  p.wpacked = aux.d_wpacked; p.consts = aux.d_consts;
   p.pts = pts; p.viewdirs = nullptr; p.rays = rays; p.z = z;
-  p.S = S; p.N = N; p.CH = ld_emb; p.raw = grad_emb;
+  p.S = S; p.N = N; p.CH = ld_out; p.raw = out;
   p.num_tiles = (int32_t)((S + kTileM - 1) / kTileM);
   p.status = ctx->d_status;
   p.dbg = ctx->dbg_timeline;
   p.grad_in = grad_h;
-  return launch_mlp(ctx->bwd_launch, ctx->passes, ctx->fmt, kMlpBackward, (cudaStream_t)stream);
+  p.stash = stash;
+  p.grad_scale = grad_scale;
+  p.grad_unscale = 1.0f / grad_scale;
+  return launch_mlp(aux.launch, ctx->passes, ctx->fmt, kMlpBackward, (cudaStream_t)stream);
+}
+
+// dL/d(embedded xyz) through the trunk (the tensor-core part of the MLP backward): the forward
+// trunk is recomputed per tile (sign patterns stay in shared memory), then the layers run in reverse on the same tiles
+// with the transposed weight stream.  grad_h = dL/dh of the trunk output [R*N, W]; grad_emb [R*N, ld_emb], the first
+// 3 + 6*xyz_res columns of a row are the gradient (ld_emb = 64 with a 16-byte aligned base: vector stores).
+// stash (nullable) [2D-1, R*N, W] fp32 receives every A operand on the way: H_i (i < D-1) in slot i, the
+// pre-activation gradient dZ_j in slot 2D-2-j - the operands of the weight-gradient GEMMs dW_j = dZ_j^T H_{j-1}.
+// grad_scale: a power of two the incoming gradient is multiplied by on load (every gradient leaving the kernel is
+// divided by it again): gradients of a mean-reduced loss are ~1e-6, far below the normal range of the fp16 operand
+// parts; scale so that max |grad_h| * grad_scale is a few hundred (the pass is linear, the scaling exact).
+extern "C" int pnr_mlp_backward_trunk(pnr_ctx* ctx, const float* pts, const float* rays, const float* z, int64_t R,
+                                      int32_t N, const float* grad_h, float grad_scale, float* grad_emb, int32_t ld_emb,
+                                      float* stash, void* stream) {
+  if (R == 0) return PNR_OK;
+  PNR_CHECK_ARG(ctx && grad_h && grad_emb, "pnr_mlp_backward_trunk: null pointer");
+  PNR_CHECK_ARG(ld_emb >= 3 + 6 * ctx->cfg.xyz_res, "pnr_mlp_backward_trunk: ld_emb=%d < %d columns", ld_emb,
+                3 + 6 * ctx->cfg.xyz_res);
+  int gexp = 0;
+  PNR_CHECK_ARG(grad_scale > 0.f && grad_scale < 1.0e30f && grad_scale > 1.0e-30f && frexpf(grad_scale, &gexp) == 0.5f,
+                "pnr_mlp_backward_trunk: grad_scale=%g must be a positive power of two", (double)grad_scale);
+  return aux_launch(ctx, ctx->bwd, "pnr_mlp_backward_trunk", pts, rays, z, R, N, grad_h, grad_scale, grad_emb, ld_emb, stash,
+                    stream);
+}
+
+// The trunk's output activations h [R*N, W] (what alpha_linear, feature_linear and the heads read): the forward
+// trunk on the same tiles, last layer written out.  The training forward needs it once per step: everything
+// after the trunk is differentiated by the caller (torch), everything before it by pnr_mlp_backward_trunk.
+extern "C" int pnr_mlp_trunk_forward(pnr_ctx* ctx, const float* pts, const float* rays, const float* z, int64_t R,
+                                     int32_t N, float* h_out, void* stream) {
+  if (R == 0) return PNR_OK;
+  PNR_CHECK_ARG(ctx && h_out, "pnr_mlp_trunk_forward: null pointer");
+  PNR_CHECK_ARG((reinterpret_cast<uintptr_t>(h_out) & 15) == 0, "pnr_mlp_trunk_forward: h_out must be 16-byte aligned");
+  return aux_launch(ctx, ctx->trunk_fwd, "pnr_mlp_trunk_forward", pts, rays, z, R, N, nullptr, 1.0f, h_out, ctx->cfg.W, nullptr, stream);
 }
 
 namespace pnr {

@@ -13,6 +13,7 @@ CPU tensors raise.
 from __future__ import annotations
 
 import ctypes as C
+import math
 from typing import List, Optional
 
 import torch
@@ -187,30 +188,51 @@ class Network(nn.Module):
                                                       _capi.stream_ptr()), "pnr_mlp_composite")
         return out
 
-    def backward_trunk(self, grad_h: torch.Tensor, pts: Optional[torch.Tensor] = None,
-                       rays: Optional[torch.Tensor] = None, z: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """First slice of the MLP backward (pnr_mlp_backward_trunk): dL/d(embedded xyz) [S, 3 + 6*xyz_res] from
-        grad_h = dL/dh of the trunk output [S, W], for the samples given as pts [S,3] or as (rays [R,6], z [R,N]).
-        What autograd computes through `pts_linears` (ReLUs, skip concatenation) of the reference Network."""
+    def _samples(self, pts, rays, z):
         if pts is not None:
-            S_, N = pts.shape[0], 1
-            R = S_
-            dev = pts.device
-        else:
-            R, N = z.shape
-            S_ = R * N
-            dev = rays.device
+            return pts.shape[0], 1, pts.shape[0], pts.device
+        R, N = z.shape
+        return R, N, R * N, rays.device
+
+    def trunk_forward(self, pts: Optional[torch.Tensor] = None, rays: Optional[torch.Tensor] = None,
+                      z: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """h [S, W]: the output of the trunk (`pts_linears`, after the last ReLU) for the samples given as pts [S,3]
+        or as (rays [R,6], z [R,N]) - pnr_mlp_trunk_forward.  The input of alpha / feature / view / rgb / heads."""
+        R, N, S_, dev = self._samples(pts, rays, z)
+        ctx = self.pack(dev if (pts if pts is not None else rays).is_cuda else None)
+        h = torch.empty(S_, self.W, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _capi.check(_capi.lib().pnr_mlp_trunk_forward(
+                ctx, _capi.ptr(pts, torch.float32, "pts"), _capi.ptr(rays, torch.float32, "rays"),
+                _capi.ptr(z, torch.float32, "z"), R, N, _capi.ptr(h), _capi.stream_ptr()), "pnr_mlp_trunk_forward")
+        return h
+
+    def backward_trunk(self, grad_h: torch.Tensor, pts: Optional[torch.Tensor] = None,
+                       rays: Optional[torch.Tensor] = None, z: Optional[torch.Tensor] = None,
+                       stash: bool = False, grad_scale: Optional[float] = None):
+        """The tensor-core part of the MLP backward (pnr_mlp_backward_trunk): dL/d(embedded xyz) [S, 3 + 6*xyz_res] from
+        grad_h = dL/dh of the trunk output [S, W], for the samples given as pts [S,3] or as (rays [R,6], z [R,N]).
+        What autograd computes through `pts_linears` (ReLUs, skip concatenation) of the reference Network.
+        stash=True also returns the operands of the weight-gradient GEMMs, [2D-1, S, W] fp32: slot i < D-1 = the
+        activations H_i of layer i, slot 2D-2-j = dZ_j, the gradient w.r.t. layer j's pre-activation.
+        grad_scale: the power of two grad_h is multiplied by inside the kernel (and the results divided by); default:
+        the one that brings max |grad_h| to ~256 (one reduction over grad_h; the pass is linear, the scaling exact)."""
+        R, N, S_, dev = self._samples(pts, rays, z)
         assert grad_h.shape == (S_, self.W), f"grad_h must be [{S_}, {self.W}]"
         ctx = self.pack(dev if grad_h.is_cuda else None)
         Ex = 3 + 6 * self.Lx
         ld = (Ex + 15) // 16 * 16                  # rows padded to whole 16-column groups: 16-byte stores in the kernel
         out = torch.empty(S_, ld, dtype=torch.float32, device=dev)
+        st = torch.empty(2 * self.D - 1, S_, self.W, dtype=torch.float32, device=dev) if stash else None
+        if grad_scale is None:
+            m = float(grad_h.abs().max()) if grad_h.is_cuda else 0.0
+            grad_scale = 2.0 ** max(-100, min(100, round(math.log2(256.0 / m)))) if m > 0.0 and math.isfinite(m) else 1.0
         with torch.cuda.device(dev):
             _capi.check(_capi.lib().pnr_mlp_backward_trunk(
                 ctx, _capi.ptr(pts, torch.float32, "pts"), _capi.ptr(rays, torch.float32, "rays"),
-                _capi.ptr(z, torch.float32, "z"), R, N, _capi.ptr(grad_h, torch.float32, "grad_h"), _capi.ptr(out), ld,
-                _capi.stream_ptr()), "pnr_mlp_backward_trunk")
-        return out[:, :Ex]
+                _capi.ptr(z, torch.float32, "z"), R, N, _capi.ptr(grad_h, torch.float32, "grad_h"), float(grad_scale),
+                _capi.ptr(out), ld, _capi.ptr(st), _capi.stream_ptr()), "pnr_mlp_backward_trunk")
+        return (out[:, :Ex], st) if stash else out[:, :Ex]
 
     def range_status(self, reset: bool = True) -> int:
         """Sticky range-check word of this network's fused-MLP launches (synchronises the current stream).

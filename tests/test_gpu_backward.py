@@ -171,6 +171,24 @@ def test_mlp_backward_trunk_rays_mode_is_deterministic_and_chunk_invariant():
     assert torch.equal(a[lo:hi], d)
 
 
+def test_mlp_backward_trunk_small_gradients_are_scaled():
+    """Gradients of a mean-reduced loss are ~1e-6: the wrapper's power-of-two scaling keeps the fp16 operand parts in
+    the normal range, so the result is the O(1) result times the factor - bit for bit when the factor is a power of two."""
+    cfg = make_cfg("cfg2")
+    net = S.init_network_weights(make_network(cfg), seed=9).to(DEV)
+    g = torch.Generator().manual_seed(4)
+    pts = ((torch.rand(900, 3, generator=g) * 2 - 1) * 3).to(DEV)
+    grad_h = torch.randn(900, cfg.W, generator=g).to(DEV)
+    big = net.backward_trunk(grad_h, pts=pts)
+    small = net.backward_trunk(grad_h * 2.0 ** -20, pts=pts)
+    assert torch.equal(small * 2.0 ** 20, big)
+    unscaled = net.backward_trunk(grad_h * 2.0 ** -20, pts=pts, grad_scale=1.0)      # what happens without it
+    assert float((unscaled * 2.0 ** 20 - big).abs().max() / big.abs().max()) > 1e-4
+    from panopticnerf_b200 import _capi
+    with pytest.raises(_capi.PnrError, match="power of two"):
+        net.backward_trunk(grad_h, pts=pts, grad_scale=3.0)
+
+
 def test_mlp_backward_trunk_rejects_what_it_does_not_implement():
     from panopticnerf_b200 import _capi
     cfg = make_cfg("cfg2", precision="fp16")
@@ -191,8 +209,95 @@ def test_mlp_backward_trunk_unpadded_rows_match_padded():
     n, Ex = 700, 3 + 6 * cfg.xyz_res
     pts = ((torch.rand(n, 3, generator=g) * 2 - 1) * 3).to(DEV)
     grad_h = torch.randn(n, cfg.W, generator=g).to(DEV)
-    padded = net.backward_trunk(grad_h, pts=pts)
+    padded = net.backward_trunk(grad_h, pts=pts, grad_scale=256.0)
     out = torch.full((n, Ex), float("nan"), device=DEV)
     _capi.check(_capi.lib().pnr_mlp_backward_trunk(net.pack(torch.device(DEV)), pts.data_ptr(), None, None, n, 1,
-                                                   grad_h.data_ptr(), out.data_ptr(), Ex, _capi.stream_ptr()))
+                                                   grad_h.data_ptr(), 256.0, out.data_ptr(), Ex, None, _capi.stream_ptr()))
     assert torch.equal(out, padded)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The whole Network.forward backward: every parameter's gradient vs autograd through the oracle network (float64).
+# ------------------------------------------------------------------------------------------------------------------
+def _oracle_net(cfg, net_cpu):
+    onet = O.Network(cfg).double()
+    onet.load_state_dict({k: v.double() for k, v in net_cpu.state_dict().items()})
+    return onet
+
+
+def _min_preactivation(onet, pts, vd):
+    """Smallest |pre-activation| over every ReLU of the network, per sample (float64 oracle forward)."""
+    ex, ed = O.embed(pts, onet.Lx).double(), O.embed(vd, onet.Ld).double()
+    m = torch.full((pts.shape[0],), float("inf"), dtype=torch.float64)
+    track = lambda t: torch.minimum(m, t.abs().min(dim=1).values)
+    h = ex
+    with torch.no_grad():
+        for i, lin in enumerate(onet.pts_linears):
+            pre = lin(h); m = track(pre); h = torch.relu(pre)
+            if i == onet.skip:
+                h = torch.cat([ex, h], -1)
+        m = track(onet.views_linears[0](torch.cat([onet.feature_linear(h), ed], -1)))
+        if onet.C > 0:
+            m = track(onet.semantic_linears[0](h))
+        if onet.K > 0:
+            m = track(onet.instance_linears[0](h))
+    return m
+
+
+@pytest.mark.parametrize("preset,over,n", [("cfg2", {}, 4000), ("cfg3", {}, 3000), ("cfg1", dict(D=5, W=128, num_classes=7), 1500),
+                                           ("cfg2", dict(precision="bf16x3"), 30000)])
+def test_network_backward_every_parameter(preset, over, n):
+    """Weight gradients are sums over samples, and relu' is discontinuous: one unit taking the other branch moves a
+    whole sample's contribution (~1/sqrt(n) of the sum).  So the comparison runs on the samples whose pre-activations
+    all stay clear of zero by 100x the rounding error of the mode under test (30x in bf16x3) - the same samples on both sides."""
+    from panopticnerf_b200.lib.train import network_backward
+    cfg = make_cfg(preset, **over)
+    net = S.init_network_weights(make_network(cfg), seed=11)
+    onet = _oracle_net(cfg, net)
+    g = torch.Generator().manual_seed(n)
+    pts = (torch.rand(n, 3, generator=g) * 2 - 1) * 4
+    vd = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1)
+    keep = _min_preactivation(onet, pts, vd) >= (3e-4 if cfg.precision == "bf16x3" else 3e-5)
+    pts, vd = pts[keep].contiguous(), vd[keep].contiguous()
+    n = pts.shape[0]
+    assert n >= 600, f"only {n} samples clear of the ReLU kinks"
+    d_raw = torch.randn(n, 4 + cfg.num_classes + cfg.num_instances, generator=g)
+    net = net.to(DEV)
+    got = network_backward(net, d_raw.to(DEV), pts=pts.to(DEV), viewdirs=vd.to(DEV), return_input_grad=True)
+    assert net.range_status() == 0
+    raw = onet(pts.double(), vd.double())
+    raw.backward(d_raw.double())
+    ref = {k: p.grad for k, p in onet.named_parameters()}
+    assert set(ref) == set(got) - {"embedded_xyz"}
+    tol = 2e-4 if cfg.precision == "bf16x3" else 1e-4
+    for name, r in ref.items():
+        assert got[name].shape == r.shape
+        assert_close(got[name].cpu().double(), r, rms(r), f"{preset} {over} d/d{name}", rel=tol)
+    # gradients of a mean-reduced loss are tiny: the same call with d_raw * 2^-20 gives the same gradients * 2^-20
+    small = network_backward(net, (d_raw * 2.0 ** -20).to(DEV), pts=pts.to(DEV), viewdirs=vd.to(DEV))
+    for name in ("pts_linears.0.weight", f"pts_linears.{cfg.D - 1}.bias", "rgb_linear.weight"):
+        assert_close(small[name].cpu().double() * 2.0 ** 20, ref[name], rms(ref[name]), f"{preset} {over} small d/d{name}", rel=tol)
+
+
+def test_training_step_through_the_fused_path_reduces_the_loss():
+    """A few SGD steps on raw = net(pts, viewdirs) -> ||raw - target||^2, forward on the fused kernel, backward through
+    network_backward: the loss goes down, and the first step's gradients equal torch autograd through the same modules."""
+    from panopticnerf_b200.lib.train import network_forward_autograd
+    from panopticnerf_b200.lib.train.mlp_backward import _tail
+    cfg = make_cfg("cfg2", num_classes=5)
+    net = S.init_network_weights(make_network(cfg), seed=4).to(DEV)
+    g = torch.Generator().manual_seed(0)
+    pts = ((torch.rand(4096, 3, generator=g) * 2 - 1) * 3).to(DEV)
+    vd = torch.nn.functional.normalize(torch.randn(4096, 3, generator=g), dim=-1).to(DEV)
+    target = torch.randn(4096, 4 + 5, generator=g).to(DEV) * 0.1
+    opt = torch.optim.SGD(net.parameters(), lr=0.05)
+    losses = []
+    for _ in range(6):
+        opt.zero_grad()
+        raw = network_forward_autograd(net, pts, vd)
+        loss = ((raw - target) ** 2).mean()
+        loss.backward()
+        assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
+        opt.step()
+        losses.append(float(loss))
+    assert all(b < a for a, b in zip(losses, losses[1:])) and losses[-1] < 0.97 * losses[0], losses

@@ -32,7 +32,7 @@ for prec in precs:
             torch.cuda.synchronize()
             a.record()
             if which == "b":
-                net.backward_trunk(grad_h, rays=rays, z=z)
+                net.backward_trunk(grad_h, rays=rays, z=z, grad_scale=64.0)
             else:
                 net.forward_rays(rays, z)
             b.record()
