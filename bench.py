@@ -507,7 +507,38 @@ def main():
                           "note": "both passes run the full network (heads included), so the algorithmic FLOPs are "
                                   "256 evaluations x 1 345 792 per ray; one pnr_render_fused call, default workspace; "
                                   "compositing runs in the MLP kernel's epilogue (raw is never written)"}}
-        del r3, n3, b3, o3
+        del r3, b3, o3
+        # the training step of the same network on the library's kernels: 2048 rays x 192 samples,
+        # forward + losses + backward to every parameter.  Informational; a failure here must not cost the bench line.
+        try:
+            from panopticnerf_b200.lib.train import training_step
+            g3 = torch.Generator().manual_seed(0)
+            Rt, Nt = 2048, 192
+            rays_t = torch.cat([torch.randn(Rt, 3, generator=g3) * 0.5,
+                                torch.nn.functional.normalize(torch.randn(Rt, 3, generator=g3), dim=-1)], -1).to(dev)
+            z_t = torch.sort(torch.rand(Rt, Nt, generator=g3) * 6 + 0.5, -1).values.to(dev)
+            batch_t = {"rgb": torch.rand(Rt, 3, generator=g3).to(dev), "depth": (torch.rand(Rt, generator=g3) * 6).to(dev),
+                       "pseudo_label": torch.randint(-1, c3.num_classes, (Rt,), generator=g3).to(dev)}
+            tt = []
+            for i in range(2 + 3):
+                for prm in n3.parameters():
+                    prm.grad = None
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                training_step(n3, rays_t, z_t, batch_t, (1.0, 0.1, 1.0, 0.0))
+                b.record()
+                torch.cuda.synchronize()
+                if i >= 2:
+                    tt.append(a.elapsed_time(b))
+            mst = statistics.median(tt)
+            extra["train_step_cfg3"] = {
+                "workload": f"{Rt} rays x {Nt} samples, cfg3 network: forward (fused MLP + compositing) + loss kernel + "
+                            "backward to every parameter (trunk on the fused tensor-core kernel, tail + weight-gradient "
+                            "GEMMs through torch)", "ms_per_step": mst, "rays_per_s": Rt / (mst / 1e3),
+                "samples_per_s": Rt * Nt / (mst / 1e3)}
+        except Exception as exc:   # noqa: BLE001
+            extra["train_step_cfg3"] = {"error": repr(exc)[:300]}
+        del n3
 
     # ---------------- CPU baseline (rank 0, N=1): oracle port on the host cores, bounded strip + measured parity
     cpu_baseline, parity = None, None

@@ -102,13 +102,15 @@ struct Builder {
   // (the x3 modes, K = 64 per stage: 75.4 k -> 71.5 k cycles per tile); the 1-pass modes keep one block.
   bool split_e1;
   bool acc_flip = true;             // odd tiles use the accumulator columns XOR 128 when the program allows it
+  bool view_upper = true;           // both-heads programs: the view step accumulates in columns 128.. (build_program)
   bool out_of_fp16_range = false;   // a weight (after the feature_linear fold) exceeds 65504 or is not finite
   std::string err;
 
   Builder(int passes_, int fmt_) : passes(passes_), fmt(fmt_) {
     memset(&prog, 0, sizeof(prog));
     split_e1 = passes == 3;
-    if (const char* v = getenv("PNR_ACC_FLIP")) acc_flip = *v != '0';   // tuning aid (A/B on the GPU)
+    if (const char* v = getenv("PNR_ACC_FLIP")) acc_flip = *v != '0';   // tuning aids (A/B on the GPU)
+    if (const char* v = getenv("PNR_VIEW_UPPER")) view_upper = *v != '0';
   }
 
   int add_consts(const float* src, int n_valid, int n_pad) {
@@ -490,7 +492,7 @@ static int build_program(const pnr_config& c, const float* const* t, const int64
     fold_b[n_] = (float)accb;
   }
   const Mat m_fold{fold.data(), W2, W + Ed};
-  auto add_view = [&]() {  // view branch [h, gamma(d)] -> relu -> rgb (CUDA cores) ; writes rgb + sigma
+  auto add_view = [&](int acc_col) {  // view branch [h, gamma(d)] -> relu -> rgb (CUDA cores) ; writes rgb + sigma
     EpiDesc ed{};
     ed.kind = EPI_VIEW_RGB;
     ed.bias_off = (uint16_t)bld.add_consts(fold_b.data(), W2, W2);
@@ -501,7 +503,7 @@ static int build_program(const pnr_config& c, const float* const* t, const int64
     // (Accumulating the view step in the UPPER half of the accumulator region, so that the next tile's first layer
     // can be issued right behind the view MMAs, was measured: the stall only moves in front of the view step -
     // the tile boundary is bound by the serial epilogues of view + layer 0, 71.6 k vs 71.9 k cycles per tile.)
-    ok = ok && bld.add_step(segs, W2, kColAcc, ed, false);
+    ok = ok && bld.add_step(segs, W2, acc_col, ed, false);
   };
   // heads: hidden layer -> logits
   auto add_head = [&](const Mat& m1, const float* b1, const Mat& m2, const float* b2, int nout, int out_off) {
@@ -528,7 +530,10 @@ static int build_program(const pnr_config& c, const float* const* t, const int64
     // columns [0, W/2), h1 = instance logits from [W/2, W).  Per tile: 11 steps instead of 13, and the serial chain
     // hidden -> epilogue -> logits -> epilogue runs once, not twice (r2 timeline: ~30 k of a cfg3 tile's ~99 k
     // cycles went into the two head chains for ~10 k cycles of tensor work).
-    add_view();
+    // The view step accumulates in the UPPER accumulator half here: the hidden step's first half (columns 0..127) is
+    // then free to start right behind the view MMAs instead of waiting for the view epilogue to drain columns 0..127
+    // (timeline r2, cfg3: the hidden step's first stage waited ~4 k cycles of a 94 k tile for it).
+    add_view(bld.view_upper ? kColAcc + 128 : kColAcc);
     hid_w.resize((size_t)W * W);
     hid_b.resize(W);
     memcpy(hid_w.data(), m_s1.w, sizeof(float) * (size_t)W2 * W);
@@ -556,7 +561,7 @@ static int build_program(const pnr_config& c, const float* const* t, const int64
   } else {
     if (ok && C > 0) add_head(m_s1, b_s1, m_s2, b_s2, C, 4);
     if (ok && K > 0) add_head(m_i1, b_i1, m_i2, b_i2, K, 4 + C);
-    add_view();
+    add_view(kColAcc);
   }
   if (!ok) return set_error(PNR_ERR_UNSUPPORTED, "pnr_load_weights: program build failed: %s", bld.err.c_str());
   if ((int)bld.consts.size() > kMaxConsts)

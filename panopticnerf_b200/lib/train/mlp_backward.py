@@ -87,6 +87,45 @@ class _NetworkFn(torch.autograd.Function):
         return (None, None, None) + tuple(g[n] for n in ctx.names)
 
 
+class _NetworkRaysFn(torch.autograd.Function):
+    """raw [R,N,CH] = Network.forward_rays(rays, z) on the fused kernel, differentiable w.r.t. the parameters."""
+
+    @staticmethod
+    def forward(ctx, net, rays, z, *params):
+        ctx.net, ctx.names = net, [n for n, _ in net.named_parameters()]
+        ctx.save_for_backward(rays, z)
+        with torch.no_grad():
+            return net.forward_rays(rays, z)
+
+    @staticmethod
+    def backward(ctx, d_raw):
+        rays, z = ctx.saved_tensors
+        g = network_backward(ctx.net, d_raw.contiguous(), rays=rays, z=z)
+        return (None, None, None) + tuple(g[n] for n in ctx.names)
+
+
+def network_forward_rays_autograd(net, rays: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
+    """`net.forward_rays(rays, z)` (points and view directions formed in the kernel) with gradients to the parameters."""
+    return _NetworkRaysFn.apply(net, rays.contiguous(), z.contiguous(), *[p for _, p in net.named_parameters()])
+
+
+def training_step(net, rays: torch.Tensor, z: torch.Tensor, batch: Dict[str, torch.Tensor], weights=(1.0, 0.1, 1.0, 1.0),
+                  white_bkgd: bool = False, sem_is_prob: bool = False, sample_box: Optional[torch.Tensor] = None,
+                  box_sem: Optional[torch.Tensor] = None, mask_outside: bool = False):
+    """One pass of the reference NetworkWrapper's job for one set of samples: raw = net(rays, z) (fused MLP kernel),
+    maps = raw2outputs (compositing kernel), loss terms (loss kernel), and back: dL/dmaps (loss kernel) -> dL/draw
+    (pnr_composite_backward) -> dL/dparameters (network_backward).  Leaves the gradients in `p.grad` like
+    `loss.backward()` does; returns (total, terms).  Depths z are treated as constants (the sampler is not
+    differentiated, as in the reference)."""
+    from .losses import panoptic_losses
+    raw = network_forward_rays_autograd(net, rays, z)
+    out = P.raw2outputs_autograd(raw, z, rays[:, 3:].contiguous(), white_bkgd=white_bkgd, num_classes=net.C,
+                                 num_instances=net.K, sample_box=sample_box, box_sem=box_sem, mask_outside=mask_outside)
+    total, terms = panoptic_losses(out, batch, weights, sem_is_prob=sem_is_prob)
+    total.backward()
+    return total.detach(), terms
+
+
 def network_forward_autograd(net, pts: torch.Tensor, viewdirs: torch.Tensor) -> torch.Tensor:
     """`net(pts, viewdirs)` whose result back-propagates into `net.parameters()` through `network_backward`."""
     return _NetworkFn.apply(net, pts, viewdirs, *[p for _, p in net.named_parameters()])
