@@ -102,7 +102,7 @@ struct Builder {
   // (the x3 modes, K = 64 per stage: 75.4 k -> 71.5 k cycles per tile); the 1-pass modes keep one block.
   bool split_e1;
   bool acc_flip = true;             // odd tiles use the accumulator columns XOR 128 when the program allows it
-  bool view_upper = true;           // both-heads programs: the view step accumulates in columns 128.. (build_program)
+  bool view_one_half = true;        // the view step is issued as one N = W/2 half
   bool out_of_fp16_range = false;   // a weight (after the feature_linear fold) exceeds 65504 or is not finite
   std::string err;
 
@@ -110,7 +110,7 @@ struct Builder {
     memset(&prog, 0, sizeof(prog));
     split_e1 = passes == 3;
     if (const char* v = getenv("PNR_ACC_FLIP")) acc_flip = *v != '0';   // tuning aids (A/B on the GPU)
-    if (const char* v = getenv("PNR_VIEW_UPPER")) view_upper = *v != '0';
+    if (const char* v = getenv("PNR_VIEW_ONE_HALF")) view_one_half = *v != '0';
   }
 
   int add_consts(const float* src, int n_valid, int n_pad) {
@@ -503,7 +503,11 @@ static int build_program(const pnr_config& c, const float* const* t, const int64
     // (Accumulating the view step in the UPPER half of the accumulator region, so that the next tile's first layer
     // can be issued right behind the view MMAs, was measured: the stall only moves in front of the view step -
     // the tile boundary is bound by the serial epilogues of view + layer 0, 71.6 k vs 71.9 k cycles per tile.)
-    ok = ok && bld.add_step(segs, W2, acc_col, ed, false);
+    // ONE N = W/2 half: as two N = 64 halves the view step's 108 MMAs cost ~66 cycles each for half the columns
+    // (an M=128 N=64 K=16 MMA is no faster than 0.84 of an N=128 one: profiles/r01_mma_rate_probe.log) - 7-8 k cycles
+    // of tensor pipe at the one place of the tile where nothing else can be issued.  What the halves bought, the view
+    // epilogue's first part overlapping the second half's MMAs, is worth less than that.
+    ok = ok && bld.add_step(segs, W2, acc_col, ed, false, nullptr, (bld.view_one_half && W2 <= 128) ? W2 : 0);
   };
   // heads: hidden layer -> logits
   auto add_head = [&](const Mat& m1, const float* b1, const Mat& m2, const float* b2, int nout, int out_off) {
@@ -530,10 +534,9 @@ static int build_program(const pnr_config& c, const float* const* t, const int64
     // columns [0, W/2), h1 = instance logits from [W/2, W).  Per tile: 11 steps instead of 13, and the serial chain
     // hidden -> epilogue -> logits -> epilogue runs once, not twice (r2 timeline: ~30 k of a cfg3 tile's ~99 k
     // cycles went into the two head chains for ~10 k cycles of tensor work).
-    // The view step accumulates in the UPPER accumulator half here: the hidden step's first half (columns 0..127) is
-    // then free to start right behind the view MMAs instead of waiting for the view epilogue to drain columns 0..127
-    // (timeline r2, cfg3: the hidden step's first stage waited ~4 k cycles of a 94 k tile for it).
-    add_view(bld.view_upper ? kColAcc + 128 : kColAcc);
+    // (The view step accumulating in the UPPER accumulator half, so that the hidden step's first half can start right
+    // behind the view MMAs, was measured on the cfg3 frame: 411.8 vs 408.9 ms - no gain, not kept.)
+    add_view(kColAcc);
     hid_w.resize((size_t)W * W);
     hid_b.resize(W);
     memcpy(hid_w.data(), m_s1.w, sizeof(float) * (size_t)W2 * W);

@@ -18,6 +18,26 @@ import torch.nn.functional as F
 from ..networks.renderer import panopticnerf_renderer as P
 
 
+def _tf32_parts(x: torch.Tensor):
+    """x = hi + lo with hi exactly representable in TF32 (10 mantissa bits; the low 13 bits cleared)."""
+    hi = (x.contiguous().view(torch.int32) & -8192).view(torch.float32)
+    return hi, x - hi
+
+
+def matmul_3xtf32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a @ b to ~2^-20 per product on the TF32 tensor cores: hi.hi + lo.hi + hi.lo with fp32 accumulation (the same
+    3-pass split the fused kernel uses with fp16 parts, here with TF32's fp32 exponent range: no scaling needed).
+    The library's fp32 GEMM without tensor cores is ~10x slower and would dominate a training step."""
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        ah, al = _tf32_parts(a)
+        bh, bl = _tf32_parts(b)
+        return ah @ bh + (al @ bh + ah @ bl)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+
+
 def _tail(net, h: torch.Tensor, ed: torch.Tensor) -> torch.Tensor:
     """raw from the trunk output: the reference Network.forward after `pts_linears` (same module names)."""
     sigma = net.alpha_linear(h)
@@ -60,7 +80,7 @@ def network_backward(net, d_raw: torch.Tensor, pts: Optional[torch.Tensor] = Non
         for j in range(D):
             dZ = st[2 * D - 2 - j]
             inp = ex if j == 0 else (torch.cat([ex, st[j - 1]], -1) if j == net.skip + 1 else st[j - 1])
-            grads[f"pts_linears.{j}.weight"] = dZ.t() @ inp
+            grads[f"pts_linears.{j}.weight"] = matmul_3xtf32(dZ.t(), inp)
             grads[f"pts_linears.{j}.bias"] = dZ.sum(0)
     finally:
         torch.backends.cuda.matmul.allow_tf32 = tf32

@@ -190,7 +190,10 @@ def test_the_checker_sees_a_missing_wait():
     """Drop one stage's wait on E1 and the same analysis must find an unordered conflict (the check is not vacuous)."""
     cfg = make_cfg("cfg2")
     prog, _, _ = build(cfg, S.init_network_weights(make_network(cfg), seed=0))
-    victim = next(i for i in range(prog.n_stages) if prog.st[i].flags & F_WAIT_E1 and not prog.st[i].flags & F_WAIT_E0)
+    # a stage inside a trunk layer (the tile's first step follows a step whose second epilogue part may be empty)
+    first_of_step1 = [i for i in range(prog.n_stages) if prog.st[i].flags & F_WAIT_E0][1]
+    victim = next(i for i in range(first_of_step1, prog.n_stages)
+                  if prog.st[i].flags & F_WAIT_E1 and not prog.st[i].flags & F_WAIT_E0)
     needs = prog.is_[victim].needs
     prog.is_[victim].needs = (needs & 0xFF00FFFF) | ((((needs >> 16) & 0xFF) - 1) << 16)
     _, bad = unordered_conflicts(prog)

@@ -249,7 +249,7 @@ def _min_preactivation(onet, pts, vd):
 def test_network_backward_every_parameter(preset, over, n):
     """Weight gradients are sums over samples, and relu' is discontinuous: one unit taking the other branch moves a
     whole sample's contribution (~1/sqrt(n) of the sum).  So the comparison runs on the samples whose pre-activations
-    all stay clear of zero by 100x the rounding error of the mode under test (30x in bf16x3) - the same samples on both sides."""
+    all stay clear of zero by 100x the rounding error of the mode under test (10x in bf16x3) - the same samples on both sides."""
     from panopticnerf_b200.lib.train import network_backward
     cfg = make_cfg(preset, **over)
     net = S.init_network_weights(make_network(cfg), seed=11)
@@ -257,7 +257,7 @@ def test_network_backward_every_parameter(preset, over, n):
     g = torch.Generator().manual_seed(n)
     pts = (torch.rand(n, 3, generator=g) * 2 - 1) * 4
     vd = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1)
-    keep = _min_preactivation(onet, pts, vd) >= (3e-4 if cfg.precision == "bf16x3" else 3e-5)
+    keep = _min_preactivation(onet, pts, vd) >= (1e-4 if cfg.precision == "bf16x3" else 3e-5)
     pts, vd = pts[keep].contiguous(), vd[keep].contiguous()
     n = pts.shape[0]
     assert n >= 600, f"only {n} samples clear of the ReLU kinks"
@@ -333,5 +333,8 @@ def test_training_step_end_to_end_matches_the_oracle_chain():
     assert float(terms["sem"]) == pytest.approx(float(terms_ref[2]), rel=1e-4)
     for (name, p), (_, q) in zip(net.named_parameters(), onet.named_parameters()):
         a, b = p.grad.cpu().double().reshape(-1), q.grad.reshape(-1)
+        if float(b.norm()) == 0.0:                 # no loss term reaches this parameter (the instance head here)
+            assert float(a.norm()) == 0.0, name
+            continue
         cos = float((a * b).sum() / (a.norm() * b.norm()))
         assert cos >= 0.999 and abs(float(a.norm() / b.norm()) - 1.0) < 1e-2, f"{name}: cosine {cos:.6f}, norm ratio {float(a.norm() / b.norm()):.4f}"
