@@ -280,6 +280,7 @@ int pnr_sample_pdf(const float* z, const float* weights, int64_t R, int32_t N, i
 #define PNR_PROGRAM_SPLIT_E1 4  /* flags: E1 signalled in two blocks */
 #define PNR_PROGRAM_NO_SPLIT 8  /* flags: start from one-block epilogues instead of the precision's default */
 #define PNR_PROGRAM_BACKWARD 16 /* flags: the backward program of the trunk (pnr_mlp_backward_trunk) instead */
+#define PNR_PROGRAM_VIEW_PRODUCERS 32 /* flags: the variant whose view epilogue runs on the producer warps (no heads) */
 int pnr_program_host(const pnr_config* cfg, const float* const* tensors_host, const int64_t* shapes, int32_t n,
                      int32_t flags, void* program, size_t program_cap, size_t* program_bytes,
                      void* wpacked, size_t wpacked_cap, size_t* wpacked_bytes,

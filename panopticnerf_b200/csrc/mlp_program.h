@@ -20,6 +20,14 @@
 // range straddles column 128): the first half of layer 0 then lands in the half the previous tile's last step does
 // not use and is issued right behind it.  Everything else (K order, activation columns) is unchanged.
 //
+// VIEW ON PRODUCERS (networks without heads, forward).  The view step is the tile's last; its epilogue (ReLU, the
+// 3 x W/2 rgb dot products on CUDA cores, the raw store) sits in front of the next tile's layer-0 epilogue on the
+// epilogue warps - the one resource the tile boundary is bound by (timeline r2: ~3.5 k of a 70 k-cycle tile).  In such
+// programs (view_step >= 0) the four positional-encoding warps - one thread per row, idle most of the tile - run it
+// instead: the view step's last stage commits to its own mbarrier (F_COMMIT_VIEW), the epilogue warps skip the step
+// (it is not part of the E0 / E1 counts), the producer warp of a lane quarter reads its 32 rows' accumulators, and a
+// fourth counter (+1 per producer warp and tile) gates the first stage of the next tile that reuses those columns.
+//
 // BACKWARD (first slice of the training path: dL/d(embedded input) through the trunk, on the same tiles).  A backward
 // program is the trunk's forward steps - whose EPI_RELU_TO_A epilogues also save the 16-column sign patterns of their
 // activations in shared memory (slot n_valid-1; the view-direction embedding's region, unused here) - followed by one
@@ -72,7 +80,8 @@ enum : uint16_t {
   F_COMMIT_ACC1 = 16,   // last stage of the step: signal E1
   F_COMMIT_WAR = 32,    // last stage reading the activation columns E0 of THIS step overwrites
   F_WAIT_EMB = 64, F_RELEASE_EMB = 128, F_WAIT_DIR = 256, F_RELEASE_DIR = 512,
-  F_WAIT_E1A = 1024     // first stage that touches anything E1 part a of the previous step reads or writes
+  F_WAIT_E1A = 1024,    // first stage that touches anything E1 part a of the previous step reads or writes
+  F_COMMIT_VIEW = 2048  // VIEW-ON-PRODUCERS programs: last stage of the view step (instead of F_COMMIT_ACC0/1)
 };
 enum : uint8_t { EPI_RELU_TO_A = 0, EPI_VIEW_RGB = 2, EPI_LOGITS = 3,   // (1 was a linear hand-over: feature_linear is folded now)
                  // backward programs (BWD kernels, see "BACKWARD" below):
@@ -135,13 +144,13 @@ struct MlpProgram {
   int32_t Lx, Ld;
   int32_t passes;                          // 1 or 3
   int32_t acc_flip;                        // 1: odd tiles use the accumulator columns XOR 128 (see below)
-  int32_t reserved_;
+  int32_t view_step;                       // >= 0: this (last) step's epilogue runs on the producer warps (see below)
   StageDesc st[kMaxStages];
   IssueDesc is[kMaxStages];
   EpiDesc ep[kMaxSteps];
 };
 
-enum { kMlpForward = 0, kMlpComposite = 1, kMlpBackward = 2 };   // launch_mlp's `mode`
+enum { kMlpForward = 0, kMlpComposite = 1, kMlpBackward = 2, kMlpForwardVP = 3 };   // launch_mlp's `mode`
 
 // Launch arguments of the fused kernel (device pointers).
 struct MlpParams {

@@ -315,10 +315,13 @@ __device__ __forceinline__ constexpr uint32_t inf_bits16() {
 //
 // BWD = true  : the program is a backward program (mlp_program.h): the forward trunk with its ReLU sign patterns kept
 // in shared memory, then the layers in reverse with transposed weights; input `grad_in`, output `raw`.
-template <int PASSES, int FMT, bool COMP, bool BWD = false>
+//
+// VP = true   : the program's view step (its last) has its epilogue on the producer warps (mlp_program.h).
+template <int PASSES, int FMT, bool COMP, bool BWD = false, bool VP = false>
 __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kMlpThreads, 1)
 mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
   static_assert(!(COMP && BWD), "the compositing epilogue belongs to forward programs");
+  static_assert(!(VP && (COMP || BWD)), "view-on-producers programs are plain forward programs");
   extern __shared__ __align__(1024) uint8_t smem[];
   const MlpParams& p = L.p;
   const MlpProgram& prog = L.prog;
@@ -356,10 +359,12 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
   const uint32_t bar_emb_empty = smem_u32(&bars[2 * kRing + 5]);
   const uint32_t bar_dir_full = smem_u32(&bars[2 * kRing + 6]);   // [2]
   const uint32_t bar_dir_empty = smem_u32(&bars[2 * kRing + 8]);  // [2]
+  const uint32_t bar_view_full = smem_u32(&bars[2 * kRing + 10]); // VP: the view step's accumulator is complete
   // 32-bit words (each in its own 8-byte slot)
   const uint32_t cnt_e0 = smem_u32(&bars[24]);      // epilogue -> MMA counters: +1 per epilogue warp and part
   const uint32_t cnt_e1a = smem_u32(&bars[25]);
   const uint32_t cnt_e1 = smem_u32(&bars[26]);
+  const uint32_t cnt_v = smem_u32(&bars[27]);       // VP: view epilogues done, +1 per producer warp and tile
   volatile uint32_t* issued_w = reinterpret_cast<volatile uint32_t*>(bars + 29);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
   const uint32_t ready_word = smem_u32(bars + 31);   // number of weight stages whose operands have all landed
@@ -381,6 +386,7 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
       mbar_init(bar_dir_empty + 8 * h, 1);
     }
     mbar_init(bar_war, 1);
+    mbar_init(bar_view_full, 1);
     for (int w = 24; w < 32; ++w) bars[w] = 0ull;
     mbar_init(bar_emb_full, kProWarps * 32);
     mbar_init(bar_emb_empty, 1);
@@ -392,6 +398,7 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int n_stages = prog.n_stages, n_steps = prog.n_steps;
+  const int n_esteps = VP ? n_steps - 1 : n_steps;   // steps whose epilogue the epilogue warps run
 
   if (warp < kEpiWarps) {
     // =============================================================== epilogue warps
@@ -422,7 +429,7 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
       float* qsum_q = qsum + (par * 4 + q) * kCompChPad;             // this quarter's partial sums of this tile
       float w_mine = 0.f;                                            // this row's compositing weight (COMP)
       float sig = 0.f;
-      for (int st = 0; st < n_steps; ++st, ++gstep) {
+      for (int st = 0; st < n_esteps; ++st, ++gstep) {
         const EpiDesc ed = prog.ep[st];
         const uint32_t parity = gstep & 1u;
         const float* bias = consts + ed.bias_off;
@@ -555,6 +562,7 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
             if (ed.sigma) {
               part[(ch * kTileM + row) * 4 + 3] = sig;
               sig = 0.f;
+              if (VP) __threadfence_block();   // read by a producer warp, which synchronises through the MMA chain only
             }
             if (ed.kind == EPI_VIEW_RGB) {
               float* mine = part + (ch * kTileM + row) * 4;
@@ -685,6 +693,51 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
     uint8_t* emb_hi = smem + kSmemEmb;
     uint8_t* emb_lo = emb_hi + kEmbPartBytes;
     const int Lx = prog.Lx, Ld = prog.Ld;
+    // VP: the view step's epilogue of tile t for this thread's row - what the epilogue warps do for EPI_VIEW_RGB, in
+    // the same summation order (the two column shares' partial sums, share 0 first), so the results are bit-identical
+    auto view_epilogue = [&](int t) {
+      const EpiDesc ed = prog.ep[prog.view_step];
+      const float* bias = consts + ed.bias_off;
+      const float* aux = consts + ed.aux_off;
+      const int64_t sv = tile_base(t) + row;
+      const int q = warp & 3;                                   // this warp's TMEM lane quarter = its 32 rows
+      const uint32_t tmem_lane = tmem + ((uint32_t)(q * 32) << 16);
+      const int flip = (prog.acc_flip && (t & 1)) ? 128 : 0;
+      const int ng = (int)ed.n >> 4, half = (ng + 1) / 2;       // share 0: groups [0, half), share 1: [half, ng)
+      mbar_wait_backoff(bar_view_full, (uint32_t)(t & 1));
+      tc_fence_after();
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
+      uint32_t ra[16], rb[16];
+      tmem_ld16(tmem_lane + (uint32_t)(((int)ed.acc_col) ^ flip), ra);
+#pragma unroll 1
+      for (int g = 0; g < ng; g += 2) {
+        const bool two = g + 1 < ng;
+        tc_wait_ld();
+        if (two) tmem_ld16(tmem_lane + (uint32_t)(((int)ed.acc_col + (g + 1) * 16) ^ flip), rb);
+        if (g < half) epi_group_rgb(ra, g, ed, bias, aux, a0, a1, a2);
+        else epi_group_rgb(ra, g, ed, bias, aux, b0, b1, b2);
+        if (two) {
+          tc_wait_ld();
+          if (g + 2 < ng) tmem_ld16(tmem_lane + (uint32_t)(((int)ed.acc_col + (g + 2) * 16) ^ flip), ra);
+          if (g + 1 < half) epi_group_rgb(rb, g + 1, ed, bias, aux, a0, a1, a2);
+          else epi_group_rgb(rb, g + 1, ed, bias, aux, b0, b1, b2);
+        }
+      }
+      if (sv < p.S) {
+        const float* b3 = consts + prog.rgb_bias_off;
+        const float o0 = a0 + b0 + b3[0], o1 = a1 + b1 + b3[1], o2 = a2 + b2 + b3[2];
+        const float o3 = part[row * 4 + 3] + part[(kTileM + row) * 4 + 3] + consts[prog.sigma_bias_off];
+        float* dst = p.raw + sv * p.CH;
+        if (p.CH == 4) {
+          *reinterpret_cast<float4*>(dst) = make_float4(o0, o1, o2, o3);
+        } else {
+          dst[0] = o0; dst[1] = o1; dst[2] = o2; dst[3] = o3;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) red_add_smem(cnt_v, 1u);
+    };
     for (int it = 0; it < n_iter; ++it) {
       int64_t s = tile_base(it) + row;
       if (s >= p.S) s = p.S - 1;  // clamp: tail rows compute on a valid sample, results are discarded
@@ -720,7 +773,9 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
         fence_proxy_async_smem();
         mbar_arrive(bar_dir_full + 8 * b);
       }
+      if (VP && it >= 1) view_epilogue(it - 1);   // (this tile's embeddings first: the MMAs of its layer 0 follow the view MMAs)
     }
+    if (VP && n_iter >= 1) view_epilogue(n_iter - 1);
   } else if (warp == kEpiWarps + kProWarps) {
     // =============================================================== TMA producer (one elected thread)
     if (elect_one()) {
@@ -753,7 +808,7 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
     // is two shared-memory round trips (~100 cycles; the mbarrier relay it replaces took ~560, timeline v10).
     if (elect_one()) {
       uint32_t gs = 0;
-      uint32_t have_e0 = 0, have_e1a = 0, have_e1 = 0;   // last values read from the hand-off counters
+      uint32_t have_e0 = 0, have_e1a = 0, have_e1 = 0, have_v = 0;   // last values read from the hand-off counters
       auto spin = [&](uint32_t addr, uint32_t target, uint32_t& have, const char* what) {
         if ((int32_t)(have - target) >= 0) return;
         const long long t0 = clock64();
@@ -766,7 +821,7 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
       };
       for (int it = 0; it < n_iter; ++it) {
         const int b = it & 1;
-        const uint32_t step_base = (uint32_t)(it * n_steps) - 1u;   // needs are stored + 1
+        const uint32_t step_base = (uint32_t)(it * n_esteps) - 1u;   // needs are stored + 1
         uint32_t needs = prog.is[0].needs;
 #pragma unroll 1
         for (int si = 0; si < n_stages; ++si, ++gs) {
@@ -780,6 +835,7 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
           spin(cnt_e0, (step_base + (needs & 0xFFu)) * kEpiWarps, have_e0, "E0");
           spin(cnt_e1a, (step_base + ((needs >> 8) & 0xFFu)) * kEpiWarps, have_e1a, "E1a");
           spin(cnt_e1, (step_base + ((needs >> 16) & 0xFFu)) * kEpiWarps, have_e1, "E1");
+          if (VP && (needs >> 24)) spin(cnt_v, (uint32_t)it * kProWarps, have_v, "view");   // previous tile's view epilogue
           tc_fence_before();
           st_release_smem(ready_word, gs + 1);
           needs = needs_next;
@@ -896,12 +952,13 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
           if (rec) p.dbg[si * 5 + 2] = clock64();
 #endif
           tc_commit_multicast(bar_empty + 8 * slot, (uint16_t)((1u << kClusterSize) - 1u));   // slot free in all CTAs
-          if (flags & (F_RELEASE_EMB | F_RELEASE_DIR | F_COMMIT_WAR | F_COMMIT_ACC0 | F_COMMIT_ACC1)) {
+          if (flags & (F_RELEASE_EMB | F_RELEASE_DIR | F_COMMIT_WAR | F_COMMIT_ACC0 | F_COMMIT_ACC1 | F_COMMIT_VIEW)) {
             if (flags & F_RELEASE_EMB) tc_commit(bar_emb_empty);
             if (flags & F_RELEASE_DIR) tc_commit(bar_dir_empty + 8 * b);
             if (flags & F_COMMIT_WAR) tc_commit(bar_war);
             if (flags & F_COMMIT_ACC0) tc_commit(bar_acc_full);
             if (flags & F_COMMIT_ACC1) tc_commit(bar_acc_full + 8);
+            if (VP && (flags & F_COMMIT_VIEW)) tc_commit(bar_view_full);
           }
 #ifdef PNR_TIMELINE
           if (rec) { p.dbg[si * 5 + 3] = clock64(); p.dbg[si * 5 + 4] = p.dbg[si * 5 + 3]; }
@@ -921,24 +978,24 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
 // Per-device launch state: the > 48 KB dynamic shared-memory opt-in is a per-device function attribute, and so
 // is the SM count the persistent grid is sized by.
 struct DeviceState {
-  bool attr_done[2][2][3] = {};   // [x3][bf16][plain / compositing epilogue / backward program]
+  bool attr_done[2][2][4] = {};   // [x3][bf16][plain / compositing epilogue / backward program / view on producers]
 };
 static DeviceState g_dev[kMaxDevices];
 static std::mutex g_dev_mutex;
 
-template <int PASSES, int FMT, bool COMP, bool BWD = false>
+template <int PASSES, int FMT, bool COMP, bool BWD = false, bool VP = false>
 static int launch_one(const MlpLaunch& L, int dev, int grid, cudaStream_t stream) {
   constexpr int kSmem = COMP ? kSmemTotalComp : kSmemTotal;
   {
     std::lock_guard<std::mutex> lock(g_dev_mutex);
-    bool& done = g_dev[dev].attr_done[PASSES == 3][FMT == kFmtBF16][BWD ? 2 : (COMP ? 1 : 0)];
+    bool& done = g_dev[dev].attr_done[PASSES == 3][FMT == kFmtBF16][VP ? 3 : (BWD ? 2 : (COMP ? 1 : 0))];
     if (!done) {
-      PNR_CUDA(cudaFuncSetAttribute(mlp_fused_kernel<PASSES, FMT, COMP, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      PNR_CUDA(cudaFuncSetAttribute(mlp_fused_kernel<PASSES, FMT, COMP, BWD, VP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     kSmem));
       done = true;
     }
   }
-  mlp_fused_kernel<PASSES, FMT, COMP, BWD><<<grid, kMlpThreads, kSmem, stream>>>(L);
+  mlp_fused_kernel<PASSES, FMT, COMP, BWD, VP><<<grid, kMlpThreads, kSmem, stream>>>(L);
   PNR_LAUNCH_CHECK("mlp_fused_kernel");
   return PNR_OK;
 }
@@ -965,6 +1022,13 @@ int launch_mlp(MlpLaunch& L, int passes, int fmt, int mode, cudaStream_t stream)
     if (passes != 3) return set_error(PNR_ERR_UNSUPPORTED, "backward programs run in the x3 precisions only");
     return fmt == kFmtF16 ? launch_one<3, kFmtF16, false, true>(L, dev, grid, stream)
                           : launch_one<3, kFmtBF16, false, true>(L, dev, grid, stream);
+  }
+  if (mode == kMlpForwardVP) {
+    if (L.prog.view_step < 0) return set_error(PNR_ERR_STATE, "launch_mlp: not a view-on-producers program");
+#define PNR_LAUNCH_VP(P, F) launch_one<P, F, false, false, true>(L, dev, grid, stream)
+    if (fmt == kFmtF16) return passes == 3 ? PNR_LAUNCH_VP(3, kFmtF16) : PNR_LAUNCH_VP(1, kFmtF16);
+    return passes == 3 ? PNR_LAUNCH_VP(3, kFmtBF16) : PNR_LAUNCH_VP(1, kFmtBF16);
+#undef PNR_LAUNCH_VP
   }
 #define PNR_LAUNCH(P, F) (composite ? launch_one<P, F, true>(L, dev, grid, stream) : launch_one<P, F, false>(L, dev, grid, stream))
   if (fmt == kFmtF16) return passes == 3 ? PNR_LAUNCH(3, kFmtF16) : PNR_LAUNCH(1, kFmtF16);

@@ -38,6 +38,8 @@ struct pnr_ctx {
   MlpLaunch launch;             // launch.prog = this context's program; launch.p is filled per call.  The whole
                                 // struct travels as the kernel's __grid_constant__ parameter: nothing is shared
                                 // between contexts, streams, devices or CUDA-graph replays.
+  MlpLaunch launch_vp;          // the same stages with the view epilogue on the producer warps (networks without heads;
+  bool has_vp = false;          //   pnr_mlp_forward uses it, pnr_mlp_composite keeps the standard program)
   uint8_t* d_wpacked = nullptr;
   float* d_consts = nullptr;
   uint32_t* d_status = nullptr; // sticky range-check word of the fused MLP (bit 0: activation out of operand range)
@@ -103,6 +105,7 @@ struct Builder {
   bool split_e1;
   bool acc_flip = true;             // odd tiles use the accumulator columns XOR 128 when the program allows it
   bool view_one_half = true;        // the view step is issued as one N = W/2 half
+  bool view_on_producers = false;   // the (last, one-half) view step's epilogue runs on the producer warps (mlp_program.h)
   bool out_of_fp16_range = false;   // a weight (after the feature_linear fold) exceeds 65504 or is not finite
   std::string err;
 
@@ -254,11 +257,21 @@ struct Builder {
     for (int i = 0; i < prog.n_stages; ++i)
       flip = flip && prog.st[i].acc_col / 128 == (prog.st[i].acc_col + prog.st[i].n - 1) / 128;
     prog.acc_flip = flip ? 1 : 0;
+    // view on producers: the view step must be the tile's last, issued as one half, with at least one step before it
+    const bool vp = view_on_producers && S >= 2 && prog.ep[S - 1].kind == EPI_VIEW_RGB && prog.ep[S - 1].n0 == prog.ep[S - 1].n;
+    prog.view_step = vp ? S - 1 : -1;
+    if (vp) {
+      StageDesc& last = prog.st[steps[S - 1].first_stage + steps[S - 1].n_stages - 1];
+      last.flags = (uint16_t)((last.flags & ~(F_COMMIT_ACC0 | F_COMMIT_ACC1)) | F_COMMIT_VIEW);
+    }
     std::vector<int> at_a(S), at_b(S);
     for (int s = 0; s < S; ++s) {
       const StepInfo& in = steps[s];
       const int end = in.first_stage + in.n_stages;
-      const EpiDesc& pe = prog.ep[(s + S - 1) % S];
+      // the step whose E0 / E1 counts precede this one's: cyclically the tile's last step - the last one the
+      // epilogue warps run, i.e. not the view step of a view-on-producers program
+      const int prev_step = (s == 0) ? (vp ? S - 2 : S - 1) : s - 1;
+      const EpiDesc& pe = prog.ep[prev_step];
       const bool split = in.n0_stage < end;
       auto first_touch = [&](Foot f) {
         if (s == 0 && prog.acc_flip) {   // the previous step ran in the other tile parity: its accumulator columns
@@ -273,7 +286,7 @@ struct Builder {
         else if (split && at > in.n0_stage) at = in.n0_stage;   // never later than the first stage of h1
         return at;
       };
-      const int prev = (s + S - 1) % S;
+      const int prev = prev_step;
       at_b[s] = first_touch(pe.n1a < pe.n ? epi_foot(prev, pe.n1a, pe.n) : epi_foot(prev, pe.n0, pe.n));
       at_a[s] = pe.n1a < pe.n ? first_touch(epi_foot(prev, pe.n0, pe.n1a)) : at_b[s];
       if (at_a[s] > at_b[s]) at_a[s] = at_b[s];                 // "E1 done" implies "E1 part a done"
@@ -288,13 +301,27 @@ struct Builder {
         for (int i = in.first_stage; i < end; ++i)
           if (stage_touches(prog.st[i], f)) war = i;
       }
-      prog.st[war].flags |= F_COMMIT_WAR;
+      // (the epilogue warps count one write-after-read phase per step THEY run: none for a producer-run view step)
+      if (!(vp && s == S - 1)) prog.st[war].flags |= F_COMMIT_WAR;
+    }
+    // view on producers: the first stage of the tile that touches the accumulator columns the previous tile's view
+    // epilogue reads (the other tile parity's image when the program flips) and every stage after it wait for it
+    int v_from = prog.n_stages;
+    if (vp) {
+      const EpiDesc& ve = prog.ep[S - 1];
+      Foot f{ve.acc_col, ve.acc_col + ve.n, 0, 0, 0, 0};
+      if (prog.acc_flip) { f.acc0 ^= 128; f.acc1 = f.acc0 + ve.n; }
+      for (int i = 0; i < prog.n_stages && v_from == prog.n_stages; ++i)
+        if (stage_touches(prog.st[i], f)) v_from = i;
+      // no stage of the next tile touches them (narrow networks in a flipping program: the columns come up again one
+      // tile later): gate the whole next tile - the count is per tile, and a done epilogue stays done
+      if (v_from == prog.n_stages) v_from = 0;
     }
     for (int s = 0; s < S; ++s) {
       const StepInfo& in = steps[s];
       for (int i = in.first_stage; i < in.first_stage + in.n_stages; ++i)
         prog.is[i].needs = (uint32_t)(s + 1) | ((uint32_t)(i >= at_a[s] ? s + 1 : s) << 8) |
-                           ((uint32_t)(i >= at_b[s] ? s + 1 : s) << 16);
+                           ((uint32_t)(i >= at_b[s] ? s + 1 : s) << 16) | ((uint32_t)(i >= v_from ? 1 : 0) << 24);
     }
     for (int i = 0; i < prog.n_stages; ++i) {   // issue table (flags are final now)
       const StageDesc& sd = prog.st[i];
@@ -361,6 +388,7 @@ extern "C" int pnr_create(const pnr_config* cfg, pnr_ctx** out) {
   c->passes = precision_passes(cfg->precision);
   c->fmt = precision_fmt(cfg->precision);
   memset(&c->launch, 0, sizeof(c->launch));
+  memset(&c->launch_vp, 0, sizeof(c->launch_vp));
   cudaError_t e = cudaMalloc(&c->d_status, sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMemset(c->d_status, 0, sizeof(uint32_t));
   if (e != cudaSuccess) {
@@ -676,6 +704,16 @@ extern "C" int pnr_load_weights(pnr_ctx* ctx, const float* const* t, const int64
   Builder bld(ctx->passes, ctx->fmt);
   const int rc = build_program(c, t, shapes, n, bld);
   if (rc != PNR_OK) return rc;
+  ctx->has_vp = false;
+  if (c.num_classes == 0 && c.num_instances == 0 && !(getenv("PNR_VIEW_PRODUCERS") && *getenv("PNR_VIEW_PRODUCERS") == '0')) {
+    Builder vp(ctx->passes, ctx->fmt);
+    vp.view_on_producers = true;
+    if (build_program(c, t, shapes, n, vp) == PNR_OK && vp.prog.view_step >= 0 && vp.wbuf == bld.wbuf &&
+        vp.consts == bld.consts) {   // same packed stream and constants: only flags and hand-off counts differ
+      ctx->launch_vp.prog = vp.prog;
+      ctx->has_vp = true;
+    }
+  }
 
   DeviceGuard guard(c.device);
   // (plain cudaFree / cudaMemcpy: they synchronise with the device, so no launch still reads the old buffers)
@@ -704,11 +742,12 @@ extern "C" int pnr_program_host(const pnr_config* cfg, const float* const* t, co
                                 size_t* n_consts) {
   PNR_CHECK_ARG(cfg && t && shapes && program_bytes && wpacked_bytes && n_consts, "pnr_program_host: null pointer");
   if (const int rc = check_config(cfg)) return rc;
-  PNR_CHECK_ARG((flags & ~(PNR_PROGRAM_SPLIT_E1 | PNR_PROGRAM_NO_SPLIT | PNR_PROGRAM_BACKWARD)) == 0,
+  PNR_CHECK_ARG((flags & ~(PNR_PROGRAM_SPLIT_E1 | PNR_PROGRAM_NO_SPLIT | PNR_PROGRAM_BACKWARD | PNR_PROGRAM_VIEW_PRODUCERS)) == 0,
                 "pnr_program_host: unknown flags 0x%x", flags);
   Builder bld(precision_passes(cfg->precision), precision_fmt(cfg->precision));
   if (flags & PNR_PROGRAM_NO_SPLIT) bld.split_e1 = false;
   if (flags & PNR_PROGRAM_SPLIT_E1) bld.split_e1 = true;
+  if (flags & PNR_PROGRAM_VIEW_PRODUCERS) bld.view_on_producers = true;
   const int rc = (flags & PNR_PROGRAM_BACKWARD) ? build_backward_program(*cfg, t, shapes, n, bld)
                                                 : build_program(*cfg, t, shapes, n, bld);
   if (rc != PNR_OK) return rc;
@@ -759,7 +798,9 @@ static int mlp_forward_impl(pnr_ctx* ctx, const float* pts, const float* viewdir
   const int64_t S = R * (int64_t)N;
   if (S == 0) return PNR_OK;
   PNR_CHECK_ARG((S + kTileM - 1) / kTileM < (int64_t)1 << 31, "pnr_mlp_forward: too many samples");
-  MlpParams& p = ctx->launch.p;
+  MlpLaunch& L = ctx->has_vp ? ctx->launch_vp : ctx->launch;
+  MlpParams& p = L.p;
+  memset(&p, 0, sizeof(p));
   p.wpacked = ctx->d_wpacked; p.consts = ctx->d_consts;
   p.pts = pts; p.viewdirs = viewdirs; p.rays = rays; p.z = z;
   p.S = S; p.N = N; p.CH = 4 + ctx->cfg.num_classes + ctx->cfg.num_instances; p.raw = raw;
@@ -767,7 +808,7 @@ static int mlp_forward_impl(pnr_ctx* ctx, const float* pts, const float* viewdir
   p.status = ctx->d_status;
   p.dbg = dbg;
   DeviceGuard guard(ctx->cfg.device);   // launch on the context's device whatever the caller's current one is
-  return launch_mlp(ctx->launch, ctx->passes, ctx->fmt, kMlpForward, (cudaStream_t)stream);
+  return launch_mlp(L, ctx->passes, ctx->fmt, ctx->has_vp ? kMlpForwardVP : kMlpForward, (cudaStream_t)stream);
 }
 
 extern "C" int pnr_mlp_composite(pnr_ctx* ctx, const float* rays, const float* z, int64_t R, int32_t N,

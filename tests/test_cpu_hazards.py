@@ -14,8 +14,8 @@ import pytest
 
 from panopticnerf_b200 import make_cfg, make_network, synthetic as S
 from test_cpu_program import (A_TMEM, EPI_LOADG_TO_A, EPI_MASK_TO_A, EPI_RELU_TO_A, F_COMMIT_ACC0, F_COMMIT_ACC1,
-                              F_COMMIT_WAR, F_WAIT_E0, F_WAIT_E1, F_WAIT_E1A, PROGRAM_BACKWARD, PROGRAM_NO_SPLIT,
-                              PROGRAM_SPLIT_E1, build)
+                              F_COMMIT_VIEW, F_COMMIT_WAR, F_WAIT_E0, F_WAIT_E1, F_WAIT_E1A, PROGRAM_BACKWARD,
+                              PROGRAM_NO_SPLIT, PROGRAM_SPLIT_E1, PROGRAM_VIEW_PRODUCERS, build)
 
 
 def overlap(a, b):
@@ -29,6 +29,8 @@ def events_and_edges(prog, tiles=3):
       ('W0', t, s)   E0's stores                         (after war_ok)
       ('E1a', t, s) / ('E1b', t, s) E1's loads + stores, part a / b (after acc_full[1])
       ('D0', t, s), ('D1a', t, s), ('D1', t, s)   the three hand-off counters reaching this step's count
+      ('EV', t), ('DV', t)   view-on-producers programs: the view epilogue of tile t on the producer warps (after the
+                             view step's own commit) and its counter; that step has no E0 / E1 events
     Returns (reads, writes, edges)."""
     x3 = prog.passes == 3
     steps = []
@@ -37,8 +39,10 @@ def events_and_edges(prog, tiles=3):
             steps.append([])
         steps[-1].append(i)
     n_steps = len(steps)
+    vs = prog.view_step                                  # -1, or the (last) step the producer warps finish
+    n_esteps = n_steps - 1 if vs >= 0 else n_steps       # steps in the E0 / E1 counts
     reads, writes, edges = {}, {}, []
-    order = [(t, s) for t in range(tiles) for s in range(n_steps)]
+    order = [(t, s) for t in range(tiles) for s in range(n_esteps)]     # what the epilogue warps run, in their order
     gidx = {ts: k for k, ts in enumerate(order)}
 
     def fl(t, a0, a1):
@@ -58,7 +62,7 @@ def events_and_edges(prog, tiles=3):
         return r, w
 
     prev_stage = None
-    for t, s in order:
+    for t, s in [(t, s) for t in range(tiles) for s in range(n_steps)]:
         ed = prog.ep[s]
         to_a = ed.kind in (EPI_RELU_TO_A, EPI_MASK_TO_A, EPI_LOADG_TO_A)
         for i in steps[s]:
@@ -79,12 +83,23 @@ def events_and_edges(prog, tiles=3):
                 edges += [(ev, ("E1a", t, s)), (ev, ("E1b", t, s))]
             if sd.flags & F_COMMIT_WAR:
                 edges.append((ev, ("W0", t, s)))
+            if sd.flags & F_COMMIT_VIEW:
+                edges.append((ev, ("EV", t)))
+            if (prog.is_[i].needs >> 24) and t >= 1:
+                edges.append((("DV", t - 1), ev))
             # hand-off counts: v - 1 steps of this tile (and all earlier tiles) have completed that part
             needs = prog.is_[i].needs
             for shift, name in ((0, "D0"), (8, "D1a"), (16, "D1")):
-                g = t * n_steps + ((needs >> shift) & 0xFF) - 2       # global index of the last step required
+                g = t * n_esteps + ((needs >> shift) & 0xFF) - 2      # global index of the last step required
                 if g >= 0:
                     edges.append(((name,) + order[g], ev))
+        if s == vs:      # the producer warps read the whole accumulator of the step and write nothing to tensor memory
+            reads[("EV", t)], writes[("EV", t)] = cols(t, ed, 0, ed.n, False)[0], []
+            reads[("DV", t)], writes[("DV", t)] = [], []
+            edges.append((("EV", t), ("DV", t)))
+            if t >= 1:
+                edges.append((("DV", t - 1), ("DV", t)))      # each producer warp runs the tiles in order
+            continue
         # a step issued as one half signals acc_full[0] and [1] from its last stage
         if not any(prog.st[i].flags & F_COMMIT_ACC0 for i in steps[s]):
             edges += [(("S", t, steps[s][-1]), (e, t, s)) for e in ("L0", "W0")]
@@ -164,6 +179,24 @@ def test_backward_program_conflicts_are_ordered(preset, over, flags):
     checked, bad = unordered_conflicts(prog)
     assert checked > 20
     assert not bad, f"{preset} {over} flags={flags}: unordered tensor-memory conflicts, e.g. {bad[:3]}"
+
+
+@pytest.mark.parametrize("preset,over", [("cfg2", {}), ("cfg2", dict(precision="fp16")), ("cfg1", {}), ("cfg1", dict(D=3, W=128, xyz_res=4)),
+                                         ("cfg2", dict(precision="bf16x3", D=5, W=128))])
+@pytest.mark.parametrize("flags", [0, PROGRAM_NO_SPLIT])
+def test_view_on_producers_conflicts_are_ordered(preset, over, flags):
+    """The variant whose view epilogue runs on the producer warps (own commit barrier, own counter) under the same
+    analysis; and dropping the gate on the producer counter is noticed."""
+    cfg = make_cfg(preset, **over)
+    prog, _, _ = build(cfg, S.init_network_weights(make_network(cfg), seed=0), flags=flags | PROGRAM_VIEW_PRODUCERS)
+    assert prog.view_step == prog.n_steps - 1
+    checked, bad = unordered_conflicts(prog)
+    assert checked > 20
+    assert not bad, f"{preset} {over} flags={flags}: unordered tensor-memory conflicts, e.g. {bad[:3]}"
+    for i in range(prog.n_stages):
+        prog.is_[i].needs &= 0x00FFFFFF
+    _, bad = unordered_conflicts(prog)
+    assert bad
 
 
 @pytest.mark.parametrize("preset,over", [("cfg2", {}), ("cfg3", {}), ("cfg2", dict(D=5, W=128, num_classes=7, num_instances=3))])

@@ -18,6 +18,8 @@ K_MAX_STAGES, K_MAX_STEPS = 256, 24
 A_TMEM, A_EMB, A_DIR = 0, 1, 2
 F_FIRST, F_WAIT_E0, F_WAIT_E1, F_COMMIT_ACC0, F_COMMIT_ACC1, F_COMMIT_WAR = 1, 2, 4, 8, 16, 32
 F_WAIT_E1A = 1024
+F_COMMIT_VIEW = 2048
+PROGRAM_VIEW_PRODUCERS = 32
 PROGRAM_SPLIT_E1, PROGRAM_NO_SPLIT = 4, 8
 EPI_RELU_TO_A, EPI_VIEW_RGB, EPI_LOGITS = 0, 2, 3
 EPI_MASK_TO_A, EPI_LOADG_TO_A, EPI_GRAD_OUT = 4, 5, 6          # backward programs
@@ -44,7 +46,7 @@ class EpiDesc(C.Structure):
 class MlpProgram(C.Structure):
     _fields_ = [("n_stages", C.c_int32), ("n_steps", C.c_int32), ("n_consts", C.c_int32),
                 ("sigma_bias_off", C.c_int32), ("rgb_bias_off", C.c_int32), ("Lx", C.c_int32), ("Ld", C.c_int32),
-                ("passes", C.c_int32), ("acc_flip", C.c_int32), ("reserved_", C.c_int32), ("st", StageDesc * K_MAX_STAGES), ("is_", IssueDesc * K_MAX_STAGES),
+                ("passes", C.c_int32), ("acc_flip", C.c_int32), ("view_step", C.c_int32), ("st", StageDesc * K_MAX_STAGES), ("is_", IssueDesc * K_MAX_STAGES),
                 ("ep", EpiDesc * K_MAX_STEPS)]
 
 
@@ -185,10 +187,15 @@ def replay(prog, w16, consts, cfg, pts, viewdirs, operand_precision: bool = Fals
 def check_invariants(prog, stages_of):
     """Every step signals each accumulator half once, waits for the previous step's epilogues once, and releases
     the activation columns its first epilogue overwrites once."""
-    for idxs in stages_of:
+    for s, idxs in enumerate(stages_of):
         fl = [prog.st[i].flags for i in idxs]
         assert sum(bool(f & F_WAIT_E0) for f in fl) == 1 and fl[0] & F_WAIT_E0
         assert sum(bool(f & F_WAIT_E1) for f in fl) == 1 and sum(bool(f & F_WAIT_E1A) for f in fl) == 1
+        if s == prog.view_step:      # its epilogue runs on the producer warps: one commit, to its own barrier
+            assert fl[-1] & F_COMMIT_VIEW and not any(f & (F_COMMIT_ACC0 | F_COMMIT_ACC1 | F_COMMIT_WAR) for f in fl)
+            assert s == prog.n_steps - 1 and prog.ep[s].n0 == prog.ep[s].n
+            continue
+        assert not any(f & F_COMMIT_VIEW for f in fl)
         assert sum(bool(f & F_COMMIT_ACC1) for f in fl) == 1 and fl[-1] & F_COMMIT_ACC1
         assert sum(bool(f & F_COMMIT_ACC0) for f in fl) <= 1
         assert sum(bool(f & F_COMMIT_WAR) for f in fl) == 1
@@ -208,6 +215,7 @@ def check_invariants(prog, stages_of):
             needs = prog.is_[i].needs
             assert needs & 0xFF == s + 1
             assert (needs >> 8) & 0xFF == s + int(seen_a) and (needs >> 16) & 0xFF == s + int(seen_b)
+            assert (needs >> 24) in (0, 1) and (prog.view_step >= 0 or needs >> 24 == 0)
             assert not (seen_b and not seen_a)            # "E1 done" is never required before "E1 part a done"
 
 
@@ -259,6 +267,32 @@ def test_operand_precision_of_each_mode(precision, bound):
     assert worst <= bound, f"{precision}: {worst:.3e} > {bound:.1e}"
     if precision in ("fp16", "bf16"):
         assert worst > 1e-4          # and really outside the tolerance: the mode must stay labelled "fast"
+
+
+@pytest.mark.parametrize("preset,over", [("cfg2", {}), ("cfg1", {}), ("cfg2", dict(precision="fp16")), ("cfg1", dict(D=3, W=128, xyz_res=4))])
+def test_view_on_producers_program(preset, over):
+    """The variant whose view epilogue runs on the producer warps: same stages, packed weights, constants and replayed
+    outputs as the standard program; only the view step's commits and the hand-off counts differ."""
+    cfg = make_cfg(preset, **over)
+    net = S.init_network_weights(make_network(cfg), seed=3)
+    std, w16, consts = build(cfg, net)
+    vp, w16v, constsv = build(cfg, net, flags=PROGRAM_VIEW_PRODUCERS)
+    assert std.view_step == -1 and vp.view_step == vp.n_steps - 1 and vp.n_stages == std.n_stages
+    assert np.array_equal(w16, w16v) and np.array_equal(consts, constsv)
+    g = torch.Generator().manual_seed(5)
+    pts = (torch.rand(130, 3, generator=g) * 2 - 1) * 4
+    vd = torch.nn.functional.normalize(torch.randn(130, 3, generator=g), dim=-1)
+    a, stages_of = replay(vp, w16v, constsv, cfg, pts, vd)
+    b, _ = replay(std, w16, consts, cfg, pts, vd)
+    assert np.array_equal(a, b)
+    check_invariants(vp, stages_of)
+    v = [prog_needs >> 24 for prog_needs in (vp.is_[i].needs for i in range(vp.n_stages))]
+    assert v[-1] == 1 and v == sorted(v)                 # from the first stage that reuses the view columns on
+    if cfg.W >= 256:
+        assert v[0] == 0                                 # the first half of layer 0 lands in the other accumulator half
+    cfg_h = make_cfg("cfg3")
+    with_heads, _, _ = build(cfg_h, S.init_network_weights(make_network(cfg_h), seed=0), flags=PROGRAM_VIEW_PRODUCERS)
+    assert with_heads.view_step == -1                                    # the view step is not the last one there
 
 
 def trunk_grad_oracle(cfg, net, pts, grad_h):
