@@ -272,6 +272,14 @@ int pnr_mlp_trunk_forward(pnr_ctx* ctx, const float* pts, const float* rays, con
 int pnr_sample_pdf(const float* z, const float* weights, int64_t R, int32_t N, int32_t Ni,
                    const float* u, float* z_fine, int64_t* idx, float* z_all, void* stream);
 
+/* Refresh the weights of a loaded context from DEVICE tensors (same list, order and shapes as pnr_load_weights; fp32,
+ * contiguous), stream-ordered on `stream`: what a training loop calls after every optimiser step.  The structure of
+ * the per-tile programs does not depend on the values, so nothing is rebuilt or copied through the host: the packed
+ * 16-bit streams and constant tables of the forward program (and of the trunk-forward / backward programs once they
+ * exist) are rewritten by kernels, including the feature_linear fold.  Bit-identical to a fresh pnr_load_weights of the
+ * same values.  A weight outside the fp16 range sets bit 1 of the status word (pnr_status) in the fp16 modes. */
+int pnr_update_weights(pnr_ctx* ctx, const float* const* device_tensors, int32_t n, void* stream);
+
 /* Host-only twin of pnr_load_weights (no CUDA call, no context): builds the per-tile program of the fused MLP
  * kernel, the packed 16-bit weight stream and the constant table for `cfg` and returns them in caller buffers
  * (each may be NULL to query sizes only).  `program` receives the MlpProgram struct of csrc/mlp_program.h.

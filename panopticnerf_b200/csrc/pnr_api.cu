@@ -53,9 +53,22 @@ struct pnr_ctx {
     MlpLaunch launch;
     uint8_t* d_wpacked = nullptr;
     float* d_consts = nullptr;
+    size_t n_w = 0, n_c = 0;           // packed 16-bit elements / constants
   };
   Aux bwd;                             // forward trunk + the layers in reverse (pnr_mlp_backward_trunk)
   Aux trunk_fwd;                       // forward trunk only, output = its activations (pnr_mlp_trunk_forward)
+  // device-side weight updates (pnr_update_weights): V = all input tensors concatenated + the derived (folded) values,
+  // and per program the plan "packed element p = part wpart[p] of V[widx[p]]" (Builder index mode)
+  struct Plan {
+    bool ready = false;
+    int32_t* d_widx = nullptr; uint8_t* d_wpart = nullptr; size_t n_w = 0;
+    int32_t* d_cidx = nullptr; size_t n_c = 0;
+  };
+  Plan plan_main, plan_bwd, plan_tf;
+  float* d_V = nullptr;
+  std::vector<int64_t> v_off, all_shapes;   // position of every input tensor in V; the shapes given to pnr_load_weights
+  int64_t v_total = 0, v_derived = 0;
+  bool device_weights = false;              // the weights in V are newer than the host copies (aux programs re-pack from V)
 };
 
 // ---------------------------------------------------------------- host-side 16-bit split (RNE, = cvt.rn.*.f32)
@@ -107,6 +120,15 @@ struct Builder {
   bool view_one_half = true;        // the view step is issued as one N = W/2 half
   bool view_on_producers = false;   // the (last, one-half) view step's epilogue runs on the producer warps (mlp_program.h)
   bool out_of_fp16_range = false;   // a weight (after the feature_linear fold) exceeds 65504 or is not finite
+  // INDEX MODE (device-side weight updates, weights_update.cu): the builder is run once on tensors whose VALUES are
+  // their own position (+1) in the concatenation V of all input tensors followed by the derived values (the folded
+  // view matrix and bias, which build_program then fills with positions instead of arithmetic).  Everything else in a
+  // program's packed stream and constant table is a copy of one source value, so this run yields, per packed element,
+  // where it comes from (wsrc, 0 = padding) and which 16-bit part it is (wpart) - the plan a kernel replays on device.
+  bool index_mode = false;
+  int64_t derived_base = 0;         // position of the first derived value in V
+  std::vector<float> wsrc;
+  std::vector<uint8_t> wpart;
   std::string err;
 
   Builder(int passes_, int fmt_) : passes(passes_), fmt(fmt_) {
@@ -128,13 +150,19 @@ struct Builder {
     const size_t base = wbuf.size();
     const int n_pad = n_rows;
     wbuf.resize(base + (size_t)n_pad * kcores * 8);
+    if (index_mode) { wsrc.resize(wbuf.size(), 0.f); wpart.resize(wbuf.size(), 0); }
     for (int kc = 0; kc < kcores; ++kc)
       for (int nn = 0; nn < n_pad; ++nn)
         for (int e = 0; e < 8; ++e) {
           const int n = row0 + nn;
           const int k = k0 + kc * 8 + e;
           const float w = (n < m.out && k < kvalid) ? m.w[(size_t)n * m.in + col0 + k] : 0.f;
-          if (!(w >= -65504.f && w <= 65504.f)) out_of_fp16_range = true;   // also catches NaN
+          if (index_mode) {
+            wsrc[base + ((size_t)kc * n_pad + nn) * 8 + e] = w;
+            wpart[base + ((size_t)kc * n_pad + nn) * 8 + e] = (uint8_t)part;
+          } else if (!(w >= -65504.f && w <= 65504.f)) {
+            out_of_fp16_range = true;   // also catches NaN
+          }
           uint16_t v;
           if (fmt == 1) {
             const uint16_t h = f2bf(w);
@@ -408,6 +436,10 @@ extern "C" int pnr_destroy(pnr_ctx* ctx) {
   cudaFree(ctx->bwd.d_consts);
   cudaFree(ctx->trunk_fwd.d_wpacked);
   cudaFree(ctx->trunk_fwd.d_consts);
+  for (pnr_ctx::Plan* pl : {&ctx->plan_main, &ctx->plan_bwd, &ctx->plan_tf}) {
+    cudaFree(pl->d_widx); cudaFree(pl->d_wpart); cudaFree(pl->d_cidx);
+  }
+  cudaFree(ctx->d_V);
   cudaFree(ctx->d_status);
   delete ctx;
   return PNR_OK;
@@ -507,7 +539,11 @@ static int build_program(const pnr_config& c, const float* const* t, const int64
   // One 256x256 GEMM per sample (11 % of the MLP) and its epilogue disappear; the view step reads the trunk
   // output h directly.
   std::vector<float> fold((size_t)W2 * (W + Ed)), fold_b(W2);
-  for (int n_ = 0; n_ < W2; ++n_) {
+  if (bld.index_mode) {   // derived values: positions in V's derived area (filled on device by fold_kernel)
+    for (size_t i = 0; i < fold.size(); ++i) fold[i] = (float)(bld.derived_base + (int64_t)i + 1);
+    for (int n_ = 0; n_ < W2; ++n_) fold_b[n_] = (float)(bld.derived_base + (int64_t)fold.size() + n_ + 1);
+  }
+  for (int n_ = 0; n_ < W2 && !bld.index_mode; ++n_) {
     const float* vrow = m_view.w + (size_t)n_ * (W + Ed);
     for (int k = 0; k < W; ++k) {
       double acc = 0.0;
@@ -726,6 +762,18 @@ extern "C" int pnr_load_weights(pnr_ctx* ctx, const float* const* t, const int64
   ctx->launch.prog = bld.prog;
   // host copy of the trunk for the backward program (built on the first pnr_mlp_backward_trunk after this load)
   ctx->bwd.ready = ctx->trunk_fwd.ready = false;
+  for (pnr_ctx::Plan* pl : {&ctx->plan_main, &ctx->plan_bwd, &ctx->plan_tf}) {
+    cudaFree(pl->d_widx); cudaFree(pl->d_wpart); cudaFree(pl->d_cidx);
+    *pl = pnr_ctx::Plan();
+  }
+  cudaFree(ctx->d_V);
+  ctx->d_V = nullptr;
+  ctx->device_weights = false;
+  ctx->all_shapes.assign(shapes, shapes + 2 * n);
+  ctx->v_off.assign(n, 0);
+  ctx->v_total = 0;
+  for (int i = 0; i < n; ++i) { ctx->v_off[i] = ctx->v_total; ctx->v_total += shapes[2 * i] * shapes[2 * i + 1]; }
+  ctx->v_derived = (int64_t)(c.W / 2) * (c.W + 3 + 6 * c.view_res) + c.W / 2;   // folded view matrix + bias
   ctx->host_trunk.clear();
   ctx->host_trunk_shapes.assign(shapes, shapes + 4 * c.D);
   for (int i = 0; i < 2 * c.D; ++i)
@@ -850,7 +898,151 @@ extern "C" int pnr_mlp_composite(pnr_ctx* ctx, const float* rays, const float* z
 
 
 // Build (once per weight load) the second program `aux` runs and upload its packed weights / constants.
-static int ensure_aux(pnr_ctx* ctx, pnr_ctx::Aux& aux, bool forward_only) {
+// ------------------------------------------------------------------------------------------------ device-side updates
+// A training loop changes the weights every step; re-running the host builder (three programs, ~30 ms each) and
+// copying the parameters to the host and back would cost more than the step itself.  The structure of a program does
+// not depend on the values, so the builder is run ONCE in index mode and the packed streams / constant tables are
+// refreshed on the device from the caller's DEVICE tensors: V <- tensors, fold_kernel (the feature_linear fold, same
+// double-precision sums in the same order as the host), pack / constants kernels per program.  Bit-identical to a
+// fresh pnr_load_weights of the same values (tests/test_gpu_backward.py::test_update_weights_equals_fresh_load).
+namespace {
+
+__device__ __forceinline__ uint16_t dev_f2bf(float x) {   // = the host f2bf (RNE on the bit pattern)
+  const uint32_t u = __float_as_uint(x);
+  return (uint16_t)((u + 0x7FFFu + ((u >> 16) & 1u)) >> 16);
+}
+
+__global__ void pack_from_plan_kernel(const float* __restrict__ V, const int32_t* __restrict__ idx,
+                                      const uint8_t* __restrict__ part, size_t n, int fmt, uint16_t* __restrict__ out,
+                                      uint32_t* status) {
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const float w = idx[p] < 0 ? 0.f : V[idx[p]];
+  uint16_t v;
+  if (fmt == 1) {
+    const uint16_t h = dev_f2bf(w);
+    v = part[p] == 0 ? h : dev_f2bf(w - __uint_as_float((uint32_t)h << 16));
+  } else {
+    if (!(w >= -65504.f && w <= 65504.f) && status != nullptr) atomicOr(status, 2u);   // weight outside the fp16 range
+    const __half h = __float2half_rn(w);
+    const __half r = part[p] == 0 ? h : __float2half_rn(w - __half2float(h));
+    v = __half_as_ushort(r);
+  }
+  out[p] = v;
+}
+
+__global__ void consts_from_plan_kernel(const float* __restrict__ V, const int32_t* __restrict__ idx, size_t n,
+                                        float* __restrict__ out) {
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) out[p] = idx[p] < 0 ? 0.f : V[idx[p]];
+}
+
+// W' = W_view[:, :W] W_feat,  b' = W_view[:, :W] b_feat + b_view (double sums, j ascending, as on the host); the
+// gamma(d) columns of W_view are copied.  One thread per element of [W2, W + Ed] (+ one column for the bias).
+__global__ void fold_kernel(float* V, int64_t off_view_w, int64_t off_view_b, int64_t off_feat_w, int64_t off_feat_b,
+                            int W, int W2, int Ed, int64_t off_fold, int64_t off_fold_b) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int cols = W + Ed + 1;
+  if (i >= W2 * cols) return;
+  const int n = i / cols, k = i % cols;
+  const float* vrow = V + off_view_w + (int64_t)n * (W + Ed);
+  if (k < W) {
+    double acc = 0.0;
+    for (int j = 0; j < W; ++j) acc += (double)vrow[j] * (double)V[off_feat_w + (int64_t)j * W + k];
+    V[off_fold + (int64_t)n * (W + Ed) + k] = (float)acc;
+  } else if (k < W + Ed) {
+    V[off_fold + (int64_t)n * (W + Ed) + k] = vrow[k];
+  } else {
+    double acc = (double)V[off_view_b + n];
+    for (int j = 0; j < W; ++j) acc += (double)vrow[j] * (double)V[off_feat_b + j];
+    V[off_fold_b + n] = (float)acc;
+  }
+}
+
+}  // namespace
+
+// which: 0 = the forward program, 1 = backward, 2 = trunk forward.  Index-mode build -> plan on the device.
+static int ensure_plan(pnr_ctx* ctx, pnr_ctx::Plan& plan, int which, size_t expect_w, size_t expect_c) {
+  if (plan.ready) return PNR_OK;
+  const int n = (int)ctx->v_off.size();
+  if (ctx->v_total + ctx->v_derived + 1 >= (int64_t)1 << 24)
+    return set_error(PNR_ERR_UNSUPPORTED, "pnr_update_weights: %lld values do not index exactly in fp32", (long long)ctx->v_total);
+  std::vector<std::vector<float>> it(n);
+  std::vector<const float*> tp(n);
+  for (int i = 0; i < n; ++i) {
+    const int64_t cnt = ctx->all_shapes[2 * i] * ctx->all_shapes[2 * i + 1];
+    it[i].resize((size_t)cnt);
+    for (int64_t j = 0; j < cnt; ++j) it[i][(size_t)j] = (float)(ctx->v_off[i] + j + 1);
+    tp[i] = it[i].data();
+  }
+  Builder bld(ctx->passes, ctx->fmt);
+  bld.index_mode = true;
+  bld.derived_base = ctx->v_total;
+  const int rc = which == 0 ? build_program(ctx->cfg, tp.data(), ctx->all_shapes.data(), n, bld)
+                            : build_backward_program(ctx->cfg, tp.data(), ctx->all_shapes.data(), n, bld, which == 2);
+  if (rc != PNR_OK) return rc;
+  if (bld.wbuf.size() != expect_w || bld.consts.size() != expect_c)
+    return set_error(PNR_ERR_STATE, "pnr_update_weights: plan / program size mismatch (%zu/%zu vs %zu/%zu)", bld.wbuf.size(),
+                     bld.consts.size(), expect_w, expect_c);
+  std::vector<int32_t> widx(bld.wsrc.size()), cidx(bld.consts.size());
+  for (size_t i = 0; i < widx.size(); ++i) widx[i] = (int32_t)bld.wsrc[i] - 1;
+  for (size_t i = 0; i < cidx.size(); ++i) cidx[i] = (int32_t)bld.consts[i] - 1;
+  plan.n_w = widx.size();
+  plan.n_c = cidx.size();
+  PNR_CUDA(cudaMalloc(&plan.d_widx, plan.n_w * 4));
+  PNR_CUDA(cudaMalloc(&plan.d_wpart, plan.n_w));
+  PNR_CUDA(cudaMalloc(&plan.d_cidx, plan.n_c * 4));
+  PNR_CUDA(cudaMemcpy(plan.d_widx, widx.data(), plan.n_w * 4, cudaMemcpyHostToDevice));
+  PNR_CUDA(cudaMemcpy(plan.d_wpart, bld.wpart.data(), plan.n_w, cudaMemcpyHostToDevice));
+  PNR_CUDA(cudaMemcpy(plan.d_cidx, cidx.data(), plan.n_c * 4, cudaMemcpyHostToDevice));
+  plan.ready = true;
+  return PNR_OK;
+}
+
+static int repack_from_V(pnr_ctx* ctx, pnr_ctx::Plan& plan, uint8_t* d_wpacked, float* d_consts, cudaStream_t st) {
+  pack_from_plan_kernel<<<(unsigned)((plan.n_w + 255) / 256), 256, 0, st>>>(ctx->d_V, plan.d_widx, plan.d_wpart, plan.n_w, ctx->fmt,
+                                                                              reinterpret_cast<uint16_t*>(d_wpacked), ctx->d_status);
+  PNR_LAUNCH_CHECK("pack_from_plan_kernel");
+  consts_from_plan_kernel<<<(unsigned)((plan.n_c + 255) / 256), 256, 0, st>>>(ctx->d_V, plan.d_cidx, plan.n_c, d_consts);
+  PNR_LAUNCH_CHECK("consts_from_plan_kernel");
+  return PNR_OK;
+}
+
+extern "C" int pnr_update_weights(pnr_ctx* ctx, const float* const* device_tensors, int32_t n, void* stream) {
+  PNR_CHECK_ARG(ctx && device_tensors, "pnr_update_weights: null pointer");
+  if (!ctx->loaded) return set_error(PNR_ERR_STATE, "pnr_update_weights: pnr_load_weights has not been called (it fixes the shapes)");
+  PNR_CHECK_ARG(n == (int)ctx->v_off.size(), "pnr_update_weights: got %d tensors, pnr_load_weights had %d", n, (int)ctx->v_off.size());
+  for (int i = 0; i < n; ++i) PNR_CHECK_ARG(device_tensors[i], "pnr_update_weights: tensor %d is null", i);
+  DeviceGuard guard(ctx->cfg.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!ctx->d_V) PNR_CUDA(cudaMalloc(&ctx->d_V, (size_t)(ctx->v_total + ctx->v_derived) * 4));
+  if (const int rc = ensure_plan(ctx, ctx->plan_main, 0, ctx->wpacked_bytes / 2, (size_t)ctx->launch.prog.n_consts)) return rc;
+  for (int i = 0; i < n; ++i)
+    PNR_CUDA(cudaMemcpyAsync(ctx->d_V + ctx->v_off[i], device_tensors[i],
+                             (size_t)(ctx->all_shapes[2 * i] * ctx->all_shapes[2 * i + 1]) * 4, cudaMemcpyDeviceToDevice, st));
+  const int D = ctx->cfg.D, W = ctx->cfg.W, W2 = W / 2, Ed = 3 + 6 * ctx->cfg.view_res;
+  // tensor order (pnr_load_weights): trunk (w, b) x D, alpha, feature, view, rgb, heads
+  const int64_t off_feat_w = ctx->v_off[2 * D + 2], off_feat_b = ctx->v_off[2 * D + 3];
+  const int64_t off_view_w = ctx->v_off[2 * D + 4], off_view_b = ctx->v_off[2 * D + 5];
+  const int64_t off_fold = ctx->v_total, off_fold_b = ctx->v_total + (int64_t)W2 * (W + Ed);
+  fold_kernel<<<(W2 * (W + Ed + 1) + 127) / 128, 128, 0, st>>>(ctx->d_V, off_view_w, off_view_b, off_feat_w, off_feat_b, W, W2, Ed,
+                                                               off_fold, off_fold_b);
+  PNR_LAUNCH_CHECK("fold_kernel");
+  if (const int rc = repack_from_V(ctx, ctx->plan_main, ctx->d_wpacked, ctx->d_consts, st)) return rc;
+  ctx->device_weights = true;
+  // the aux programs that exist follow; the others are packed from V when they are first built
+  if (ctx->bwd.ready) {
+    if (const int rc = ensure_plan(ctx, ctx->plan_bwd, 1, ctx->bwd.n_w, ctx->bwd.n_c)) return rc;
+    if (const int rc = repack_from_V(ctx, ctx->plan_bwd, ctx->bwd.d_wpacked, ctx->bwd.d_consts, st)) return rc;
+  }
+  if (ctx->trunk_fwd.ready) {
+    if (const int rc = ensure_plan(ctx, ctx->plan_tf, 2, ctx->trunk_fwd.n_w, ctx->trunk_fwd.n_c)) return rc;
+    if (const int rc = repack_from_V(ctx, ctx->plan_tf, ctx->trunk_fwd.d_wpacked, ctx->trunk_fwd.d_consts, st)) return rc;
+  }
+  return PNR_OK;
+}
+
+static int ensure_aux(pnr_ctx* ctx, pnr_ctx::Aux& aux, bool forward_only, cudaStream_t st) {
   if (aux.ready) return PNR_OK;
   Builder bld(ctx->passes, ctx->fmt);
   std::vector<const float*> tp;
@@ -866,7 +1058,14 @@ static int ensure_aux(pnr_ctx* ctx, pnr_ctx::Aux& aux, bool forward_only) {
   PNR_CUDA(cudaMemcpy(aux.d_consts, bld.consts.data(), bld.consts.size() * 4, cudaMemcpyHostToDevice));
   memset(&aux.launch.p, 0, sizeof(MlpParams));
   aux.launch.prog = bld.prog;
+  aux.n_w = bld.wbuf.size();
+  aux.n_c = bld.consts.size();
   aux.ready = true;
+  if (ctx->device_weights) {   // the host copies are older than the weights in V: pack this program from V
+    pnr_ctx::Plan& plan = forward_only ? ctx->plan_tf : ctx->plan_bwd;
+    if (const int rc = ensure_plan(ctx, plan, forward_only ? 2 : 1, aux.n_w, aux.n_c)) return rc;
+    return repack_from_V(ctx, plan, aux.d_wpacked, aux.d_consts, st);
+  }
   return PNR_OK;
 }
 
@@ -880,7 +1079,7 @@ static int aux_launch(pnr_ctx* ctx, pnr_ctx::Aux& aux, const char* what, const f
   PNR_CHECK_ARG((S + kTileM - 1) / kTileM < (int64_t)1 << 31, "%s: too many samples", what);
   PNR_CHECK_ARG(stash == nullptr || (reinterpret_cast<uintptr_t>(stash) & 15) == 0, "%s: stash must be 16-byte aligned", what);
   DeviceGuard guard(ctx->cfg.device);
-  if (const int rc = ensure_aux(ctx, aux, grad_h == nullptr)) return rc;
+  if (const int rc = ensure_aux(ctx, aux, grad_h == nullptr, (cudaStream_t)stream)) return rc;
   MlpParams& p = aux.launch.p;
   p.wpacked = aux.d_wpacked; p.consts = aux.d_consts;
   p.pts = pts; p.viewdirs = nullptr; p.rays = rays; p.z = z;

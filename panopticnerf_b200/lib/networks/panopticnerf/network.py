@@ -98,6 +98,17 @@ class Network(nn.Module):
         if self._ctx is not None and key == self._ctx_key:
             return self._ctx
         L = _capi.lib()
+        if self._ctx is not None and key[:2] == self._ctx_key[:2] and self._fast_update:
+            # same device, precision and architecture, new values (an optimiser step): refresh the packed streams on the
+            # device from the parameters themselves (pnr_update_weights) - no host copy, no rebuild
+            dev_t = []
+            for lin in self._linears():
+                dev_t += [lin.weight.detach().to(torch.float32).contiguous(), lin.bias.detach().to(torch.float32).contiguous()]
+            ptrs = (C.c_void_p * len(dev_t))(*[_capi.ptr(t, torch.float32, "parameter") for t in dev_t])
+            with torch.cuda.device(device):
+                _capi.check(L.pnr_update_weights(self._ctx, ptrs, len(dev_t), _capi.stream_ptr()), "pnr_update_weights")
+            self._ctx_key = key
+            return self._ctx
         self.release()
         cfg = _capi.PnrConfig(self.D, self.W, self.Lx, self.Ld, self.C, self.K,
                               _capi.PREC[self.precision], device.index if device.index is not None
@@ -234,6 +245,8 @@ class Network(nn.Module):
                 _capi.ptr(out), ld, _capi.ptr(st), _capi.stream_ptr()), "pnr_mlp_backward_trunk")
         return (out[:, :Ex], st) if stash else out[:, :Ex]
 
+    _fast_update = True      # class-level switch (tests compare against the full reload)
+
     def range_status(self, reset: bool = True) -> int:
         """Sticky range-check word of this network's fused-MLP launches (synchronises the current stream).
         Bit 0 set: an activation left the range of the 16-bit operand format (fp16 modes: |x| > 65504) or was not
@@ -249,7 +262,11 @@ class Network(nn.Module):
 
     def check_range(self) -> None:
         """Raise if a launch since the last check overflowed the operand format (never silent)."""
-        if self.range_status(reset=True) & 1:
+        st = self.range_status(reset=True)
+        if st & 2:
+            raise _capi.PnrError(f"Network: a weight is outside the fp16 range (|w| > 65504 or not finite) after an update - "
+                                 "the packed weights are invalid; use cfg.precision = 'bf16x3'")
+        if st & 1:
             raise _capi.PnrError(
                 f"Network: an activation left the range of the {self.precision} tensor-core operands (|x| > 65504 "
                 "or non-finite) - the MLP outputs of this call are invalid; use cfg.precision = 'bf16x3'")

@@ -24,30 +24,55 @@ def _tf32_parts(x: torch.Tensor):
     return hi, x - hi
 
 
-def matmul_3xtf32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    """a @ b to ~2^-20 per product on the TF32 tensor cores: hi.hi + lo.hi + hi.lo with fp32 accumulation (the same
-    3-pass split the fused kernel uses with fp16 parts, here with TF32's fp32 exponent range: no scaling needed).
-    The library's fp32 GEMM without tensor cores is ~10x slower and would dominate a training step."""
+def matmul_3xtf32(a: torch.Tensor, b: torch.Tensor, trans_a: bool = False, trans_b: bool = False) -> torch.Tensor:
+    """op(a) @ op(b) to ~2^-20 per product on the TF32 tensor cores: hi.hi + lo.hi + hi.lo with fp32 accumulation (the
+    same 3-pass split the fused kernel uses with fp16 parts, here with TF32's fp32 exponent range: no scaling needed).
+    The library's fp32 GEMM without tensor cores is ~10x slower and would dominate a training step.  The transposes
+    are views (the BLAS takes them as operand flags): a [S, W] gradient is never copied into [W, S]."""
     tf32 = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = True
     try:
         ah, al = _tf32_parts(a)
         bh, bl = _tf32_parts(b)
+        if trans_a:
+            ah, al = ah.t(), al.t()
+        if trans_b:
+            bh, bl = bh.t(), bl.t()
         return ah @ bh + (al @ bh + ah @ bl)
     finally:
         torch.backends.cuda.matmul.allow_tf32 = tf32
 
 
+class _Linear3x(torch.autograd.Function):
+    """F.linear whose three GEMMs (forward, dL/dx, dL/dW) are 3xTF32: the layers after the trunk at tensor-core speed
+    with fp32-grade results."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        return matmul_3xtf32(x, weight, trans_b=True) + bias
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        g = g.contiguous()
+        return matmul_3xtf32(g, weight), matmul_3xtf32(g, x, trans_a=True), g.sum(0)
+
+
+def _lin(layer, x):
+    return _Linear3x.apply(x, layer.weight, layer.bias)
+
+
 def _tail(net, h: torch.Tensor, ed: torch.Tensor) -> torch.Tensor:
     """raw from the trunk output: the reference Network.forward after `pts_linears` (same module names)."""
-    sigma = net.alpha_linear(h)
-    feat = net.feature_linear(h)
-    g = F.relu(net.views_linears[0](torch.cat([feat, ed], -1)))
-    outs = [net.rgb_linear(g), sigma]
+    sigma = _lin(net.alpha_linear, h)
+    feat = _lin(net.feature_linear, h)
+    g = F.relu(_lin(net.views_linears[0], torch.cat([feat, ed], -1)))
+    outs = [_lin(net.rgb_linear, g), sigma]
     if net.C > 0:
-        outs.append(net.semantic_linears[1](F.relu(net.semantic_linears[0](h))))
+        outs.append(_lin(net.semantic_linears[1], F.relu(_lin(net.semantic_linears[0], h))))
     if net.K > 0:
-        outs.append(net.instance_linears[1](F.relu(net.instance_linears[0](h))))
+        outs.append(_lin(net.instance_linears[1], F.relu(_lin(net.instance_linears[0], h))))
     return torch.cat(outs, -1)
 
 
@@ -80,7 +105,7 @@ def network_backward(net, d_raw: torch.Tensor, pts: Optional[torch.Tensor] = Non
         for j in range(D):
             dZ = st[2 * D - 2 - j]
             inp = ex if j == 0 else (torch.cat([ex, st[j - 1]], -1) if j == net.skip + 1 else st[j - 1])
-            grads[f"pts_linears.{j}.weight"] = matmul_3xtf32(dZ.t(), inp)
+            grads[f"pts_linears.{j}.weight"] = matmul_3xtf32(dZ, inp, trans_a=True)
             grads[f"pts_linears.{j}.bias"] = dZ.sum(0)
     finally:
         torch.backends.cuda.matmul.allow_tf32 = tf32

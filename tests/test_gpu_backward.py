@@ -338,3 +338,39 @@ def test_training_step_end_to_end_matches_the_oracle_chain():
             continue
         cos = float((a * b).sum() / (a.norm() * b.norm()))
         assert cos >= 0.999 and abs(float(a.norm() / b.norm()) - 1.0) < 1e-2, f"{name}: cosine {cos:.6f}, norm ratio {float(a.norm() / b.norm()):.4f}"
+
+
+@pytest.mark.parametrize("preset,over", [("cfg2", {}), ("cfg3", {}), ("cfg2", dict(precision="bf16x3")), ("cfg1", dict(num_classes=5))])
+def test_update_weights_equals_fresh_load(preset, over):
+    """After an optimiser-like change of every parameter, the device-side refresh (pnr_update_weights: no host copy, no
+    rebuild) gives bit for bit what a fresh context packed on the host gives - forward, trunk forward and trunk backward,
+    whether the auxiliary programs existed before the update or are first built after it."""
+    from panopticnerf_b200.lib.networks.panopticnerf.network import Network
+    cfg = make_cfg(preset, **over)
+    g = torch.Generator().manual_seed(1)
+    n = 700
+    pts = ((torch.rand(n, 3, generator=g) * 2 - 1) * 3).to(DEV)
+    vd = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1).to(DEV)
+    grad_h = torch.randn(n, cfg.W, generator=g).to(DEV)
+    net = S.init_network_weights(make_network(cfg), seed=5).to(DEV)
+    late = S.init_network_weights(make_network(cfg), seed=5).to(DEV)      # its aux programs are first built AFTER the update
+    net(pts, vd); net.trunk_forward(pts=pts); net.backward_trunk(grad_h, pts=pts)   # all three programs exist
+    late(pts, vd)
+    ctx_before = net._ctx
+    with torch.no_grad():
+        for k, (p, q) in enumerate(zip(net.parameters(), late.parameters())):
+            d = torch.randn(p.shape, generator=torch.Generator().manual_seed(100 + k)).to(DEV) * 0.05
+            p.add_(d); q.add_(d)
+    got = (net(pts, vd), net.trunk_forward(pts=pts), net.backward_trunk(grad_h, pts=pts, grad_scale=64.0))
+    assert net._ctx == ctx_before                           # refreshed in place
+    got_late = (late(pts, vd), late.trunk_forward(pts=pts), late.backward_trunk(grad_h, pts=pts, grad_scale=64.0))
+    Network._fast_update = False
+    try:
+        fresh = S.init_network_weights(make_network(cfg), seed=5).to(DEV)
+        fresh.load_state_dict(net.state_dict())
+        ref = (fresh(pts, vd), fresh.trunk_forward(pts=pts), fresh.backward_trunk(grad_h, pts=pts, grad_scale=64.0))
+    finally:
+        Network._fast_update = True
+    for a, b, c in zip(got, got_late, ref):
+        assert torch.equal(a, c) and torch.equal(b, c)
+    assert net.range_status() == 0
