@@ -220,7 +220,34 @@ __global__ void __launch_bounds__(kPdfWarps * 32) sample_pdf_kernel(
     zz[i] = z[r * N + i];
   }
   __syncwarp();
-  if (lane == 0) pnr_pdf_cdf(w, N, cdf);
+  {
+    // pnr_pdf_cdf (ray_math.h: two sequential running sums in double, rounded to fp32 per element) as a warp scan.
+    // Bit-identical to the sequential order because every partial sum is EXACT in double: the addends w + 1e-5 are fp32
+    // values in [2^-17, 2^1) (lowest set bit >= 2^-40) and at most 254 of them stay below 2^8 - 49 bits; the pdf values
+    // are fp32 in [2^-25, 2) and their sums stay below 2 - 50 bits.  (Weights outside [0, 1] - not produced by the
+    // compositing - could round differently in the two orders.)
+    const int nw = N - 2, per = (nw + 31) >> 5;
+    const int k0 = min(lane * per, nw), k1 = min(k0 + per, nw);
+    double part = 0.0;
+    for (int k = k0; k < k1; ++k) part = __dadd_rn(part, (double)__fadd_rn(w[k + 1], 1e-5f));
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) part = __dadd_rn(part, __shfl_xor_sync(0xffffffffu, part, d));
+    const float total = (float)part;
+    double mine = 0.0;
+    for (int k = k0; k < k1; ++k) mine = __dadd_rn(mine, (double)__fdiv_rn(__fadd_rn(w[k + 1], 1e-5f), total));
+    double incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const double t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl = __dadd_rn(incl, t);
+    }
+    double acc = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) { acc = 0.0; cdf[0] = 0.f; }
+    for (int k = k0; k < k1; ++k) {
+      acc = __dadd_rn(acc, (double)__fdiv_rn(__fadd_rn(w[k + 1], 1e-5f), total));
+      cdf[k + 1] = (float)acc;
+    }
+  }
   __syncwarp();
   const int Nb = N - 1;
   int P = 1;

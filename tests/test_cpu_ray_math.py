@@ -152,3 +152,30 @@ def test_fisheye_unprojection_order(emu):
     emu.emu_fisheye(H, W, (C.c_float * 7)(*k), _p(out))
     ref = O.generate_rays(H, W, k, torch.eye(4)[:3], "fisheye")
     assert torch.equal(out, ref[:, 3:]) and torch.isfinite(out).all()
+
+
+def test_pdf_cdf_sums_are_order_independent():
+    """The sample_pdf kernel computes the two running sums of pnr_pdf_cdf as a warp scan (32 chunks, tree order)
+    instead of sequentially.  That is bit-identical only because every partial sum is exact in double for weights in
+    [0, 1]; check the claim on adversarial weights: chunked / tree-ordered double sums == sequential double sums."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    for N in (3, 5, 64, 192, 256):
+        nw = N - 2
+        cases = [rng.random(N), np.zeros(N), np.ones(N), rng.random(N) * 1e-7, 1.0 - rng.random(N) * 2.0 ** -23,
+                 np.where(rng.random(N) < 0.5, 1.0, 2.0 ** -30 * rng.random(N)), rng.random(N) ** 8]
+        for wts in cases:
+            v = (wts.astype(np.float32)[1:-1] + np.float32(1e-5)).astype(np.float32)
+            seq = np.cumsum(v.astype(np.float64))                      # sequential, one rounding per step (none needed)
+            total = np.float32(seq[-1]) if nw else np.float32(0)
+            per = (nw + 31) // 32
+            chunks = [v[i:i + per].astype(np.float64) for i in range(0, max(nw, 1), per)]
+            tree = [c.sum() for c in chunks]
+            while len(tree) > 1:                                        # pairwise, like the shuffle ladder
+                tree = [tree[i] + (tree[i + 1] if i + 1 < len(tree) else 0.0) for i in range(0, len(tree), 2)]
+            assert np.float32(tree[0]) == total and tree[0] == seq[-1]
+            pdf = (v / total).astype(np.float32)
+            seq2 = np.cumsum(pdf.astype(np.float64))
+            offs = np.concatenate([[0.0], np.cumsum([c.sum() for c in (pdf[i:i + per].astype(np.float64) for i in range(0, nw, per))])])
+            par = np.concatenate([offs[j] + np.cumsum(pdf[i:i + per].astype(np.float64)) for j, i in enumerate(range(0, nw, per))])
+            assert np.array_equal(par.astype(np.float32), seq2.astype(np.float32)) and np.array_equal(par, seq2)
