@@ -214,6 +214,12 @@ int pnr_panoptic_fuse(const float* semantic_map, const float* instance_map, int6
 int pnr_hashgrid_encode(const float* x, int64_t n, const float* aabb, const float* table, int32_t L, int32_t F,
                         int32_t T_log2, float base_resolution, float per_level_scale, float* out, void* stream);
 
+/* Gradient of pnr_hashgrid_encode w.r.t. its table: grad_table [L, 2^T_log2, F] += scatter of grad_out [n, L*F] with the
+ * forward's corner weights (fp32 atomic adds: ACCUMULATES - zero grad_table first; the summation order, hence the last
+ * bits, vary between runs).  Same arguments as the forward. */
+int pnr_hashgrid_backward(const float* x, int64_t n, const float* aabb, const float* grad_out, int32_t L, int32_t F,
+                          int32_t T_log2, float base_resolution, float per_level_scale, float* grad_table, void* stream);
+
 /* a8 + a9 in ONE kernel: Network.forward with the compositing done in the MLP's epilogue - per-sample alpha /
  * transmittance / weight right after the sigma-producing layer, colours and logits reduced on chip per ray - so the
  * network outputs `raw` [R,N,4+C+K] (456 B per sample with both heads) are never written to memory; only

@@ -170,6 +170,65 @@ __global__ void __launch_bounds__(256) hashgrid_kernel(HashArgs a) {
   }
 }
 
+// Gradient of the encoder w.r.t. its table: dL/dtable[l, idx, f] += w_corner * dL/dout[i, l*F + f] over the 8 corners
+// of every point's cell - the same thread layout and index arithmetic as the forward kernel, scatter instead of gather
+// (fp32 atomic adds at L2; colliding points are what a hash table is for, so the summation order - and the last bits -
+// vary from run to run, as in every hash-grid trainer).  grad_table is ACCUMULATED into (zero it first).
+template <int F>
+__global__ void __launch_bounds__(256) hashgrid_backward_kernel(HashArgs a, const float* __restrict__ gout, float* gtab) {
+  constexpr int LPT = 8 / F;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int l0 = blockIdx.y * LPT;
+  if (i >= a.n) return;
+  const uint32_t T = 1u << a.T_log2, mask = T - 1u;
+  float v[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    float t = a.x[i * 3 + d];
+    if (a.aabb) t = __fdiv_rn(__fsub_rn(t, a.aabb[d]), __fsub_rn(a.aabb[3 + d], a.aabb[d]));
+    v[d] = fminf(fmaxf(t, 0.0f), 1.0f);
+  }
+  const float* go = gout + i * (int64_t)(a.L * F);
+#pragma unroll
+  for (int ll = 0; ll < LPT; ++ll) {
+    const int l = l0 + ll;
+    if (l >= a.L) break;
+    const uint32_t res = a.res[l], res1 = res + 1u;
+    const float res_f = (float)res;
+    const bool dense = (uint64_t)res1 * res1 * res1 <= (uint64_t)T;
+    float w[3], g[F];
+    uint32_t c[3];
+#pragma unroll
+    for (int f = 0; f < F; ++f) g[f] = go[l * F + f];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float p = __fmul_rn(v[d], res_f);
+      float fl = floorf(p);
+      if (fl >= res_f) fl = res_f - 1.0f;
+      c[d] = (uint32_t)fl;
+      w[d] = __fsub_rn(p, fl);
+    }
+    float* tab = gtab + (size_t)l * T * F;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint32_t dx = k & 1, dy = (k >> 1) & 1, dz = k >> 2;
+      const float wx = dx ? w[0] : __fsub_rn(1.0f, w[0]);
+      const float wy = dy ? w[1] : __fsub_rn(1.0f, w[1]);
+      const float wz = dz ? w[2] : __fsub_rn(1.0f, w[2]);
+      const float wk = __fmul_rn(__fmul_rn(wx, wy), wz);
+      const uint32_t idx = hash_index(c[0] + dx, c[1] + dy, c[2] + dz, res1, dense, mask);
+      if (F == 2) {
+        atomicAdd(reinterpret_cast<float2*>(tab) + idx, make_float2(wk * g[0], wk * g[1]));
+      } else if (F == 4) {
+        atomicAdd(reinterpret_cast<float4*>(tab) + idx, make_float4(wk * g[0], wk * g[1], wk * g[2], wk * g[3]));
+      } else {
+#pragma unroll
+        for (int f = 0; f < F; ++f) atomicAdd(tab + (size_t)idx * F + f, wk * g[f]);
+      }
+    }
+  }
+}
+
 }  // namespace
 }  // namespace pnr
 
@@ -211,6 +270,30 @@ extern "C" int pnr_hashgrid_encode(const float* x, int64_t n, const float* aabb,
   PNR_LAUNCH_CHECK("hashgrid_kernel");
   return PNR_OK;
 }
+
+extern "C" int pnr_hashgrid_backward(const float* x, int64_t n, const float* aabb, const float* grad_out, int32_t L, int32_t F,
+                                     int32_t T_log2, float base_resolution, float per_level_scale, float* grad_table,
+                                     void* stream) {
+  if (n == 0) return PNR_OK;
+  PNR_CHECK_ARG(x && grad_out && grad_table && n > 0, "pnr_hashgrid_backward: null pointer");
+  PNR_CHECK_ARG(L >= 1 && L <= 32 && (F == 1 || F == 2 || F == 4 || F == 8), "pnr_hashgrid_backward: L=%d F=%d (L in [1,32], F in {1,2,4,8})", L, F);
+  PNR_CHECK_ARG(T_log2 >= 4 && T_log2 <= 28, "pnr_hashgrid_backward: T_log2=%d outside [4,28]", T_log2);
+  PNR_CHECK_ARG(base_resolution >= 1.0f && per_level_scale >= 1.0f, "pnr_hashgrid_backward: base_resolution / per_level_scale < 1");
+  PNR_CHECK_ARG((double)base_resolution * pow((double)per_level_scale, (double)(L - 1)) < 1048576.0, "pnr_hashgrid_backward: finest resolution >= 2^20");
+  HashArgs a{x, n, nullptr, nullptr, aabb, L, F, T_log2, {}};
+  for (int l = 0; l < L; ++l) a.res[l] = (uint32_t)floor((double)base_resolution * pow((double)per_level_scale, (double)l));
+  const int lpt = 8 / F;
+  const dim3 grid((unsigned)((n + 255) / 256), (unsigned)((L + lpt - 1) / lpt));
+  switch (F) {
+    case 1: hashgrid_backward_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(a, grad_out, grad_table); break;
+    case 2: hashgrid_backward_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(a, grad_out, grad_table); break;
+    case 4: hashgrid_backward_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(a, grad_out, grad_table); break;
+    default: hashgrid_backward_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(a, grad_out, grad_table); break;
+  }
+  PNR_LAUNCH_CHECK("hashgrid_backward_kernel");
+  return PNR_OK;
+}
+
 
 // ------------------------------------------------------------------------------------------------ losses
 // SURVEY 8(f) rank 2, the loss side (the reference's NetworkWrapper computes these with torch ops on the rendered
