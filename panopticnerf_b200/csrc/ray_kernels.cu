@@ -261,6 +261,34 @@ __global__ void __launch_bounds__(kPdfWarps * 32) sample_pdf_kernel(
     all[N + j] = zf;
   }
   if (z_all == nullptr) return;
+  __syncwarp();
+  // Merge of the coarse depths (ascending by construction) with the fine ones.  When the fine depths are ascending too
+  // - they are whenever u is (the deterministic sampler's linspace; the inverse CDF is monotone) - every element's
+  // place in the merged row is its own index plus its rank in the other list (strict on one side, non-strict on the
+  // other, so ties get distinct places): two binary searches per element instead of a 36-pass bitonic sort of the
+  // padded row.  Same values in the same order either way; jittered (unsorted) u takes the sort.
+  bool sorted = true;
+  for (int j = lane; j + 1 < Ni; j += 32) sorted = sorted && (all[N + j] <= all[N + j + 1]);
+  for (int i = lane; i + 1 < N; i += 32) sorted = sorted && (zz[i] <= zz[i + 1]);
+  sorted = __all_sync(0xffffffffu, sorted);
+  if (sorted) {
+    // the merged row goes straight to global memory (each place is written exactly once)
+    float* out = z_all + r * (int64_t)(N + Ni);
+    const float* fine = all + N;
+    for (int i = lane; i < N; i += 32) {      // coarse element i: + number of fine depths strictly below it
+      const float v = zz[i];
+      int lo = 0, hi = Ni;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (fine[mid] < v) lo = mid + 1; else hi = mid; }
+      out[i + lo] = v;
+    }
+    for (int j = lane; j < Ni; j += 32) {     // fine element j: + number of coarse depths <= it
+      const float v = fine[j];
+      int lo = 0, hi = N;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (zz[mid] <= v) lo = mid + 1; else hi = mid; }
+      out[j + lo] = v;
+    }
+    return;
+  }
   for (int i = lane; i < N; i += 32) all[i] = zz[i];
   for (int i = N + Ni + lane; i < P; i += 32) all[i] = __int_as_float(0x7f800000);
   __syncwarp();

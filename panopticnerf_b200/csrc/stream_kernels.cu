@@ -401,8 +401,11 @@ __global__ void __launch_bounds__(kCompWarps * 32) fixed_maps_kernel(
     const int32_t sl = i < N ? sample_box[r * N + i] : -1;
     const int32_t id_s = (fsem != nullptr && sl >= 0 && sl < B) ? box_sem[sl] : -1;
     const int32_t id_i = (finst != nullptr && sl >= 0 && sl < B) ? box_inst[sl] : -1;
-    const int n = N - i0 < 32 ? N - i0 : 32;
-    for (int j = 0; j < n; ++j) {
+    // only the samples that lie in a primitive contribute (in sample order, so the sums are unchanged)
+    unsigned todo = __ballot_sync(0xffffffffu, id_s >= 0 || id_i >= 0);
+    while (todo) {
+      const int j = __ffs(todo) - 1;
+      todo &= todo - 1;
       const float wj = __shfl_sync(0xffffffffu, wl, j);
       const int32_t cs = __shfl_sync(0xffffffffu, id_s, j), ci = __shfl_sync(0xffffffffu, id_i, j);
 #pragma unroll
