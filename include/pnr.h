@@ -271,6 +271,39 @@ int pnr_mlp_backward_trunk(pnr_ctx* ctx, const float* pts, const float* rays, co
 int pnr_mlp_trunk_forward(pnr_ctx* ctx, const float* pts, const float* rays, const float* z, int64_t R, int32_t N,
                           float* h_out, void* stream);
 
+/* a8 backward, weight gradients: dW [No, Ni] (row stride ld_w) (+)= dZ^T X and db [No] (+)= column
+ * sums of dZ (NULL: skipped), for dZ [S, No] (row stride ld_dz) and X [S, Ni] (row stride ld_x), fp32, No, Ni <= 256
+ * (wider layers - the skip layer's [gamma(x), h], the view layer's [feature, gamma(d)] - are split by columns into
+ * two calls on the same dZ).  A split-K GEMM over the samples on the tensor cores: every CTA accumulates its share of
+ * the samples in tensor memory (operands split into 16-bit hi / lo parts on the fly, hi.hi + lo.hi + hi.lo, fp32
+ * accumulation), the partial products are added in a fixed order by a second kernel (deterministic).
+ * precision = PNR_PREC_BF16X3 (~2^-17 per product, fp32 exponent range: gradients need no scaling) or PNR_PREC_FP16X3
+ * (~2^-21 per product; dz_scale - DEVICE scalar or NULL - is a power of two dZ is multiplied by on load and dW divided
+ * by, exact, so that the fp16 parts of ~1e-6 gradients stay normal; |X| and |dZ * scale| must stay below 65504).
+ * accumulate != 0 adds to dW / db instead of overwriting them.
+ * workspace: pnr_wgrad_workspace_bytes(No, Ni) bytes of device scratch (16-byte aligned) on the current device.
+ * Replaces the trunk's dW_j = dZ_j^T [H_{j-1}] on pnr_mlp_backward_trunk's stash and the weight gradients of the
+ * layers after the trunk; the reference gets them from torch.autograd through nn.Linear. */
+size_t pnr_wgrad_workspace_bytes(int32_t No, int32_t Ni);
+int pnr_wgrad(const float* dz, int64_t ld_dz, int32_t No, const float* x, int64_t ld_x, int32_t Ni, int64_t S,
+              int32_t precision, const float* dz_scale, float* dW, int64_t ld_w, float* db, int32_t accumulate,
+              void* workspace, size_t workspace_bytes, void* stream);
+
+/* a8 on the training path, the layers AFTER the trunk (alpha / feature / view / rgb / heads):
+ * y [S, N] (row stride ld_y) = act(x W^T + bias) for x [S, K] (row stride ld_x), fp32, N <= 256, K <= 512, on the
+ * tensor cores with the 3-product 16-bit operand split of the fused MLP kernel (precision = PNR_PREC_FP16X3 or
+ * PNR_PREC_BF16X3), fp32 accumulation in tensor memory.  W is [N, K] (row stride ld_w), or with transposed != 0 a
+ * [K, N] matrix read transposed: dL/dx = g W of a layer y = x W^T is pnr_linear(g, W, transposed = 1).  bias [N] or
+ * NULL; relu != 0 applies max(., 0).  in_scale: DEVICE scalar or NULL - a power of two the rows of x are multiplied
+ * by on load, the result divided by it (exact): gradients of a mean-reduced loss are ~1e-6 and their fp16 parts would
+ * go subnormal unscaled.  workspace: pnr_linear_workspace_bytes(N, K) bytes, 16-byte aligned (the packed weights).
+ * The render path does not use this (there these layers are steps of the fused kernel); the reference runs
+ * nn.Linear / autograd here. */
+size_t pnr_linear_workspace_bytes(int32_t N, int32_t K);
+int pnr_linear(const float* x, int64_t ld_x, int32_t K, const float* W, int64_t ld_w, int32_t transposed,
+               const float* bias, int32_t N, int64_t S, int32_t relu, int32_t precision, const float* in_scale,
+               float* y, int64_t ld_y, void* workspace, size_t workspace_bytes, void* stream);
+
 /* a10: sample_pdf + merge.  z [R,N] coarse depths, weights [R,N] coarse weights; bins are the mid
  * points, the pdf is weights[1:-1]+1e-5.  u [R,Ni] is required (deterministic sampler: the host's
  * linspace(0,1,Ni) broadcast over rays, so the values are the caller's, bit for bit).

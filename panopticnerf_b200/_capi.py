@@ -102,6 +102,10 @@ SIGNATURES = {
     "pnr_label_tiles": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "pnr_composite_backward": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp,
                                          _i32, C.POINTER(PnrCompositeGrads), _vp, _vp]),
+    "pnr_wgrad_workspace_bytes": (C.c_size_t, [_i32, _i32]),
+    "pnr_wgrad": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i32, _i64, _i32, _vp, _vp, _i64, _vp, _i32, _vp, C.c_size_t, _vp]),
+    "pnr_linear_workspace_bytes": (C.c_size_t, [_i32, _i32]),
+    "pnr_linear": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _i64, _vp, C.c_size_t, _vp]),
     "pnr_sample_pdf": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "pnr_update_weights": (C.c_int, [_vp, C.POINTER(_vp), _i32, _vp]),
     "pnr_program_host": (C.c_int, [C.POINTER(PnrConfig), C.POINTER(_vp), C.POINTER(_i64), _i32, _i32, _vp, C.c_size_t,

@@ -5,17 +5,26 @@ The work is split where the network splits:
     `pnr_mlp_trunk_forward` gives the trunk output h, `pnr_mlp_backward_trunk` recomputes the trunk per tile, runs
     the layers in reverse with the transposed weight stream and keeps every operand of the weight-gradient GEMMs
     (activations H_i, pre-activation gradients dZ_j) in one fp32 stash;
+  * every weight / bias gradient - the trunk's dW_j = dZ_j^T H_{j-1} on that stash and those of the layers after the
+    trunk - is a split-K GEMM over the samples on the tensor cores (`wgrad` -> pnr_wgrad, csrc/wgrad_tc05.cu);
   * the layers after the trunk (alpha / feature / view / rgb / the two heads: small GEMMs with K <= W) are
-    differentiated by torch on h - plain library GEMMs, which is also what the trunk's dW_j = dZ_j^T H_{j-1} are.
+    differentiated by torch on h: their forward and input-gradient GEMMs are library GEMMs (3xTF32).
 Nothing here imports the oracle; tests compare every parameter's gradient with autograd through the oracle network."""
 from __future__ import annotations
 
-from typing import Dict, Optional
+import os
+from typing import Dict, Optional, Tuple
 
 import torch
 import torch.nn.functional as F
 
+from ... import _capi
 from ..networks.renderer import panopticnerf_renderer as P
+
+_WGRAD_WS: Dict[Tuple[int, int], torch.Tensor] = {}     # (device, stream) -> scratch of pnr_wgrad (partial products)
+# Bring-up switch: "1" = every GEMM of the training path on the library's own tensor-core kernels (pnr_linear,
+# pnr_wgrad); "0" = the 3xTF32 cuBLAS GEMMs they replace.
+_NATIVE = os.environ.get("PNR_TRAIN_NATIVE", "0") != "0"
 
 
 def _tf32_parts(x: torch.Tensor):
@@ -25,10 +34,7 @@ def _tf32_parts(x: torch.Tensor):
 
 
 def matmul_3xtf32(a: torch.Tensor, b: torch.Tensor, trans_a: bool = False, trans_b: bool = False) -> torch.Tensor:
-    """op(a) @ op(b) to ~2^-20 per product on the TF32 tensor cores: hi.hi + lo.hi + hi.lo with fp32 accumulation (the
-    same 3-pass split the fused kernel uses with fp16 parts, here with TF32's fp32 exponent range: no scaling needed).
-    The library's fp32 GEMM without tensor cores is ~10x slower and would dominate a training step.  The transposes
-    are views (the BLAS takes them as operand flags): a [S, W] gradient is never copied into [W, S]."""
+    """op(a) @ op(b) to ~2^-20 per product on the TF32 tensor cores through the library BLAS: hi.hi + lo.hi + hi.lo."""
     tf32 = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = True
     try:
@@ -43,36 +49,148 @@ def matmul_3xtf32(a: torch.Tensor, b: torch.Tensor, trans_a: bool = False, trans
         torch.backends.cuda.matmul.allow_tf32 = tf32
 
 
+def _rows(t: torch.Tensor, name: str) -> torch.Tensor:
+    """[S, n] fp32 CUDA matrix whose rows are contiguous (any row stride: column blocks of a wider matrix are views)."""
+    if not t.is_cuda:
+        raise _capi.PnrError(f"wgrad: {name} must be a CUDA tensor (no CPU fallback)")
+    if t.dtype != torch.float32 or t.dim() != 2:
+        raise _capi.PnrError(f"wgrad: {name} must be a 2-D float32 tensor, got {t.dtype} {tuple(t.shape)}")
+    if (t.shape[1] > 1 and t.stride(1) != 1) or (t.shape[0] > 1 and t.stride(0) < t.shape[1]):
+        t = t.contiguous()
+    return t
+
+
+def wgrad(dz: torch.Tensor, x: torch.Tensor, bias: bool = True, precision: str = "bf16x3",
+          scale: Optional[torch.Tensor] = None):
+    """(dW [No, Ni], db [No] or None) = (dz^T @ x, dz.sum(0)) for dz [S, No], x [S, Ni] (fp32, No <= 256): the weight
+    and bias gradient of y = x W^T + b from dz = dL/dy, on the tensor cores (pnr_wgrad: 16-bit hi / lo operand parts,
+    fp32 accumulation in tensor memory, deterministic).  Ni > 256 (the skip and view layers' concatenated inputs) is
+    covered by one call per 256-column block of x; neither dz^T nor a split copy of an operand is materialised.
+    precision "bf16x3": ~2^-17 per product, no scaling needed; "fp16x3": ~2^-21 per product with `scale`, a device
+    scalar power of two (`_pow2_scale(dz)`) that keeps the fp16 parts of tiny gradients normal."""
+    dz, x = _rows(dz, "dz"), _rows(x, "x")
+    S_, No = dz.shape
+    Ni = x.shape[1]
+    if x.shape[0] != S_ or x.device != dz.device:
+        raise _capi.PnrError(f"wgrad: dz {tuple(dz.shape)} on {dz.device} vs x {tuple(x.shape)} on {x.device}")
+    if No > 256:
+        raise _capi.PnrError(f"wgrad: {No} output features (the library handles layers up to 256 wide)")
+    if precision not in ("fp16x3", "bf16x3"):
+        raise _capi.PnrError(f"wgrad: precision {precision!r} (the training path runs in the x3 precisions)")
+    L = _capi.lib()
+    dW = torch.empty(No, Ni, dtype=torch.float32, device=dz.device)
+    db = torch.empty(No, dtype=torch.float32, device=dz.device) if bias else None
+    ld_dz = dz.stride(0) if S_ > 1 else No
+    ld_x = x.stride(0) if S_ > 1 else Ni
+    with torch.cuda.device(dz.device):
+        stream = _capi.stream_ptr()
+        key = (dz.device.index, stream)
+        need = int(L.pnr_wgrad_workspace_bytes(256, 256))
+        ws = _WGRAD_WS.get(key)
+        if ws is None or ws.numel() < need:
+            ws = _WGRAD_WS[key] = torch.empty(need, dtype=torch.uint8, device=dz.device)
+        for c0 in range(0, Ni, 256):
+            n = min(256, Ni - c0)
+            _capi.check(L.pnr_wgrad(dz.data_ptr(), ld_dz, No, x.data_ptr() + 4 * c0, ld_x, n, S_, _capi.PREC[precision],
+                                    _capi.ptr(scale, torch.float32, "scale"), dW.data_ptr() + 4 * c0, Ni, db.data_ptr() if (bias and c0 == 0) else None, 0,
+                                    ws.data_ptr(), ws.numel(), stream), "pnr_wgrad")
+    return dW, db
+
+
+_LINEAR_WS: Dict[Tuple[int, int], torch.Tensor] = {}    # (device, stream) -> scratch of pnr_linear (packed weights)
+
+
+def _pow2_scale(g: torch.Tensor) -> torch.Tensor:
+    """Device scalar 2^k that brings max |g| to ~256 (1 when g is all zero / not finite): computed on the device, no
+    host synchronisation.  The scaled product is divided by it again in the kernel - exact, it only keeps the fp16
+    operand parts of tiny gradients out of the subnormal range."""
+    m = torch.linalg.vector_norm(g, ord=float('inf'))                 # max |.| without an |g| temporary
+    ok = (m > 0) & torch.isfinite(m)
+    k = torch.clamp(torch.round(torch.log2(256.0 / torch.where(ok, m, torch.ones_like(m)))), -100.0, 100.0)
+    return torch.where(ok, torch.exp2(k), torch.ones_like(k)).to(torch.float32).reshape(1)
+
+
+def _pow2_scales(t: torch.Tensor):
+    """`_pow2_scale` of every slice t[i] of a [n, S, W] tensor, from one reduction: a list of n device scalars."""
+    m = torch.linalg.vector_norm(t, ord=float('inf'), dim=(1, 2))      # max |.| without an |t| temporary
+    ok = (m > 0) & torch.isfinite(m)
+    k = torch.clamp(torch.round(torch.log2(256.0 / torch.where(ok, m, torch.ones_like(m)))), -100.0, 100.0)
+    v = torch.where(ok, torch.exp2(k), torch.ones_like(k)).to(torch.float32).contiguous()
+    return [v[i:i + 1] for i in range(v.shape[0])]
+
+
+def linear3x(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False,
+             transposed: bool = False, precision: str = "fp16x3", scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """act(x @ weight.T + bias) [S, N] for x [S, K], weight [N, K] - or x @ weight for weight [K, N] with
+    transposed=True (the input gradient of a linear layer) - on the tensor cores (pnr_linear, csrc/linear_tc05.cu:
+    16-bit hi / lo operand parts, hi.hi + lo.hi + hi.lo, fp32 accumulation).  N <= 256, K <= 512.
+    scale: device scalar power of two applied to x inside the kernel and removed from the result (gradients)."""
+    x = _rows(x, "x")
+    w = _rows(weight, "weight")
+    S_, K = x.shape
+    N = w.shape[1] if transposed else w.shape[0]
+    if (w.shape[0] if transposed else w.shape[1]) != K or w.device != x.device:
+        raise _capi.PnrError(f"linear3x: x {tuple(x.shape)} vs weight {tuple(weight.shape)} (transposed={transposed})")
+    if precision not in ("fp16x3", "bf16x3"):
+        raise _capi.PnrError(f"linear3x: precision {precision!r} (the training path runs in the x3 precisions)")
+    L = _capi.lib()
+    y = torch.empty(S_, N, dtype=torch.float32, device=x.device)
+    b = bias.detach().to(torch.float32).contiguous() if bias is not None else None
+    with torch.cuda.device(x.device):
+        stream = _capi.stream_ptr()
+        key = (x.device.index, stream)
+        need = int(L.pnr_linear_workspace_bytes(N, K))
+        if need == 0:
+            raise _capi.PnrError(f"linear3x: N = {N} (<= 256) / K = {K} (<= 512) outside what pnr_linear handles")
+        ws = _LINEAR_WS.get(key)
+        if ws is None or ws.numel() < need:
+            ws = _LINEAR_WS[key] = torch.empty(max(need, 1 << 19), dtype=torch.uint8, device=x.device)
+        _capi.check(L.pnr_linear(x.data_ptr(), x.stride(0) if S_ > 1 else K, K, w.data_ptr(), w.stride(0) if w.shape[0] > 1 else w.shape[1],
+                                 int(transposed), _capi.ptr(b, torch.float32, "bias"), N, S_, int(relu), _capi.PREC[precision],
+                                 _capi.ptr(scale, torch.float32, "scale"), y.data_ptr(), N, ws.data_ptr(), ws.numel(), stream),
+                    "pnr_linear")
+    return y
+
+
 class _Linear3x(torch.autograd.Function):
-    """F.linear whose three GEMMs (forward, dL/dx, dL/dW) are 3xTF32: the layers after the trunk at tensor-core speed
-    with fp32-grade results."""
+    """F.linear whose three GEMMs run on the library's tensor-core kernels: forward and dL/dx through pnr_linear
+    (the network's operand format; the gradient scaled by a power of two), dL/dW and dL/db through pnr_wgrad."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, precision):
         ctx.save_for_backward(x, weight)
-        return matmul_3xtf32(x, weight, trans_b=True) + bias
+        ctx.precision = precision
+        if not _NATIVE:
+            return matmul_3xtf32(x, weight, trans_b=True) + bias
+        return linear3x(x, weight, bias, precision=precision)
 
     @staticmethod
     def backward(ctx, g):
         x, weight = ctx.saved_tensors
         g = g.contiguous()
-        return matmul_3xtf32(g, weight), matmul_3xtf32(g, x, trans_a=True), g.sum(0)
+        if not _NATIVE:
+            return matmul_3xtf32(g, weight), matmul_3xtf32(g, x, trans_a=True), g.sum(0), None
+        sc = _pow2_scale(g) if ctx.precision == "fp16x3" else None      # one scale for both gradient GEMMs of the layer
+        dx = linear3x(g, weight, transposed=True, precision=ctx.precision, scale=sc) if ctx.needs_input_grad[0] else None
+        dW, db = wgrad(g, x, precision=ctx.precision, scale=sc)
+        return dx, dW, db, None
 
 
-def _lin(layer, x):
-    return _Linear3x.apply(x, layer.weight, layer.bias)
+def _lin(layer, x, precision):
+    return _Linear3x.apply(x, layer.weight, layer.bias, precision)
 
 
 def _tail(net, h: torch.Tensor, ed: torch.Tensor) -> torch.Tensor:
     """raw from the trunk output: the reference Network.forward after `pts_linears` (same module names)."""
-    sigma = _lin(net.alpha_linear, h)
-    feat = _lin(net.feature_linear, h)
-    g = F.relu(_lin(net.views_linears[0], torch.cat([feat, ed], -1)))
-    outs = [_lin(net.rgb_linear, g), sigma]
+    pr = net.precision if net.precision in ("fp16x3", "bf16x3") else "fp16x3"
+    sigma = _lin(net.alpha_linear, h, pr)
+    feat = _lin(net.feature_linear, h, pr)
+    g = F.relu(_lin(net.views_linears[0], torch.cat([feat, ed], -1), pr))
+    outs = [_lin(net.rgb_linear, g, pr), sigma]
     if net.C > 0:
-        outs.append(_lin(net.semantic_linears[1], F.relu(_lin(net.semantic_linears[0], h))))
+        outs.append(_lin(net.semantic_linears[1], F.relu(_lin(net.semantic_linears[0], h, pr)), pr))
     if net.K > 0:
-        outs.append(_lin(net.instance_linears[1], F.relu(_lin(net.instance_linears[0], h))))
+        outs.append(_lin(net.instance_linears[1], F.relu(_lin(net.instance_linears[0], h, pr)), pr))
     return torch.cat(outs, -1)
 
 
@@ -102,11 +220,20 @@ def network_backward(net, d_raw: torch.Tensor, pts: Optional[torch.Tensor] = Non
         d_emb, st = net.backward_trunk(g[0].contiguous(), pts=pts, rays=rays, z=z, stash=True)
         ex = P.embed(pts_.contiguous(), net.Lx)
         D = net.D
+        pr = net.precision if net.precision in ("fp16x3", "bf16x3") else "fp16x3"
+        # fp16 parts: one power-of-two scale per dZ_j, all D of them from one reduction over the stash (on the device)
+        scales = _pow2_scales(st[D - 1:])[::-1] if (_NATIVE and pr == "fp16x3") else [None] * D
         for j in range(D):
             dZ = st[2 * D - 2 - j]
-            inp = ex if j == 0 else (torch.cat([ex, st[j - 1]], -1) if j == net.skip + 1 else st[j - 1])
-            grads[f"pts_linears.{j}.weight"] = matmul_3xtf32(dZ, inp, trans_a=True)
-            grads[f"pts_linears.{j}.bias"] = dZ.sum(0)
+            if not _NATIVE:
+                inp = ex if j == 0 else (torch.cat([ex, st[j - 1]], -1) if j == net.skip + 1 else st[j - 1])
+                dW, db = matmul_3xtf32(dZ, inp, trans_a=True), dZ.sum(0)
+            elif j == net.skip + 1:        # input [gamma(x), H_{j-1}]: two column blocks of dW, no concatenated copy
+                dWx, db = wgrad(dZ, ex, precision=pr, scale=scales[j])
+                dW = torch.cat([dWx, wgrad(dZ, st[j - 1], bias=False, precision=pr, scale=scales[j])[0]], -1)
+            else:
+                dW, db = wgrad(dZ, ex if j == 0 else st[j - 1], precision=pr, scale=scales[j])
+            grads[f"pts_linears.{j}.weight"], grads[f"pts_linears.{j}.bias"] = dW, db
     finally:
         torch.backends.cuda.matmul.allow_tf32 = tf32
     if return_input_grad:

@@ -374,3 +374,132 @@ def test_update_weights_equals_fresh_load(preset, over):
     for a, b, c in zip(got, got_late, ref):
         assert torch.equal(a, c) and torch.equal(b, c)
     assert net.range_status() == 0
+
+
+# ------------------------------------------------------------------------------------------------
+# pnr_wgrad: the weight-gradient GEMM over the samples (csrc/wgrad_tc05.cu) vs float64 on the CPU
+# ------------------------------------------------------------------------------------------------
+import os
+_bringup = pytest.mark.skipif(os.environ.get("PNR_TEST_NEW_KERNELS", "0") == "0",
+                              reason="pnr_wgrad / pnr_linear bring-up: enabled once validated on a B200")
+
+
+def _wgrad_case(S_, No, Ni, seed, gscale=1e-6):
+    g = torch.Generator().manual_seed(seed)
+    dz = torch.randn(S_, No, generator=g) * gscale * (0.1 + torch.rand(1, No, generator=g) * 3.0)   # gradients: tiny, uneven
+    dz = dz * (torch.rand(S_, No, generator=g) < 0.6)                                              # ReLU-gated zeros
+    x = torch.relu(torch.randn(S_, Ni, generator=g)) + 0.05 * torch.randn(S_, Ni, generator=g)
+    return dz, x
+
+
+@_bringup
+@pytest.mark.parametrize("prec", ["fp16x3", "bf16x3"])
+@pytest.mark.parametrize("S_,No,Ni", [(4096, 256, 256), (5000, 256, 63), (777, 128, 283), (33, 1, 256), (1, 3, 128),
+                                      (20011, 45, 128), (148 * 32 * 3 + 5, 64, 319), (31, 256, 16), (200, 130, 17)])
+def test_wgrad_matches_float64(S_, No, Ni, prec):
+    from panopticnerf_b200.lib.train.mlp_backward import wgrad, _pow2_scale
+    dz, x = _wgrad_case(S_, No, Ni, seed=S_ + No + Ni)
+    dzd = dz.to(DEV)
+    dW, db = wgrad(dzd, x.to(DEV), precision=prec, scale=_pow2_scale(dzd) if prec == "fp16x3" else None)
+    torch.cuda.synchronize()
+    ref_W = dz.double().t() @ x.double()
+    ref_b = dz.double().sum(0)
+    eW = float((dW.cpu().double() - ref_W).abs().max() / rms(ref_W))
+    eb = float((db.cpu().double() - ref_b).abs().max() / max(rms(ref_b), 1e-30))
+    print(f"wgrad {prec} S={S_} No={No} Ni={Ni}: max err / rms  dW {eW:.2e}  db {eb:.2e}")
+    # operand parts: fp16 ~2^-21 per product (measured model on the CPU: 5e-7 of the RMS), bf16 ~2^-17 (2.6e-5);
+    # fp32 accumulation over the samples adds ~1e-6
+    assert eW <= (2e-5 if prec == "fp16x3" else 1e-4), f"wgrad dW: {eW:.2e}"
+    assert eb <= 1e-4, f"wgrad db: {eb:.2e}"
+
+
+@_bringup
+def test_wgrad_views_determinism_and_errors():
+    from panopticnerf_b200.lib.train.mlp_backward import wgrad
+    from panopticnerf_b200 import _capi
+    dz, x = _wgrad_case(3000, 200, 300, seed=5)
+    dzd, xd = dz.to(DEV), x.to(DEV)
+    # column blocks of wider matrices are views with a row stride: no copies, same numbers as the contiguous blocks
+    a_W, a_b = wgrad(dzd[:, 8:136], xd[:, 20:276])
+    b_W, b_b = wgrad(dzd[:, 8:136].contiguous(), xd[:, 20:276].contiguous())
+    assert torch.equal(a_W, b_W) and torch.equal(a_b, b_b)
+    # deterministic: partial products are added in a fixed order
+    c_W, c_b = wgrad(dzd, xd)
+    d_W, d_b = wgrad(dzd, xd)
+    assert torch.equal(c_W, d_W) and torch.equal(c_b, d_b)
+    assert wgrad(dzd, xd, bias=False)[1] is None
+    with pytest.raises(_capi.PnrError):
+        wgrad(dz, x)                                  # CPU tensors: no fallback
+    with pytest.raises(_capi.PnrError):
+        wgrad(torch.zeros(10, 300, device=DEV), xd[:10])   # more than 256 output features
+    # fp16 parts without the scale lose the ~1e-6 gradients (that is what `scale` is for); with it they beat bf16
+    ref = dz.double().t() @ x.double()
+    from panopticnerf_b200.lib.train.mlp_backward import _pow2_scale
+    err = lambda W: float((W.cpu().double() - ref).abs().max() / rms(ref))
+    e_bf, e_fp, e_raw = err(c_W), err(wgrad(dzd, xd, precision="fp16x3", scale=_pow2_scale(dzd))[0]), err(wgrad(dzd, xd, precision="fp16x3")[0])
+    print(f"wgrad err/rms: bf16x3 {e_bf:.1e}  fp16x3 scaled {e_fp:.1e}  fp16x3 unscaled {e_raw:.1e}")
+    assert e_fp < e_bf < 1e-4 and e_raw > 10 * e_fp
+    # large magnitudes and exact zeros survive the bf16 split (fp32 exponent range)
+    big = torch.full((64, 16), 3.0e30, device=DEV)
+    one = torch.zeros(64, 16, device=DEV)
+    one[:, 0] = 1.0e-3
+    W, _ = wgrad(big, one)
+    assert torch.isfinite(W).all() and abs(float(W[0, 0]) / (64 * 3.0e27) - 1.0) < 1e-4 and float(W[:, 1:].abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------------
+# pnr_linear: y = act(x W^T + b) of the layers after the trunk on the training path (csrc/linear_tc05.cu)
+# ------------------------------------------------------------------------------------------------
+@_bringup
+@pytest.mark.parametrize("S_,K,N,relu,prec", [(4096, 256, 256, False, "fp16x3"), (1000, 283, 128, True, "fp16x3"),
+                                             (130, 256, 1, False, "fp16x3"), (5000, 128, 45, False, "bf16x3"),
+                                             (129, 128, 3, False, "fp16x3"), (148 * 128 * 2 + 77, 256, 128, True, "bf16x3"),
+                                             (7, 27, 64, False, "fp16x3"), (300, 512, 256, False, "fp16x3")])
+def test_linear3x_matches_float64(S_, K, N, relu, prec):
+    from panopticnerf_b200.lib.train.mlp_backward import linear3x
+    g = torch.Generator().manual_seed(S_ + K + N)
+    x = torch.randn(S_, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g) * 0.1
+    y = linear3x(x.to(DEV), w.to(DEV), b.to(DEV), relu=relu, precision=prec)
+    torch.cuda.synchronize()
+    ref = x.double() @ w.double().t() + b.double()
+    if relu:
+        ref = ref.clamp(min=0)
+    e = float((y.cpu().double() - ref).abs().max() / rms(ref))
+    print(f"linear3x S={S_} K={K} N={N} relu={relu} {prec}: max err / rms {e:.2e}")
+    tol_scale = 1.0 if prec == "fp16x3" else 2.0
+    assert e <= 1e-4 * tol_scale, f"linear3x: {e:.2e}"
+
+
+@_bringup
+def test_linear3x_transposed_scaled_gradients_and_views():
+    from panopticnerf_b200.lib.train.mlp_backward import linear3x, _pow2_scale
+    from panopticnerf_b200 import _capi
+    g = torch.Generator().manual_seed(11)
+    S_, N, K = 3000, 128, 283                       # a layer y = x W^T with x [S, 283], W [128, 283]; gradient g [S, 128]
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    gy = (torch.randn(S_, N, generator=g) * 3e-7).to(DEV)          # a mean-reduced loss: ~1e-7
+    sc = _pow2_scale(gy)
+    assert float(sc) == 2.0 ** round(float(torch.log2(256.0 / gy.abs().max())))
+    dx = linear3x(gy, w, transposed=True, precision="fp16x3", scale=sc)
+    ref = gy.cpu().double() @ w.cpu().double()
+    e = float((dx.cpu().double() - ref).abs().max() / rms(ref))
+    print(f"linear3x dgrad fp16x3 scaled: max err / rms {e:.2e}")
+    assert dx.shape == (S_, K) and e <= 1e-4
+    # unscaled, the fp16 parts of such gradients are subnormal or zero: the scale is what keeps the product exact
+    bad = linear3x(gy, w, transposed=True, precision="fp16x3")
+    assert float((bad.cpu().double() - ref).abs().max() / rms(ref)) > 10 * e
+    # the range-safe format needs no scale
+    dxb = linear3x(gy, w, transposed=True, precision="bf16x3")
+    assert float((dxb.cpu().double() - ref).abs().max() / rms(ref)) <= 2e-4
+    # row-strided views (a column block of a wider matrix), deterministic
+    wide = torch.randn(500, 300, generator=g).to(DEV)
+    a = linear3x(wide[:, 10:266], w[:, :256].contiguous())
+    b2 = linear3x(wide[:, 10:266].contiguous(), w[:, :256].contiguous())
+    assert torch.equal(a, b2) and torch.equal(a, linear3x(wide[:, 10:266], w[:, :256].contiguous()))
+    with pytest.raises(_capi.PnrError):
+        linear3x(wide.cpu(), w.cpu())
+    with pytest.raises(_capi.PnrError):
+        linear3x(wide, torch.zeros(300, 300, device=DEV))          # N > 256
+    assert _pow2_scale(torch.zeros(4, 4, device=DEV)).item() == 1.0
