@@ -533,8 +533,8 @@ def main():
             mst = statistics.median(tt)
             extra["train_step_cfg3"] = {
                 "workload": f"{Rt} rays x {Nt} samples, cfg3 network: forward (fused MLP + compositing) + loss kernel + "
-                            "backward to every parameter (trunk on the fused tensor-core kernel, tail + weight-gradient "
-                            "GEMMs through torch)", "ms_per_step": mst, "rays_per_s": Rt / (mst / 1e3),
+                            "backward to every parameter (trunk on the fused tensor-core kernel, the layers after it on "
+                            "pnr_linear, every weight gradient on pnr_wgrad: no library GEMM)", "ms_per_step": mst, "rays_per_s": Rt / (mst / 1e3),
                 "samples_per_s": Rt * Nt / (mst / 1e3)}
         except Exception as exc:   # noqa: BLE001
             extra["train_step_cfg3"] = {"error": repr(exc)[:300]}

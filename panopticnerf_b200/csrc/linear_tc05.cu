@@ -7,9 +7,11 @@
 //   y[s, n] = act( sum_k x[s, k] W[n, k] + b[n] ),   s < S (10^5 .. 10^7 samples),  K <= 512,  N <= 256
 //
 // Persistent, one CTA per SM, tiles of 128 samples (UMMA M = 128 = tensor-memory lanes):
-//   * warps 4-11 (producers): lane = sample row, 8 consecutive features per 16-byte load pair; the values are scaled
-//     (a power of two for gradients, exact), split into 16-bit hi / lo parts and written as core-matrix rows of the
-//     no-swizzle K-major A operand, one 64-feature K chunk per stage (2 stages);
+//   * warps 4-11 (producers): a warp instruction reads two rows' 256-byte K chunk, 16 bytes per lane (fully
+//     coalesced); the values are scaled (a power of two for gradients, exact), split into 16-bit hi / lo parts and
+//     written as half core-matrix rows (8-byte stores) of the no-swizzle K-major A operand, one 64-feature K chunk per
+//     stage (2 stages).  The K-cores of the A images are 2064 bytes apart instead of 2048 (the descriptor's leading
+//     byte offset is free to say so): the 16 lanes that share a row then hit 16 different 8-byte bank slots;
 //   * warp 12: streams the matching K chunk of the weights - packed once per call by linear_pack_kernel into hi / lo
 //     images of [8 K-cores][NP rows][16 B] - with cp.async.bulk into a 2-stage ring (64 KB stages, L2-resident source);
 //   * warp 13: one elected lane issues tcgen05.mma kind::f16, M = 128, N = NP, K = 16, both operands from shared
@@ -28,14 +30,16 @@ constexpr int kLnEpiWarps = 4, kLnProWarps = 8;
 constexpr int kLnThreads = (kLnEpiWarps + kLnProWarps + 2) * 32;   // + weight stream warp + MMA warp = 448
 constexpr int kLnTile = 128;
 constexpr int kLnChunk = 64;                             // K per stage
-constexpr int kLnAPart = 8 * kLnTile * 16;               // one 16-bit image of the A chunk: 16 KB
+constexpr int kLnALbo = kLnTile * 16 + 16;               // distance of K-adjacent core matrices in the A images (padded: banks)
+constexpr int kLnAPart = 8 * kLnALbo;                    // one 16-bit image of the A chunk
 constexpr int kLnAStage = 2 * kLnAPart;                  // hi + lo
 constexpr int kLnBStageMax = 2 * 8 * 256 * 16;           // hi + lo images of a [64 K][256 rows] weight chunk: 64 KB
 constexpr int kLnRing = 2;
 constexpr int kLnSmemA = 0;
 constexpr int kLnSmemB = kLnRing * kLnAStage;            // 64 KB
 constexpr int kLnSmemBars = kLnSmemB + kLnRing * kLnBStageMax;   // 192 KB
-constexpr int kLnSmemTotal = kLnSmemBars + 256;
+constexpr int kLnSmemBias = kLnSmemBars + 256;                  // [256] bias, zero-padded
+constexpr int kLnSmemTotal = kLnSmemBias + 256 * 4;
 
 struct LinearParams {
   const float* x; int64_t ld_x; int K;
@@ -86,6 +90,8 @@ __global__ void __launch_bounds__(kLnThreads, 1) linear_kernel(const LinearParam
   const int n_chunks = p.n_chunks;
   const uint32_t b_stage_bytes = (uint32_t)(2 * 8 * p.NP * 16);
 
+  float* bias_s = reinterpret_cast<float*>(smem + kLnSmemBias);
+  for (int n = threadIdx.x; n < 256; n += blockDim.x) bias_s[n] = (p.bias != nullptr && n < p.N) ? p.bias[n] : 0.f;
   if (warp == 0) {
     tmem_alloc<512>(smem_u32(tmem_slot));
     tmem_relinquish();
@@ -137,8 +143,7 @@ __global__ void __launch_bounds__(kLnThreads, 1) linear_kernel(const LinearParam
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int n = c0 + j;
-            float t = __uint_as_float(r[j]) * inv + ((p.bias != nullptr && n < p.N) ? __ldg(p.bias + n) : 0.f);
+            const float t = __uint_as_float(r[j]) * inv + bias_s[c0 + j];
             v[j] = p.relu ? fmaxf(t, 0.f) : t;
           }
           if (s < p.S) {
@@ -159,48 +164,62 @@ __global__ void __launch_bounds__(kLnThreads, 1) linear_kernel(const LinearParam
     }
   } else if (warp < kLnEpiWarps + kLnProWarps) {
     // =============================================================== producers: x rows -> A chunk images
-    const int t = threadIdx.x - kLnEpiWarps * 32;        // 0..255
-    const int row = t & (kLnTile - 1), kh = t >> 7;      // this thread's row ; K-cores 4 kh .. 4 kh + 3 of the chunk
+    // warp w: rows 16 w .. 16 w + 15 of the tile, two rows per instruction; lane: row parity (lane >> 4), 16-byte
+    // segment of the row's 256-byte chunk (lane & 15) = features 4 seg .. 4 seg + 3 = half (seg & 1) of K-core seg >> 1
+    const int pw = warp - kLnEpiWarps;
+    const int seg = lane & 15, kc = seg >> 1, half = seg & 1;
     uint32_t ga = 0;
+    const bool k_ragged = (p.K & 3) != 0;
     for (int it = 0; it < n_iter; ++it) {
-      const int64_t s = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kLnTile + row;
-      const bool live = s < p.S;
-      const float* xr = p.x + (live ? s : 0) * p.ld_x;
+      const int64_t s0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kLnTile + pw * 16 + (lane >> 4);
+      const int64_t left = p.S - s0;                       // this lane's rows are s0 + 2 i: how many of them exist
+      const int nvr = left <= 0 ? 0 : (left >= 16 ? 8 : (int)((left + 1) >> 1));
+      const float* xrow = p.x + s0 * p.ld_x + seg * 4;     // (never dereferenced when nvr == 0)
+      const int64_t step = 2 * p.ld_x;
 #pragma unroll 1
       for (int c = 0; c < n_chunks; ++c, ++ga) {
         const uint32_t slot = ga & 1u, ph = (ga >> 1) & 1u;
-        float v[4][8];
-        const int k0 = c * kLnChunk + kh * 32;
-        if (p.vec_in) {
+        const int k = c * kLnChunk + seg * 4;
+        const int kr = p.K - k;                            // features of this lane's segment that exist (<= 0: none)
+        const float* q = xrow + c * kLnChunk;
+        float4 v[8];
+        if (p.vec_in) {      // 16-byte loads: rows 16-byte aligned and at least round-up-4(K) floats long
 #pragma unroll
-          for (int kc = 0; kc < 4; ++kc) {
-            const int k = k0 + kc * 8;
-            // K is a multiple of 4 on this path: a 16-byte load is either wholly inside the row or wholly outside
-            const float4 a = (live && k < p.K) ? __ldg(reinterpret_cast<const float4*>(xr + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 bq = (live && k + 4 < p.K) ? __ldg(reinterpret_cast<const float4*>(xr + k + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            v[kc][0] = a.x; v[kc][1] = a.y; v[kc][2] = a.z; v[kc][3] = a.w;
-            v[kc][4] = bq.x; v[kc][5] = bq.y; v[kc][6] = bq.z; v[kc][7] = bq.w;
+          for (int i = 0; i < 8; ++i) {
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (kr > 0 && i < nvr) v[i] = __ldg(reinterpret_cast<const float4*>(q));
+            q += step;
+          }
+          if (k_ragged && c + 1 == n_chunks && kr > 0 && kr < 4) {   // the segment that straddles K: drop what lies beyond
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (kr < 2) v[i].y = 0.f;
+              if (kr < 3) v[i].z = 0.f;
+              v[i].w = 0.f;
+            }
           }
         } else {
 #pragma unroll
-          for (int kc = 0; kc < 4; ++kc) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int k = k0 + kc * 8 + j;
-              v[kc][j] = (live && k < p.K) ? __ldg(xr + k) : 0.f;
+          for (int i = 0; i < 8; ++i) {
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < nvr) {
+              if (kr > 0) v[i].x = __ldg(q);
+              if (kr > 1) v[i].y = __ldg(q + 1);
+              if (kr > 2) v[i].z = __ldg(q + 2);
+              if (kr > 3) v[i].w = __ldg(q + 3);
             }
+            q += step;
           }
         }
         mbar_wait_backoff(bar_a_empty + 8 * slot, ph ^ 1u);
-        uint8_t* stage = smem + kLnSmemA + slot * kLnAStage;
+        uint8_t* img = smem + kLnSmemA + slot * kLnAStage + kc * kLnALbo + (pw * 16 + (lane >> 4)) * 16 + half * 8;
 #pragma unroll
-        for (int kc = 0; kc < 4; ++kc) {
-          uint32_t h[4], l[4];
-#pragma unroll
-          for (int qd = 0; qd < 4; ++qd) split_x2<FMT>(v[kc][2 * qd] * sc, v[kc][2 * qd + 1] * sc, h[qd], l[qd]);
-          uint8_t* img = stage + ((kh * 4 + kc) * kLnTile + row) * 16;
-          *reinterpret_cast<uint4*>(img) = make_uint4(h[0], h[1], h[2], h[3]);
-          *reinterpret_cast<uint4*>(img + kLnAPart) = make_uint4(l[0], l[1], l[2], l[3]);
+        for (int i = 0; i < 8; ++i) {
+          uint32_t h0, l0, h1, l1;
+          split_x2<FMT>(v[i].x * sc, v[i].y * sc, h0, l0);
+          split_x2<FMT>(v[i].z * sc, v[i].w * sc, h1, l1);
+          *reinterpret_cast<uint2*>(img + i * 32) = make_uint2(h0, h1);
+          *reinterpret_cast<uint2*>(img + i * 32 + kLnAPart) = make_uint2(l0, l1);
         }
         fence_proxy_async_smem();
         mbar_arrive(bar_a_full + 8 * slot);
@@ -243,8 +262,8 @@ __global__ void __launch_bounds__(kLnThreads, 1) linear_kernel(const LinearParam
           const int ksteps = kleft >= kLnChunk ? kLnChunk / 16 : (kleft + 15) / 16;
 #pragma unroll 1
           for (int ks = 0; ks < ksteps; ++ks) {
-            const uint32_t a = sa + (uint32_t)ks * 2u * (kLnTile * 16u), bb = sb + (uint32_t)ks * 2u * b_lbo;
-            const uint64_t a_hi = make_smem_desc_noswz(a, kLnTile * 16, 128), a_lo = make_smem_desc_noswz(a + kLnAPart, kLnTile * 16, 128);
+            const uint32_t a = sa + (uint32_t)ks * 2u * kLnALbo, bb = sb + (uint32_t)ks * 2u * b_lbo;
+            const uint64_t a_hi = make_smem_desc_noswz(a, kLnALbo, 128), a_lo = make_smem_desc_noswz(a + kLnAPart, kLnALbo, 128);
             const uint64_t b_hi = make_smem_desc_noswz(bb, b_lbo, 128), b_lo = make_smem_desc_noswz(bb + b_part, b_lbo, 128);
             mma_ss(d_tmem, a_hi, b_hi, idesc, (c == 0 && ks == 0) ? 0u : 1u);
             mma_ss(d_tmem, a_lo, b_hi, idesc, 1u);
@@ -324,7 +343,7 @@ extern "C" int pnr_linear(const float* x, int64_t ld_x, int32_t K, const float* 
   p.NP = (N + 15) / 16 * 16;
   p.n_chunks = (K + kLnChunk - 1) / kLnChunk;
   p.relu = relu != 0;
-  p.vec_in = (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (ld_x & 3) == 0 && (K & 3) == 0;
+  p.vec_in = (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (ld_x & 3) == 0 && ld_x >= (K + 3) / 4 * 4;
   p.vec_out = (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (ld_y & 3) == 0;
   p.in_scale = in_scale;
   uint8_t* wpk = static_cast<uint8_t*>(workspace);

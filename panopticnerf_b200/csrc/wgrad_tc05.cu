@@ -94,30 +94,42 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams 
     const float* src[4];
     int64_t ld[4];
     int row[4];          // row in the operand image (= feature index)
-    bool on[4], isA[4], real[4];
+    bool on[4], isA[4];
+    float mul[4];        // what the loaded values are multiplied by: the gradient scale (A), 1 (B), 0 past the operand's width
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int fg = fg0 + 4 * j;
       isA[j] = fg < nA;
       on[j] = fg < nA + nB;
       row[j] = (isA[j] ? fg : fg - nA) * 32 + lane;
-      real[j] = on[j] && row[j] < (isA[j] ? p.No : p.Ni);      // rows past the operand's width hold zeros
-      src[j] = (isA[j] ? p.dz : p.x) + row[j];
+      const bool real = on[j] && row[j] < (isA[j] ? p.No : p.Ni);
+      mul[j] = real ? (isA[j] ? sc : 1.0f) : 0.f;
+      // rows past the operand's width read column 0 (a valid address) and are zeroed by `mul`; their products only reach
+      // accumulator rows / columns nobody reads
+      src[j] = (isA[j] ? p.dz : p.x) + (real ? row[j] : 0);
       ld[j] = isA[j] ? p.ld_dz : p.ld_x;
     }
+    // One slab's loads: 8 consecutive samples per item, one pointer increment per load, predicated on a warp-uniform
+    // count (only the launch's very last slab is partial).
     auto load_slab = [&](int i, float (&v)[4][8]) {
       const int64_t s0 = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * kWgSlab + kg * 8;
+      const int64_t left = p.S - s0;
+      const int nv = left >= 8 ? 8 : (left > 0 ? (int)left : 0);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
+        if (!on[j]) continue;
+        const float* q = src[j] + s0 * ld[j];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[j][k] = (real[j] && s0 + k < p.S) ? __ldg(src[j] + (s0 + k) * ld[j]) : 0.f;
+        for (int k = 0; k < 8; ++k) {
+          v[j][k] = 0.f;
+          if (k < nv) v[j][k] = __ldg(q);
+          q += ld[j];
+        }
       }
     };
     float db[4] = {0.f, 0.f, 0.f, 0.f};
-    float cur[4][8], nxt[4][8];
-    load_slab(0, cur);
-#pragma unroll 1
-    for (int i = 0; i < n_mine; ++i) {
+    // convert + store slab i from `cur` while slab i + 1 is on its way into `nxt`; warp 0 then issues the slab's MMAs
+    auto do_slab = [&](int i, float (&cur)[4][8], float (&nxt)[4][8]) {
       const uint32_t slot = (uint32_t)i % kWgRing, ph = ((uint32_t)i / kWgRing) & 1u;
       if (i + 1 < n_mine) load_slab(i + 1, nxt);
       mbar_wait_backoff(bar_empty + 8 * slot, ph ^ 1u);
@@ -126,8 +138,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams 
       for (int j = 0; j < 4; ++j) {
         if (!on[j]) continue;
         uint32_t h[4], l[4];
-#pragma unroll
-        const float m = isA[j] ? sc : 1.0f;
+        const float m = mul[j];
 #pragma unroll
         for (int q = 0; q < 4; ++q) split_x2<FMT>(cur[j][2 * q] * m, cur[j][2 * q + 1] * m, h[q], l[q]);
         uint8_t* img = stage + (isA[j] ? 0 : 2 * kWgPart) + (kg * kWgRows + row[j]) * 16;
@@ -166,13 +177,18 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams 
         }
         __syncwarp();
       }
-      if (i + 1 < n_mine) {
+    };
+    float va[4][8], vb[4][8];    // two register buffers, used alternately (no copies between iterations)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < 4; ++j) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) cur[j][k] = nxt[j][k];
-        }
-      }
+      for (int k = 0; k < 8; ++k) { va[j][k] = 0.f; vb[j][k] = 0.f; }
+    }
+    load_slab(0, va);
+#pragma unroll 1
+    for (int i = 0; i < n_mine; i += 2) {
+      do_slab(i, va, vb);
+      if (i + 1 < n_mine) do_slab(i + 1, vb, va);
     }
     // ---- bias partial sums: 4 sample groups per feature, added in a fixed order
 #pragma unroll

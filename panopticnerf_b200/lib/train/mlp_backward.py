@@ -8,11 +8,11 @@ The work is split where the network splits:
   * every weight / bias gradient - the trunk's dW_j = dZ_j^T H_{j-1} on that stash and those of the layers after the
     trunk - is a split-K GEMM over the samples on the tensor cores (`wgrad` -> pnr_wgrad, csrc/wgrad_tc05.cu);
   * the layers after the trunk (alpha / feature / view / rgb / the two heads: small GEMMs with K <= W) are
-    differentiated by torch on h: their forward and input-gradient GEMMs are library GEMMs (3xTF32).
+    differentiated layer by layer by autograd on h, each node's forward and input-gradient GEMM on `linear3x` ->
+    pnr_linear (csrc/linear_tc05.cu).  No library GEMM is left on this path.
 Nothing here imports the oracle; tests compare every parameter's gradient with autograd through the oracle network."""
 from __future__ import annotations
 
-import os
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -22,39 +22,14 @@ from ... import _capi
 from ..networks.renderer import panopticnerf_renderer as P
 
 _WGRAD_WS: Dict[Tuple[int, int], torch.Tensor] = {}     # (device, stream) -> scratch of pnr_wgrad (partial products)
-# Bring-up switch: "1" = every GEMM of the training path on the library's own tensor-core kernels (pnr_linear,
-# pnr_wgrad); "0" = the 3xTF32 cuBLAS GEMMs they replace.
-_NATIVE = os.environ.get("PNR_TRAIN_NATIVE", "0") != "0"
-
-
-def _tf32_parts(x: torch.Tensor):
-    """x = hi + lo with hi exactly representable in TF32 (10 mantissa bits; the low 13 bits cleared)."""
-    hi = (x.contiguous().view(torch.int32) & -8192).view(torch.float32)
-    return hi, x - hi
-
-
-def matmul_3xtf32(a: torch.Tensor, b: torch.Tensor, trans_a: bool = False, trans_b: bool = False) -> torch.Tensor:
-    """op(a) @ op(b) to ~2^-20 per product on the TF32 tensor cores through the library BLAS: hi.hi + lo.hi + hi.lo."""
-    tf32 = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = True
-    try:
-        ah, al = _tf32_parts(a)
-        bh, bl = _tf32_parts(b)
-        if trans_a:
-            ah, al = ah.t(), al.t()
-        if trans_b:
-            bh, bl = bh.t(), bl.t()
-        return ah @ bh + (al @ bh + ah @ bl)
-    finally:
-        torch.backends.cuda.matmul.allow_tf32 = tf32
 
 
 def _rows(t: torch.Tensor, name: str) -> torch.Tensor:
     """[S, n] fp32 CUDA matrix whose rows are contiguous (any row stride: column blocks of a wider matrix are views)."""
     if not t.is_cuda:
-        raise _capi.PnrError(f"wgrad: {name} must be a CUDA tensor (no CPU fallback)")
+        raise _capi.PnrError(f"{name} must be a CUDA tensor (panopticnerf_b200 has no CPU fallback)")
     if t.dtype != torch.float32 or t.dim() != 2:
-        raise _capi.PnrError(f"wgrad: {name} must be a 2-D float32 tensor, got {t.dtype} {tuple(t.shape)}")
+        raise _capi.PnrError(f"{name} must be a 2-D float32 tensor, got {t.dtype} {tuple(t.shape)}")
     if (t.shape[1] > 1 and t.stride(1) != 1) or (t.shape[0] > 1 and t.stride(0) < t.shape[1]):
         t = t.contiguous()
     return t
@@ -68,7 +43,7 @@ def wgrad(dz: torch.Tensor, x: torch.Tensor, bias: bool = True, precision: str =
     covered by one call per 256-column block of x; neither dz^T nor a split copy of an operand is materialised.
     precision "bf16x3": ~2^-17 per product, no scaling needed; "fp16x3": ~2^-21 per product with `scale`, a device
     scalar power of two (`_pow2_scale(dz)`) that keeps the fp16 parts of tiny gradients normal."""
-    dz, x = _rows(dz, "dz"), _rows(x, "x")
+    dz, x = _rows(dz, "wgrad: dz"), _rows(x, "wgrad: x")
     S_, No = dz.shape
     Ni = x.shape[1]
     if x.shape[0] != S_ or x.device != dz.device:
@@ -85,15 +60,15 @@ def wgrad(dz: torch.Tensor, x: torch.Tensor, bias: bool = True, precision: str =
     with torch.cuda.device(dz.device):
         stream = _capi.stream_ptr()
         key = (dz.device.index, stream)
-        need = int(L.pnr_wgrad_workspace_bytes(256, 256))
         ws = _WGRAD_WS.get(key)
-        if ws is None or ws.numel() < need:
-            ws = _WGRAD_WS[key] = torch.empty(need, dtype=torch.uint8, device=dz.device)
+        if ws is None:
+            ws = _WGRAD_WS[key] = torch.empty(int(L.pnr_wgrad_workspace_bytes(256, 256)), dtype=torch.uint8, device=dz.device)
         for c0 in range(0, Ni, 256):
             n = min(256, Ni - c0)
             _capi.check(L.pnr_wgrad(dz.data_ptr(), ld_dz, No, x.data_ptr() + 4 * c0, ld_x, n, S_, _capi.PREC[precision],
-                                    _capi.ptr(scale, torch.float32, "scale"), dW.data_ptr() + 4 * c0, Ni, db.data_ptr() if (bias and c0 == 0) else None, 0,
-                                    ws.data_ptr(), ws.numel(), stream), "pnr_wgrad")
+                                    _capi.ptr(scale, torch.float32, "scale"), dW.data_ptr() + 4 * c0, Ni,
+                                    db.data_ptr() if (bias and c0 == 0) else None, 0, ws.data_ptr(), ws.numel(), stream),
+                        "pnr_wgrad")
     return dW, db
 
 
@@ -120,35 +95,45 @@ def _pow2_scales(t: torch.Tensor):
 
 
 def linear3x(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False,
-             transposed: bool = False, precision: str = "fp16x3", scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+             transposed: bool = False, precision: str = "fp16x3", scale: Optional[torch.Tensor] = None,
+             out_cols: int = 0) -> torch.Tensor:
     """act(x @ weight.T + bias) [S, N] for x [S, K], weight [N, K] - or x @ weight for weight [K, N] with
     transposed=True (the input gradient of a linear layer) - on the tensor cores (pnr_linear, csrc/linear_tc05.cu:
-    16-bit hi / lo operand parts, hi.hi + lo.hi + hi.lo, fp32 accumulation).  N <= 256, K <= 512.
-    scale: device scalar power of two applied to x inside the kernel and removed from the result (gradients)."""
-    x = _rows(x, "x")
-    w = _rows(weight, "weight")
+    16-bit hi / lo operand parts, hi.hi + lo.hi + hi.lo, fp32 accumulation).  K <= 512; more than 256 outputs run as
+    one call per 256-column block of the result.
+    scale: device scalar power of two applied to x inside the kernel and removed from the result (gradients).
+    out_cols > N: the result is returned inside a [S, out_cols] buffer whose extra columns are zero (rows padded to a
+    multiple of 4 floats keep the kernels on their 16-byte load / store paths)."""
+    x = _rows(x, "linear3x: x")
+    w = _rows(weight, "linear3x: weight")
     S_, K = x.shape
     N = w.shape[1] if transposed else w.shape[0]
     if (w.shape[0] if transposed else w.shape[1]) != K or w.device != x.device:
         raise _capi.PnrError(f"linear3x: x {tuple(x.shape)} vs weight {tuple(weight.shape)} (transposed={transposed})")
     if precision not in ("fp16x3", "bf16x3"):
         raise _capi.PnrError(f"linear3x: precision {precision!r} (the training path runs in the x3 precisions)")
+    if K > 512:
+        raise _capi.PnrError(f"linear3x: K = {K} inputs (pnr_linear handles up to 512)")
     L = _capi.lib()
-    y = torch.empty(S_, N, dtype=torch.float32, device=x.device)
+    ld_y = max(N, int(out_cols))
+    y = torch.empty(S_, ld_y, dtype=torch.float32, device=x.device)
+    if ld_y > N:
+        y[:, N:].zero_()
     b = bias.detach().to(torch.float32).contiguous() if bias is not None else None
+    ld_w = w.stride(0) if w.shape[0] > 1 else w.shape[1]
     with torch.cuda.device(x.device):
         stream = _capi.stream_ptr()
         key = (x.device.index, stream)
-        need = int(L.pnr_linear_workspace_bytes(N, K))
-        if need == 0:
-            raise _capi.PnrError(f"linear3x: N = {N} (<= 256) / K = {K} (<= 512) outside what pnr_linear handles")
         ws = _LINEAR_WS.get(key)
-        if ws is None or ws.numel() < need:
-            ws = _LINEAR_WS[key] = torch.empty(max(need, 1 << 19), dtype=torch.uint8, device=x.device)
-        _capi.check(L.pnr_linear(x.data_ptr(), x.stride(0) if S_ > 1 else K, K, w.data_ptr(), w.stride(0) if w.shape[0] > 1 else w.shape[1],
-                                 int(transposed), _capi.ptr(b, torch.float32, "bias"), N, S_, int(relu), _capi.PREC[precision],
-                                 _capi.ptr(scale, torch.float32, "scale"), y.data_ptr(), N, ws.data_ptr(), ws.numel(), stream),
-                    "pnr_linear")
+        if ws is None:
+            ws = _LINEAR_WS[key] = torch.empty(int(L.pnr_linear_workspace_bytes(256, 512)), dtype=torch.uint8, device=x.device)
+        for c0 in range(0, N, 256):      # more than 256 outputs (the view layer's 283-wide input gradient): column blocks
+            n = min(256, N - c0)
+            w_ptr = w.data_ptr() + 4 * (c0 if transposed else c0 * ld_w)
+            _capi.check(L.pnr_linear(x.data_ptr(), x.stride(0) if S_ > 1 else K, K, w_ptr, ld_w, int(transposed),
+                                     (b.data_ptr() + 4 * c0) if b is not None else None, n, S_, int(relu), _capi.PREC[precision],
+                                     _capi.ptr(scale, torch.float32, "scale"), y.data_ptr() + 4 * c0, ld_y, ws.data_ptr(), ws.numel(),
+                                     stream), "pnr_linear")
     return y
 
 
@@ -158,21 +143,19 @@ class _Linear3x(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, precision):
+        # x may carry zero columns behind the layer's inputs (rows padded to a multiple of 4 floats: `_tail`)
         ctx.save_for_backward(x, weight)
         ctx.precision = precision
-        if not _NATIVE:
-            return matmul_3xtf32(x, weight, trans_b=True) + bias
-        return linear3x(x, weight, bias, precision=precision)
+        return linear3x(x[:, :weight.shape[1]], weight, bias, precision=precision)
 
     @staticmethod
     def backward(ctx, g):
         x, weight = ctx.saved_tensors
         g = g.contiguous()
-        if not _NATIVE:
-            return matmul_3xtf32(g, weight), matmul_3xtf32(g, x, trans_a=True), g.sum(0), None
         sc = _pow2_scale(g) if ctx.precision == "fp16x3" else None      # one scale for both gradient GEMMs of the layer
-        dx = linear3x(g, weight, transposed=True, precision=ctx.precision, scale=sc) if ctx.needs_input_grad[0] else None
-        dW, db = wgrad(g, x, precision=ctx.precision, scale=sc)
+        dx = (linear3x(g, weight, transposed=True, precision=ctx.precision, scale=sc, out_cols=x.shape[1])
+              if ctx.needs_input_grad[0] else None)
+        dW, db = wgrad(g, x[:, :weight.shape[1]], precision=ctx.precision, scale=sc)
         return dx, dW, db, None
 
 
@@ -185,7 +168,9 @@ def _tail(net, h: torch.Tensor, ed: torch.Tensor) -> torch.Tensor:
     pr = net.precision if net.precision in ("fp16x3", "bf16x3") else "fp16x3"
     sigma = _lin(net.alpha_linear, h, pr)
     feat = _lin(net.feature_linear, h, pr)
-    g = F.relu(_lin(net.views_linears[0], torch.cat([feat, ed], -1), pr))
+    pad = (-(feat.shape[1] + ed.shape[1])) % 4            # rows of the concatenated input padded to 16 bytes
+    parts = [feat, ed] + ([feat.new_zeros(feat.shape[0], pad)] if pad else [])
+    g = F.relu(_lin(net.views_linears[0], torch.cat(parts, -1), pr))
     outs = [_lin(net.rgb_linear, g, pr), sigma]
     if net.C > 0:
         outs.append(_lin(net.semantic_linears[1], F.relu(_lin(net.semantic_linears[0], h, pr)), pr))
@@ -207,35 +192,27 @@ def network_backward(net, d_raw: torch.Tensor, pts: Optional[torch.Tensor] = Non
         pts_, vd = pts.reshape(-1, 3), viewdirs.reshape(-1, 3)
     S_ = pts_.shape[0]
     d_raw = d_raw.reshape(S_, -1).to(torch.float32)
-    tf32 = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = False                    # the library GEMMs below are fp32
-    try:
-        h = net.trunk_forward(pts=pts, rays=rays, z=z).requires_grad_(True)
-        ed = P.embed(vd.contiguous(), net.Ld)
-        tail_named = [(n, p) for n, p in net.named_parameters() if not n.startswith("pts_linears.")]
-        with torch.enable_grad():
-            raw = _tail(net, h, ed)
-            g = torch.autograd.grad(raw, [h] + [p for _, p in tail_named], d_raw, allow_unused=True)
-        grads = {n: (gi if gi is not None else torch.zeros_like(p)) for (n, p), gi in zip(tail_named, g[1:])}
-        d_emb, st = net.backward_trunk(g[0].contiguous(), pts=pts, rays=rays, z=z, stash=True)
-        ex = P.embed(pts_.contiguous(), net.Lx)
-        D = net.D
-        pr = net.precision if net.precision in ("fp16x3", "bf16x3") else "fp16x3"
-        # fp16 parts: one power-of-two scale per dZ_j, all D of them from one reduction over the stash (on the device)
-        scales = _pow2_scales(st[D - 1:])[::-1] if (_NATIVE and pr == "fp16x3") else [None] * D
-        for j in range(D):
-            dZ = st[2 * D - 2 - j]
-            if not _NATIVE:
-                inp = ex if j == 0 else (torch.cat([ex, st[j - 1]], -1) if j == net.skip + 1 else st[j - 1])
-                dW, db = matmul_3xtf32(dZ, inp, trans_a=True), dZ.sum(0)
-            elif j == net.skip + 1:        # input [gamma(x), H_{j-1}]: two column blocks of dW, no concatenated copy
-                dWx, db = wgrad(dZ, ex, precision=pr, scale=scales[j])
-                dW = torch.cat([dWx, wgrad(dZ, st[j - 1], bias=False, precision=pr, scale=scales[j])[0]], -1)
-            else:
-                dW, db = wgrad(dZ, ex if j == 0 else st[j - 1], precision=pr, scale=scales[j])
-            grads[f"pts_linears.{j}.weight"], grads[f"pts_linears.{j}.bias"] = dW, db
-    finally:
-        torch.backends.cuda.matmul.allow_tf32 = tf32
+    h = net.trunk_forward(pts=pts, rays=rays, z=z).requires_grad_(True)
+    ed = P.embed(vd.contiguous(), net.Ld)
+    tail_named = [(n, p) for n, p in net.named_parameters() if not n.startswith("pts_linears.")]
+    with torch.enable_grad():
+        raw = _tail(net, h, ed)
+        g = torch.autograd.grad(raw, [h] + [p for _, p in tail_named], d_raw, allow_unused=True)
+    grads = {n: (gi if gi is not None else torch.zeros_like(p)) for (n, p), gi in zip(tail_named, g[1:])}
+    d_emb, st = net.backward_trunk(g[0].contiguous(), pts=pts, rays=rays, z=z, stash=True)
+    ex = P.embed(pts_.contiguous(), net.Lx)
+    D = net.D
+    pr = net.precision if net.precision in ("fp16x3", "bf16x3") else "fp16x3"
+    # fp16 parts: one power-of-two scale per dZ_j, all D of them from one reduction over the stash (on the device)
+    scales = _pow2_scales(st[D - 1:])[::-1] if pr == "fp16x3" else [None] * D
+    for j in range(D):
+        dZ = st[2 * D - 2 - j]
+        if j == net.skip + 1:        # input [gamma(x), H_{j-1}]: two column blocks of dW, no concatenated copy
+            dWx, db = wgrad(dZ, ex, precision=pr, scale=scales[j])
+            dW = torch.cat([dWx, wgrad(dZ, st[j - 1], bias=False, precision=pr, scale=scales[j])[0]], -1)
+        else:
+            dW, db = wgrad(dZ, ex if j == 0 else st[j - 1], precision=pr, scale=scales[j])
+        grads[f"pts_linears.{j}.weight"], grads[f"pts_linears.{j}.bias"] = dW, db
     if return_input_grad:
         grads["embedded_xyz"] = d_emb
     return grads

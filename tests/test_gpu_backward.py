@@ -379,11 +379,6 @@ def test_update_weights_equals_fresh_load(preset, over):
 # ------------------------------------------------------------------------------------------------
 # pnr_wgrad: the weight-gradient GEMM over the samples (csrc/wgrad_tc05.cu) vs float64 on the CPU
 # ------------------------------------------------------------------------------------------------
-import os
-_bringup = pytest.mark.skipif(os.environ.get("PNR_TEST_NEW_KERNELS", "0") == "0",
-                              reason="pnr_wgrad / pnr_linear bring-up: enabled once validated on a B200")
-
-
 def _wgrad_case(S_, No, Ni, seed, gscale=1e-6):
     g = torch.Generator().manual_seed(seed)
     dz = torch.randn(S_, No, generator=g) * gscale * (0.1 + torch.rand(1, No, generator=g) * 3.0)   # gradients: tiny, uneven
@@ -392,7 +387,6 @@ def _wgrad_case(S_, No, Ni, seed, gscale=1e-6):
     return dz, x
 
 
-@_bringup
 @pytest.mark.parametrize("prec", ["fp16x3", "bf16x3"])
 @pytest.mark.parametrize("S_,No,Ni", [(4096, 256, 256), (5000, 256, 63), (777, 128, 283), (33, 1, 256), (1, 3, 128),
                                       (20011, 45, 128), (148 * 32 * 3 + 5, 64, 319), (31, 256, 16), (200, 130, 17)])
@@ -413,7 +407,6 @@ def test_wgrad_matches_float64(S_, No, Ni, prec):
     assert eb <= 1e-4, f"wgrad db: {eb:.2e}"
 
 
-@_bringup
 def test_wgrad_views_determinism_and_errors():
     from panopticnerf_b200.lib.train.mlp_backward import wgrad
     from panopticnerf_b200 import _capi
@@ -450,7 +443,6 @@ def test_wgrad_views_determinism_and_errors():
 # ------------------------------------------------------------------------------------------------
 # pnr_linear: y = act(x W^T + b) of the layers after the trunk on the training path (csrc/linear_tc05.cu)
 # ------------------------------------------------------------------------------------------------
-@_bringup
 @pytest.mark.parametrize("S_,K,N,relu,prec", [(4096, 256, 256, False, "fp16x3"), (1000, 283, 128, True, "fp16x3"),
                                              (130, 256, 1, False, "fp16x3"), (5000, 128, 45, False, "bf16x3"),
                                              (129, 128, 3, False, "fp16x3"), (148 * 128 * 2 + 77, 256, 128, True, "bf16x3"),
@@ -472,7 +464,6 @@ def test_linear3x_matches_float64(S_, K, N, relu, prec):
     assert e <= 1e-4 * tol_scale, f"linear3x: {e:.2e}"
 
 
-@_bringup
 def test_linear3x_transposed_scaled_gradients_and_views():
     from panopticnerf_b200.lib.train.mlp_backward import linear3x, _pow2_scale
     from panopticnerf_b200 import _capi
@@ -501,5 +492,7 @@ def test_linear3x_transposed_scaled_gradients_and_views():
     with pytest.raises(_capi.PnrError):
         linear3x(wide.cpu(), w.cpu())
     with pytest.raises(_capi.PnrError):
-        linear3x(wide, torch.zeros(300, 300, device=DEV))          # N > 256
+        linear3x(torch.zeros(8, 600, device=DEV), torch.zeros(16, 600, device=DEV))          # K > 512
+    y300 = linear3x(wide, torch.eye(300, device=DEV))              # more than 256 outputs: column blocks
+    assert float((y300 - wide).abs().max()) <= 1e-5 * float(wide.abs().max())
     assert _pow2_scale(torch.zeros(4, 4, device=DEV)).item() == 1.0

@@ -5,7 +5,22 @@ from pathlib import Path
 import torch
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
-from panopticnerf_b200.lib.train.mlp_backward import wgrad, matmul_3xtf32, _pow2_scale
+from panopticnerf_b200.lib.train.mlp_backward import wgrad, _pow2_scale
+
+
+def matmul_3xtf32(a, b, trans_a=False):   # what the training path used before: three TF32 library GEMMs on split operands
+    def parts(t):
+        hi = (t.contiguous().view(torch.int32) & -8192).view(torch.float32)
+        return hi, t - hi
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    ah, al = parts(a); bh, bl = parts(b)
+    if trans_a:
+        ah, al = ah.t(), al.t()
+    y = ah @ bh + (al @ bh + ah @ bl)
+    torch.backends.cuda.matmul.allow_tf32 = old
+    return y
+
 
 DEV = "cuda:0"
 S_ = int(sys.argv[1]) if len(sys.argv) > 1 else 393216
