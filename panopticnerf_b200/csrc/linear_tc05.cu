@@ -10,14 +10,15 @@
 //   * warps 4-11 (producers): a warp instruction reads two rows' 256-byte K chunk, 16 bytes per lane (fully
 //     coalesced); the values are scaled (a power of two for gradients, exact), split into 16-bit hi / lo parts and
 //     written as half core-matrix rows (8-byte stores) of the no-swizzle K-major A operand, one 64-feature K chunk per
-//     stage (2 stages).  The K-cores of the A images are 2064 bytes apart instead of 2048 (the descriptor's leading
+//     stage (2 stages), the next chunk's loads in flight meanwhile.  The K-cores of the A images are 2064 bytes apart instead of 2048 (the descriptor's leading
 //     byte offset is free to say so): the 16 lanes that share a row then hit 16 different 8-byte bank slots;
 //   * warp 12: streams the matching K chunk of the weights - packed once per call by linear_pack_kernel into hi / lo
 //     images of [8 K-cores][NP rows][16 B] - with cp.async.bulk into a 2-stage ring (64 KB stages, L2-resident source);
 //   * warp 13: one elected lane issues tcgen05.mma kind::f16, M = 128, N = NP, K = 16, both operands from shared
 //     memory, hi.hi + lo.hi + hi.lo, into one of TWO 256-column accumulators (tile parity);
-//   * warps 0-3 (epilogue): tcgen05.ld the finished accumulator, * 1/scale, + bias, optional ReLU, 16-byte stores
-//     to the sample's row of y - while the MMAs of the next tile fill the other accumulator.
+//   * warps 0-3 (epilogue): tcgen05.ld the finished accumulator, * 1/scale, + bias, optional ReLU, 32-byte stores
+//     (STG.256: one whole sector per lane; with 16-byte stores a third of the kernel's L2 sector traffic was half-used
+//     sectors, ncu) to the sample's row of y - while the MMAs of the next tile fill the other accumulator.
 // HBM-bound by construction for the shapes of this network (4 (K + N) bytes per sample against 6 K N tensor flops).
 #include <cstddef>
 #include <mutex>
@@ -47,7 +48,7 @@ struct LinearParams {
   const float* bias;      // [N] or NULL
   float* y; int64_t ld_y; int N;
   int64_t S;
-  int NP, n_chunks, relu, vec_in, vec_out;
+  int NP, n_chunks, relu, vec_in, vec_out, vec8_out;
   const float* in_scale;  // device scalar (power of two) applied to x; the result is divided by it.  NULL: 1
 };
 
@@ -147,7 +148,10 @@ __global__ void __launch_bounds__(kLnThreads, 1) linear_kernel(const LinearParam
             v[j] = p.relu ? fmaxf(t, 0.f) : t;
           }
           if (s < p.S) {
-            if (p.vec_out && c0 + 16 <= p.N) {
+            if (p.vec8_out && c0 + 16 <= p.N) {
+              st_global_v8(dst + c0, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+              st_global_v8(dst + c0 + 8, v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]);
+            } else if (p.vec_out && c0 + 16 <= p.N) {
               float4* d4 = reinterpret_cast<float4*>(dst + c0);
 #pragma unroll
               for (int c = 0; c < 4; ++c) d4[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
@@ -168,62 +172,81 @@ __global__ void __launch_bounds__(kLnThreads, 1) linear_kernel(const LinearParam
     // segment of the row's 256-byte chunk (lane & 15) = features 4 seg .. 4 seg + 3 = half (seg & 1) of K-core seg >> 1
     const int pw = warp - kLnEpiWarps;
     const int seg = lane & 15, kc = seg >> 1, half = seg & 1;
-    uint32_t ga = 0;
     const bool k_ragged = (p.K & 3) != 0;
-    for (int it = 0; it < n_iter; ++it) {
+    const int n_total = n_iter * n_chunks;               // chunks this CTA converts, tile after tile
+    // loads of chunk (it, c): this lane's 16-byte segment of 8 rows (two rows apart), predicated per lane
+    auto load_chunk = [&](int it, int c, float4 (&v)[8]) {
       const int64_t s0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kLnTile + pw * 16 + (lane >> 4);
       const int64_t left = p.S - s0;                       // this lane's rows are s0 + 2 i: how many of them exist
       const int nvr = left <= 0 ? 0 : (left >= 16 ? 8 : (int)((left + 1) >> 1));
-      const float* xrow = p.x + s0 * p.ld_x + seg * 4;     // (never dereferenced when nvr == 0)
+      const int k = c * kLnChunk + seg * 4;
+      const int kr = p.K - k;                              // features of this lane's segment that exist (<= 0: none)
+      const float* q = p.x + s0 * p.ld_x + k;              // (never dereferenced when nvr == 0 or kr <= 0)
       const int64_t step = 2 * p.ld_x;
-#pragma unroll 1
-      for (int c = 0; c < n_chunks; ++c, ++ga) {
-        const uint32_t slot = ga & 1u, ph = (ga >> 1) & 1u;
-        const int k = c * kLnChunk + seg * 4;
-        const int kr = p.K - k;                            // features of this lane's segment that exist (<= 0: none)
-        const float* q = xrow + c * kLnChunk;
-        float4 v[8];
-        if (p.vec_in) {      // 16-byte loads: rows 16-byte aligned and at least round-up-4(K) floats long
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (kr > 0 && i < nvr) v[i] = __ldg(reinterpret_cast<const float4*>(q));
-            q += step;
-          }
-          if (k_ragged && c + 1 == n_chunks && kr > 0 && kr < 4) {   // the segment that straddles K: drop what lies beyond
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if (kr < 2) v[i].y = 0.f;
-              if (kr < 3) v[i].z = 0.f;
-              v[i].w = 0.f;
-            }
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (i < nvr) {
-              if (kr > 0) v[i].x = __ldg(q);
-              if (kr > 1) v[i].y = __ldg(q + 1);
-              if (kr > 2) v[i].z = __ldg(q + 2);
-              if (kr > 3) v[i].w = __ldg(q + 3);
-            }
-            q += step;
-          }
-        }
-        mbar_wait_backoff(bar_a_empty + 8 * slot, ph ^ 1u);
-        uint8_t* img = smem + kLnSmemA + slot * kLnAStage + kc * kLnALbo + (pw * 16 + (lane >> 4)) * 16 + half * 8;
+      if (p.vec_in) {        // 16-byte loads: rows 16-byte aligned and at least round-up-4(K) floats long
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          uint32_t h0, l0, h1, l1;
-          split_x2<FMT>(v[i].x * sc, v[i].y * sc, h0, l0);
-          split_x2<FMT>(v[i].z * sc, v[i].w * sc, h1, l1);
-          *reinterpret_cast<uint2*>(img + i * 32) = make_uint2(h0, h1);
-          *reinterpret_cast<uint2*>(img + i * 32 + kLnAPart) = make_uint2(l0, l1);
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (kr > 0 && i < nvr) v[i] = __ldg(reinterpret_cast<const float4*>(q));
+          q += step;
         }
-        fence_proxy_async_smem();
-        mbar_arrive(bar_a_full + 8 * slot);
+        if (k_ragged && c + 1 == n_chunks && kr > 0 && kr < 4) {   // the segment that straddles K: drop what lies beyond
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (kr < 2) v[i].y = 0.f;
+            if (kr < 3) v[i].z = 0.f;
+            v[i].w = 0.f;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i < nvr) {
+            if (kr > 0) v[i].x = __ldg(q);
+            if (kr > 1) v[i].y = __ldg(q + 1);
+            if (kr > 2) v[i].z = __ldg(q + 2);
+            if (kr > 3) v[i].w = __ldg(q + 3);
+          }
+          q += step;
+        }
       }
+    };
+    // L2 prefetch of the chunk after the one being loaded (registers hold one chunk in flight per thread; a prefetch
+    // costs none): the warp's 16 rows x 256 bytes are 32 lines, one per lane
+    auto prefetch_chunk = [&](int it, int c) {
+      const int64_t s = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kLnTile + pw * 16 + (lane >> 1);
+      const int k = c * kLnChunk + (lane & 1) * 32;
+      if (s < p.S && k < p.K) prefetch_l2(p.x + s * p.ld_x + k);
+    };
+    int it_n = 0, c_n = 0;                                 // the chunk the next load_chunk fetches
+    auto advance = [&]() { if (++c_n == n_chunks) { c_n = 0; ++it_n; } };
+    // convert + store chunk g from `cur` while chunk g + 1 is on its way into `nxt`
+    auto do_chunk = [&](int g, float4 (&cur)[8], float4 (&nxt)[8]) {
+      const uint32_t slot = (uint32_t)g & 1u, ph = ((uint32_t)g >> 1) & 1u;
+      if (g + 1 < n_total) { load_chunk(it_n, c_n, nxt); advance(); }
+      if (g + 2 < n_total) prefetch_chunk(it_n, c_n);
+      mbar_wait_backoff(bar_a_empty + 8 * slot, ph ^ 1u);
+      uint8_t* img = smem + kLnSmemA + slot * kLnAStage + kc * kLnALbo + (pw * 16 + (lane >> 4)) * 16 + half * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        uint32_t h0, l0, h1, l1;
+        split_x2<FMT>(cur[i].x * sc, cur[i].y * sc, h0, l0);
+        split_x2<FMT>(cur[i].z * sc, cur[i].w * sc, h1, l1);
+        *reinterpret_cast<uint2*>(img + i * 32) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(img + i * 32 + kLnAPart) = make_uint2(l0, l1);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(bar_a_full + 8 * slot);
+    };
+    float4 va[8], vb[8];     // two register buffers, used alternately
+    load_chunk(0, 0, va);
+    advance();
+    if (n_total > 1) prefetch_chunk(it_n, c_n);
+#pragma unroll 1
+    for (int g = 0; g < n_total; g += 2) {
+      do_chunk(g, va, vb);
+      if (g + 1 < n_total) do_chunk(g + 1, vb, va);
     }
   } else if (warp == kLnEpiWarps + kLnProWarps) {
     // =============================================================== weight stream (one elected thread)
@@ -345,6 +368,7 @@ extern "C" int pnr_linear(const float* x, int64_t ld_x, int32_t K, const float* 
   p.relu = relu != 0;
   p.vec_in = (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (ld_x & 3) == 0 && ld_x >= (K + 3) / 4 * 4;
   p.vec_out = (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (ld_y & 3) == 0;
+  p.vec8_out = (reinterpret_cast<uintptr_t>(y) & 31) == 0 && (ld_y & 7) == 0;
   p.in_scale = in_scale;
   uint8_t* wpk = static_cast<uint8_t*>(workspace);
   return precision == PNR_PREC_FP16X3 ? linear_launch<kFmtF16>(p, W, ld_w, transposed != 0, wpk, dev, st)

@@ -97,6 +97,13 @@ __device__ __forceinline__ void red_add_smem(uint32_t addr, uint32_t v) {
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
+// 256-bit global store (sm_100: STG.256): one full 32-byte sector per lane - rows written by one thread each leave the
+// SM as whole sectors instead of two half-sector requests.  p must be 32-byte aligned.
+__device__ __forceinline__ void st_global_v8(float* p, float a, float b, float c, float d, float e, float f, float g, float h) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d),
+               "f"(e), "f"(f), "f"(g), "f"(h)
+               : "memory");
+}
 __device__ __forceinline__ uint32_t ld_volatile_smem(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.volatile.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");

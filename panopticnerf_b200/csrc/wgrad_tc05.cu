@@ -8,18 +8,22 @@
 // accumulates its 256 x 256 partial product in TENSOR MEMORY over all of its slabs (two M = 128 accumulators of
 // N <= 256 columns = all 512 columns), and writes it out once; a second kernel adds the partials in CTA order
 // (deterministic: no atomics).  Per slab:
-//   * 16 producer warps read the fp32 rows (lane = feature, 8 consecutive samples per thread - every load a
-//     coalesced 128-byte row segment), split each value into bf16 hi / lo parts and write them as 16-byte rows of
-//     the UMMA no-swizzle K-major core matrices (K = samples): what a thread holds IS one core-matrix row, so the
-//     transposition dZ -> dZ^T costs nothing.  The next slab's loads are in flight while a slab is converted.
+//   * 16 warps, one work item each: (operand, half of its 256 feature rows, 8 of the slab's 32 samples).  A lane reads
+//     4 consecutive features of 8 consecutive samples - per sample row one fully coalesced 512-byte warp request of
+//     16-byte loads (ncu: with 4-byte loads the same bytes in flight gave 34 % of the DRAM peak; the limit is requests
+//     in flight, not bytes) - splits each value into 16-bit hi / lo parts and writes them as 16-byte rows of the UMMA
+//     no-swizzle K-major core matrices (K = samples): a thread's 8 samples of one feature ARE one core-matrix row, so
+//     the transposition dZ -> dZ^T costs nothing.  The 8-row groups of the images are 144 bytes apart instead of 128
+//     (the descriptor's stride byte offset is free to say so): the four feature rows of a lane and those of the
+//     lanes next to it then fall into different banks.  The next slab's loads are in flight while a slab is converted.
 //   * one elected lane of warp 0 (after its own share of the slab) issues tcgen05.mma kind::f16 (bf16 operands, fp32
 //     accumulate), both operands from shared memory (512 threads = 128 registers each; a 17th warp would cost 32):
 //     A = dZ^T (M = 128 output features x K = 16 samples), B = X^T (N = Ni padded to 16, K-major), three products
 //     per K step: hi.hi + lo.hi + hi.lo.  bf16 parts: ~2^-17 per product, fp32 exponent range, gradients need no
 //     scaling.  fp16 parts: ~2^-21 per product; dZ is multiplied by a caller-supplied power of two on load (a device
 //     scalar, exact) so that the parts of ~1e-6 gradients stay normal, and the sums are divided by it at the end.
-//   * a 3-deep ring of 64 KB stages (A hi, A lo, B hi, B lo images of [4 K-cores][256 rows][16 B]); full / empty
-//     mbarriers, the empty ones arrived by tcgen05.commit.
+//   * a 3-deep ring of 72 KB stages (A hi, A lo, B hi, B lo images of [4 K-cores][32 row groups][144 B]); full /
+//     empty mbarriers, the empty ones arrived by tcgen05.commit.
 // The kernel is HBM-bound by construction: 2 KB of fp32 operands per sample against 2 * 3 * 256 * 256 tensor flops
 // (~50 tensor-pipe cycles per sample and SM): algorithmic bytes = 4 (No + Ni) per sample.
 #include <cstddef>
@@ -33,18 +37,20 @@ constexpr int kWgProWarps = 16;
 constexpr int kWgThreads = kWgProWarps * 32;
 constexpr int kWgSlab = 32;                         // samples per stage
 constexpr int kWgRows = 256;                        // rows of one operand image
-constexpr int kWgPart = kWgRows * kWgSlab * 2;      // one 16-bit image: [4 K-cores][256 rows][16 B] = 16 KB
+constexpr int kWgSbo = 128 + 16;                    // 8-row groups: 128 bytes of core matrix + 16 bytes of padding (banks)
+constexpr uint32_t kWgLbo = (kWgRows / 8) * kWgSbo; // K-adjacent core matrices: 4608 bytes
+constexpr int kWgPart = (kWgSlab / 8) * kWgLbo;     // one 16-bit image: [4 K-cores][32 row groups][144 B] = 18 KB
 constexpr int kWgStage = 4 * kWgPart;               // A hi, A lo, B hi, B lo
 constexpr int kWgRing = 3;
 constexpr int kWgSmemBars = kWgRing * kWgStage;     // mbarriers + tensor-memory slot
 constexpr int kWgSmemDb = kWgSmemBars + 128;        // [4 sample groups][256] partial bias sums
 constexpr int kWgSmemTotal = kWgSmemDb + 4 * kWgRows * 4;
-constexpr uint32_t kWgLbo = kWgRows * 16;           // K-adjacent core matrices
 
 struct WgradParams {
   const float* dz; int64_t ld_dz; int No;
   const float* x; int64_t ld_x; int Ni;
   int64_t S;
+  int vec_a, vec_b;   // 16-byte loads possible (base and row stride 16-byte aligned)
   int mh;        // M halves of 128 output features
   int NP;        // Ni padded to a multiple of 16
   float* part;   // [grid][mh * 128][NP]
@@ -83,72 +89,84 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams 
   const uint32_t tmem = *tmem_slot;
 
   {
-    // =============================================================== producers: fp32 rows -> bf16 hi / lo core-matrix rows
-    // Work items of a slab: (operand row group of 32 features, group of 8 samples).  Warp w always takes sample group
-    // w % 4 and the row groups w / 4 + 4 j (A = dZ groups first, then B = X groups): the mapping is static, so a
-    // thread's partial bias sums stay in registers over the whole launch.
-    const int kg = warp & 3, fg0 = warp >> 2;
-    const int nA = p.mh * 4, nB = (p.NP + 31) >> 5;
+    // =============================================================== producers: fp32 rows -> 16-bit hi / lo core-matrix rows
+    // warp w: operand w >> 3 (0 = A = dZ, 1 = B = X), feature half (w >> 2) & 1, sample group w & 3 of the slab.  The
+    // mapping is static, so a thread's partial bias sums stay in registers over the whole launch.
+    const int kg = warp & 3, fh = (warp >> 2) & 1;
+    const bool isA = warp < 8;
+    const int F = isA ? p.No : p.Ni;                                   // the operand's width
+    const bool on = isA ? fh < p.mh : fh * 128 < p.NP;                 // this warp's rows exist in the MMA
+    const bool vec = (isA ? p.vec_a : p.vec_b) != 0;
+    const int f0 = fh * 128 + 4 * lane;                                // this lane's 4 features = 4 image rows
     const uint32_t idesc = make_idesc_f32acc(128, p.NP, FMT);
     const float sc = p.a_scale != nullptr ? __ldg(p.a_scale) : 1.0f;
-    const float* src[4];
-    int64_t ld[4];
-    int row[4];          // row in the operand image (= feature index)
-    bool on[4], isA[4];
-    float mul[4];        // what the loaded values are multiplied by: the gradient scale (A), 1 (B), 0 past the operand's width
+    const int64_t ld = isA ? p.ld_dz : p.ld_x;
+    // features past the operand's width: multiplied by 0 (their products only reach accumulator rows / columns nobody
+    // reads); a lane wholly outside reads feature 0 instead (a valid address)
+    float mul[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int fg = fg0 + 4 * j;
-      isA[j] = fg < nA;
-      on[j] = fg < nA + nB;
-      row[j] = (isA[j] ? fg : fg - nA) * 32 + lane;
-      const bool real = on[j] && row[j] < (isA[j] ? p.No : p.Ni);
-      mul[j] = real ? (isA[j] ? sc : 1.0f) : 0.f;
-      // rows past the operand's width read column 0 (a valid address) and are zeroed by `mul`; their products only reach
-      // accumulator rows / columns nobody reads
-      src[j] = (isA[j] ? p.dz : p.x) + (real ? row[j] : 0);
-      ld[j] = isA[j] ? p.ld_dz : p.ld_x;
-    }
-    // One slab's loads: 8 consecutive samples per item, one pointer increment per load, predicated on a warp-uniform
-    // count (only the launch's very last slab is partial).
-    auto load_slab = [&](int i, float (&v)[4][8]) {
+    for (int c = 0; c < 4; ++c) mul[c] = (on && f0 + c < F) ? (isA ? sc : 1.0f) : 0.f;
+    const float* src = (isA ? p.dz : p.x) + ((on && f0 < F) ? f0 : 0);
+    // One slab's loads: this lane's 4 features of 8 consecutive samples, predicated on a warp-uniform count (only the
+    // launch's very last slab is partial).
+    auto load_slab = [&](int i, float4 (&v)[8]) {
       const int64_t s0 = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * kWgSlab + kg * 8;
       const int64_t left = p.S - s0;
-      const int nv = left >= 8 ? 8 : (left > 0 ? (int)left : 0);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (!on[j]) continue;
-        const float* q = src[j] + s0 * ld[j];
+      const int nv = !on ? 0 : (left >= 8 ? 8 : (left > 0 ? (int)left : 0));
+      const float* q = src + s0 * ld;
+      if (vec) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          v[j][k] = 0.f;
-          if (k < nv) v[j][k] = __ldg(q);
-          q += ld[j];
+          v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (k < nv) v[k] = __ldg(reinterpret_cast<const float4*>(q));
+          q += ld;
+        }
+      } else {      // rows not 16-byte aligned (odd widths): 4-byte loads; columns past the width are not touched
+        const int nc = F - f0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (k < nv) {
+            v[k].x = __ldg(q);
+            if (nc > 1) v[k].y = __ldg(q + 1);
+            if (nc > 2) v[k].z = __ldg(q + 2);
+            if (nc > 3) v[k].w = __ldg(q + 3);
+          }
+          q += ld;
         }
       }
     };
+    // L2 prefetch of slab i (two slabs ahead of the one being converted): registers hold one slab in flight per thread,
+    // which at ~2 us of loaded DRAM latency is not enough bytes in flight to fill the memory system; a prefetch costs
+    // no register.  The warp's 8 rows x 512 bytes are 32 lines: one per lane.
+    const float* pf_src = (isA ? p.dz : p.x) + fh * 128 + (lane & 3) * 32;
+    auto prefetch_slab = [&](int i) {
+      const int64_t s = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * kWgSlab + kg * 8 + (lane >> 2);
+      if (on && s < p.S && fh * 128 + (lane & 3) * 32 < F) prefetch_l2(pf_src + s * ld);
+    };
     float db[4] = {0.f, 0.f, 0.f, 0.f};
     // convert + store slab i from `cur` while slab i + 1 is on its way into `nxt`; warp 0 then issues the slab's MMAs
-    auto do_slab = [&](int i, float (&cur)[4][8], float (&nxt)[4][8]) {
+    auto do_slab = [&](int i, float4 (&cur)[8], float4 (&nxt)[8]) {
       const uint32_t slot = (uint32_t)i % kWgRing, ph = ((uint32_t)i / kWgRing) & 1u;
       if (i + 1 < n_mine) load_slab(i + 1, nxt);
+      if (i + 2 < n_mine) prefetch_slab(i + 2);
       mbar_wait_backoff(bar_empty + 8 * slot, ph ^ 1u);
       uint8_t* stage = smem + slot * kWgStage;
+      if (on) {
+        // row r = f0 + c of the image: 8-row group r / 8 at kWgSbo bytes each, 16 bytes per row inside it
+        uint8_t* img = stage + (isA ? 0 : 2 * kWgPart) + kg * kWgLbo + (f0 >> 3) * kWgSbo + (f0 & 7) * 16;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (!on[j]) continue;
-        uint32_t h[4], l[4];
-        const float m = mul[j];
+        for (int c = 0; c < 4; ++c) {
+          const float m = mul[c];
+          float x[8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) split_x2<FMT>(cur[j][2 * q] * m, cur[j][2 * q + 1] * m, h[q], l[q]);
-        uint8_t* img = stage + (isA[j] ? 0 : 2 * kWgPart) + (kg * kWgRows + row[j]) * 16;
-        *reinterpret_cast<uint4*>(img) = make_uint4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<uint4*>(img + kWgPart) = make_uint4(l[0], l[1], l[2], l[3]);
-        if (isA[j]) {
-          float s = 0.f;
+          for (int k = 0; k < 8; ++k) x[k] = (c == 0 ? cur[k].x : c == 1 ? cur[k].y : c == 2 ? cur[k].z : cur[k].w);
+          uint32_t h[4], l[4];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) s += cur[j][k];
-          db[j] += s;
+          for (int q = 0; q < 4; ++q) split_x2<FMT>(x[2 * q] * m, x[2 * q + 1] * m, h[q], l[q]);
+          *reinterpret_cast<uint4*>(img + c * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(img + c * 16 + kWgPart) = make_uint4(l[0], l[1], l[2], l[3]);
+          if (isA) db[c] += ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
         }
       }
       fence_proxy_async_smem();            // generic-proxy stores -> visible to the tensor core's async proxy
@@ -163,10 +181,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams 
             const uint32_t d_tmem = tmem + (uint32_t)(h * 256);
 #pragma unroll
             for (int ks = 0; ks < kWgSlab / 16; ++ks) {
-              const uint32_t a = sa + (uint32_t)(h * 128 * 16) + (uint32_t)ks * 2u * kWgLbo;
+              const uint32_t a = sa + (uint32_t)(h * 16 * kWgSbo) + (uint32_t)ks * 2u * kWgLbo;
               const uint32_t b = sa + 2u * kWgPart + (uint32_t)ks * 2u * kWgLbo;
-              const uint64_t a_hi = make_smem_desc_noswz(a, kWgLbo, 128), a_lo = make_smem_desc_noswz(a + kWgPart, kWgLbo, 128);
-              const uint64_t b_hi = make_smem_desc_noswz(b, kWgLbo, 128), b_lo = make_smem_desc_noswz(b + kWgPart, kWgLbo, 128);
+              const uint64_t a_hi = make_smem_desc_noswz(a, kWgLbo, kWgSbo), a_lo = make_smem_desc_noswz(a + kWgPart, kWgLbo, kWgSbo);
+              const uint64_t b_hi = make_smem_desc_noswz(b, kWgLbo, kWgSbo), b_lo = make_smem_desc_noswz(b + kWgPart, kWgLbo, kWgSbo);
               mma_ss(d_tmem, a_hi, b_hi, idesc, (i == 0 && ks == 0) ? 0u : 1u);
               mma_ss(d_tmem, a_lo, b_hi, idesc, 1u);
               mma_ss(d_tmem, a_hi, b_lo, idesc, 1u);
@@ -178,22 +196,19 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams 
         __syncwarp();
       }
     };
-    float va[4][8], vb[4][8];    // two register buffers, used alternately (no copies between iterations)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { va[j][k] = 0.f; vb[j][k] = 0.f; }
-    }
+    float4 va[8], vb[8];    // two register buffers, used alternately (no copies between iterations)
     load_slab(0, va);
+    if (n_mine > 1) prefetch_slab(1);
 #pragma unroll 1
     for (int i = 0; i < n_mine; i += 2) {
       do_slab(i, va, vb);
       if (i + 1 < n_mine) do_slab(i + 1, vb, va);
     }
     // ---- bias partial sums: 4 sample groups per feature, added in a fixed order
+    if (on && isA) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (on[j] && isA[j]) dbs[kg * kWgRows + row[j]] = db[j];
+      for (int c = 0; c < 4; ++c) dbs[kg * kWgRows + f0 + c] = db[c];
+    }
     __syncthreads();
     if (p.dbp != nullptr && (int)threadIdx.x < p.mh * 128) {
       const int f = threadIdx.x;
@@ -313,6 +328,8 @@ extern "C" int pnr_wgrad(const float* dz, int64_t ld_dz, int32_t No, const float
   p.part = static_cast<float*>(workspace);
   p.dbp = db != nullptr ? p.part + (size_t)grid * mh * 128 * NP : nullptr;
   p.a_scale = dz_scale;
+  p.vec_a = (reinterpret_cast<uintptr_t>(dz) & 15) == 0 && (ld_dz & 3) == 0;
+  p.vec_b = (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (ld_x & 3) == 0;
   if (grid > 0) {
     const int rc = precision == PNR_PREC_FP16X3 ? wgrad_launch<kFmtF16>(p, grid, dev, st) : wgrad_launch<kFmtBF16>(p, grid, dev, st);
     if (rc != PNR_OK) return rc;

@@ -43,7 +43,9 @@ def case(K, N, relu, transposed, gscale, prec):
     w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
     b = None if transposed else (torch.randn(N, generator=g) * 0.1).to(DEV)
     sc = _pow2_scale(x) if (transposed and prec == "fp16x3") else None
-    f = lambda: linear3x(x, w, b, relu=relu, transposed=transposed, precision=prec, scale=sc)
+    pad = (-(K if transposed else N)) % 8 if transposed else 0      # the training path pads gradient rows to 32 bytes
+    f = lambda: linear3x(x, w, b, relu=relu, transposed=transposed, precision=prec, scale=sc,
+                         out_cols=(K + pad) if transposed else 0)[:, :(K if transposed else N)]
     lib = lambda: (tf32x3(x, w) if transposed else tf32x3(x, w.t()) + b)
     t_k, t_l = timed(f), timed(lib)
     ref = (x.double() @ w.double()) if transposed else (x.double() @ w.double().t() + b.double())
