@@ -10,9 +10,9 @@ timeout 200 python tools/profile_train_step.py cfg3 > gpurun_out/r02_train_step_
 timeout 100 python tools/time_wgrad.py 2>&1 | tail -1
 timeout 100 python tools/time_wgrad.py 393216 256 63 2>&1 | tail -1
 timeout 100 python tools/time_linear.py 2>&1 | tail -3
-timeout 400 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r2_final2.json 2> gpurun_out/bench_r2_final2.err; tail -c 600 gpurun_out/bench_r2_final2.json; tail -2 gpurun_out/bench_r2_final2.err
+timeout 400 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_r2_final2.json 2> gpurun_out/bench_r2_final2.err; tail -c 600 gpurun_out/bench_r2_final2.json; tail -2 gpurun_out/bench_r2_final2.err
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:wgrad_kernel -s 2 -c 1 -o gpurun_out/r02_wgrad \
     python tools/time_wgrad.py > /dev/null 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:linear_kernel -s 2 -c 1 -o gpurun_out/r02_linear \
-    python tools/time_linear.py > /dev/null 2>&1
+    python tools/time_linear.py 393216 256 256 > /dev/null 2>&1
 ls -la gpurun_out/*.ncu-rep
