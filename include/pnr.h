@@ -261,13 +261,17 @@ int pnr_composite_backward(const float* raw, const float* z, const float* rays, 
  * hundred, or the fp16 operand parts of small gradients go subnormal (1.0 when grad_h is already O(1)). */
 int pnr_mlp_backward_trunk(pnr_ctx* ctx, const float* pts, const float* rays, const float* z, int64_t R, int32_t N,
                            const float* grad_h, float grad_scale, float* grad_emb, int32_t ld_emb, float* stash,
-                           void* stream);
+                           uint32_t* stash_absmax, void* stream);
 /* The weight gradients of the trunk come from `stash` [2D-1, R*N, W] fp32 (NULL: not kept): every A operand the
  * kernel produces on the way - slot i < D-1: H_i, the activations of forward layer i; slot 2D-2-j: dZ_j, the gradient
  * w.r.t. layer j's pre-activation - so that dW_j = dZ_j^T [H_{j-1} (, gamma(x))], db_j = sum_s dZ_j are plain GEMMs
  * / reductions for the caller's BLAS.  pnr_mlp_trunk_forward returns the trunk's output h [R*N, W] (16-byte
  * aligned), the input of the layers after the trunk (alpha / feature / view / rgb / heads), which the caller
- * differentiates itself to obtain grad_h. */
+ * differentiates itself to obtain grad_h.
+ * stash_absmax (nullable; needs stash) [2D-1] u32, zeroed by the call: slot k receives the largest magnitude written
+ * to stash slot k, as the bit pattern of its 16-bit hi part in the context's operand format (fp16 / bf16) and for
+ * the gradient slots BEFORE the division by grad_scale - enough to pick pnr_wgrad's power-of-two dz_scale without
+ * another pass over the stash. */
 int pnr_mlp_trunk_forward(pnr_ctx* ctx, const float* pts, const float* rays, const float* z, int64_t R, int32_t N,
                           float* h_out, void* stream);
 

@@ -188,6 +188,10 @@ struct MlpParams {
   // (output rows, stashed dZ) by grad_unscale = 1 / grad_scale: a power of two chosen by the caller so that the
   // 16-bit operand parts of small gradients stay in the normal range (the backward pass is linear in grad_in)
   float grad_scale, grad_unscale;
+  // optional [2D-1] words, zeroed by the launcher: slot k receives (atomic max) the largest |value| the kernel put into
+  // stash slot k, as the bit pattern of its 16-bit hi part in the operand format and BEFORE grad_unscale is applied -
+  // what the caller needs to pick the power-of-two scale of the weight-gradient GEMM without another pass over the stash
+  uint32_t* stash_absmax;
 };
 
 // What a launch carries: arguments + the context's program, as ONE __grid_constant__ kernel parameter.

@@ -371,6 +371,8 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
 
   // ---- one-time setup: constants to shared memory, barriers, tensor memory
   for (int i = threadIdx.x; i < prog.n_consts; i += blockDim.x) consts[i] = p.consts[i];
+  // backward programs: `part` (unused there) holds this CTA's largest operand pattern per step (MlpParams::stash_absmax)
+  if (BWD) for (int i = threadIdx.x; i < kMaxSteps; i += blockDim.x) reinterpret_cast<uint32_t*>(part)[i] = 0u;
   if (warp == 0) {
     tmem_alloc<512>(smem_u32(tmem_slot));
     tmem_relinquish();
@@ -436,6 +438,7 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
         const float* aux = consts + ed.aux_off;
         const bool to_a = BWD ? epi_writes_a(ed.kind) : ed.kind == EPI_RELU_TO_A;
         float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+        uint32_t smax = 0;   // backward programs: largest hi-part magnitudes of the A operand this step produces (16x2)
         // backward programs: this row's sign patterns and its row of the incoming gradient (tail rows read row S-1)
         uint16_t* mask_row = reinterpret_cast<uint16_t*>(smem + kSmemMask) + row;
         const float* gin = (BWD && ed.kind == EPI_LOADG_TO_A) ? p.grad_in + (valid ? s : p.S - 1) * (int64_t)ed.n : nullptr;
@@ -496,12 +499,12 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
                 const int after = (g + 2 < hi) ? g + 2 : nxt;
                 tc_wait_ld();
                 if (two) tmem_ld16(acc_of(g + 1), rb);
-                if (BWD) epi_group_bwd<PASSES, FMT>(ra, g, ed, bias, mask_row, gin, stash_row, p.grad_scale, p.grad_unscale, vmax, ha, la);
+                if (BWD) epi_group_bwd<PASSES, FMT>(ra, g, ed, bias, mask_row, gin, stash_row, p.grad_scale, p.grad_unscale, smax, ha, la);
                 else epi_group_act<PASSES, FMT>(ra, g, ed, bias, aux, sig, vmax, ha, la);
                 if (two) {
                   tc_wait_ld();
                   if (after >= 0) tmem_ld16(acc_of(after), ra);
-                  if (BWD) epi_group_bwd<PASSES, FMT>(rb, g + 1, ed, bias, mask_row, gin, stash_row, p.grad_scale, p.grad_unscale, vmax, hb, lb);
+                  if (BWD) epi_group_bwd<PASSES, FMT>(rb, g + 1, ed, bias, mask_row, gin, stash_row, p.grad_scale, p.grad_unscale, smax, hb, lb);
                   else epi_group_act<PASSES, FMT>(rb, g + 1, ed, bias, aux, sig, vmax, hb, lb);
                 } else if (after >= 0) {
                   tmem_ld16(acc_of(after), ra);
@@ -597,6 +600,15 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
 #ifdef PNR_TIMELINE
           if (rec) p.dbg[4096 + (st * 2 + h) * 3 + 2] = clock64();
 #endif
+        }
+        if (BWD) {
+          vmax = __vimax3_u16x2(vmax, smax, 0u);          // the range check sees every step
+          if (p.stash_absmax != nullptr && to_a && ed.out_off1 != 0) {   // per-step maximum of what went to the stash
+            uint32_t m = smax & 0xFFFFu;
+            if ((smax >> 16) > m) m = smax >> 16;
+            m = __reduce_max_sync(0xffffffffu, m);
+            if (lane == 0) atomicMax(reinterpret_cast<uint32_t*>(part) + st, m);
+          }
         }
         if (COMP && ed.sigma) {
           // ---- per-sample weights of this tile, right after the sigma-producing layer handed over (the MMAs go on
@@ -971,6 +983,11 @@ mlp_fused_kernel(const __grid_constant__ MlpLaunch L) {
   }
   tc_fence_before();
   __syncthreads();
+  if (BWD && p.stash_absmax != nullptr && (int)threadIdx.x < prog.n_steps) {   // this CTA's maxima -> the launch's
+    const EpiDesc& e = prog.ep[threadIdx.x];
+    const uint32_t m = reinterpret_cast<const uint32_t*>(part)[threadIdx.x];
+    if (epi_writes_a(e.kind) && e.out_off1 != 0 && m != 0u) atomicMax(p.stash_absmax + (e.out_off1 - 1), m);
+  }
   cluster_sync();   // no CTA may exit while its peer can still multicast into it or arrive on its barriers
   if (warp == 0) tmem_dealloc<512>(tmem);
 }

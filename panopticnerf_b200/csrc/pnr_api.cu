@@ -1071,7 +1071,7 @@ static int ensure_aux(pnr_ctx* ctx, pnr_ctx::Aux& aux, bool forward_only, cudaSt
 
 static int aux_launch(pnr_ctx* ctx, pnr_ctx::Aux& aux, const char* what, const float* pts, const float* rays, const float* z,
                       int64_t R, int32_t N, const float* grad_h, float grad_scale, float* out, int32_t ld_out, float* stash,
-                      void* stream) {
+                      uint32_t* stash_absmax, void* stream) {
   if (!ctx->loaded) return set_error(PNR_ERR_STATE, "%s: pnr_load_weights has not been called", what);
   PNR_CHECK_ARG(R > 0 && N >= 1, "%s: bad sizes R=%lld N=%d", what, (long long)R, N);
   PNR_CHECK_ARG(pts || (rays && z), "%s: need pts or (rays, z)", what);
@@ -1089,6 +1089,9 @@ static int aux_launch(pnr_ctx* ctx, pnr_ctx::Aux& aux, const char* what, const f
   p.dbg = ctx->dbg_timeline;
   p.grad_in = grad_h;
   p.stash = stash;
+  p.stash_absmax = stash_absmax;
+  if (stash_absmax != nullptr)
+    PNR_CUDA(cudaMemsetAsync(stash_absmax, 0, sizeof(uint32_t) * (size_t)(2 * ctx->cfg.D - 1), (cudaStream_t)stream));
   p.grad_scale = grad_scale;
   p.grad_unscale = 1.0f / grad_scale;
   return launch_mlp(aux.launch, ctx->passes, ctx->fmt, kMlpBackward, (cudaStream_t)stream);
@@ -1105,7 +1108,7 @@ static int aux_launch(pnr_ctx* ctx, pnr_ctx::Aux& aux, const char* what, const f
 // parts; scale so that max |grad_h| * grad_scale is a few hundred (the pass is linear, the scaling exact).
 extern "C" int pnr_mlp_backward_trunk(pnr_ctx* ctx, const float* pts, const float* rays, const float* z, int64_t R,
                                       int32_t N, const float* grad_h, float grad_scale, float* grad_emb, int32_t ld_emb,
-                                      float* stash, void* stream) {
+                                      float* stash, uint32_t* stash_absmax, void* stream) {
   if (R == 0) return PNR_OK;
   PNR_CHECK_ARG(ctx && grad_h && grad_emb, "pnr_mlp_backward_trunk: null pointer");
   PNR_CHECK_ARG(ld_emb >= 3 + 6 * ctx->cfg.xyz_res, "pnr_mlp_backward_trunk: ld_emb=%d < %d columns", ld_emb,
@@ -1113,8 +1116,9 @@ extern "C" int pnr_mlp_backward_trunk(pnr_ctx* ctx, const float* pts, const floa
   int gexp = 0;
   PNR_CHECK_ARG(grad_scale > 0.f && grad_scale < 1.0e30f && grad_scale > 1.0e-30f && frexpf(grad_scale, &gexp) == 0.5f,
                 "pnr_mlp_backward_trunk: grad_scale=%g must be a positive power of two", (double)grad_scale);
+  PNR_CHECK_ARG(stash_absmax == nullptr || stash != nullptr, "pnr_mlp_backward_trunk: stash_absmax without a stash");
   return aux_launch(ctx, ctx->bwd, "pnr_mlp_backward_trunk", pts, rays, z, R, N, grad_h, grad_scale, grad_emb, ld_emb, stash,
-                    stream);
+                    stash_absmax, stream);
 }
 
 // The trunk's output activations h [R*N, W] (what alpha_linear, feature_linear and the heads read): the forward
@@ -1125,7 +1129,7 @@ extern "C" int pnr_mlp_trunk_forward(pnr_ctx* ctx, const float* pts, const float
   if (R == 0) return PNR_OK;
   PNR_CHECK_ARG(ctx && h_out, "pnr_mlp_trunk_forward: null pointer");
   PNR_CHECK_ARG((reinterpret_cast<uintptr_t>(h_out) & 15) == 0, "pnr_mlp_trunk_forward: h_out must be 16-byte aligned");
-  return aux_launch(ctx, ctx->trunk_fwd, "pnr_mlp_trunk_forward", pts, rays, z, R, N, nullptr, 1.0f, h_out, ctx->cfg.W, nullptr, stream);
+  return aux_launch(ctx, ctx->trunk_fwd, "pnr_mlp_trunk_forward", pts, rays, z, R, N, nullptr, 1.0f, h_out, ctx->cfg.W, nullptr, nullptr, stream);
 }
 
 namespace pnr {

@@ -220,14 +220,17 @@ class Network(nn.Module):
 
     def backward_trunk(self, grad_h: torch.Tensor, pts: Optional[torch.Tensor] = None,
                        rays: Optional[torch.Tensor] = None, z: Optional[torch.Tensor] = None,
-                       stash: bool = False, grad_scale: Optional[float] = None):
+                       stash: bool = False, grad_scale: Optional[float] = None, absmax: bool = False):
         """The tensor-core part of the MLP backward (pnr_mlp_backward_trunk): dL/d(embedded xyz) [S, 3 + 6*xyz_res] from
         grad_h = dL/dh of the trunk output [S, W], for the samples given as pts [S,3] or as (rays [R,6], z [R,N]).
         What autograd computes through `pts_linears` (ReLUs, skip concatenation) of the reference Network.
         stash=True also returns the operands of the weight-gradient GEMMs, [2D-1, S, W] fp32: slot i < D-1 = the
         activations H_i of layer i, slot 2D-2-j = dZ_j, the gradient w.r.t. layer j's pre-activation.
         grad_scale: the power of two grad_h is multiplied by inside the kernel (and the results divided by); default:
-        the one that brings max |grad_h| to ~256 (one reduction over grad_h; the pass is linear, the scaling exact)."""
+        the one that brings max |grad_h| to ~256 (one reduction over grad_h; the pass is linear, the scaling exact).
+        absmax=True (with stash) also returns a device tensor [2D-1] fp32: the largest |value| in every stash slot (to
+        the 11 / 8 bits of the operand format's hi part), collected by the kernel itself - what picks the
+        power-of-two scale of the weight-gradient GEMMs without another pass over the stash."""
         R, N, S_, dev = self._samples(pts, rays, z)
         assert grad_h.shape == (S_, self.W), f"grad_h must be [{S_}, {self.W}]"
         ctx = self.pack(dev if grad_h.is_cuda else None)
@@ -235,6 +238,7 @@ class Network(nn.Module):
         ld = (Ex + 15) // 16 * 16                  # rows padded to whole 16-column groups: 16-byte stores in the kernel
         out = torch.empty(S_, ld, dtype=torch.float32, device=dev)
         st = torch.empty(2 * self.D - 1, S_, self.W, dtype=torch.float32, device=dev) if stash else None
+        am = torch.empty(2 * self.D - 1, dtype=torch.int32, device=dev) if (stash and absmax) else None
         if grad_scale is None:
             m = float(grad_h.abs().max()) if grad_h.is_cuda else 0.0
             grad_scale = 2.0 ** max(-100, min(100, round(math.log2(256.0 / m)))) if m > 0.0 and math.isfinite(m) else 1.0
@@ -242,7 +246,13 @@ class Network(nn.Module):
             _capi.check(_capi.lib().pnr_mlp_backward_trunk(
                 ctx, _capi.ptr(pts, torch.float32, "pts"), _capi.ptr(rays, torch.float32, "rays"),
                 _capi.ptr(z, torch.float32, "z"), R, N, _capi.ptr(grad_h, torch.float32, "grad_h"), float(grad_scale),
-                _capi.ptr(out), ld, _capi.ptr(st), _capi.stream_ptr()), "pnr_mlp_backward_trunk")
+                _capi.ptr(out), ld, _capi.ptr(st), _capi.ptr(am), _capi.stream_ptr()), "pnr_mlp_backward_trunk")
+        if am is not None:
+            # 16-bit patterns of the operand format -> magnitudes; the gradient slots (D-1 ..) were seen scaled
+            half = torch.float16 if self.precision.startswith("fp16") else torch.bfloat16
+            mag = am.to(torch.int16).view(half).to(torch.float32)
+            mag[self.D - 1:] /= float(grad_scale)
+            return out[:, :Ex], st, mag
         return (out[:, :Ex], st) if stash else out[:, :Ex]
 
     _fast_update = True      # class-level switch (tests compare against the full reload)

@@ -87,7 +87,11 @@ def _pow2_scale(g: torch.Tensor) -> torch.Tensor:
 
 def _pow2_scales(t: torch.Tensor):
     """`_pow2_scale` of every slice t[i] of a [n, S, W] tensor, from one reduction: a list of n device scalars."""
-    m = torch.linalg.vector_norm(t, ord=float('inf'), dim=(1, 2))      # max |.| without an |t| temporary
+    return _pow2_from_max(torch.linalg.vector_norm(t, ord=float('inf'), dim=(1, 2)))   # max |.| without an |t| temporary
+
+
+def _pow2_from_max(m: torch.Tensor):
+    """A list of device scalars 2^k, one per entry of m [n] (max |.| of n tensors), bringing each maximum to ~256."""
     ok = (m > 0) & torch.isfinite(m)
     k = torch.clamp(torch.round(torch.log2(256.0 / torch.where(ok, m, torch.ones_like(m)))), -100.0, 100.0)
     v = torch.where(ok, torch.exp2(k), torch.ones_like(k)).to(torch.float32).contiguous()
@@ -151,7 +155,7 @@ class _Linear3x(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         x, weight = ctx.saved_tensors
-        g = g.contiguous()
+        g = _rows(g, "gradient")          # column blocks of dL/draw arrive as row-strided views: read in place, no copy
         sc = _pow2_scale(g) if ctx.precision == "fp16x3" else None      # one scale for both gradient GEMMs of the layer
         dx = (linear3x(g, weight, transposed=True, precision=ctx.precision, scale=sc, out_cols=x.shape[1])
               if ctx.needs_input_grad[0] else None)
@@ -199,12 +203,12 @@ def network_backward(net, d_raw: torch.Tensor, pts: Optional[torch.Tensor] = Non
         raw = _tail(net, h, ed)
         g = torch.autograd.grad(raw, [h] + [p for _, p in tail_named], d_raw, allow_unused=True)
     grads = {n: (gi if gi is not None else torch.zeros_like(p)) for (n, p), gi in zip(tail_named, g[1:])}
-    d_emb, st = net.backward_trunk(g[0].contiguous(), pts=pts, rays=rays, z=z, stash=True)
+    d_emb, st, st_max = net.backward_trunk(g[0].contiguous(), pts=pts, rays=rays, z=z, stash=True, absmax=True)
     ex = P.embed(pts_.contiguous(), net.Lx)
     D = net.D
     pr = net.precision if net.precision in ("fp16x3", "bf16x3") else "fp16x3"
-    # fp16 parts: one power-of-two scale per dZ_j, all D of them from one reduction over the stash (on the device)
-    scales = _pow2_scales(st[D - 1:])[::-1] if pr == "fp16x3" else [None] * D
+    # fp16 parts: one power-of-two scale per dZ_j, from the maxima the backward kernel collected while writing the stash
+    scales = _pow2_from_max(st_max[D - 1:])[::-1] if pr == "fp16x3" else [None] * D
     for j in range(D):
         dZ = st[2 * D - 2 - j]
         if j == net.skip + 1:        # input [gamma(x), H_{j-1}]: two column blocks of dW, no concatenated copy

@@ -41,3 +41,29 @@ def test_rows_keeps_row_strided_views_and_copies_what_the_kernels_cannot_address
         MB.wgrad(t, t)
     with pytest.raises(_capi.PnrError):
         MB.linear3x(t, t)
+
+
+def test_new_entry_points_validate_their_arguments_before_touching_the_device():
+    """pnr_wgrad / pnr_linear refuse bad arguments with PNR_ERR_ARG and a message (no CUDA call is made on that path,
+    so this runs without a GPU); the workspace queries are pure arithmetic."""
+    L = _capi.lib()
+    assert L.pnr_linear_workspace_bytes(256, 512) == 8 * 2 * 8 * 256 * 16      # 8 K-chunks of hi + lo images
+    assert L.pnr_linear_workspace_bytes(300, 64) == 0 and L.pnr_linear_workspace_bytes(16, 600) == 0
+    assert L.pnr_wgrad_workspace_bytes(300, 16) == 0 and L.pnr_wgrad_workspace_bytes(16, 0) == 0
+    n = L.pnr_wgrad_workspace_bytes(256, 256)
+    assert n > 0 and n % ((2 * 128 * 256 + 256) * 4) == 0                     # one partial product + bias row per SM
+    prec = _capi.PREC["fp16x3"]
+    rc = L.pnr_wgrad(None, 256, 256, None, 256, 256, 10, prec, None, None, 256, None, 0, None, 0, None)
+    assert rc == -1 and b"required" in L.pnr_last_error()
+    rc = L.pnr_wgrad(64, 256, 300, 64, 256, 256, 10, prec, None, 64, 256, None, 0, None, 0, None)   # (never dereferenced)
+    assert rc == -1 and b"No = 300" in L.pnr_last_error()
+    rc = L.pnr_wgrad(64, 100, 256, 64, 256, 256, 10, prec, None, 64, 256, None, 0, None, 0, None)
+    assert rc == -1 and b"leading dimensions" in L.pnr_last_error()
+    rc = L.pnr_wgrad(64, 256, 256, 64, 256, 256, 10, _capi.PREC["fp16"], None, 64, 256, None, 0, None, 0, None)
+    assert rc == -1 and b"x3 precisions" in L.pnr_last_error()
+    rc = L.pnr_linear(None, 256, 256, None, 256, 0, None, 256, 10, 0, prec, None, None, 256, None, 0, None)
+    assert rc == -1 and b"required" in L.pnr_last_error()
+    rc = L.pnr_linear(64, 256, 600, 64, 600, 0, None, 256, 10, 0, prec, None, 64, 256, None, 0, None)
+    assert rc == -1 and b"K = 600" in L.pnr_last_error()
+    rc = L.pnr_linear(64, 256, 256, 64, 256, 0, None, 256, 10, 0, prec, None, 64, 256, None, 0, None)
+    assert rc == -1 and b"workspace" in L.pnr_last_error()

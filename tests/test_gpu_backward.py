@@ -212,7 +212,7 @@ def test_mlp_backward_trunk_unpadded_rows_match_padded():
     padded = net.backward_trunk(grad_h, pts=pts, grad_scale=256.0)
     out = torch.full((n, Ex), float("nan"), device=DEV)
     _capi.check(_capi.lib().pnr_mlp_backward_trunk(net.pack(torch.device(DEV)), pts.data_ptr(), None, None, n, 1,
-                                                   grad_h.data_ptr(), 256.0, out.data_ptr(), Ex, None, _capi.stream_ptr()))
+                                                   grad_h.data_ptr(), 256.0, out.data_ptr(), Ex, None, None, _capi.stream_ptr()))
     assert torch.equal(out, padded)
 
 
@@ -374,6 +374,28 @@ def test_update_weights_equals_fresh_load(preset, over):
     for a, b, c in zip(got, got_late, ref):
         assert torch.equal(a, c) and torch.equal(b, c)
     assert net.range_status() == 0
+
+
+def test_backward_trunk_collects_the_stash_maxima():
+    """The backward kernel reports the largest |value| of every stash slot (what scales the weight-gradient GEMMs):
+    equal to a reduction over the stash itself up to the 11 bits of an fp16 hi part."""
+    import panopticnerf_b200 as PN
+    from panopticnerf_b200 import synthetic as S
+    cfg = PN.make_cfg("cfg1")
+    net = S.init_network_weights(PN.make_network(cfg)).to(DEV)
+    g = torch.Generator().manual_seed(3)
+    n = 1000
+    pts = (torch.rand(n, 3, generator=g) * 2 - 1).to(DEV)
+    grad_h = (torch.randn(n, net.W, generator=g) * 2e-6).to(DEV)
+    _, st, mx = net.backward_trunk(grad_h, pts=pts, stash=True, absmax=True)
+    ref = st.abs().amax(dim=(1, 2))
+    assert mx.shape == ref.shape and torch.isfinite(mx).all()
+    rel = ((mx - ref).abs() / ref.clamp(min=1e-30)).max()
+    assert float(rel) <= 2.0 ** -10, f"stash maxima off by {float(rel):.2e}"
+    # and the two ways of getting the GEMM scales agree
+    from panopticnerf_b200.lib.train.mlp_backward import _pow2_scales, _pow2_from_max
+    a, b = _pow2_scales(st[net.D - 1:]), _pow2_from_max(mx[net.D - 1:])
+    assert all(float(x) in (float(y), 2 * float(y), 0.5 * float(y)) for x, y in zip(a, b))   # a rounding boundary apart at most
 
 
 # ------------------------------------------------------------------------------------------------
