@@ -15,9 +15,11 @@
 //     no-swizzle K-major core matrices (K = samples): a thread's 8 samples of one feature ARE one core-matrix row, so
 //     the transposition dZ -> dZ^T costs nothing.  The 8-row groups of the images are 144 bytes apart instead of 128
 //     (the descriptor's stride byte offset is free to say so): the four feature rows of a lane and those of the
-//     lanes next to it then fall into different banks.  The next slab's loads are in flight while a slab is converted.
-//   * one elected lane of warp 0 (after its own share of the slab) issues tcgen05.mma kind::f16 (bf16 operands, fp32
-//     accumulate), both operands from shared memory (512 threads = 128 registers each; a 17th warp would cost 32):
+//     lanes next to it then fall into different banks.  The next slab's loads are in flight while a slab is converted
+//     (two register buffers used alternately), and the slab after that is prefetched into L2: one slab per thread in
+//     registers is 64 KB in flight per SM, not enough at ~2 us of loaded DRAM latency, and a prefetch costs no register.
+//   * one elected lane of warp 0 (after its own share of the slab) issues tcgen05.mma kind::f16 (fp16 or bf16 operands,
+//     fp32 accumulate), both operands from shared memory (512 threads = 128 registers each; a 17th warp would cost 32):
 //     A = dZ^T (M = 128 output features x K = 16 samples), B = X^T (N = Ni padded to 16, K-major), three products
 //     per K step: hi.hi + lo.hi + hi.lo.  bf16 parts: ~2^-17 per product, fp32 exponent range, gradients need no
 //     scaling.  fp16 parts: ~2^-21 per product; dZ is multiplied by a caller-supplied power of two on load (a device
@@ -25,7 +27,9 @@
 //   * a 3-deep ring of 72 KB stages (A hi, A lo, B hi, B lo images of [4 K-cores][32 row groups][144 B]); full /
 //     empty mbarriers, the empty ones arrived by tcgen05.commit.
 // The kernel is HBM-bound by construction: 2 KB of fp32 operands per sample against 2 * 3 * 256 * 256 tensor flops
-// (~50 tensor-pipe cycles per sample and SM): algorithmic bytes = 4 (No + Ni) per sample.
+// (~50 tensor-pipe cycles per sample and SM): algorithmic bytes = 4 (No + Ni) per sample.  Measured (B200, 256 x 256,
+// profiles/r02_wgrad_final_ncu.txt): 4.1 TB/s of operand reads at 393 k samples, 4.8 TB/s at 4 M (62 % / 73 % of the
+// measured 6.58 TB/s copy peak); DRAM traffic = the algorithmic bytes.
 #include <cstddef>
 #include <mutex>
 #include "common.cuh"
