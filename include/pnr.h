@@ -264,8 +264,8 @@ int pnr_mlp_backward_trunk(pnr_ctx* ctx, const float* pts, const float* rays, co
                            uint32_t* stash_absmax, void* stream);
 /* The weight gradients of the trunk come from `stash` [2D-1, R*N, W] fp32 (NULL: not kept): every A operand the
  * kernel produces on the way - slot i < D-1: H_i, the activations of forward layer i; slot 2D-2-j: dZ_j, the gradient
- * w.r.t. layer j's pre-activation - so that dW_j = dZ_j^T [H_{j-1} (, gamma(x))], db_j = sum_s dZ_j are plain GEMMs
- * / reductions for the caller's BLAS.  pnr_mlp_trunk_forward returns the trunk's output h [R*N, W] (16-byte
+ * w.r.t. layer j's pre-activation - so that dW_j = dZ_j^T [H_{j-1} (, gamma(x))], db_j = sum_s dZ_j are GEMMs over
+ * the samples: pnr_wgrad.  pnr_mlp_trunk_forward returns the trunk's output h [R*N, W] (16-byte
  * aligned), the input of the layers after the trunk (alpha / feature / view / rgb / heads), which the caller
  * differentiates itself to obtain grad_h.
  * stash_absmax (nullable; needs stash) [2D-1] u32, zeroed by the call: slot k receives the largest magnitude written
