@@ -539,6 +539,42 @@ def main():
         except Exception as exc:   # noqa: BLE001
             extra["train_step_cfg3"] = {"error": repr(exc)[:300]}
         del n3
+        # the two HBM-bound GEMM kernels of that step, timed alone against the measured copy bandwidth (operands of
+        # 403 MB each: larger than L2, no flush needed).  Informational; a failure here must not cost the bench line.
+        try:
+            from panopticnerf_b200.lib.train.mlp_backward import wgrad, linear3x, _pow2_scale
+            gg = torch.Generator().manual_seed(1)
+            Sg = 393216
+            dz_g = (torch.randn(Sg, 256, generator=gg) * 1e-6).to(dev)
+            x_g = torch.relu(torch.randn(Sg, 256, generator=gg)).to(dev)
+            w_g = (torch.randn(256, 256, generator=gg) / 16.0).to(dev)
+            sc_g = _pow2_scale(dz_g)
+
+            def _median_ms(fn, reps=5, warm=2):
+                ts = []
+                for i in range(warm + reps):
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    fn()
+                    b.record()
+                    torch.cuda.synchronize()
+                    if i >= warm:
+                        ts.append(a.elapsed_time(b))
+                return statistics.median(ts)
+
+            t_w = _median_ms(lambda: wgrad(dz_g, x_g, precision="fp16x3", scale=sc_g))
+            t_l = _median_ms(lambda: linear3x(x_g, w_g, precision="fp16x3"))
+            hbm = float(peaks()["hbm_gbs"])
+            byt = 4.0 * Sg * 512
+            extra["train_gemms"] = {
+                "workload": f"{Sg} samples x 256 x 256, fp16x3: pnr_wgrad (dW = dZ^T X + column sums; reads dZ and X) and "
+                            "pnr_linear (y = x W^T; reads x, writes y); algorithmic bytes = 2 KB per sample each",
+                "wgrad": {"ms": t_w, "achieved_gbs": byt / t_w / 1e6, "frac_of_hbm_peak": byt / t_w / 1e6 / hbm},
+                "linear": {"ms": t_l, "achieved_gbs": byt / t_l / 1e6, "frac_of_hbm_peak": byt / t_l / 1e6 / hbm},
+                "peak_gbs": hbm, "bound": "hbm"}
+            del dz_g, x_g, w_g
+        except Exception as exc:   # noqa: BLE001
+            extra["train_gemms"] = {"error": repr(exc)[:300]}
 
     # ---------------- CPU baseline (rank 0, N=1): oracle port on the host cores, bounded strip + measured parity
     cpu_baseline, parity = None, None
