@@ -67,3 +67,32 @@ def test_new_entry_points_validate_their_arguments_before_touching_the_device():
     assert rc == -1 and b"K = 600" in L.pnr_last_error()
     rc = L.pnr_linear(64, 256, 256, 64, 256, 0, None, 256, 10, 0, prec, None, 64, 256, None, 0, None)
     assert rc == -1 and b"workspace" in L.pnr_last_error()
+
+
+def test_operand_split_error_model_of_the_gradient_gemms():
+    """What the 16-bit hi / lo operand parts of pnr_wgrad / pnr_linear can and cannot represent, with exact (float64)
+    accumulation: hi.hi + lo.hi + hi.lo on ~1e-6 gradients.  fp16 parts need the power-of-two scale (unscaled, the
+    gradients fall below fp16's subnormal spacing), and with it they are ~50x more accurate than bf16 parts; both are
+    inside the path's 1e-4.  These are the levels the GPU tests' thresholds are set against."""
+    g = torch.Generator().manual_seed(0)
+    S_, No, Ni = 4096, 64, 96
+    dz = torch.randn(S_, No, generator=g) * 1e-6 * (0.1 + torch.rand(1, No, generator=g) * 3.0)
+    dz = dz * (torch.rand(S_, No, generator=g) < 0.6)
+    x = torch.relu(torch.randn(S_, Ni, generator=g)) + 0.05 * torch.randn(S_, Ni, generator=g)
+    ref = dz.double().t() @ x.double()
+
+    def three_products(a, b, dt):
+        ah = a.to(dt).float()
+        al = (a - ah).to(dt).float()
+        bh = b.to(dt).float()
+        bl = (b - bh).to(dt).float()
+        ah, al, bh, bl = (t.double() for t in (ah, al, bh, bl))
+        return ah.t() @ bh + al.t() @ bh + ah.t() @ bl
+
+    err = lambda y: float((y - ref).abs().max() / ref.pow(2).mean().sqrt())
+    sc = float(MB._pow2_scale(dz))
+    e_fp16 = err(three_products(dz * sc, x, torch.float16) / sc)
+    e_bf16 = err(three_products(dz, x, torch.bfloat16))
+    e_raw = err(three_products(dz, x, torch.float16))
+    assert e_fp16 < 2e-6 and 5e-6 < e_bf16 < 6e-5 and e_fp16 < e_bf16 / 10
+    assert e_raw > 1e-3                                  # unscaled fp16 parts: the gradients are mostly gone
